@@ -1,0 +1,66 @@
+// common.cuh -- shared helpers of libb200serve.so (error plumbing, launch accounting, model ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/b200serve.h"
+
+namespace b2s {
+
+// ---- error plumbing: thread-local message behind b2s_last_error() -----------------------------
+std::string &tls_error();
+int fail(int code, const char *fmt, ...);
+int fail_cuda(cudaError_t e, const char *what);
+
+#define B2S_CUDA(call)                                              \
+    do {                                                            \
+        cudaError_t _e = (call);                                    \
+        if (_e != cudaSuccess) return ::b2s::fail_cuda(_e, #call);  \
+    } while (0)
+
+#define B2S_TRY(call)             \
+    do {                          \
+        int _s = (call);          \
+        if (_s != 0) return _s;   \
+    } while (0)
+
+// every kernel launch of the library goes through this counter (bench.py "gpu_launches")
+extern std::atomic<uint64_t> g_launch_count;
+inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+inline size_t dtype_size(int dt)
+{
+    switch (dt) {
+    case B2S_F32: case B2S_I32: case B2S_U32: return 4;
+    case B2S_F64: case B2S_I64: case B2S_U64: return 8;
+    case B2S_U8: case B2S_I8: case B2S_BOOL: return 1;
+    case B2S_F16: return 2;
+    default: return 0;
+    }
+}
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- internal model interface: each model kind implements launch() on a stream -----------------
+struct Model {
+    int device = 0;
+    b2s_model_info info{};
+    virtual ~Model() {}
+    // bytes of per-stream device scratch needed for batches of up to max_rows rows
+    virtual size_t scratch_bytes(int64_t max_rows, int64_t max_row_elems) const = 0;
+    // enqueue the model's kernels; d_in/d_out are device pointers; `scratch` is zero-initialised
+    // once at stream creation and must be left zeroed where the kernels rely on it
+    virtual int launch(cudaStream_t st, int64_t n_rows, const void *const *d_in,
+                       void *const *d_out, const int64_t *d_row_offsets, void *scratch,
+                       size_t scratch_bytes) = 0;
+};
+
+int forest_model_create(int device, const void *blob, size_t bytes, Model **out);
+int linear_model_create(int device, const void *blob, size_t bytes, Model **out);
+
+}  // namespace b2s

@@ -1,0 +1,269 @@
+"""Model ingestion: turn the files the reference's engines load into packed blobs for libb200serve.
+
+Reference loaders replaced (load-time only; nothing here is on the request path):
+  * xgboost.Booster().load_model(path)   clearml_serving/serving/preprocess_service.py:475-476
+  * joblib.load(path) of an sklearn model clearml_serving/serving/preprocess_service.py:457
+The device layouts are documented in csrc/forest.cu and csrc/linear.cu.
+"""
+import json
+import struct
+
+import numpy as np
+
+from . import native
+
+_IDENTITY_OBJECTIVES = ("reg:squarederror", "reg:linear", "reg:absoluteerror",
+                        "reg:pseudohubererror", "binary:logitraw")
+
+
+class PackedModel(object):
+    """kind + blob + the I/O description the engine needs."""
+
+    def __init__(self, kind, blob, description):
+        self.kind = kind
+        self.blob = blob
+        self.description = description
+
+
+# --------------------------------------------------------------------------------------------
+# forests
+# --------------------------------------------------------------------------------------------
+
+def _skl_threshold_to_f32_strict(thr64):
+    """sklearn goes left iff fp32 x <= thr64.  Exact fp32 restatement: x < nextafter(down32(thr64), +inf)
+    where down32 rounds toward -inf to fp32 (for fp32 x: x <= thr64 <=> x <= down32(thr64))."""
+    thr64 = np.asarray(thr64, dtype=np.float64)
+    with np.errstate(over="ignore"):
+        t = thr64.astype(np.float32)
+    too_big = t.astype(np.float64) > thr64
+    t = np.where(too_big, np.nextafter(t, np.float32(-np.inf)), t).astype(np.float32)
+    return np.nextafter(t, np.float32(np.inf)).astype(np.float32)
+
+
+def pack_forest(forest, mode, base=0.0, scale=1.0, divisor=1.0):
+    """forest: source form (dict of arrays: tree_offset,left,right,feat,thr,default_left,value,
+    n_features; children local to each tree, left<0 => leaf).
+    mode 'xgb': fp32 sequential sum, split `x < float32(thr)`.
+    mode 'skl': fp64 sequential sum of scale*value, split `x <= thr64`, result / divisor."""
+    if mode not in ("xgb", "skl"):
+        raise ValueError("pack_forest: mode must be 'xgb' or 'skl'")
+    off = np.asarray(forest["tree_offset"], dtype=np.int64)
+    n_trees = len(off) - 1
+    n_features = int(forest["n_features"])
+    if n_trees <= 0:
+        raise ValueError("pack_forest: empty forest")
+    left = np.asarray(forest["left"], dtype=np.int64)
+    right = np.asarray(forest["right"], dtype=np.int64)
+    feat = np.asarray(forest["feat"], dtype=np.int64)
+    thr = np.asarray(forest["thr"], dtype=np.float64)
+    dl = np.asarray(forest["default_left"], dtype=np.int64)
+    value = np.asarray(forest["value"], dtype=np.float64)
+
+    feat_bits = max(1, int(n_features - 1).bit_length())
+    left_bits = 31 - feat_bits
+    f64 = mode == "skl"
+    thr32 = _skl_threshold_to_f32_strict(thr) if f64 else thr.astype(np.float32)
+
+    new_off = [0]
+    val_bits = []
+    meta = []
+    leaf64 = []
+    for t in range(n_trees):
+        s, e = int(off[t]), int(off[t + 1])
+        n = e - s
+        if n <= 0:
+            raise ValueError("pack_forest: tree {} has no nodes".format(t))
+        if n >= (1 << left_bits):
+            raise ValueError("pack_forest: tree {} has {} nodes; {} features leave room for {}".format(
+                t, n, n_features, (1 << left_bits) - 1))
+        # breadth-first renumbering so that right child == left child + 1
+        order = [0]
+        new_left = {}
+        qi = 0
+        while qi < len(order):
+            old = order[qi]
+            l_old = int(left[s + old])
+            if l_old >= 0:
+                r_old = int(right[s + old])
+                if not (0 <= l_old < n and 0 <= r_old < n):
+                    raise ValueError("pack_forest: tree {} has a child index out of range".format(t))
+                new_left[qi] = len(order)
+                order.append(l_old)
+                order.append(r_old)
+                if len(order) > n:
+                    raise ValueError("pack_forest: tree {} is not a tree (node reached twice)".format(t))
+            qi += 1
+        order = np.asarray(order, dtype=np.int64) + s
+        is_leaf = left[order] < 0
+        m = np.zeros(len(order), dtype=np.uint32)
+        v = np.zeros(len(order), dtype=np.uint32)
+        for new_i, nl in new_left.items():
+            g = order[new_i]
+            f = int(feat[g])
+            if not (0 <= f < n_features):
+                raise ValueError("pack_forest: feature index {} out of range".format(f))
+            m[new_i] = np.uint32(f | (int(dl[g] != 0) << feat_bits) | (nl << (feat_bits + 1)))
+        v[~is_leaf] = thr32[order[~is_leaf]].view(np.uint32)
+        if f64:
+            lv = (np.float64(scale) * value[order[is_leaf]]).astype(np.float64)
+            v[is_leaf] = np.arange(len(leaf64), len(leaf64) + lv.size, dtype=np.uint32)
+            leaf64.extend(lv.tolist())
+        else:
+            v[is_leaf] = value[order[is_leaf]].astype(np.float32).view(np.uint32)
+        val_bits.append(v)
+        meta.append(m)
+        new_off.append(new_off[-1] + len(order))
+
+    val_bits = np.concatenate(val_bits)
+    meta = np.concatenate(meta)
+    nodes = (val_bits.astype(np.uint64) | (meta.astype(np.uint64) << np.uint64(32))).astype("<u8")
+    toff = np.asarray(new_off, dtype="<u4")
+    toff_bytes = toff.tobytes()
+    if len(toff_bytes) % 8:
+        toff_bytes += b"\0" * (8 - len(toff_bytes) % 8)
+    leaf64 = np.asarray(leaf64, dtype="<f8")
+    base_v = float(base) if f64 else float(np.float32(base))
+    header = struct.pack("<4sIIIIIIIIIdd", b"B2SF", 1, n_trees, n_features, int(nodes.size), feat_bits,
+                         1 if f64 else 0, int(leaf64.size), 0, 0, base_v, float(divisor))
+    blob = header + toff_bytes + nodes.tobytes() + leaf64.tobytes()
+    desc = dict(kind="forest", mode=mode, n_trees=n_trees, n_features=n_features, n_nodes=int(nodes.size),
+                input_dtype="float32", output_dtype="float64" if f64 else "float32")
+    return PackedModel(native.MODEL_FOREST, blob, desc)
+
+
+def parse_xgboost_json(model):
+    """XGBoost JSON model schema (learner.gradient_booster.model.trees[*]) -> (source form, base_score).
+    Accepts a dict, a JSON string/bytes, or a path."""
+    if isinstance(model, (bytes, bytearray)):
+        model = json.loads(model.decode("utf-8"))
+    elif isinstance(model, str):
+        if model.lstrip().startswith("{"):
+            model = json.loads(model)
+        else:
+            with open(model, "rb") as f:
+                head = f.read(1)
+                f.seek(0)
+                if head != b"{":
+                    raise ValueError(
+                        "b200 engine: '{}' is not an XGBoost JSON model (save it with "
+                        "Booster.save_model('model.json'))".format(model))
+                model = json.load(f)
+    learner = model["learner"]
+    objective = learner.get("objective", {}).get("name", "reg:squarederror")
+    if objective not in _IDENTITY_OBJECTIVES:
+        raise ValueError("b200 engine: XGBoost objective '{}' is not supported yet (identity-link "
+                         "objectives only: {})".format(objective, ", ".join(_IDENTITY_OBJECTIVES)))
+    lmp = learner["learner_model_param"]
+    if int(lmp.get("num_class", "0") or 0) > 1 or int(lmp.get("num_target", "1") or 1) > 1:
+        raise ValueError("b200 engine: multi-class / multi-target XGBoost models are not supported yet")
+    gb = learner["gradient_booster"]
+    if gb.get("name", "gbtree") not in ("gbtree",):
+        raise ValueError("b200 engine: booster '{}' is not supported (gbtree only)".format(gb.get("name")))
+    base_score = np.float32(float(lmp.get("base_score", "0.5")))
+    n_features = int(lmp["num_feature"])
+    trees = gb["model"]["trees"]
+    off, left, right, feat, thr, dl, val = [0], [], [], [], [], [], []
+    for t in trees:
+        if any(int(x) != 0 for x in t.get("split_type", [])) or len(t.get("categories", [])):
+            raise ValueError("b200 engine: categorical splits are not supported")
+        l = np.asarray(t["left_children"], dtype=np.int32)
+        cond = np.asarray(t["split_conditions"], dtype=np.float64)
+        left.append(l)
+        right.append(np.asarray(t["right_children"], dtype=np.int32))
+        feat.append(np.asarray(t["split_indices"], dtype=np.int32))
+        thr.append(cond)
+        dl.append(np.asarray(t["default_left"], dtype=np.uint8))
+        val.append(cond)  # a leaf keeps its value in split_conditions
+        off.append(off[-1] + len(l))
+    forest = dict(tree_offset=np.asarray(off, np.int32), left=np.concatenate(left),
+                  right=np.concatenate(right), feat=np.concatenate(feat), thr=np.concatenate(thr),
+                  default_left=np.concatenate(dl), value=np.concatenate(val), n_features=n_features)
+    return forest, float(base_score)
+
+
+def pack_xgboost_json(model):
+    forest, base_score = parse_xgboost_json(model)
+    return pack_forest(forest, "xgb", base=base_score)
+
+
+def _forest_from_sklearn_trees(estimators, n_features):
+    off, left, right, feat, thr, dl, val = [0], [], [], [], [], [], []
+    for e in estimators:
+        t = e.tree_
+        if t.value.shape[1] != 1 or t.value.shape[2] != 1:
+            raise ValueError("b200 engine: multi-output / classification trees are not supported yet")
+        left.append(t.children_left.astype(np.int32))
+        right.append(t.children_right.astype(np.int32))
+        feat.append(np.maximum(t.feature, 0).astype(np.int32))
+        thr.append(t.threshold.astype(np.float64))
+        mg = getattr(t, "missing_go_to_left", None)
+        dl.append(np.asarray(mg, dtype=np.uint8) if mg is not None else np.zeros(t.node_count, np.uint8))
+        val.append(t.value[:, 0, 0].astype(np.float64))
+        off.append(off[-1] + t.node_count)
+    return dict(tree_offset=np.asarray(off, np.int32), left=np.concatenate(left), right=np.concatenate(right),
+                feat=np.concatenate(feat), thr=np.concatenate(thr), default_left=np.concatenate(dl),
+                value=np.concatenate(val), n_features=int(n_features))
+
+
+# --------------------------------------------------------------------------------------------
+# linear
+# --------------------------------------------------------------------------------------------
+
+def pack_linear(coef, intercept, classes):
+    coef = np.atleast_2d(np.asarray(coef, dtype=np.float64))
+    intercept = np.atleast_1d(np.asarray(intercept, dtype=np.float64))
+    classes = np.asarray(classes, dtype=np.int64)
+    n_out, n_features = coef.shape
+    if intercept.size != n_out:
+        raise ValueError("pack_linear: intercept size mismatch")
+    if classes.size != (2 if n_out == 1 else n_out):
+        raise ValueError("pack_linear: classes size mismatch")
+    header = struct.pack("<4sIIIII", b"B2SL", 1, n_features, n_out, int(classes.size), 0)
+    blob = header + coef.astype("<f8").tobytes() + intercept.astype("<f8").tobytes() + classes.astype("<i8").tobytes()
+    desc = dict(kind="linear", n_features=n_features, n_out=n_out, input_dtype="float64", output_dtype="int64")
+    return PackedModel(native.MODEL_LINEAR, blob, desc)
+
+
+# --------------------------------------------------------------------------------------------
+# dispatch on what the reference's engines would have loaded
+# --------------------------------------------------------------------------------------------
+
+def pack_sklearn(model):
+    """An (unpickled) sklearn estimator -> PackedModel. Supported: GradientBoostingRegressor
+    (squared_error), RandomForestRegressor / ExtraTreesRegressor, DecisionTreeRegressor,
+    LogisticRegression-like linear classifiers (coef_/intercept_/classes_ with integer classes)."""
+    name = type(model).__name__
+    if name == "GradientBoostingRegressor":
+        if getattr(model, "loss", "squared_error") != "squared_error":
+            raise ValueError("b200 engine: GradientBoostingRegressor loss '{}' not supported".format(model.loss))
+        init = getattr(model, "init_", None)
+        const = getattr(init, "constant_", None)
+        if const is None:
+            raise ValueError("b200 engine: GradientBoostingRegressor with a custom init estimator is not supported")
+        forest = _forest_from_sklearn_trees([e[0] for e in model.estimators_], model.n_features_in_)
+        return pack_forest(forest, "skl", base=float(np.ravel(const)[0]), scale=float(model.learning_rate), divisor=1.0)
+    if name in ("RandomForestRegressor", "ExtraTreesRegressor"):
+        if getattr(model, "n_outputs_", 1) != 1:
+            raise ValueError("b200 engine: multi-output forests are not supported")
+        forest = _forest_from_sklearn_trees(model.estimators_, model.n_features_in_)
+        return pack_forest(forest, "skl", base=0.0, scale=1.0, divisor=float(len(model.estimators_)))
+    if name in ("DecisionTreeRegressor", "ExtraTreeRegressor"):
+        forest = _forest_from_sklearn_trees([model], model.n_features_in_)
+        # DecisionTreeRegressor.predict returns value[leaf]: 0 + v is exact, / 1 is exact
+        return pack_forest(forest, "skl", base=0.0, scale=1.0, divisor=1.0)
+    if hasattr(model, "coef_") and hasattr(model, "intercept_") and hasattr(model, "classes_"):
+        classes = np.asarray(model.classes_)
+        if not np.issubdtype(classes.dtype, np.integer):
+            raise ValueError("b200 engine: only integer class labels are supported for linear classifiers")
+        return pack_linear(model.coef_, model.intercept_, classes)
+    raise ValueError("b200 engine: unsupported sklearn model type '{}'".format(name))
+
+
+def load_model_file(path):
+    """Sniff the model file the reference would hand to xgboost / joblib and pack it."""
+    with open(path, "rb") as f:
+        head = f.read(16)
+    if head.lstrip()[:1] == b"{":
+        return pack_xgboost_json(path)
+    import joblib  # noqa  (the reference's sklearn engine loads with joblib too)
+    return pack_sklearn(joblib.load(path))

@@ -1,0 +1,387 @@
+"""ctypes binding of libb200serve.so (include/b200serve.h).
+
+There is NO fallback: if the shared library is missing or a CUDA device is absent every compute
+entry point raises.  Importing this module only dlopens the library (works on a CPU-only box so
+the symbol-export test can run); `init()` needs a GPU.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200serve.so")
+
+B2S_OK = 0
+B2S_ERR_INVALID = -1
+B2S_ERR_CUDA = -2
+B2S_ERR_OOM = -3
+B2S_ERR_NOT_INITIALISED = -4
+B2S_ERR_BUSY = -5
+B2S_ERR_NOT_READY = 1
+
+MODEL_FOREST, MODEL_LINEAR, MODEL_GRAPH = 1, 2, 3
+
+DTYPES = {  # b2s_dtype <-> numpy
+    0: np.float32, 1: np.float64, 2: np.int32, 3: np.int64, 4: np.uint8, 5: np.int8,
+    6: np.bool_, 7: np.uint64, 8: np.float16, 9: np.uint32,
+}
+DTYPE_CODES = {np.dtype(v): k for k, v in DTYPES.items()}
+MAX_DIMS = 8
+
+
+class Tensor(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("ndim", ctypes.c_int32),
+                ("shape", ctypes.c_int64 * MAX_DIMS)]
+
+
+class ModelInfo(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("n_inputs", ctypes.c_int32), ("n_outputs", ctypes.c_int32),
+                ("in_dtype", ctypes.c_int32 * 4), ("out_dtype", ctypes.c_int32 * 4),
+                ("in_row_elems", ctypes.c_int64 * 4), ("out_row_elems", ctypes.c_int64 * 4),
+                ("weight_bytes", ctypes.c_int64), ("algo_bytes_fixed", ctypes.c_int64),
+                ("algo_bytes_per_row", ctypes.c_int64)]
+
+
+class B2SError(ValueError):
+    """Raised for every non-zero status. A ValueError so the reference's REST layer maps it to 422
+    (clearml_serving/serving/main.py:155-161) -- and a message containing "CUDA out of memory. "
+    triggers its restart path (main.py:116-123)."""
+
+    def __init__(self, code, message):
+        super(B2SError, self).__init__(message)
+        self.code = code
+
+
+# (name, restype, argtypes): must list every prototype of include/b200serve.h
+_vp, _i, _i32, _i64, _u64, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64,
+                                  ctypes.c_uint64, ctypes.c_size_t)
+_P = ctypes.POINTER
+PROTOTYPES = [
+    ("b2s_init", _i, [_i, _sz]),
+    ("b2s_shutdown", _i, []),
+    ("b2s_abi_version", _i, []),
+    ("b2s_last_error", ctypes.c_char_p, []),
+    ("b2s_launch_count", _u64, []),
+    ("b2s_device_count", _i, []),
+    ("b2s_model_load", _i, [_i, _i, _vp, _sz, ctypes.c_char_p, _P(_u64)]),
+    ("b2s_model_free", _i, [_u64]),
+    ("b2s_model_get_info", _i, [_u64, _P(ModelInfo)]),
+    ("b2s_stream_create", _i, [_u64, _i64, _i64, _i, _P(_u64)]),
+    ("b2s_stream_destroy", _i, [_u64]),
+    ("b2s_stream_synchronize", _i, [_u64]),
+    ("b2s_stream_cuda_handle", _vp, [_u64]),
+    ("b2s_infer_batch", _i, [_u64, _u64, _i32, _P(Tensor), _P(Tensor), _P(_u64)]),
+    ("b2s_slot_acquire", _i, [_u64, _P(_i32), _P(_vp), _P(_vp)]),
+    ("b2s_slot_submit", _i, [_u64, _u64, _i32, _i64, _vp, _P(_u64)]),
+    ("b2s_slot_release", _i, [_u64, _i32]),
+    ("b2s_event_wait", _i, [_u64]),
+    ("b2s_event_query", _i, [_u64]),
+    ("b2s_infer_device", _i, [_u64, _u64, _i64, _P(_vp), _P(_vp), _vp]),
+    ("b2s_device_malloc", _i, [_i, _sz, _P(_vp)]),
+    ("b2s_device_free", _i, [_i, _vp]),
+    ("b2s_memcpy_h2d", _i, [_i, _vp, _vp, _sz]),
+    ("b2s_memcpy_d2h", _i, [_i, _vp, _vp, _sz]),
+    ("b2s_flush_l2", _i, [_i]),
+    ("b2s_timer_create", _i, [_u64, _P(_u64)]),
+    ("b2s_timer_start", _i, [_u64]),
+    ("b2s_timer_stop", _i, [_u64]),
+    ("b2s_timer_elapsed_ms", _i, [_u64, _P(ctypes.c_float)]),
+    ("b2s_timer_destroy", _i, [_u64]),
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+_inited_devices = set()
+
+
+def lib():
+    """dlopen libb200serve.so (built in-tree by clearml_serving_b200.build). Fails loudly."""
+    global _lib
+    if _lib is None:
+        with _lib_lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "libb200serve.so is missing at {} -- build it with `python -m clearml_serving_b200.build` "
+                        "(there is no CPU fallback for the b200 engine)".format(LIB_PATH))
+                l = ctypes.CDLL(LIB_PATH)
+                for name, restype, argtypes in PROTOTYPES:
+                    fn = getattr(l, name)
+                    fn.restype = restype
+                    fn.argtypes = argtypes
+                if l.b2s_abi_version() != 1:
+                    raise RuntimeError("libb200serve.so ABI version mismatch")
+                _lib = l
+    return _lib
+
+
+def last_error():
+    msg = lib().b2s_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc):
+    if rc != 0:
+        raise B2SError(rc, "b200serve: {}".format(last_error() or "error {}".format(rc)))
+
+
+def device_count():
+    return int(lib().b2s_device_count())
+
+
+def init(device=0, pinned_arena_bytes=0):
+    check(lib().b2s_init(int(device), int(pinned_arena_bytes)))
+    _inited_devices.add(int(device))
+
+
+def ensure_init(device=0, pinned_arena_bytes=0):
+    if int(device) not in _inited_devices:
+        init(device, pinned_arena_bytes)
+
+
+def shutdown():
+    check(lib().b2s_shutdown())
+    _inited_devices.clear()
+
+
+def launch_count():
+    return int(lib().b2s_launch_count())
+
+
+def flush_l2(device=0):
+    check(lib().b2s_flush_l2(int(device)))
+
+
+class Model(object):
+    def __init__(self, kind, blob, device=0):
+        ensure_init(device)
+        self.device = int(device)
+        self.kind = int(kind)
+        blob = bytes(blob)
+        h = ctypes.c_uint64(0)
+        check(lib().b2s_model_load(self.device, self.kind, blob, len(blob), None, ctypes.byref(h)))
+        self.handle = h.value
+        info = ModelInfo()
+        check(lib().b2s_model_get_info(self.handle, ctypes.byref(info)))
+        self.info = info
+        self.n_inputs = info.n_inputs
+        self.n_outputs = info.n_outputs
+        self.in_dtypes = [np.dtype(DTYPES[info.in_dtype[i]]) for i in range(info.n_inputs)]
+        self.out_dtypes = [np.dtype(DTYPES[info.out_dtype[i]]) for i in range(info.n_outputs)]
+        self.in_row_elems = [int(info.in_row_elems[i]) for i in range(info.n_inputs)]
+        self.out_row_elems = [int(info.out_row_elems[i]) for i in range(info.n_outputs)]
+
+    def algo_bytes(self, n_rows):
+        return int(self.info.algo_bytes_fixed) + int(n_rows) * int(self.info.algo_bytes_per_row)
+
+    def free(self):
+        if self.handle:
+            try:
+                check(lib().b2s_model_free(self.handle))
+            finally:
+                self.handle = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", 0) and _lib is not None:
+                lib().b2s_model_free(self.handle)
+        except Exception:  # noqa
+            pass
+
+
+def _view(ptr, nbytes, dtype):
+    buf = (ctypes.c_char * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype)
+
+
+class Slot(object):
+    """A pinned staging slot exposed as numpy views (inputs: [max_rows, row_elems])."""
+    __slots__ = ("index", "inputs", "outputs")
+
+    def __init__(self, index, inputs, outputs):
+        self.index, self.inputs, self.outputs = index, inputs, outputs
+
+
+class Stream(object):
+    """One CUDA stream + pinned staging slots: one per endpoint."""
+
+    def __init__(self, model, max_rows, max_row_elems=0, n_slots=4):
+        self.model = model
+        self.max_rows = int(max_rows)
+        self.max_row_elems = int(max_row_elems)
+        self.n_slots = int(n_slots)
+        h = ctypes.c_uint64(0)
+        check(lib().b2s_stream_create(model.handle, self.max_rows, self.max_row_elems, self.n_slots, ctypes.byref(h)))
+        self.handle = h.value
+        self._slot_views = {}
+
+    # ---- general C-ABI path: per-request host tensors, gather/scatter inside the library --------
+    def infer_batch(self, requests, outputs=None):
+        """requests: list (per request) of list (per model input) of C-contiguous numpy arrays.
+        Returns (event, outs) where outs[r][o] are numpy arrays filled when wait(event) returns."""
+        m = self.model
+        n_req = len(requests)
+        tin = (Tensor * (n_req * m.n_inputs))()
+        tout = (Tensor * (n_req * m.n_outputs))()
+        outs = []
+        keep = []
+        for r, req in enumerate(requests):
+            rows = None
+            for i in range(m.n_inputs):
+                a = req[i]
+                if not (isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]):
+                    a = np.ascontiguousarray(a)
+                keep.append(a)
+                t = tin[r * m.n_inputs + i]
+                t.data = a.ctypes.data
+                code = DTYPE_CODES.get(a.dtype)
+                if code is None:
+                    raise B2SError(B2S_ERR_INVALID, "b200serve: unsupported input dtype {}".format(a.dtype))
+                t.dtype = code
+                t.ndim = a.ndim if a.ndim > 0 else 1
+                if a.ndim == 0:
+                    t.shape[0] = 1
+                for d in range(a.ndim):
+                    t.shape[d] = a.shape[d]
+                if m.in_row_elems[i] > 0:
+                    rows = a.size // m.in_row_elems[i]
+            rows = rows or 0
+            ro = []
+            for o in range(m.n_outputs):
+                if outputs is not None:
+                    buf = outputs[r][o]
+                else:
+                    shape = (rows,) if m.out_row_elems[o] == 1 else (rows, m.out_row_elems[o])
+                    buf = np.empty(shape, dtype=m.out_dtypes[o])
+                ro.append(buf)
+                tout[r * m.n_outputs + o].data = buf.ctypes.data
+            outs.append(ro)
+        ev = ctypes.c_uint64(0)
+        check(lib().b2s_infer_batch(m.handle, self.handle, n_req, tin, tout, ctypes.byref(ev)))
+        return ev.value, outs, keep
+
+    # ---- staged path: collate straight into the pinned slot -------------------------------------
+    def acquire(self):
+        m = self.model
+        idx = ctypes.c_int32(-1)
+        ins = (ctypes.c_void_p * 4)()
+        outs = (ctypes.c_void_p * 4)()
+        check(lib().b2s_slot_acquire(self.handle, ctypes.byref(idx), ins, outs))
+        slot = self._slot_views.get(idx.value)
+        if slot is None:
+            vin, vout = [], []
+            for i in range(m.n_inputs):
+                re = m.in_row_elems[i]
+                if re > 0:
+                    v = _view(ins[i], self.max_rows * re * m.in_dtypes[i].itemsize, m.in_dtypes[i]).reshape(self.max_rows, re)
+                else:
+                    v = _view(ins[i], self.max_rows * self.max_row_elems * m.in_dtypes[i].itemsize, m.in_dtypes[i])
+                vin.append(v)
+            for o in range(m.n_outputs):
+                re = m.out_row_elems[o]
+                v = _view(outs[o], self.max_rows * re * m.out_dtypes[o].itemsize, m.out_dtypes[o])
+                vout.append(v if re == 1 else v.reshape(self.max_rows, re))
+            slot = Slot(idx.value, vin, vout)
+            self._slot_views[idx.value] = slot
+        return slot
+
+    def submit(self, slot, n_rows, row_offsets=None):
+        ev = ctypes.c_uint64(0)
+        ro = None
+        if row_offsets is not None:
+            row_offsets = np.ascontiguousarray(row_offsets, dtype=np.int64)
+            ro = row_offsets.ctypes.data
+        check(lib().b2s_slot_submit(self.model.handle, self.handle, slot.index, int(n_rows), ro, ctypes.byref(ev)))
+        return ev.value
+
+    def release(self, slot):
+        check(lib().b2s_slot_release(self.handle, slot.index))
+
+    @staticmethod
+    def wait(event):
+        check(lib().b2s_event_wait(event))
+
+    @staticmethod
+    def query(event):
+        rc = lib().b2s_event_query(event)
+        if rc == B2S_ERR_NOT_READY:
+            return False
+        check(rc)
+        return True
+
+    def synchronize(self):
+        check(lib().b2s_stream_synchronize(self.handle))
+
+    def cuda_handle(self):
+        return lib().b2s_stream_cuda_handle(self.handle)
+
+    def infer_device(self, n_rows, d_in, d_out, d_row_offsets=None):
+        ins = (ctypes.c_void_p * 4)(*[int(p) for p in d_in])
+        outs = (ctypes.c_void_p * 4)(*[int(p) for p in d_out])
+        check(lib().b2s_infer_device(self.model.handle, self.handle, int(n_rows), ins, outs,
+                                     int(d_row_offsets) if d_row_offsets else None))
+
+    def destroy(self):
+        if self.handle:
+            try:
+                check(lib().b2s_stream_destroy(self.handle))
+            finally:
+                self.handle = 0
+                self._slot_views = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", 0) and _lib is not None:
+                lib().b2s_stream_destroy(self.handle)
+        except Exception:  # noqa
+            pass
+
+
+class Timer(object):
+    def __init__(self, stream):
+        h = ctypes.c_uint64(0)
+        check(lib().b2s_timer_create(stream.handle, ctypes.byref(h)))
+        self.handle = h.value
+
+    def start(self):
+        check(lib().b2s_timer_start(self.handle))
+
+    def stop(self):
+        check(lib().b2s_timer_stop(self.handle))
+
+    def elapsed_ms(self):
+        ms = ctypes.c_float(0)
+        check(lib().b2s_timer_elapsed_ms(self.handle, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def destroy(self):
+        if self.handle:
+            lib().b2s_timer_destroy(self.handle)
+            self.handle = 0
+
+
+class DeviceBuffer(object):
+    def __init__(self, nbytes, device=0):
+        self.device = int(device)
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p(0)
+        check(lib().b2s_device_malloc(self.device, self.nbytes, ctypes.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        check(lib().b2s_memcpy_h2d(self.device, self.ptr, arr.ctypes.data, arr.nbytes))
+
+    def download(self, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        check(lib().b2s_memcpy_d2h(self.device, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().b2s_device_free(self.device, self.ptr)
+            self.ptr = 0

@@ -1,0 +1,327 @@
+"""Per-endpoint request queue and dynamic-batch scheduler (Python, as north_star requires).
+
+The reference has no such component of its own: "auto-batching" is tritonserver's dynamic batcher,
+configured by keys passed through `--aux-config` (examples/huggingface/readme.md:113) and merged
+verbatim into config.pbtxt (clearml_serving/engines/triton/triton_helper.py:326-331).  This module
+implements those semantics in front of libb200serve:
+
+  * `max_batch_size = N`: requests carry their own leading batch dim; a batch holds <= N rows.
+  * FIFO per endpoint; a batch is dispatched as soon as a staging slot is free, taking as many
+    queued requests as fit.
+  * `dynamic_batching.max_queue_delay_microseconds = D`: if the queue cannot fill a batch (or hit a
+    `preferred_batch_size`), wait up to D us from the arrival of the oldest request, then dispatch
+    what is there.  D = 0 (default) dispatches immediately.
+  * responses are per request (the batch output is split on dim 0).
+
+Threads: `dispatch` forms batches and collates the requests' rows straight into a pinned staging
+slot (numpy views over the library's arena), `complete` blocks in b2s_event_wait (GIL released),
+copies each request's rows out of the slot and resolves the futures -- one
+`loop.call_soon_threadsafe` per event loop per batch.
+"""
+import asyncio
+import collections
+import concurrent.futures
+import re
+import threading
+import time
+
+import numpy as np
+
+from . import native
+
+
+class BatchPolicy(object):
+    def __init__(self, max_batch_size=64, max_queue_delay_us=0, preferred_batch_size=None, n_slots=4):
+        self.max_batch_size = max(1, int(max_batch_size))
+        self.max_queue_delay_us = max(0, int(max_queue_delay_us))
+        self.preferred_batch_size = sorted(int(x) for x in (preferred_batch_size or []) if int(x) > 0)
+        self.n_slots = max(1, int(n_slots))
+
+    def __repr__(self):
+        return "BatchPolicy(max_batch_size={}, max_queue_delay_us={}, preferred_batch_size={}, n_slots={})".format(
+            self.max_batch_size, self.max_queue_delay_us, self.preferred_batch_size, self.n_slots)
+
+    @classmethod
+    def from_auxiliary_cfg(cls, aux, default_max_batch_size=64):
+        """`aux` is ModelEndpoint.auxiliary_cfg: a dict (possibly with dotted keys, as the CLI's
+        key=value form produces: `dynamic_batching.max_queue_delay_microseconds=5000`), a nested
+        dict, or config.pbtxt text.  Unknown keys (platform, default_model_filename ...) are ignored."""
+        flat = {}
+        if isinstance(aux, dict):
+            _flatten(aux, "", flat)
+        elif isinstance(aux, str):
+            flat = _parse_pbtxt(aux)
+        mbs = flat.get("max_batch_size", default_max_batch_size)
+        delay = flat.get("dynamic_batching.max_queue_delay_microseconds", 0)
+        pref = flat.get("dynamic_batching.preferred_batch_size", None)
+        if isinstance(pref, str):
+            pref = [int(x) for x in re.findall(r"-?\d+", pref)]
+        elif isinstance(pref, (int, float)):
+            pref = [int(pref)]
+        slots = flat.get("b200.staging_slots", 4)
+        mbs = int(mbs)
+        if mbs <= 0:  # Triton: max_batch_size 0 == batching disabled -> one request per launch
+            mbs = 1
+        return cls(max_batch_size=mbs, max_queue_delay_us=int(float(delay)), preferred_batch_size=pref,
+                   n_slots=int(slots))
+
+
+def _flatten(d, prefix, out):
+    for k, v in d.items():
+        key = "{}{}".format(prefix, k)
+        if isinstance(v, dict):
+            _flatten(v, key + ".", out)
+        else:
+            out[key] = v
+
+
+def _parse_pbtxt(text):
+    """Tiny reader for the handful of config.pbtxt keys the scheduler consumes."""
+    out = {}
+    m = re.search(r"max_batch_size\s*:\s*(\d+)", text)
+    if m:
+        out["max_batch_size"] = int(m.group(1))
+    m = re.search(r"dynamic_batching\s*:?\s*\{([^}]*)\}", text, re.S)
+    if m:
+        body = m.group(1)
+        d = re.search(r"max_queue_delay_microseconds\s*:\s*(\d+)", body)
+        if d:
+            out["dynamic_batching.max_queue_delay_microseconds"] = int(d.group(1))
+        p = re.search(r"preferred_batch_size\s*:\s*\[([^\]]*)\]", body)
+        if p:
+            out["dynamic_batching.preferred_batch_size"] = [int(x) for x in re.findall(r"\d+", p.group(1))]
+        elif re.search(r"preferred_batch_size\s*:\s*(\d+)", body):
+            out["dynamic_batching.preferred_batch_size"] = [int(x) for x in re.findall(r"preferred_batch_size\s*:\s*(\d+)", body)]
+    return out
+
+
+class _Request(object):
+    __slots__ = ("inputs", "rows", "t_enq", "loop", "afuture", "cfuture")
+
+    def __init__(self, inputs, rows):
+        self.inputs = inputs
+        self.rows = rows
+        self.t_enq = time.perf_counter()
+        self.loop = None
+        self.afuture = None
+        self.cfuture = None
+
+
+def _resolve_many(pairs):
+    for fut, result, exc in pairs:
+        if fut.done():  # cancelled / timed out by the caller
+            continue
+        if exc is not None:
+            fut.set_exception(exc)
+        else:
+            fut.set_result(result)
+
+
+class DynamicBatcher(object):
+    """Queue + scheduler of one endpoint in front of one native.Stream."""
+
+    def __init__(self, model, policy, name="endpoint", stream=None):
+        self.model = model
+        self.policy = policy
+        self.name = name
+        # `stream` is injectable so the queueing logic can be unit-tested without a GPU
+        self.stream = stream if stream is not None else native.Stream(model, policy.max_batch_size, 0, policy.n_slots)
+        self._queue = collections.deque()
+        self._queued_rows = 0
+        self._cond = threading.Condition()
+        self._inflight = collections.deque()
+        self._inflight_cond = threading.Condition()
+        self._running = True
+        self._fatal = None
+        # counters (what tritonserver's :8002/metrics used to expose for the model)
+        self.stats = dict(batches=0, requests=0, rows=0, queue_delay_us_sum=0.0, max_batch_rows=0)
+        self._dispatch_thread = threading.Thread(target=self._dispatch_loop, name="b2s-dispatch-" + name, daemon=True)
+        self._complete_thread = threading.Thread(target=self._complete_loop, name="b2s-complete-" + name, daemon=True)
+        self._dispatch_thread.start()
+        self._complete_thread.start()
+
+    # ------------------------------------------------------------------ submission
+    def _enqueue(self, req):
+        if not self._running:
+            raise ValueError("b200 engine: endpoint '{}' is shut down".format(self.name))
+        if req.rows > self.policy.max_batch_size:
+            raise ValueError("b200 engine: request with {} rows exceeds max_batch_size {}".format(
+                req.rows, self.policy.max_batch_size))
+        with self._cond:
+            self._queue.append(req)
+            self._queued_rows += req.rows
+            self._cond.notify()
+
+    def submit_async(self, inputs, rows):
+        """Called on an asyncio loop; returns an awaitable future of the list of output arrays."""
+        req = _Request(inputs, rows)
+        req.loop = asyncio.get_running_loop()
+        req.afuture = req.loop.create_future()
+        self._enqueue(req)
+        return req.afuture
+
+    def submit(self, inputs, rows):
+        """Thread-safe synchronous-style submission; returns a concurrent.futures.Future."""
+        req = _Request(inputs, rows)
+        req.cfuture = concurrent.futures.Future()
+        self._enqueue(req)
+        return req.cfuture
+
+    # ------------------------------------------------------------------ batch formation
+    def _take_batch(self):
+        """Blocks until a batch should be dispatched (SURVEY.md 5.9 rules); returns list of requests."""
+        pol = self.policy
+        with self._cond:
+            while self._running and not self._queue:
+                self._cond.wait()
+            if not self._running and not self._queue:
+                return None
+            if pol.max_queue_delay_us > 0:
+                deadline = self._queue[0].t_enq + pol.max_queue_delay_us * 1e-6
+                while self._running:
+                    rows = self._queued_rows
+                    if rows >= pol.max_batch_size:
+                        break
+                    if pol.preferred_batch_size and rows in pol.preferred_batch_size and \
+                            rows == pol.preferred_batch_size[-1]:
+                        break  # largest preferred size reached exactly: go now
+                    now = time.perf_counter()
+                    if now >= deadline:
+                        break
+                    self._cond.wait(timeout=deadline - now)
+            batch, rows = [], 0
+            limit = pol.max_batch_size
+            if pol.preferred_batch_size and self._queued_rows < pol.max_batch_size:
+                # dispatch the largest preferred size that the queue can form, else everything
+                fits = [p for p in pol.preferred_batch_size if p <= self._queued_rows]
+                if fits:
+                    limit = fits[-1]
+            while self._queue and rows + self._queue[0].rows <= limit:
+                r = self._queue.popleft()
+                rows += r.rows
+                batch.append(r)
+            if not batch and self._queue:  # head does not fit a preferred size: take it alone
+                r = self._queue.popleft()
+                rows += r.rows
+                batch.append(r)
+            self._queued_rows -= rows
+            return batch
+
+    def _dispatch_loop(self):
+        m = self.model
+        while True:
+            batch = self._take_batch()
+            if batch is None:
+                break
+            try:
+                slot = self._acquire_slot()
+                n_rows = 0
+                for i in range(m.n_inputs):
+                    parts = [r.inputs[i] for r in batch]
+                    n_rows = sum(p.shape[0] for p in parts)
+                    if len(parts) == 1:
+                        slot.inputs[i][:n_rows] = parts[0]
+                    else:
+                        np.concatenate(parts, axis=0, out=slot.inputs[i][:n_rows])
+                t_disp = time.perf_counter()
+                ev = self.stream.submit(slot, n_rows)
+                st = self.stats
+                st["batches"] += 1
+                st["requests"] += len(batch)
+                st["rows"] += n_rows
+                st["queue_delay_us_sum"] += sum((t_disp - r.t_enq) for r in batch) * 1e6
+                if n_rows > st["max_batch_rows"]:
+                    st["max_batch_rows"] = n_rows
+                with self._inflight_cond:
+                    self._inflight.append((ev, slot, batch))
+                    self._inflight_cond.notify()
+            except Exception as ex:  # a failed batch fails only its own requests
+                self._fail(batch, ex)
+
+    def _acquire_slot(self):
+        while True:
+            try:
+                return self.stream.acquire()
+            except native.B2SError as ex:
+                if ex.code != native.B2S_ERR_BUSY:
+                    raise
+            with self._inflight_cond:  # all slots in flight: wait for the completion thread
+                self._inflight_cond.wait(timeout=0.001)
+
+    # ------------------------------------------------------------------ completion
+    def _complete_loop(self):
+        m = self.model
+        while True:
+            with self._inflight_cond:
+                while self._running and not self._inflight:
+                    self._inflight_cond.wait()
+                if not self._inflight:
+                    if not self._running:
+                        break
+                    continue
+                ev, slot, batch = self._inflight.popleft()
+            try:
+                self.stream.wait(ev)
+                row = 0
+                results = []
+                for r in batch:
+                    results.append([slot.outputs[o][row:row + r.rows].copy() for o in range(m.n_outputs)])
+                    row += r.rows
+                self.stream.release(slot)
+                with self._inflight_cond:
+                    self._inflight_cond.notify_all()
+                self._resolve(batch, results, None)
+            except Exception as ex:  # noqa
+                try:
+                    self.stream.release(slot)
+                except Exception:  # noqa
+                    pass
+                self._fail(batch, ex)
+
+    def _resolve(self, batch, results, exc):
+        by_loop = {}
+        for k, r in enumerate(batch):
+            res = results[k] if results is not None else None
+            if r.cfuture is not None:
+                if exc is not None:
+                    r.cfuture.set_exception(exc)
+                else:
+                    r.cfuture.set_result(res)
+            else:
+                by_loop.setdefault(r.loop, []).append((r.afuture, res, exc))
+        for loop, pairs in by_loop.items():
+            try:
+                loop.call_soon_threadsafe(_resolve_many, pairs)
+            except RuntimeError:  # loop closed
+                pass
+
+    def _fail(self, batch, ex):
+        if not isinstance(ex, Exception):
+            ex = ValueError(str(ex))
+        self._resolve(batch, None, ex)
+
+    # ------------------------------------------------------------------ lifetime
+    def shutdown(self):
+        if not self._running:
+            return
+        self._running = False
+        with self._cond:
+            self._cond.notify_all()
+        self._dispatch_thread.join(timeout=5)
+        with self._inflight_cond:
+            self._inflight_cond.notify_all()
+        self._complete_thread.join(timeout=5)
+        pending = list(self._queue)
+        self._queue.clear()
+        if pending:
+            self._fail(pending, ValueError("b200 engine: endpoint '{}' shut down".format(self.name)))
+        try:
+            self.stream.destroy()
+        except Exception:  # noqa
+            pass
+
+    def snapshot_stats(self):
+        st = dict(self.stats)
+        st["mean_batch_rows"] = st["rows"] / st["batches"] if st["batches"] else 0.0
+        st["mean_queue_delay_us"] = st["queue_delay_us_sum"] / st["requests"] if st["requests"] else 0.0
+        return st

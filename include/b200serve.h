@@ -1,0 +1,182 @@
+/*
+ * b200serve.h -- C ABI of libb200serve.so, the B200-native (sm_100a) hot path that replaces the
+ * Triton engine path of clearml-serving.
+ *
+ * The reference has NO FFI for this path (it is 100% Python): a request crosses into the model
+ * runtime as a gRPC ModelInfer message built in
+ *     clearml_serving/serving/preprocess_service.py:374-422   (collate: np.array + protobuf contents)
+ * and comes back through
+ *     clearml_serving/serving/preprocess_service.py:430-446   (scatter: np.frombuffer + np.resize),
+ * with tritonserver (third-party) doing queue -> batch -> H2D -> model -> D2H -> split, configured by
+ *     clearml_serving/engines/triton/triton_helper.py:291-409 (config.pbtxt: dims, dtypes, max_batch).
+ * For the in-process CPU engines the same boundary is `self._model.predict(data)`
+ *     preprocess_service.py:459-464 (sklearn), :478-483 (xgboost).
+ * Each entry point below names the reference interface it stands in for.  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds to the reference to call it.
+ *
+ * Conventions: every function returns 0 on success or a negative b2s_status; the message of the
+ * last failure on the calling thread is b2s_last_error().  There is no CPU fallback: without a
+ * CUDA device b2s_init fails and every other call returns B2S_ERR_NOT_INITIALISED.
+ * A device out-of-memory message contains the literal "CUDA out of memory. " so that the reference's
+ * restart logic (clearml_serving/serving/main.py:116-123) keeps working.
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ */
+#ifndef B200SERVE_H
+#define B200SERVE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B2S_API __attribute__((visibility("default")))
+#else
+#define B2S_API
+#endif
+
+#define B2S_ABI_VERSION 1
+
+typedef enum b2s_status {
+    B2S_OK = 0,
+    B2S_ERR_INVALID = -1,         /* bad argument / malformed model blob / shape or dtype mismatch */
+    B2S_ERR_CUDA = -2,            /* CUDA runtime error (message carries the CUDA error string)    */
+    B2S_ERR_OOM = -3,             /* device or pinned arena exhausted: "CUDA out of memory. ..."    */
+    B2S_ERR_NOT_INITIALISED = -4, /* b2s_init not called / no CUDA device                           */
+    B2S_ERR_BUSY = -5,            /* all staging slots of the stream are in flight                  */
+    B2S_ERR_NOT_READY = 1         /* b2s_event_query: batch still running (not an error)            */
+} b2s_status;
+
+/* numpy-compatible element types: the dtype universe of the reference's Triton client
+ * (_content_lookup, preprocess_service.py:271-282) plus fp16 for on-device compute. */
+typedef enum b2s_dtype {
+    B2S_F32 = 0, B2S_F64 = 1, B2S_I32 = 2, B2S_I64 = 3, B2S_U8 = 4, B2S_I8 = 5,
+    B2S_BOOL = 6, B2S_U64 = 7, B2S_F16 = 8, B2S_U32 = 9
+} b2s_dtype;
+
+typedef enum b2s_model_kind {
+    B2S_MODEL_FOREST = 1, /* GBDT / random forest: replaces Booster.predict / sklearn predict      */
+    B2S_MODEL_LINEAR = 2, /* linear / logistic decision function + argmax                          */
+    B2S_MODEL_GRAPH = 3   /* op-list DL graph (ResNet / BERT class), fp16 compute                  */
+} b2s_model_kind;
+
+#define B2S_MAX_DIMS 8
+
+/* One host tensor of one request.  `data` is caller-owned host memory (need not be pinned).
+ * Stands in for InferInputTensor (name/shape/typed contents, preprocess_service.py:395-409) on the
+ * way in and for raw_output_contents[i] + shape (preprocess_service.py:432-442) on the way out. */
+typedef struct b2s_tensor {
+    void *data;
+    int32_t dtype;                 /* b2s_dtype */
+    int32_t ndim;
+    int64_t shape[B2S_MAX_DIMS];   /* leading dim = the request's own batch dim (usually 1) */
+} b2s_tensor;
+
+typedef uint64_t b2s_model_t;
+typedef uint64_t b2s_stream_t;
+typedef uint64_t b2s_event_t;
+
+/* Static description of a loaded model's I/O (what triton_helper.py:342-360 writes into
+ * config.pbtxt as input/output dims + data_type). */
+typedef struct b2s_model_info {
+    int32_t kind;
+    int32_t n_inputs;
+    int32_t n_outputs;
+    int32_t in_dtype[4];
+    int32_t out_dtype[4];
+    int64_t in_row_elems[4];   /* elements per batch row of input i  (-1 = variable length)   */
+    int64_t out_row_elems[4];  /* elements per batch row of output i                          */
+    int64_t weight_bytes;      /* bytes resident in HBM for this model                        */
+    int64_t algo_bytes_fixed;  /* algorithmic bytes per launch independent of batch rows      */
+    int64_t algo_bytes_per_row;/* algorithmic bytes per batch row (in + out)                  */
+} b2s_model_info;
+
+/* ---- library / device lifetime ------------------------------------------------------------- */
+
+/* Bind `device`, create the shared pinned staging arena (`pinned_arena_bytes`, 0 = default 64 MiB).
+ * Replaces: tritonserver start-up (triton_helper.py:245-261; --pinned-memory-pool-byte-size). */
+B2S_API int b2s_init(int device, size_t pinned_arena_bytes);
+B2S_API int b2s_shutdown(void);
+B2S_API int b2s_abi_version(void);
+B2S_API const char *b2s_last_error(void);
+/* kernels launched by this library since b2s_init (the bench's `gpu_launches` evidence) */
+B2S_API uint64_t b2s_launch_count(void);
+B2S_API int b2s_device_count(void);
+
+/* ---- models -------------------------------------------------------------------------------- */
+
+/* Load a model from a packed blob (built by clearml_serving_b200.formats from the same files the
+ * reference loads: XGBoost JSON via Booster.load_model preprocess_service.py:475-476, joblib pickles
+ * via joblib.load :457, TorchScript/ONNX placed by triton_helper.py:159-186) onto `device`.
+ * `cfg_json` may be NULL. */
+B2S_API int b2s_model_load(int device, int kind, const void *blob, size_t blob_bytes,
+                   const char *cfg_json, b2s_model_t *out_model);
+B2S_API int b2s_model_free(b2s_model_t model);
+B2S_API int b2s_model_get_info(b2s_model_t model, b2s_model_info *out_info);
+
+/* ---- streams: one CUDA stream + staging slots per endpoint ----------------------------------- */
+
+/* One stream per endpoint (north_star: "one CUDA stream per endpoint with a shared pinned staging
+ * arena").  `max_rows` = the endpoint's max_batch_size (auxiliary_cfg, examples/huggingface/
+ * readme.md:113); `n_slots` batches may be in flight at once (0 = default 4).  `max_row_elems`
+ * bounds variable-length inputs (ignored for fixed-width models, pass 0). */
+B2S_API int b2s_stream_create(b2s_model_t model, int64_t max_rows, int64_t max_row_elems, int n_slots,
+                      b2s_stream_t *out_stream);
+B2S_API int b2s_stream_destroy(b2s_stream_t stream);
+B2S_API int b2s_stream_synchronize(b2s_stream_t stream);
+/* raw cudaStream_t, for callers that record their own CUDA events on it (bench.py) */
+B2S_API void *b2s_stream_cuda_handle(b2s_stream_t stream);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+/* Collate n_req requests (each with model.n_inputs tensors, row-major in[req * n_inputs + i]) into
+ * the stream's next pinned slot, H2D, run the model's kernels, D2H; all asynchronous on the stream.
+ * `out[req * n_outputs + o].data` must point at caller-owned host buffers large enough for the
+ * request's rows; they are filled by b2s_event_wait (scatter).  Shapes of `out` are written back.
+ * Replaces: the whole TritonPreprocessRequest.process round trip (preprocess_service.py:385-446)
+ * plus tritonserver's dynamic-batch execution. */
+B2S_API int b2s_infer_batch(b2s_model_t model, b2s_stream_t stream, int32_t n_req,
+                    const b2s_tensor *in, b2s_tensor *out, b2s_event_t *out_done);
+
+/* Zero-copy variant for hosts that collate straight into the pinned slot (the Python scheduler):
+ * acquire a free slot, write rows into in_ptr[i] (row-major, model dtype), submit, then read
+ * out_ptr[o] after b2s_event_wait and release.  For variable-length inputs `row_offsets`
+ * (int64[n_rows+1], element offsets into each ragged input) is passed at submit. */
+B2S_API int b2s_slot_acquire(b2s_stream_t stream, int32_t *out_slot, void **in_ptr /*[n_inputs]*/,
+                     void **out_ptr /*[n_outputs]*/);
+B2S_API int b2s_slot_submit(b2s_model_t model, b2s_stream_t stream, int32_t slot, int64_t n_rows,
+                    const int64_t *row_offsets, b2s_event_t *out_done);
+B2S_API int b2s_slot_release(b2s_stream_t stream, int32_t slot);
+
+/* Completion: wait (blocking, no GIL needed) / poll.  b2s_event_wait performs the scatter of
+ * b2s_infer_batch outputs into the per-request buffers and frees the slot. */
+B2S_API int b2s_event_wait(b2s_event_t ev);
+B2S_API int b2s_event_query(b2s_event_t ev);
+
+/* Device-resident execution (inputs/outputs already in HBM; used for kernel-only timing and by
+ * hosts that own device memory).  d_in[i] / d_out[o] are device pointers on the model's device. */
+B2S_API int b2s_infer_device(b2s_model_t model, b2s_stream_t stream, int64_t n_rows,
+                     const void *const *d_in, void *const *d_out, const int64_t *d_row_offsets);
+
+/* Plain device memory helpers so a host needs no other CUDA binding. */
+B2S_API int b2s_device_malloc(int device, size_t bytes, void **out_ptr);
+B2S_API int b2s_device_free(int device, void *ptr);
+B2S_API int b2s_memcpy_h2d(int device, void *dst, const void *src, size_t bytes);
+B2S_API int b2s_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
+/* Overwrite a buffer larger than L2 (benchmark hygiene: cold-cache timing). */
+B2S_API int b2s_flush_l2(int device);
+
+/* CUDA-event timers on a library stream (device time, not wall clock). */
+typedef uint64_t b2s_timer_t;
+B2S_API int b2s_timer_create(b2s_stream_t stream, b2s_timer_t *out_timer);
+B2S_API int b2s_timer_start(b2s_timer_t timer);
+B2S_API int b2s_timer_stop(b2s_timer_t timer);
+B2S_API int b2s_timer_elapsed_ms(b2s_timer_t timer, float *out_ms); /* synchronises on the stop event */
+B2S_API int b2s_timer_destroy(b2s_timer_t timer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SERVE_H */
