@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- requests/sec (+ p50/p99 latency) of the b200 hot path on BASELINE.json configs[1]:
+synthetic 1000-tree x depth-6 XGBoost-semantics regressor, 32 float32 features, max_batch=64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A STEP = one pass of the hot path over one scheduler batch of 64 single-row requests.
+  value   device-resident: the batch is already in HBM; one forest kernel launch per step, timed with
+          CUDA events on the launching stream, L2 flushed before every timed step
+  e2e     the same batch through the C ABI with HOST buffers: b2s_infer_batch (collate into the pinned
+          slot, H2D, kernel, result written back to the host) + b2s_event_wait (scatter to the 64
+          per-request buffers), wall clock, up to 4 batches in flight
+  plugin  the metric BASELINE.json names, through the reference-facing plugin API
+          (B200PreprocessRequest.process under asyncio): closed-loop req/s and open-loop Poisson
+          (lambda = 2000 req/s) p50/p99 latency
+  roofline / cpu_baseline: see DESIGN.md ("Measurement")
+N > 1: one process per GPU, independent replicas (requests are independent: no data-path collective,
+weak scaling); NCCL only for the timing barrier / max-over-ranks reduction.
+"""
+import argparse
+import asyncio
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TREES, DEPTH, N_FEATURES, MAX_BATCH = 1000, 6, 32, 64
+WORKLOAD = "xgboost-synth-1000trees-depth6-32feat-f32_maxbatch64"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic_bytes():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "forest_pairs_traffic.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except Exception:  # noqa
+            return None
+    return None
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def _dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def _barrier_sync(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize(local)
+
+
+def _max_over_ranks(dist, local, x):
+    if dist is None:
+        return float(x)
+    import torch
+    t = torch.tensor([float(x)], device="cuda:%d" % local, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(dist, local, x):
+    if dist is None:
+        return float(x)
+    import torch
+    t = torch.tensor([float(x)], device="cuda:%d" % local, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def _make_model():
+    from oracle import oracle as orc
+    forest = orc.synth_xgb_forest(n_trees=N_TREES, depth=DEPTH, n_features=N_FEATURES, seed=0)
+    return forest
+
+
+def _cpu_loop(forest, steps=None, seconds=None, warmup=3):
+    """The oracle port (no compiled reference exists: clearml-serving is pure Python and xgboost is
+    not installable) on the host cores: one step = one batch of 64 rows, OpenMP over rows, every
+    host thread the box offers.  Returns (steps_done, seconds, threads)."""
+    from oracle import oracle as orc
+    h = orc.ForestHandle(forest)
+    threads = orc.max_threads()
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((256, MAX_BATCH, N_FEATURES)).astype(np.float32)
+    out = np.empty(MAX_BATCH, np.float32)
+    for w in range(warmup):
+        h.predict_xgb_into(X[w % 256], 0.5, out, threads)
+    n = 0
+    t0 = time.perf_counter()
+    if steps is not None:
+        for n in range(steps):
+            h.predict_xgb_into(X[n % 256], 0.5, out, threads)
+        n = steps
+    else:
+        while time.perf_counter() - t0 < seconds:
+            h.predict_xgb_into(X[n % 256], 0.5, out, threads)
+            n += 1
+    return n, time.perf_counter() - t0, threads
+
+
+def _cpu_baseline(forest, seconds):
+    n, dt, threads = _cpu_loop(forest, seconds=seconds)
+    return dict(value=n * MAX_BATCH / dt, unit="requests/s", cores=int(min(threads, MAX_BATCH)), kind="port",
+                sample="{} batches of {} rows in {:.1f}s; oracle/forest_oracle.c (restatement of the xgboost CPU "
+                       "predictor), OpenMP over rows, {} host threads available".format(n, MAX_BATCH, dt, threads))
+
+
+def run_reference(args):
+    # rank 0 alone runs the CPU arm; the other ranks exit 0 without work (no process group needed)
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    forest = _make_model()
+    W = max(args.warmup, 3)
+    n, dt, threads = _cpu_loop(forest, steps=args.steps, warmup=W)
+    value = args.steps * MAX_BATCH / dt
+    line = dict(metric="requests/sec", value=value, unit="requests/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=W, ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, step="one batch of 64 single-row requests", l2="n/a (CPU)"),
+                cpu_baseline=dict(value=value, unit="requests/s", cores=int(min(threads, MAX_BATCH)), kind="port",
+                                  sample="{} steps x {} rows; oracle port of the xgboost CPU predictor, OpenMP over "
+                                         "rows, {} host threads available".format(args.steps, MAX_BATCH, threads)),
+                e2e=dict(value=value, unit="requests/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def _plugin_metrics(forest, device, seconds=2.0, lam=2000.0):
+    """requests/s + latency through B200PreprocessRequest.process (the reference-facing plugin API)."""
+    from clearml_serving_b200 import BasePreprocessRequest, ModelEndpoint, formats
+    packed = formats.pack_forest(forest, "xgb", base=0.5)
+    ep = ModelEndpoint(engine_type="b200", serving_url="bench_xgb",
+                       auxiliary_cfg={"max_batch_size": MAX_BATCH, "dynamic_batching.max_queue_delay_microseconds": 1000,
+                                      "b200.device": device})
+    cls = BasePreprocessRequest.get_engine_cls("b200")
+    eng = cls.__new__(cls)
+    BasePreprocessRequest.__init__(eng, model_endpoint=ep, task=None)
+    eng._model = packed
+    eng._b200_setup()
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((4096, 1, N_FEATURES)).astype(np.float32)
+    out = {}
+
+    async def closed_loop(conc):
+        stop = time.perf_counter() + seconds
+        count = 0
+
+        async def worker(w):
+            nonlocal count
+            i = w
+            while time.perf_counter() < stop:
+                await eng.process(X[i % 4096], {}, None)
+                i += conc
+                count += 1
+        t0 = time.perf_counter()
+        await asyncio.gather(*[worker(w) for w in range(conc)])
+        return count / (time.perf_counter() - t0)
+
+    async def open_loop():
+        loop = asyncio.get_running_loop()
+        n = int(lam * seconds)
+        gaps = np.random.default_rng(2).exponential(1.0 / lam, n)
+        lat = []
+        pending = []
+
+        async def one(i):
+            t = time.perf_counter()
+            await eng.process(X[i % 4096], {}, None)
+            lat.append(time.perf_counter() - t)
+        t_next = loop.time()
+        for i in range(n):
+            t_next += gaps[i]
+            delay = t_next - loop.time()
+            if delay > 0:
+                await asyncio.sleep(delay)
+            pending.append(asyncio.ensure_future(one(i)))
+        await asyncio.gather(*pending)
+        lat = np.asarray(lat) * 1e6
+        return dict(offered_req_s=lam, completed=n, p50_us=float(np.percentile(lat, 50)),
+                    p99_us=float(np.percentile(lat, 99)), mean_us=float(lat.mean()))
+    try:
+        asyncio.run(closed_loop(64))  # warm-up
+        out["closed_loop_req_s"] = asyncio.run(closed_loop(256))
+        out["closed_loop_concurrency"] = 256
+        out["poisson"] = asyncio.run(open_loop())
+        st = eng.engine_stats()
+        out["mean_batch_rows"] = st["mean_batch_rows"]
+        out["policy"] = repr(eng._policy)
+    finally:
+        eng.unload()
+    return out
+
+
+def run_b200(args):
+    rank, world, local, dist = _dist_setup(args.gpus)
+    device = local
+    from clearml_serving_b200 import formats, native
+    native.ensure_init(device)
+    lib = native.lib()
+    forest = _make_model()
+    packed = formats.pack_forest(forest, "xgb", base=0.5)
+    model = native.Model(packed.kind, packed.blob, device=device)
+    stream = native.Stream(model, MAX_BATCH, 0, 4)
+    timer = native.Timer(stream)
+    K, W = args.steps, max(args.warmup, 3)
+
+    rng = np.random.default_rng(1)
+    n_sets = 64
+    Xs = rng.standard_normal((n_sets, MAX_BATCH, N_FEATURES)).astype(np.float32)
+
+    # correctness guard: a bench of wrong results is worthless
+    from oracle import oracle as orc
+    ev, outs, keep = stream.infer_batch([[Xs[0][i:i + 1]] for i in range(MAX_BATCH)])
+    stream.wait(ev)
+    got = np.concatenate([o[0] for o in outs])
+    if not np.array_equal(got, orc.forest_predict_xgb(forest, Xs[0], 0.5)):
+        raise SystemExit("bench: GPU results differ from the oracle -- refusing to report numbers")
+
+    # ---------------------------------------------------------------- value: device-resident
+    d_in = [native.DeviceBuffer(Xs[0].nbytes, device) for _ in range(n_sets)]
+    for b, x in zip(d_in, Xs):
+        b.upload(x)
+    d_out = native.DeviceBuffer(MAX_BATCH * 4, device)
+    for w in range(W):
+        stream.infer_device(MAX_BATCH, [d_in[w % n_sets].ptr], [d_out.ptr])
+    stream.synchronize()
+
+    clocks = ClockSampler(device)
+    launches0 = native.launch_count()
+    _barrier_sync(dist, local)
+    cold_ms = 0.0
+    for k in range(K):
+        stream.flush_l2()                          # untimed, same stream: evict model + inputs from the 126 MB L2
+        timer.start()
+        stream.infer_device(MAX_BATCH, [d_in[k % n_sets].ptr], [d_out.ptr])
+        timer.stop()
+        cold_ms += timer.elapsed_ms()
+    stream.synchronize()
+    _barrier_sync(dist, local)
+    cold_ms = _max_over_ranks(dist, local, cold_ms)
+
+    # same launches back to back, model resident in L2 (steady-state serving)
+    timer.start()
+    for k in range(K):
+        stream.infer_device(MAX_BATCH, [d_in[k % n_sets].ptr], [d_out.ptr])
+    timer.stop()
+    warm_ms = _max_over_ranks(dist, local, timer.elapsed_ms())
+
+    # ---------------------------------------------------------------- e2e: C ABI with host buffers
+    n_req = MAX_BATCH
+    tins, touts, bufs = [], [], []
+    for s in range(n_sets):
+        tin = (native.Tensor * n_req)()
+        tout = (native.Tensor * n_req)()
+        ob = np.zeros((n_req, 1), np.float32)
+        for r in range(n_req):
+            row = Xs[s][r:r + 1]
+            tin[r].data = row.ctypes.data
+            tin[r].dtype = 0
+            tin[r].ndim = 2
+            tin[r].shape[0], tin[r].shape[1] = 1, N_FEATURES
+            tout[r].data = ob[r].ctypes.data
+        tins.append(tin); touts.append(tout); bufs.append(ob)
+
+    def e2e_run(steps, depth):
+        inflight = []
+        t0 = time.perf_counter()
+        for k in range(steps):
+            if len(inflight) == depth:
+                native.check(lib.b2s_event_wait(inflight.pop(0)))
+            s = k % n_sets
+            ev = ctypes.c_uint64(0)
+            native.check(lib.b2s_infer_batch(model.handle, stream.handle, n_req, tins[s], touts[s], ctypes.byref(ev)))
+            inflight.append(ev.value)
+        for ev in inflight:
+            native.check(lib.b2s_event_wait(ev))
+        return time.perf_counter() - t0
+
+    e2e_run(W, 4)
+    _barrier_sync(dist, local)
+    e2e_s = _max_over_ranks(dist, local, e2e_run(K, 4))
+    e2e_lat_s = _max_over_ranks(dist, local, e2e_run(K, 1))
+    _barrier_sync(dist, local)
+    launches = native.launch_count() - launches0
+    clk = clocks.stop()
+    if not np.array_equal(bufs[(K - 1) % n_sets][:, 0], orc.forest_predict_xgb(forest, Xs[(K - 1) % n_sets], 0.5)):
+        raise SystemExit("bench: e2e results differ from the oracle")
+
+    # ---------------------------------------------------------------- plugin-level metric (Python API)
+    plugin = None
+    if not args.no_plugin:
+        try:
+            plugin = _plugin_metrics(forest, device)
+            if dist is not None:
+                plugin["closed_loop_req_s_all_ranks"] = _sum_over_ranks(dist, local, plugin["closed_loop_req_s"])
+        except Exception as ex:  # noqa
+            plugin = dict(error=str(ex))
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        algo = model.algo_bytes(MAX_BATCH)
+        kernel_s = cold_ms * 1e-3 / K
+        achieved = algo / kernel_s / 1e9
+        cpu = _cpu_baseline(forest, args.cpu_seconds) if world == 1 else None
+        value = world * MAX_BATCH * K / (cold_ms * 1e-3)
+        line = dict(
+            metric="requests/sec", value=value, unit="requests/s", n_gpus=world, steps=K, warmup=W,
+            ms_per_step=cold_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f32", data="synthetic",
+            config=dict(workload=WORKLOAD, step="one batch of 64 single-row requests = one kernel launch",
+                        l2="flushed (256 MiB memset on the launching stream) before every timed step; value_l2_warm is the back-to-back figure",
+                        parallelism="replicas x{} (independent requests, no collective)".format(world)),
+            value_l2_warm=world * MAX_BATCH * K / (warm_ms * 1e-3), ms_per_step_l2_warm=warm_ms / K,
+            e2e=dict(value=world * MAX_BATCH * K / e2e_s, unit="requests/s", h2d_bytes_per_step=MAX_BATCH * N_FEATURES * 4,
+                     d2h_bytes_per_step=MAX_BATCH * 4, ms_per_step=e2e_s / K * 1e3, in_flight=4,
+                     ms_per_step_serial=e2e_lat_s / K * 1e3,
+                     path="b2s_infer_batch(64 host tensors) + b2s_event_wait, wall clock"),
+            gpu_launches=int(launches),
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                          traffic=_traffic_bytes(), algorithmic_bytes_per_launch=algo, peak_source=peak_src,
+                          kernel="forest_pairs_kernel<f32>", note="latency-bound at 64 rows: 1000-add fp32 chain"),
+            cpu_baseline=cpu, clocks=clk, plugin=plugin)
+        print(json.dumps(line))
+    timer.destroy()
+    for b in d_in:
+        b.free()
+    d_out.free()
+    stream.destroy()
+    model.free()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-plugin", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

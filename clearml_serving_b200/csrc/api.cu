@@ -775,6 +775,21 @@ int b2s_flush_l2(int device)
     return 0;
 }
 
+int b2s_stream_flush_l2(b2s_stream_t stream)
+{
+    Stream *s = get_stream(stream);
+    if (!s) return fail(B2S_ERR_INVALID, "b2s_stream_flush_l2: bad handle");
+    Global &g = G();
+    B2S_CUDA(cudaSetDevice(s->device));
+    {
+        std::lock_guard<std::mutex> l(g.mu);
+        if (!g.flush_buf[s->device]) B2S_CUDA(cudaMalloc(&g.flush_buf[s->device], kFlushBytes));
+    }
+    static std::atomic<int> v{0};
+    B2S_CUDA(cudaMemsetAsync(g.flush_buf[s->device], (v++) & 0xff, kFlushBytes, s->st));
+    return 0;
+}
+
 int b2s_timer_create(b2s_stream_t stream, b2s_timer_t *out_timer)
 {
     Stream *s = get_stream(stream);

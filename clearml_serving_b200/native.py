@@ -84,6 +84,7 @@ PROTOTYPES = [
     ("b2s_memcpy_h2d", _i, [_i, _vp, _vp, _sz]),
     ("b2s_memcpy_d2h", _i, [_i, _vp, _vp, _sz]),
     ("b2s_flush_l2", _i, [_i]),
+    ("b2s_stream_flush_l2", _i, [_u64]),
     ("b2s_timer_create", _i, [_u64, _P(_u64)]),
     ("b2s_timer_start", _i, [_u64]),
     ("b2s_timer_stop", _i, [_u64]),
@@ -313,6 +314,9 @@ class Stream(object):
 
     def synchronize(self):
         check(lib().b2s_stream_synchronize(self.handle))
+
+    def flush_l2(self):
+        check(lib().b2s_stream_flush_l2(self.handle))
 
     def cuda_handle(self):
         return lib().b2s_stream_cuda_handle(self.handle)

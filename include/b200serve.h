@@ -167,6 +167,10 @@ B2S_API int b2s_memcpy_h2d(int device, void *dst, const void *src, size_t bytes)
 B2S_API int b2s_memcpy_d2h(int device, void *dst, const void *src, size_t bytes);
 /* Overwrite a buffer larger than L2 (benchmark hygiene: cold-cache timing). */
 B2S_API int b2s_flush_l2(int device);
+/* Same, but enqueued asynchronously on a library stream: the GPU stays busy while the host queues
+ * the timed launch behind it, so CUDA-event timing of a microsecond-scale kernel carries no host
+ * launch gap. */
+B2S_API int b2s_stream_flush_l2(b2s_stream_t stream);
 
 /* CUDA-event timers on a library stream (device time, not wall clock). */
 typedef uint64_t b2s_timer_t;

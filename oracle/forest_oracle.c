@@ -142,6 +142,74 @@ void oracle_linear_predict(const double *X, int64_t n_rows, int32_t n_features,
     }
 }
 
+/* ---- compact (array-of-structs) form of the same predictor, used for TIMING the CPU baseline ----
+ * Same arithmetic as oracle_forest_predict_xgb (tests assert bit-equality); the node is packed the
+ * way xgboost's RegTree::Node is (children, split index + default bit, fp32 condition/leaf), so
+ * the timed CPU arm is not handicapped by the readable SoA layout above. */
+typedef struct {
+    int32_t left, right;   /* local child ids, left < 0 => leaf */
+    uint32_t feat_dl;      /* feat | default_left << 31 */
+    float cond;            /* threshold, or leaf value */
+} oracle_cnode;
+
+typedef struct {
+    int32_t n_trees, n_features;
+    int32_t *tree_offset;
+    oracle_cnode *nodes;
+} oracle_compiled;
+
+#include <stdlib.h>
+
+oracle_compiled *oracle_forest_compile(const oracle_forest *f)
+{
+    oracle_compiled *c = (oracle_compiled *)malloc(sizeof(*c));
+    const int32_t n_nodes = f->tree_offset[f->n_trees];
+    c->n_trees = f->n_trees;
+    c->n_features = f->n_features;
+    c->tree_offset = (int32_t *)malloc(sizeof(int32_t) * (f->n_trees + 1));
+    c->nodes = (oracle_cnode *)malloc(sizeof(oracle_cnode) * n_nodes);
+    for (int32_t t = 0; t <= f->n_trees; ++t) c->tree_offset[t] = f->tree_offset[t];
+    for (int32_t i = 0; i < n_nodes; ++i) {
+        c->nodes[i].left = f->left[i];
+        c->nodes[i].right = f->right[i];
+        c->nodes[i].feat_dl = (uint32_t)f->feat[i] | (f->default_left[i] ? 0x80000000u : 0u);
+        c->nodes[i].cond = f->left[i] >= 0 ? (float)f->thr[i] : (float)f->value[i];
+    }
+    return c;
+}
+
+void oracle_compiled_free(oracle_compiled *c)
+{
+    if (!c) return;
+    free(c->tree_offset);
+    free(c->nodes);
+    free(c);
+}
+
+void oracle_compiled_predict_xgb(const oracle_compiled *c, const float *X, int64_t n_rows,
+                                 float base_score, float *out, int n_threads)
+{
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(static) if (n_threads != 1)
+#endif
+    for (int64_t i = 0; i < n_rows; ++i) {
+        const float *x = X + i * c->n_features;
+        float acc = base_score;
+        for (int32_t t = 0; t < c->n_trees; ++t) {
+            const oracle_cnode *nodes = c->nodes + c->tree_offset[t];
+            const oracle_cnode *n = nodes;
+            while (n->left >= 0) {
+                const float xv = x[n->feat_dl & 0x7fffffffu];
+                const int go_left = isnan(xv) ? (int)(n->feat_dl >> 31) : (xv < n->cond);
+                n = nodes + (go_left ? n->left : n->right);
+            }
+            acc += n->cond;
+        }
+        out[i] = acc;
+    }
+}
+
 int oracle_max_threads(void)
 {
 #ifdef _OPENMP

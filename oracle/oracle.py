@@ -71,6 +71,39 @@ def _keep(forest):
     return f, arrs
 
 
+class ForestHandle(object):
+    """Pre-compiled forest for timing loops: compact AoS nodes (oracle_forest_compile), no per-call
+    array conversion.  Bit-identical to forest_predict_xgb (tests/test_oracle.py)."""
+
+    def __init__(self, forest):
+        f, keep = _keep(forest)
+        L = lib()
+        L.oracle_forest_compile.restype = ctypes.c_void_p
+        L.oracle_forest_compile.argtypes = [ctypes.c_void_p]
+        L.oracle_compiled_free.argtypes = [ctypes.c_void_p]
+        L.oracle_compiled_free.restype = None
+        self._fn = L.oracle_compiled_predict_xgb
+        self._fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float,
+                             ctypes.c_void_p, ctypes.c_int]
+        self._fn.restype = None
+        self.n_features = int(forest["n_features"])
+        self._c = L.oracle_forest_compile(ctypes.addressof(f))
+        del keep
+
+    def predict_xgb_into(self, X, base_score, out, n_threads=1):
+        """X: C-contiguous float32 [n, F]; out: float32 [n]."""
+        self._fn(self._c, X.ctypes.data, X.shape[0], base_score, out.ctypes.data, n_threads)
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_c", None):
+                lib().oracle_compiled_free(self._c)
+                self._c = None
+        except Exception:  # noqa
+            pass
+
+
 def forest_predict_xgb(forest, X, base_score, n_threads=1):
     """XGBoost gbtree/reg:squarederror semantics (fp32 sequential margin). Returns float32[n]."""
     X = np.ascontiguousarray(X, dtype=np.float32)

@@ -73,3 +73,15 @@ def test_forest_xgb_restatement_self_consistent(ragged):
 def test_forest_xgb_empty_batch():
     f = orc.synth_xgb_forest(n_trees=3, depth=2, n_features=4, seed=0)
     assert orc.forest_predict_xgb(f, np.zeros((0, 4), np.float32), 0.5).shape == (0,)
+
+
+def test_compiled_timing_form_is_bit_identical():
+    f = orc.synth_xgb_forest(n_trees=100, depth=6, n_features=32, seed=0, ragged=True)
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((200, 32)).astype(np.float32)
+    X[rng.random(X.shape) < 0.02] = np.nan
+    h = orc.ForestHandle(f)
+    out = np.empty(200, np.float32)
+    for threads in (1, 4):
+        h.predict_xgb_into(X, 0.5, out, threads)
+        assert np.array_equal(out, orc.forest_predict_xgb(f, X, 0.5))
