@@ -33,6 +33,7 @@ from pathlib import Path
 import numpy as np
 
 from . import formats, native
+from .router import Replica, ReplicaSet, parse_devices
 from .scheduler import BatchPolicy, DynamicBatcher
 
 
@@ -277,7 +278,7 @@ class B200EngineMixin(object):
 
     def _b200_setup(self):
         ep = self.model_endpoint
-        self._device = self._pick_device()
+        aux = getattr(ep, "auxiliary_cfg", None)
         packed = None
         if self._model is not None:
             # user load() returned something: accept a PackedModel, a path, or an sklearn estimator
@@ -288,9 +289,15 @@ class B200EngineMixin(object):
                 raise ValueError("b200 engine: endpoint '{}' has no model (model_id / load())".format(ep.serving_url))
             packed = formats.load_model_file(path)
         self._packed_description = packed.description
-        self._native_model = native.Model(packed.kind, packed.blob, device=self._device)
-        self._policy = BatchPolicy.from_auxiliary_cfg(getattr(ep, "auxiliary_cfg", None))
-        self._batcher = DynamicBatcher(self._native_model, self._policy, name=str(ep.serving_url).replace("/", "_"))
+        self._policy = BatchPolicy.from_auxiliary_cfg(aux)
+        name = str(ep.serving_url).replace("/", "_")
+        replicas = []
+        for dev in parse_devices(aux, self._default_device_index()):
+            m = native.Model(packed.kind, packed.blob, device=dev)   # one full model copy per GPU
+            replicas.append(Replica(dev, m, DynamicBatcher(m, self._policy, name="{}@{}".format(name, dev))))
+        self._replicas = ReplicaSet(replicas)
+        self._native_model = replicas[0].model
+        self._batcher = replicas[0].batcher
         self._model = self._native_model
 
     @staticmethod
@@ -305,13 +312,14 @@ class B200EngineMixin(object):
             return formats.pack_sklearn(obj)
         return None
 
-    def _pick_device(self):
-        aux = getattr(self.model_endpoint, "auxiliary_cfg", None)
-        if isinstance(aux, dict) and "b200.device" in aux:
-            return int(aux["b200.device"])
+    def _default_device_index(self):
         if B200EngineMixin._default_device is not None:
             return int(B200EngineMixin._default_device)
         return int(os.environ.get("B2S_DEVICE", os.environ.get("LOCAL_RANK", 0)))
+
+    def _next_batcher(self):
+        reps = getattr(self, "_replicas", None)
+        return reps.pick().batcher if reps is not None else self._batcher
 
     # ---- request marshalling: the rules of preprocess_service.py:385-406 --------------------------
     def _marshal(self, data):
@@ -377,7 +385,7 @@ class B200EngineMixin(object):
         if self._preprocess is not None and hasattr(self._preprocess, "process"):
             return await self._preprocess.process(data, state, collect_custom_statistics_fn)
         arrays, rows = self._marshal(data)
-        fut = self._batcher.submit_async(arrays, rows)
+        fut = self._next_batcher().submit_async(arrays, rows)
         try:
             outs = await asyncio.wait_for(fut, timeout=self._timeout)
         except asyncio.TimeoutError:
@@ -387,13 +395,21 @@ class B200EngineMixin(object):
     def process_sync(self, data, timeout=None):
         """Blocking variant for non-asyncio callers (benchmarks, C++/thread hosts)."""
         arrays, rows = self._marshal(data)
-        outs = self._batcher.submit(arrays, rows).result(timeout=timeout or self._timeout)
+        outs = self._next_batcher().submit(arrays, rows).result(timeout=timeout or self._timeout)
         return self._unmarshal(outs)
 
     def engine_stats(self):
-        return self._batcher.snapshot_stats()
+        reps = getattr(self, "_replicas", None)
+        return reps.snapshot_stats() if reps is not None else self._batcher.snapshot_stats()
 
     def unload(self):
+        reps = getattr(self, "_replicas", None)
+        if reps is not None:
+            reps.shutdown()
+            self._replicas = None
+            self._batcher = None
+            self._native_model = None
+            return
         b = getattr(self, "_batcher", None)
         if b is not None:
             b.shutdown()

@@ -72,7 +72,7 @@ class FakeStream(object):
         pass
 
 
-def make_fake_engine(endpoint, model, preprocess=None, policy=None, latency_s=0.0):
+def make_fake_engine(endpoint, model, preprocess=None, policy=None, latency_s=0.0, n_replicas=1):
     """A B200PreprocessRequest whose native model/stream are the host-side fakes above (CPU suite
     only): everything above the C ABI -- marshalling, batching, futures -- is the real code."""
     from clearml_serving_b200.preprocess_service import B200PreprocessRequest
@@ -85,7 +85,12 @@ def make_fake_engine(endpoint, model, preprocess=None, policy=None, latency_s=0.
     e._native_model = model
     e._model = model
     e._policy = policy
-    e._batcher = DynamicBatcher(model, policy, name="fake",
-                                stream=FakeStream(model, policy.max_batch_size, n_slots=policy.n_slots,
-                                                  latency_s=latency_s))
+    from clearml_serving_b200.router import Replica, ReplicaSet
+    reps = []
+    for dev in range(n_replicas):
+        reps.append(Replica(dev, model, DynamicBatcher(
+            model, policy, name="fake{}".format(dev),
+            stream=FakeStream(model, policy.max_batch_size, n_slots=policy.n_slots, latency_s=latency_s))))
+    e._replicas = ReplicaSet(reps)
+    e._batcher = reps[0].batcher
     return e

@@ -273,3 +273,21 @@ def test_rest_contract_matches_reference(golden_dir):
             assert resp.json() == rec["response"], rec["name"]
     finally:
         p.shutdown()
+
+
+# ---------------------------------------------------------------- replicas (multi-GPU router)
+def test_round_robin_over_replicas():
+    from clearml_serving_b200.router import parse_devices
+    assert parse_devices({"b200.devices": "0,1,2,3"}, 0) == [0, 1, 2, 3]
+    assert parse_devices({"b200.devices": [2, 5]}, 0) == [2, 5]
+    assert parse_devices({"b200.device": 3}, 0) == [3]
+    assert parse_devices(None, 1) == [1]
+    ep = ModelEndpoint(engine_type="b200", serving_url="m")
+    eng = make_fake_engine(ep, FakeModel(n_features=2), n_replicas=4)
+    try:
+        outs = [eng.process_sync([[i, i]]) for i in range(40)]
+        assert [float(o[0]) for o in outs] == [2.0 * i for i in range(40)]
+        st = eng.engine_stats()
+        assert st["replicas"] == 4 and st["per_replica_requests"] == [10, 10, 10, 10]
+    finally:
+        eng.unload()
