@@ -74,7 +74,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libb200serve.so: compilation failed")
-    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-cudart", "static", "-lcuda"] + (["-ccbin", cxx] if cxx else [])
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-cudart", "static"] + (["-ccbin", cxx] if cxx else [])
     subprocess.check_call(link)
     return LIB
 

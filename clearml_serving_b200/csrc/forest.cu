@@ -6,14 +6,14 @@
 //   * sklearn tree ensembles via `self._model.predict(data)` (preprocess_service.py:459-464)
 //       acc = init; acc += lr*value_t(x) in fp64 in tree order; out = acc / divisor.
 // Bit-identity forces the per-row sum to be SEQUENTIAL in tree order (fp add is not associative),
-// so the design splits the work into
-//   phase 1 (parallel over (row, tree) pairs): traverse, write the leaf value to an L2-resident
-//           scratch matrix leaf[tree][row];
-//   phase 2 (ordered): the last CTA of each 32-row tile streams its column block of the leaf
-//           matrix through a cp.async shared-memory ring and one warp adds it in tree order
-//           (lane = row).  The 4-cycle FADD chain of n_trees adds is the latency floor.
+// so the work is split into
+//   phase 1 (parallel over (row, tree) pairs): traverse, produce the leaf value;
+//   phase 2 (ordered): one lane per row adds its column of leaf values in tree order.
+// Serving-size batches (<= 4096 rows) use one thread-block cluster per 32-row tile: leaf values go
+// through distributed shared memory into rank 0's SM, never through L2/HBM (forest_cluster_kernel).
+// The 4-cycle FADD chain of n_trees adds is the latency floor (~2 us for 1000 trees).
 // For very large batches a second kernel keeps one row per thread and walks all trees
-// sequentially (no scratch).
+// sequentially (forest_rows_kernel).
 //
 // HBM layout (packed by clearml_serving_b200/formats.py, validated here):
 //   nodes[]  : 8 B each  {f32 value | u32 meta}; meta = feat | default_left<<fb | left<<(fb+1)
@@ -54,18 +54,6 @@ struct ForestParams {
 
 __device__ __forceinline__ uint2 ld_node(const uint2 *p) { return __ldg(p); }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
 // One traversal step for U interleaved trees (ILP across trees; one row per thread).
 template <int U, typename XF>
 __device__ __forceinline__ void traverse(const ForestParams &p, const uint32_t (&base)[U],
@@ -93,100 +81,114 @@ __device__ __forceinline__ void traverse(const ForestParams &p, const uint32_t (
 }
 
 // ---------------------------------------------------------------------------------------------
-// Kernel B: (row, tree) pairs + ordered sum in the last CTA of each 32-row tile.
-// grid = (ceil(T / (WARPS*U)), ceil(rows / 32)); block = WARPS*32; lane = row within the tile.
+// Kernel B (serving batches): one thread-block CLUSTER per 32-row tile.
+//   * lane = row of the tile; every warp of every CTA of the cluster traverses U trees at once, so a
+//     cluster of C CTAs x WARPS warps covers C*WARPS*U trees per round with all node fetches in flight
+//     together (the forest is L2-resident; a depth-d tree costs d+1 dependent L2 round trips);
+//   * each warp writes its 32 leaf values (one per row) into the leaf matrix that lives in the
+//     shared memory of cluster rank 0 -- a coalesced 128-byte DISTRIBUTED-SHARED-MEMORY store -- so
+//     the leaf values never touch L2/HBM and no global fence / atomic hand-off is needed;
+//   * after one cluster barrier, warp 0 of rank 0 adds the column of each row in tree order out of
+//     its local shared memory (the sequential fp32/fp64 chain bit-identity demands) and writes y.
+// grid = C * ceil(rows/32) CTAs, cluster (C,1,1), block = WARPS*32, 1 CTA/SM.
+// Forests larger than one chunk (C*WARPS*U*rounds trees) loop over chunks carrying the accumulator.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(const void *local_smem, uint32_t rank)
+{
+    uint32_t la = (uint32_t)__cvta_generic_to_shared(local_smem), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(la), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, float v)
+{
+    asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, double v)
+{
+    asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
+}
+
 template <bool F64, int WARPS, int U>
-__global__ void __launch_bounds__(WARPS * 32)
-forest_pairs_kernel(ForestParams p, const float *__restrict__ X, int64_t n_rows,
-                    void *__restrict__ out, void *__restrict__ leaf_scratch, int ldb,
-                    unsigned *__restrict__ counters, int x_in_smem)
+__global__ void __launch_bounds__(WARPS * 32, 1)
+forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_rows,
+                      void *__restrict__ out, int x_in_smem, int rounds)
 {
     using acc_t = typename std::conditional<F64, double, float>::type;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ unsigned s_ticket;
-
-    float *xs = reinterpret_cast<float *>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int F = p.n_features, T = p.n_trees;
-    const int64_t r0 = (int64_t)blockIdx.y * 32;
+    const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
+    const int64_t r0 = (int64_t)(blockIdx.x / C) * 32;
     const int rows_here = (int)min((int64_t)32, n_rows - r0);
+    const int per_round = (int)C * WARPS * U;          // trees the cluster covers per round
+    const int chunk_trees = per_round * rounds;        // trees held by the leaf matrix at once
 
-    if (x_in_smem) {  // x tile, transposed + padded: xs[f*33 + r]
+    // smem: [leaf matrix: chunk_trees x 32 acc_t (used in rank 0 only)] [x tile: F x 33 floats]
+    acc_t *leafbuf = reinterpret_cast<acc_t *>(smem);
+    float *xs = reinterpret_cast<float *>(smem + (size_t)chunk_trees * 32 * sizeof(acc_t));
+    if (x_in_smem) {
         const float *src = X + r0 * F;
         for (int i = threadIdx.x; i < 32 * F; i += WARPS * 32) {
             const int r = i / F, f = i - r * F;
             xs[f * 33 + r] = (r < rows_here) ? __ldg(src + i) : 0.0f;
         }
-        __syncthreads();
     }
     const bool row_ok = lane < rows_here;
     const float *xrow = X + (r0 + (row_ok ? lane : 0)) * F;
-
-    const int t0 = (blockIdx.x * WARPS + warp) * U;
-    uint32_t base[U];
-    uint2 cur[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int t = t0 + u;
-        base[u] = (t < T) ? __ldg(p.tree_offset + t) : 0u;
-        cur[u] = (t < T) ? ld_node(p.nodes + base[u]) : make_uint2(0u, 0u);
-    }
-    if (x_in_smem) {
-        traverse<U>(p, base, cur, [&](uint32_t f) { return xs[f * 33 + lane]; });
-    } else {
-        traverse<U>(p, base, cur, [&](uint32_t f) { return __ldg(xrow + f); });
-    }
-    acc_t *leaf = reinterpret_cast<acc_t *>(leaf_scratch);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int t = t0 + u;
-        if (t < T && row_ok) {
-            acc_t v;
-            if (F64) v = (acc_t)__ldg(p.leaf64 + cur[u].x);
-            else v = (acc_t)__uint_as_float(cur[u].x);
-            leaf[(int64_t)t * ldb + r0 + lane] = v;
-        }
-    }
-
-    // ---- hand-off: last CTA of this row tile performs the ordered sum -------------------------
-    __threadfence();
+    const uint32_t leaf_remote = map_to_rank(leafbuf, 0);  // rank 0's leaf matrix, cluster address
     __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[blockIdx.y], 1u);
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
-
-    constexpr int CH = F64 ? 64 : 128;   // trees per ring stage (16 KiB)
-    constexpr int NST = 3;
-    constexpr int PPR = 32 * (int)sizeof(acc_t) / 16;  // 16-byte pieces per tree row
-    acc_t *ring = reinterpret_cast<acc_t *>(smem);
-    const acc_t *L = reinterpret_cast<const acc_t *>(leaf_scratch) + r0;
-    const int nchunks = (T + CH - 1) / CH;
-
-    auto issue = [&](int c) {
-        if (c < nchunks) {
-            const int tcount = min(CH, T - c * CH);
-            unsigned char *dst = reinterpret_cast<unsigned char *>(ring + (size_t)(c % NST) * CH * 32);
-            for (int i = threadIdx.x; i < tcount * PPR; i += WARPS * 32) {
-                const int t = i / PPR, piece = i - t * PPR;
-                cp_async16(dst + (size_t)t * 32 * sizeof(acc_t) + piece * 16,
-                           reinterpret_cast<const unsigned char *>(L + (int64_t)(c * CH + t) * ldb) + piece * 16);
-            }
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int c = 0; c < NST - 1; ++c) issue(c);
 
     acc_t acc = F64 ? (acc_t)p.base : (acc_t)(float)p.base;
-    for (int c = 0; c < nchunks; ++c) {
-        issue(c + NST - 1);
-        cp_async_wait<NST - 1>();
-        __syncthreads();
-        if (warp == 0) {
-            const int tcount = min(CH, T - c * CH);
-            const acc_t *buf = ring + (size_t)(c % NST) * CH * 32 + lane;
+    for (int chunk0 = 0; chunk0 < T; chunk0 += chunk_trees) {
+        for (int j = 0; j < rounds; ++j) {
+            const int slot0 = ((j * (int)C + (int)rank) * WARPS + warp) * U;  // slot inside the chunk
+            const int t0 = chunk0 + slot0;
+            if (t0 >= T) break;
+            uint32_t base[U];
+            uint2 cur[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = t0 + u;
+                base[u] = (t < T) ? __ldg(p.tree_offset + t) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = (t0 + u < T) ? ld_node(p.nodes + base[u]) : make_uint2(0u, 0u);
+            if (x_in_smem) {
+                traverse<U>(p, base, cur, [&](uint32_t f) { return xs[f * 33 + lane]; });
+            } else {
+                traverse<U>(p, base, cur, [&](uint32_t f) { return __ldg(xrow + f); });
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (t0 + u < T) {
+                    acc_t v;
+                    if (F64) v = (acc_t)__ldg(p.leaf64 + cur[u].x);
+                    else v = (acc_t)__uint_as_float(cur[u].x);
+                    st_cluster(leaf_remote + (uint32_t)(((slot0 + u) * 32 + lane) * sizeof(acc_t)), v);
+                }
+            }
+        }
+        cluster_sync_all();  // every leaf value of this chunk has landed in rank 0's shared memory
+        if (rank == 0 && warp == 0) {
+            const int tcount = min(chunk_trees, T - chunk0);
+            const acc_t *buf = leafbuf + lane;
             int t = 0;
             for (; t + 16 <= tcount; t += 16) {
                 acc_t v[16];
@@ -197,13 +199,12 @@ forest_pairs_kernel(ForestParams p, const float *__restrict__ X, int64_t n_rows,
             }
             for (; t < tcount; ++t) acc = acc + buf[t * 32];
         }
-        __syncthreads();
+        if (chunk0 + chunk_trees < T) cluster_sync_all();  // leaf matrix is reused by the next chunk
     }
-    if (warp == 0 && row_ok) {
+    if (rank == 0 && warp == 0 && row_ok) {
         if (F64) reinterpret_cast<double *>(out)[r0 + lane] = (double)acc / p.divisor;
         else reinterpret_cast<float *>(out)[r0 + lane] = (float)acc;
     }
-    if (threadIdx.x == 0) counters[blockIdx.y] = 0u;  // re-arm for the next launch on this stream
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,13 +265,12 @@ forest_rows_kernel(ForestParams p, const float *__restrict__ X, int64_t n_rows,
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kPairsWarps = 4;
-constexpr int kPairsU = 2;
+constexpr int kClWarps = 32;               // 1024 threads per CTA, one CTA per SM
+constexpr int kClU32 = 4, kClU64 = 2;      // trees in flight per warp (fp32 / fp64 leaf matrix)
 constexpr int kRowsBlock = 128;
 constexpr int kRowsU = 4;
-constexpr int64_t kPairsMaxRows = 8192;   // above this the rows kernel is used
-constexpr int kRingBytes = 3 * 16384;     // NST * 16 KiB
-constexpr size_t kCounterBytes = 1024;    // kPairsMaxRows/32 = 256 tile counters
+constexpr int64_t kClusterMaxRows = 4096;  // above this the one-row-per-thread kernel is used
+constexpr size_t kLeafBudget = 160 * 1024; // bytes of shared memory for the leaf matrix
 
 struct ForestModel : Model {
     ForestParams p{};
@@ -283,42 +283,51 @@ struct ForestModel : Model {
         if (d_blob) { cudaSetDevice(device); cudaFree(d_blob); }
     }
 
-    size_t scratch_bytes(int64_t max_rows, int64_t) const override
+    size_t scratch_bytes(int64_t, int64_t) const override { return 256; }
+
+    template <bool F64, int U>
+    int launch_cluster(cudaStream_t st, const float *X, int64_t n_rows, void *out)
     {
-        const int64_t rows = max_rows < kPairsMaxRows ? max_rows : kPairsMaxRows;
-        const size_t leaf = (size_t)p.n_trees * (size_t)round_up(rows, 32) * (f64 ? 8 : 4);
-        return kCounterBytes + (size_t)round_up((int64_t)leaf, 256);
+        using acc_t = typename std::conditional<F64, double, float>::type;
+        const int F = p.n_features, T = p.n_trees;
+        int C = 1;
+        while (C < 8 && C * kClWarps * U < T) C *= 2;
+        const int per_round = C * kClWarps * U;
+        const int max_rounds = (int)(kLeafBudget / ((size_t)per_round * 32 * sizeof(acc_t)));
+        int rounds = (T + per_round - 1) / per_round;
+        if (rounds > max_rounds) rounds = max_rounds;
+        if (rounds < 1) rounds = 1;
+        const size_t leaf_bytes = (size_t)per_round * rounds * 32 * sizeof(acc_t);
+        const size_t xs_bytes = (size_t)F * 33 * sizeof(float);
+        const int x_in_smem = leaf_bytes + xs_bytes + 1024 <= (size_t)max_smem_optin ? 1 : 0;
+        const size_t smem = leaf_bytes + (x_in_smem ? xs_bytes : 0);
+        const unsigned tiles = (unsigned)((n_rows + 31) / 32);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(tiles * C, 1, 1);
+        cfg.blockDim = dim3(kClWarps * 32, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B2S_CUDA(cudaLaunchKernelEx(&cfg, forest_cluster_kernel<F64, kClWarps, U>, p, X, n_rows, out, x_in_smem, rounds));
+        return 0;
     }
 
     int launch(cudaStream_t st, int64_t n_rows, const void *const *d_in, void *const *d_out,
-               const int64_t *, void *scratch, size_t scratch_sz) override
+               const int64_t *, void *, size_t) override
     {
         if (n_rows <= 0) return 0;
         const float *X = static_cast<const float *>(d_in[0]);
         void *out = d_out[0];
         const int F = p.n_features;
-        if (n_rows <= kPairsMaxRows) {
-            const int ldb = (int)round_up(n_rows, 32);
-            const size_t leaf = (size_t)p.n_trees * ldb * (f64 ? 8 : 4);
-            if (kCounterBytes + leaf > scratch_sz)
-                return fail(B2S_ERR_INVALID, "forest: batch of %lld rows exceeds the stream's max_rows scratch",
-                            (long long)n_rows);
-            // scratch = [tile counters (zeroed at stream creation, re-armed by the kernel) | leaf matrix]
-            unsigned *counters = static_cast<unsigned *>(scratch);
-            void *leaf_scratch = static_cast<unsigned char *>(scratch) + kCounterBytes;
-            const size_t xs_bytes = (size_t)F * 33 * sizeof(float);
-            const int x_in_smem = xs_bytes <= (size_t)(max_smem_optin - 1024) ? 1 : 0;
-            size_t smem = kRingBytes;
-            if (x_in_smem && xs_bytes > smem) smem = xs_bytes;
-            dim3 grid((p.n_trees + kPairsWarps * kPairsU - 1) / (kPairsWarps * kPairsU),
-                      (unsigned)((n_rows + 31) / 32));
-            if (f64) {
-                forest_pairs_kernel<true, kPairsWarps, kPairsU><<<grid, kPairsWarps * 32, smem, st>>>(
-                    p, X, n_rows, out, leaf_scratch, ldb, counters, x_in_smem);
-            } else {
-                forest_pairs_kernel<false, kPairsWarps, kPairsU><<<grid, kPairsWarps * 32, smem, st>>>(
-                    p, X, n_rows, out, leaf_scratch, ldb, counters, x_in_smem);
-            }
+        if (n_rows <= kClusterMaxRows) {
+            if (f64) B2S_TRY((launch_cluster<true, kClU64>(st, X, n_rows, out)));
+            else B2S_TRY((launch_cluster<false, kClU32>(st, X, n_rows, out)));
         } else {
             const size_t xs_bytes = (size_t)F * kRowsBlock * sizeof(float);
             const int x_in_smem = xs_bytes <= (size_t)(max_smem_optin - 1024) ? 1 : 0;
@@ -329,9 +338,9 @@ struct ForestModel : Model {
             } else {
                 forest_rows_kernel<false, kRowsBlock, kRowsU><<<grid, kRowsBlock, smem, st>>>(p, X, n_rows, out, x_in_smem);
             }
+            B2S_CUDA(cudaGetLastError());
         }
         count_launch();
-        B2S_CUDA(cudaGetLastError());
         return 0;
     }
 };
@@ -412,8 +421,8 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     m->max_smem_optin = optin;
     const int want = optin < 200 * 1024 ? optin : 200 * 1024;
-    cudaFuncSetAttribute(forest_pairs_kernel<false, kPairsWarps, kPairsU>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    cudaFuncSetAttribute(forest_pairs_kernel<true, kPairsWarps, kPairsU>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    cudaFuncSetAttribute(forest_cluster_kernel<false, kClWarps, kClU32>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    cudaFuncSetAttribute(forest_cluster_kernel<true, kClWarps, kClU64>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     cudaFuncSetAttribute(forest_rows_kernel<false, kRowsBlock, kRowsU>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     cudaFuncSetAttribute(forest_rows_kernel<true, kRowsBlock, kRowsU>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     m->max_smem_optin = want;

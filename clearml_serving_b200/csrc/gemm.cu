@@ -1,0 +1,344 @@
+// gemm.cu -- fp16/bf16 GEMM on the 5th-gen tensor cores (kernel K5 of SURVEY.md 2.2):
+//     C[M,N] = epilogue( A[M,K] . B[N,K]^T )        A, B K-major (row-major activations x nn.Linear
+//                                                    weights as stored), fp32 accumulate in TMEM
+//     epilogue: + bias[n], activation (none | GELU-erf | ReLU | tanh), + residual[m,n], cast to
+//               fp16/bf16 or fp32.
+// This is the op tritonserver's libtorch / ONNX-Runtime backends run through cuBLAS for the
+// reference's DL endpoints (clearml_serving/engines/triton/triton_helper.py:378-385 picks the
+// backend; examples/huggingface, examples/pytorch); here it is one hand-written sm_100a kernel:
+//   * operands arrive by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage smem ring,
+//   * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16) straight from shared memory,
+//   * accumulators live in TMEM, are read back with tcgen05.ld by four epilogue warps and the fused
+//     epilogue writes C exactly once.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
+// Roofline: tensor pipe (MEASURED_PEAKS.json bf16_tflops); algorithmic FLOPs = 2*M*N*K.
+#include "common.cuh"
+#include "sm100.cuh"
+
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+namespace b2s {
+
+using namespace sm100;
+
+enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
+
+struct GemmEpilogue {
+    const void *bias;      // [N] fp32 or null
+    const void *residual;  // [M, ldc] same dtype as C (16-bit) or null
+    void *C;
+    int ldc;               // elements
+    int act;
+    int out_f32;           // 1: C is fp32, 0: C is 16-bit (same format as A/B)
+    int is_bf16;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;   // 64 x 16-bit = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192;
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               int M, int N, int K, GemmEpilogue ep)
+{
+    using S = GemmSmem<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFFSET);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.y, n_blk = blockIdx.x;
+    const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_a);
+        prefetch_tensormap(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {  // TMEM: BN fp32 columns x 128 lanes
+        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                unsigned char *sb = sa + S::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (single thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_f16 = make_idesc_f16(GEMM_BM, BN, 0);
+            constexpr uint32_t idesc_bf16 = make_idesc_f16(GEMM_BM, BN, 1);
+            const uint32_t idesc = ep.is_bf16 ? idesc_bf16 : idesc_f16;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                unsigned char *sb = sa + S::A_BYTES;
+                const uint64_t adesc = make_sw128_kmajor_desc(sa);
+                const uint64_t bdesc = make_sw128_kmajor_desc(sb);
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                    umma_f16(tmem_base, desc_advance(adesc, k * 32), desc_advance(bdesc, k * 32), idesc,
+                             (uint32_t)((kb | k) != 0));
+                }
+                umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full_bar);          // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> fused bias/act/residual -> global =====
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int row = m_blk * GEMM_BM + q * 32 + lane;
+        const float *bias = static_cast<const float *>(ep.bias);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+            const int col0 = n_blk * BN + c * 32;
+            if (row < M && col0 < N) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                const int ncols = min(32, N - col0);
+                if (bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) f[j] += __ldg(bias + col0 + j);
+                }
+                if (ep.act == ACT_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                } else if (ep.act == ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                } else if (ep.act == ACT_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+                }
+                const size_t off = (size_t)row * ep.ldc + col0;
+                if (ep.out_f32) {
+                    float *C = static_cast<float *>(ep.C) + off;
+                    if (ep.residual) {
+                        const float *R = static_cast<const float *>(ep.residual) + off;
+                        for (int j = 0; j < ncols; ++j) f[j] += R[j];
+                    }
+                    if (ncols == 32 && (off & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(C + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+                        for (int j = 0; j < ncols; ++j) C[j] = f[j];
+                    }
+                } else if (ep.is_bf16) {
+                    __nv_bfloat16 *C = static_cast<__nv_bfloat16 *>(ep.C) + off;
+                    if (ep.residual) {
+                        const __nv_bfloat16 *R = static_cast<const __nv_bfloat16 *>(ep.residual) + off;
+                        for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(R[j]);
+                    }
+                    if (ncols == 32 && (off & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                            __nv_bfloat162 p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                            __nv_bfloat162 p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                            uint4 u;
+                            u.x = *reinterpret_cast<uint32_t *>(&p0);
+                            u.y = *reinterpret_cast<uint32_t *>(&p1);
+                            u.z = *reinterpret_cast<uint32_t *>(&p2);
+                            u.w = *reinterpret_cast<uint32_t *>(&p3);
+                            *reinterpret_cast<uint4 *>(C + j) = u;
+                        }
+                    } else {
+                        for (int j = 0; j < ncols; ++j) C[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else {
+                    __half *C = static_cast<__half *>(ep.C) + off;
+                    if (ep.residual) {
+                        const __half *R = static_cast<const __half *>(ep.residual) + off;
+                        if (ncols == 32 && (off & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 u = *reinterpret_cast<const uint4 *>(R + j);
+                                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 r2 = __half22float2(h[t]);
+                                    f[j + 2 * t] += r2.x;
+                                    f[j + 2 * t + 1] += r2.y;
+                                }
+                            }
+                        } else {
+                            for (int j = 0; j < ncols; ++j) f[j] += __half2float(R[j]);
+                        }
+                    }
+                    if (ncols == 32 && (off & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            __half2 p0 = __floats2half2_rn(f[j], f[j + 1]);
+                            __half2 p1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+                            __half2 p2 = __floats2half2_rn(f[j + 4], f[j + 5]);
+                            __half2 p3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+                            uint4 u;
+                            u.x = *reinterpret_cast<uint32_t *>(&p0);
+                            u.y = *reinterpret_cast<uint32_t *>(&p1);
+                            u.z = *reinterpret_cast<uint32_t *>(&p2);
+                            u.w = *reinterpret_cast<uint32_t *>(&p3);
+                            *reinterpret_cast<uint4 *>(C + j) = u;
+                        }
+                    } else {
+                        for (int j = 0; j < ncols; ++j) C[j] = __float2half_rn(f[j]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: tensor maps via the driver entry point (no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+// 2-D K-major tensor map: global [rows, K] row-major 16-bit, box [box_rows, 64], 128-byte swizzle
+int make_tmap_2d_kmajor(CUtensorMap *out, const void *base, int64_t rows, int64_t K, int64_t ld_elems,
+                        int box_rows, int is_bf16)
+{
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * 2) % 16 != 0)
+        return fail(B2S_ERR_INVALID, "gemm: operand base / leading dimension must be 16-byte aligned");
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
+                       const GemmEpilogue &ep)
+{
+    using S = GemmSmem<BN, STAGES>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, []() {
+        attr_err = cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    });
+    if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
+    dim3 grid((N + BN - 1) / BN, (M + GEMM_BM - 1) / GEMM_BM);
+    gemm_tn_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep);
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// C = epilogue(A[M,K] . B[N,K]^T).  A: lda elements per row, B: ldb elements per row.
+int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t ldb, int M, int N, int K,
+            const GemmEpilogue &ep)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    CUtensorMap ta, tb;
+    B2S_TRY(make_tmap_2d_kmajor(&ta, A, M, K, lda, GEMM_BM, ep.is_bf16));
+    if (N <= 64) {
+        B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, 64, ep.is_bf16));
+        return launch_gemm<64, 6>(st, ta, tb, M, N, K, ep);
+    }
+    B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, 128, ep.is_bf16));
+    return launch_gemm<128, 6>(st, ta, tb, M, N, K, ep);
+}
+
+}  // namespace b2s
+
+// ---------------------------------------------------------------------------------------------
+// C ABI: operator-level entry point (device pointers), used by the parity tests and the graph executor
+// ---------------------------------------------------------------------------------------------
+extern "C" B2S_API int b2s_op_gemm(int device, void *cuda_stream, const void *A, const void *B, void *C,
+                                    int M, int N, int K, const float *bias, const void *residual, int act,
+                                    int is_bf16, int out_f32)
+{
+    using namespace b2s;
+    B2S_CUDA(cudaSetDevice(device));
+    GemmEpilogue ep;
+    ep.bias = bias;
+    ep.residual = residual;
+    ep.C = C;
+    ep.ldc = N;
+    ep.act = act;
+    ep.out_f32 = out_f32;
+    ep.is_bf16 = is_bf16;
+    return gemm_tn(static_cast<cudaStream_t>(cuda_stream), A, K, B, K, M, N, K, ep);
+}

@@ -90,6 +90,7 @@ PROTOTYPES = [
     ("b2s_timer_stop", _i, [_u64]),
     ("b2s_timer_elapsed_ms", _i, [_u64, _P(ctypes.c_float)]),
     ("b2s_timer_destroy", _i, [_u64]),
+    ("b2s_op_gemm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i]),
 ]
 
 _lib = None

@@ -180,6 +180,17 @@ B2S_API int b2s_timer_stop(b2s_timer_t timer);
 B2S_API int b2s_timer_elapsed_ms(b2s_timer_t timer, float *out_ms); /* synchronises on the stop event */
 B2S_API int b2s_timer_destroy(b2s_timer_t timer);
 
+/* ---- operator-level entry points (device pointers) ------------------------------------------------
+ * The building blocks of B2S_MODEL_GRAPH models, exported so that parity tests can check each kernel
+ * against its oracle through the C ABI.  `cuda_stream` is a raw cudaStream_t (b2s_stream_cuda_handle)
+ * or NULL for the default stream.  Stand in for the cuBLAS/cuDNN calls of tritonserver's libtorch /
+ * ONNX-Runtime backends (selected by triton_helper.py:378-385). */
+
+/* C[M,N] = act(A[M,K] . B[N,K]^T + bias[N]) + residual[M,N]; A,B,residual 16-bit (fp16 or bf16),
+ * bias fp32, C 16-bit or fp32.  act: 0 none, 1 GELU(erf), 2 ReLU, 3 tanh.  tcgen05 + TMA + TMEM. */
+B2S_API int b2s_op_gemm(int device, void *cuda_stream, const void *A, const void *B, void *C, int M, int N,
+                        int K, const float *bias, const void *residual, int act, int is_bf16, int out_f32);
+
 #ifdef __cplusplus
 }
 #endif

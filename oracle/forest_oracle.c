@@ -85,8 +85,7 @@ void oracle_forest_predict_xgb(const oracle_forest *f, const float *X, int64_t n
                                float base_score, float *out, int n_threads)
 {
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
-#pragma omp parallel for schedule(static) if (n_threads != 1)
+#pragma omp parallel for schedule(static) if (n_threads != 1) num_threads(n_threads > 0 ? n_threads : omp_get_num_procs())
 #endif
     for (int64_t i = 0; i < n_rows; ++i) {
         const float *x = X + i * f->n_features;
@@ -106,8 +105,7 @@ void oracle_forest_predict_f64(const oracle_forest *f, const float *X, int64_t n
                                int n_threads)
 {
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
-#pragma omp parallel for schedule(static) if (n_threads != 1)
+#pragma omp parallel for schedule(static) if (n_threads != 1) num_threads(n_threads > 0 ? n_threads : omp_get_num_procs())
 #endif
     for (int64_t i = 0; i < n_rows; ++i) {
         const float *x = X + i * f->n_features;
@@ -190,8 +188,7 @@ void oracle_compiled_predict_xgb(const oracle_compiled *c, const float *X, int64
                                  float base_score, float *out, int n_threads)
 {
 #ifdef _OPENMP
-    if (n_threads > 0) omp_set_num_threads(n_threads);
-#pragma omp parallel for schedule(static) if (n_threads != 1)
+#pragma omp parallel for schedule(static) if (n_threads != 1) num_threads(n_threads > 0 ? n_threads : omp_get_num_procs())
 #endif
     for (int64_t i = 0; i < n_rows; ++i) {
         const float *x = X + i * c->n_features;
@@ -213,7 +210,7 @@ void oracle_compiled_predict_xgb(const oracle_compiled *c, const float *X, int64
 int oracle_max_threads(void)
 {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return omp_get_num_procs();
 #else
     return 1;
 #endif

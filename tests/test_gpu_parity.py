@@ -69,7 +69,7 @@ def test_cfg2_ragged_batch_sizes_with_nan(gpu_native, cfg2, n_rows):
 
 
 def test_cfg2_large_batch_rows_kernel_and_device_path(gpu_native, cfg2):
-    """> 8192 rows takes the one-row-per-thread kernel; also exercises b2s_infer_device."""
+    """> 4096 rows takes the one-row-per-thread kernel; also exercises b2s_infer_device."""
     forest, model = cfg2
     n = 20000
     rng = np.random.default_rng(7)
@@ -84,10 +84,10 @@ def test_cfg2_large_batch_rows_kernel_and_device_path(gpu_native, cfg2):
         st.infer_device(n, [d_in.ptr], [d_out.ptr])
         st.synchronize()
         assert np.array_equal(d_out.download(np.float32, n), want)
-        # and the pairs kernel at its upper edge, through the device path too
-        st.infer_device(8192, [d_in.ptr], [d_out.ptr])
+        # and the cluster kernel at its upper edge (128 clusters), through the device path too
+        st.infer_device(4096, [d_in.ptr], [d_out.ptr])
         st.synchronize()
-        assert np.array_equal(d_out.download(np.float32, 8192), want[:8192])
+        assert np.array_equal(d_out.download(np.float32, 4096), want[:4096])
         # linearity-free size-independent property: permuting rows permutes outputs
         perm = rng.permutation(n)
         d_in.upload(X[perm])
@@ -99,10 +99,12 @@ def test_cfg2_large_batch_rows_kernel_and_device_path(gpu_native, cfg2):
 
 
 @pytest.mark.parametrize("shape", [dict(n_trees=1, depth=1, n_features=1), dict(n_trees=3, depth=10, n_features=5),
-                                    dict(n_trees=257, depth=4, n_features=100), dict(n_trees=40, depth=3, n_features=2000)])
+                                    dict(n_trees=257, depth=4, n_features=100), dict(n_trees=40, depth=3, n_features=2000),
+                                    dict(n_trees=2500, depth=3, n_features=7)])
 def test_forest_shapes_edge_cases(gpu_native, shape):
-    """single stump, deep ragged trees, tree count not a multiple of the CTA tile, and a feature
-    count too wide for the shared-memory x tile (global-memory fallback path)."""
+    """single stump, deep ragged trees, tree count not a multiple of the cluster tile, a feature
+    count too wide for the shared-memory x tile (global-memory fallback path), and a forest larger
+    than one leaf-matrix chunk (multi-chunk loop with the accumulator carried across chunks)."""
     forest = orc.synth_xgb_forest(seed=5, ragged=shape["depth"] > 4, **shape)
     pm = formats.pack_forest(forest, "xgb", base=-1.25)
     model = gpu_native.Model(pm.kind, pm.blob, device=0)
@@ -139,7 +141,8 @@ def test_sklearn_large_forest_fp64_rows_kernel(gpu_native):
     rng = np.random.default_rng(0)
     Xtr = rng.standard_normal((400, 10))
     ytr = Xtr[:, 0] * Xtr[:, 1] + np.sin(Xtr[:, 2])
-    est = GradientBoostingRegressor(n_estimators=60, max_depth=4, random_state=0).fit(Xtr, ytr)
+    # 700 stages: more than one fp64 leaf-matrix chunk (512 trees) in the cluster kernel
+    est = GradientBoostingRegressor(n_estimators=700, max_depth=2, random_state=0).fit(Xtr, ytr)
     pm = formats.pack_sklearn(est)
     model = gpu_native.Model(pm.kind, pm.blob, device=0)
     n = 9000
