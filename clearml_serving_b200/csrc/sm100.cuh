@@ -58,9 +58,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Bounded spin: a pipeline bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
     }
 }
 
