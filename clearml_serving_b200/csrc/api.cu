@@ -403,6 +403,13 @@ int b2s_model_get_info(b2s_model_t model, b2s_model_info *out_info)
     return 0;
 }
 
+int b2s_debug_read(b2s_model_t model, long long *out64)
+{
+    Model *m = get_model(model);
+    if (!m || !out64) return fail(B2S_ERR_INVALID, "b2s_debug_read: bad handle");
+    return m->debug_read(out64);
+}
+
 int b2s_stream_create(b2s_model_t model, int64_t max_rows, int64_t max_row_elems, int n_slots,
                       b2s_stream_t *out_stream)
 {

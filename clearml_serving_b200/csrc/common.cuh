@@ -58,6 +58,8 @@ struct Model {
     virtual int launch(cudaStream_t st, int64_t n_rows, const void *const *d_in,
                        void *const *d_out, const int64_t *d_row_offsets, void *scratch,
                        size_t scratch_bytes) = 0;
+    // developer aid: copy 64 int64 of kernel phase stamps (model-specific meaning)
+    virtual int debug_read(long long *) { return fail(B2S_ERR_INVALID, "no debug data for this model kind"); }
 };
 
 int forest_model_create(int device, const void *blob, size_t bytes, Model **out);

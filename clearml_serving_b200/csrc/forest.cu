@@ -27,6 +27,7 @@
 // Algorithmic bytes per launch: sum_t (8*internal_t + 4*leaves_t) + rows*(4F + out).
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -128,8 +129,13 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, double v)
 template <bool F64, int WARPS, int U>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_rows,
-                      void *__restrict__ out, int x_in_smem, int rounds)
+                      void *__restrict__ out, int x_in_smem, int rounds, long long *__restrict__ dbg)
 {
+    // optional phase stamps (B2S_FOREST_TIMING=1): [rank][phase] SM-clock values of thread 0, tile 0
+#define B2S_STAMP(k)                                                                    \
+    do {                                                                                \
+        if (dbg && blockIdx.x < 8 && threadIdx.x == 0) dbg[blockIdx.x * 8 + (k)] = clock64(); \
+    } while (0)
     using acc_t = typename std::conditional<F64, double, float>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,6 +149,7 @@ forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_row
     // smem: [leaf matrix: chunk_trees x 32 acc_t (used in rank 0 only)] [x tile: F x 33 floats]
     acc_t *leafbuf = reinterpret_cast<acc_t *>(smem);
     float *xs = reinterpret_cast<float *>(smem + (size_t)chunk_trees * 32 * sizeof(acc_t));
+    B2S_STAMP(0);
     if (x_in_smem) {
         const float *src = X + r0 * F;
         for (int i = threadIdx.x; i < 32 * F; i += WARPS * 32) {
@@ -154,6 +161,7 @@ forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_row
     const float *xrow = X + (r0 + (row_ok ? lane : 0)) * F;
     const uint32_t leaf_remote = map_to_rank(leafbuf, 0);  // rank 0's leaf matrix, cluster address
     __syncthreads();
+    B2S_STAMP(1);
 
     acc_t acc = F64 ? (acc_t)p.base : (acc_t)(float)p.base;
     for (int chunk0 = 0; chunk0 < T; chunk0 += chunk_trees) {
@@ -185,7 +193,9 @@ forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_row
                 }
             }
         }
+        B2S_STAMP(2);
         cluster_sync_all();  // every leaf value of this chunk has landed in rank 0's shared memory
+        B2S_STAMP(3);
         if (rank == 0 && warp == 0) {
             const int tcount = min(chunk_trees, T - chunk0);
             const acc_t *buf = leafbuf + lane;
@@ -198,6 +208,7 @@ forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_row
                 for (int k = 0; k < 16; ++k) acc = acc + v[k];
             }
             for (; t < tcount; ++t) acc = acc + buf[t * 32];
+            B2S_STAMP(4);
         }
         if (chunk0 + chunk_trees < T) cluster_sync_all();  // leaf matrix is reused by the next chunk
     }
@@ -205,6 +216,7 @@ forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_row
         if (F64) reinterpret_cast<double *>(out)[r0 + lane] = (double)acc / p.divisor;
         else reinterpret_cast<float *>(out)[r0 + lane] = (float)acc;
     }
+#undef B2S_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -277,10 +289,21 @@ struct ForestModel : Model {
     void *d_blob = nullptr;
     bool f64 = false;
     int max_smem_optin = 0;
+    long long *dbg_stamps = nullptr;  // device buffer [8 CTAs][8 phases], only with B2S_FOREST_TIMING=1
 
     ~ForestModel() override
     {
         if (d_blob) { cudaSetDevice(device); cudaFree(d_blob); }
+        if (dbg_stamps) cudaFree(dbg_stamps);
+    }
+
+    int debug_read(long long *out64) override
+    {
+        if (!dbg_stamps) return fail(B2S_ERR_INVALID, "set B2S_FOREST_TIMING=1 before loading the model");
+        B2S_CUDA(cudaSetDevice(device));
+        B2S_CUDA(cudaDeviceSynchronize());
+        B2S_CUDA(cudaMemcpy(out64, dbg_stamps, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+        return 0;
     }
 
     size_t scratch_bytes(int64_t, int64_t) const override { return 256; }
@@ -314,7 +337,8 @@ struct ForestModel : Model {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        B2S_CUDA(cudaLaunchKernelEx(&cfg, forest_cluster_kernel<F64, kClWarps, U>, p, X, n_rows, out, x_in_smem, rounds));
+        B2S_CUDA(cudaLaunchKernelEx(&cfg, forest_cluster_kernel<F64, kClWarps, U>, p, X, n_rows, out, x_in_smem, rounds,
+                                    dbg_stamps));
         return 0;
     }
 
@@ -417,6 +441,11 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
     m->p.base = h.base;
     m->p.divisor = h.divisor;
 
+    const char *dbg_env = getenv("B2S_FOREST_TIMING");
+    if (dbg_env && dbg_env[0] == '1') {
+        cudaMalloc(reinterpret_cast<void **>(&m->dbg_stamps), 64 * sizeof(long long));
+        cudaMemset(m->dbg_stamps, 0, 64 * sizeof(long long));
+    }
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     m->max_smem_optin = optin;

@@ -68,6 +68,7 @@ PROTOTYPES = [
     ("b2s_model_load", _i, [_i, _i, _vp, _sz, ctypes.c_char_p, _P(_u64)]),
     ("b2s_model_free", _i, [_u64]),
     ("b2s_model_get_info", _i, [_u64, _P(ModelInfo)]),
+    ("b2s_debug_read", _i, [_u64, _vp]),
     ("b2s_stream_create", _i, [_u64, _i64, _i64, _i, _P(_u64)]),
     ("b2s_stream_destroy", _i, [_u64]),
     ("b2s_stream_synchronize", _i, [_u64]),
@@ -91,6 +92,9 @@ PROTOTYPES = [
     ("b2s_timer_elapsed_ms", _i, [_u64, _P(ctypes.c_float)]),
     ("b2s_timer_destroy", _i, [_u64]),
     ("b2s_op_gemm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i]),
+    ("b2s_op_layernorm", _i, [_i, _vp, _vp, _i64, _i, _vp, _vp, ctypes.c_float, _vp, _vp]),
+    ("b2s_op_embed_layernorm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp,
+                                    ctypes.c_float, _vp, _vp]),
 ]
 
 _lib = None

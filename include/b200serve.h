@@ -115,6 +115,8 @@ B2S_API int b2s_model_load(int device, int kind, const void *blob, size_t blob_b
                    const char *cfg_json, b2s_model_t *out_model);
 B2S_API int b2s_model_free(b2s_model_t model);
 B2S_API int b2s_model_get_info(b2s_model_t model, b2s_model_info *out_info);
+/* developer aid: 64 int64 phase stamps of the model's last launch (forest: needs B2S_FOREST_TIMING=1) */
+B2S_API int b2s_debug_read(b2s_model_t model, long long *out64);
 
 /* ---- streams: one CUDA stream + staging slots per endpoint ----------------------------------- */
 
@@ -190,6 +192,18 @@ B2S_API int b2s_timer_destroy(b2s_timer_t timer);
  * bias fp32, C 16-bit or fp32.  act: 0 none, 1 GELU(erf), 2 ReLU, 3 tanh.  tcgen05 + TMA + TMEM. */
 B2S_API int b2s_op_gemm(int device, void *cuda_stream, const void *A, const void *B, void *C, int M, int N,
                         int K, const float *bias, const void *residual, int act, int is_bf16, int out_f32);
+
+/* LayerNorm over the last dim of fp32 in[rows,H] (torch.nn.LayerNorm numerics): writes an fp16 copy
+ * (next GEMM operand) and/or an fp32 copy (residual stream); either output may be NULL. */
+B2S_API int b2s_op_layernorm(int device, void *cuda_stream, const float *in, int64_t rows, int H,
+                             const float *gamma, const float *beta, float eps, void *out16, float *out32);
+/* BERT embeddings for packed (ragged) tokens: word[id] + position[idx in sequence] + type[tt] -> LayerNorm.
+ * cu_seqlens int64[n_seq+1]; tables fp16 [vocab|max_pos|n_types, H]. */
+B2S_API int b2s_op_embed_layernorm(int device, void *cuda_stream, const int32_t *ids, const int32_t *types,
+                                   const int64_t *cu_seqlens, int n_seq, int64_t n_tokens, int H,
+                                   const void *word, const void *pos, const void *type, int vocab, int max_pos,
+                                   int n_types, const float *gamma, const float *beta, float eps, void *out16,
+                                   float *out32);
 
 #ifdef __cplusplus
 }

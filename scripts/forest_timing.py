@@ -1,0 +1,48 @@
+"""Developer aid: phase breakdown of forest_cluster_kernel (SM-clock stamps) + event timing for a few
+batch sizes.  B2S_FOREST_TIMING=1 python scripts/forest_timing.py"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+os.environ["B2S_FOREST_TIMING"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from clearml_serving_b200 import formats, native  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+native.ensure_init(0)
+forest = orc.synth_xgb_forest(1000, 6, 32, seed=0)
+pm = formats.pack_forest(forest, "xgb", base=0.5)
+model = native.Model(pm.kind, pm.blob, 0)
+stream = native.Stream(model, 4096, 0, 2)
+timer = native.Timer(stream)
+rng = np.random.default_rng(0)
+for rows in (1, 32, 64, 256, 1024, 4096):
+    X = rng.standard_normal((rows, 32)).astype(np.float32)
+    d_in = native.DeviceBuffer(X.nbytes); d_in.upload(X)
+    d_out = native.DeviceBuffer(rows * 4)
+    for _ in range(5):
+        stream.infer_device(rows, [d_in.ptr], [d_out.ptr])
+    stream.synchronize()
+    stream.flush_l2(); timer.start(); stream.infer_device(rows, [d_in.ptr], [d_out.ptr]); timer.stop(); cold = timer.elapsed_ms()
+    for _ in range(3):
+        stream.infer_device(rows, [d_in.ptr], [d_out.ptr])
+    # warm, single launch behind a busy GPU (flush of L2 would evict; use a dummy launch as queue primer)
+    stream.infer_device(rows, [d_in.ptr], [d_out.ptr])
+    timer.start(); stream.infer_device(rows, [d_in.ptr], [d_out.ptr]); timer.stop(); warm1 = timer.elapsed_ms()
+    timer.start()
+    for _ in range(50):
+        stream.infer_device(rows, [d_in.ptr], [d_out.ptr])
+    timer.stop(); warm50 = timer.elapsed_ms() / 50
+    buf = (ctypes.c_longlong * 64)()
+    native.check(native.lib().b2s_debug_read(model.handle, buf))
+    st = np.array(buf[:]).reshape(8, 8)
+    print("rows=%d cold=%.2fus warm1=%.2fus warm50=%.2fus" % (rows, cold * 1e3, warm1 * 1e3, warm50 * 1e3))
+    for r in range(min(8, st.shape[0])):
+        s = st[r]
+        if s[0] == 0:
+            continue
+        print("   cta%d: xtile=%d traverse=%d cluster_sync=%d sum=%d  total=%d cycles" % (
+            r, s[1] - s[0], s[2] - s[1], s[3] - s[2], (s[4] - s[3]) if s[4] else -1, (s[4] if s[4] else s[3]) - s[0]))
+    d_in.free(); d_out.free()
