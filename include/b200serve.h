@@ -205,6 +205,12 @@ B2S_API int b2s_op_embed_layernorm(int device, void *cuda_stream, const int32_t 
                                    int n_types, const float *gamma, const float *beta, float eps, void *out16,
                                    float *out32);
 
+/* Variable-length non-causal self-attention over packed tokens: qkv fp16 [T, 3*heads*64] (Q|K|V),
+ * out fp16 [T, heads*64]; key_mask int32[T] (0 = masked key) or NULL.  Flash-style online softmax. */
+B2S_API int b2s_op_attention(int device, void *cuda_stream, const void *qkv, const int64_t *cu_seqlens,
+                             const int32_t *key_mask, void *out, int n_seq, int max_seqlen, int heads,
+                             int head_dim);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,112 @@ def test_gemm_fused_epilogue(gpu_native, act):
     ref = _ref_act(A.astype(np.float32) @ B.astype(np.float32).T + bias, act) + res.astype(np.float32)
     got = _gemm(gpu_native, A, B, bias=bias, residual=res, act=act).astype(np.float32)
     np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
+
+
+# ---------------------------------------------------------------- LayerNorm / embedding / attention
+def _dev(native, arr):
+    b = native.DeviceBuffer(max(arr.nbytes, 16))
+    b.upload(arr)
+    return b
+
+
+@pytest.mark.parametrize("rows,H", [(1, 768), (37, 768), (1000, 1024), (5, 256), (64, 3072)])
+def test_layernorm_matches_torch(gpu_native, rows, H):
+    import torch
+    rng = np.random.default_rng(rows + H)
+    x = (rng.standard_normal((rows, H)) * 2 + 0.3).astype(np.float32)
+    gamma = rng.standard_normal(H).astype(np.float32)
+    beta = rng.standard_normal(H).astype(np.float32)
+    ref = torch.nn.functional.layer_norm(torch.from_numpy(x), (H,), torch.from_numpy(gamma), torch.from_numpy(beta), 1e-12).numpy()
+    dx, dg, db = _dev(gpu_native, x), _dev(gpu_native, gamma), _dev(gpu_native, beta)
+    d16, d32 = gpu_native.DeviceBuffer(rows * H * 2), gpu_native.DeviceBuffer(rows * H * 4)
+    try:
+        gpu_native.check(gpu_native.lib().b2s_op_layernorm(0, None, dx.ptr, rows, H, dg.ptr, db.ptr, 1e-12, d16.ptr, d32.ptr))
+        o32 = d32.download(np.float32, rows * H).reshape(rows, H)
+        o16 = d16.download(np.float16, rows * H).reshape(rows, H).astype(np.float32)
+        np.testing.assert_allclose(o32, ref, rtol=1e-5, atol=1e-5)          # fp32 path: same formula as torch
+        np.testing.assert_allclose(o16, ref, rtol=1e-3, atol=1e-3)          # fp16 rounding of the output
+    finally:
+        for b in (dx, dg, db, d16, d32):
+            b.free()
+
+
+def test_embedding_layernorm_matches_torch(gpu_native):
+    import torch
+    rng = np.random.default_rng(0)
+    H, vocab, max_pos = 768, 1000, 512
+    lens = [16, 1, 64, 200, 7]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    T = int(cu[-1])
+    ids = rng.integers(0, vocab, T).astype(np.int32)
+    types = rng.integers(0, 2, T).astype(np.int32)
+    word = (rng.standard_normal((vocab, H)) * 0.02).astype(np.float16)
+    pos = (rng.standard_normal((max_pos, H)) * 0.02).astype(np.float16)
+    typ = (rng.standard_normal((2, H)) * 0.02).astype(np.float16)
+    gamma = (1 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(H)).astype(np.float32)
+    position = np.concatenate([np.arange(n) for n in lens])
+    e = word[ids].astype(np.float32) + typ[types].astype(np.float32) + pos[position].astype(np.float32)
+    ref = torch.nn.functional.layer_norm(torch.from_numpy(e), (H,), torch.from_numpy(gamma), torch.from_numpy(beta), 1e-12).numpy()
+    bufs = [_dev(gpu_native, a) for a in (ids, types, cu, word, pos, typ, gamma, beta)]
+    d16, d32 = gpu_native.DeviceBuffer(T * H * 2), gpu_native.DeviceBuffer(T * H * 4)
+    try:
+        gpu_native.check(gpu_native.lib().b2s_op_embed_layernorm(
+            0, None, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, len(lens), T, H, bufs[3].ptr, bufs[4].ptr, bufs[5].ptr,
+            vocab, max_pos, 2, bufs[6].ptr, bufs[7].ptr, 1e-12, d16.ptr, d32.ptr))
+        o32 = d32.download(np.float32, T * H).reshape(T, H)
+        np.testing.assert_allclose(o32, ref, rtol=1e-4, atol=1e-4)
+        o16 = d16.download(np.float16, T * H).reshape(T, H).astype(np.float32)
+        np.testing.assert_allclose(o16, ref, rtol=2e-3, atol=2e-3)
+    finally:
+        for b in bufs + [d16, d32]:
+            b.free()
+
+
+@pytest.mark.parametrize("lens,masked", [([16], False), ([64, 1, 256, 100, 33], False), ([128, 77], True), ([300, 512], False)])
+def test_attention_varlen_matches_torch(gpu_native, lens, masked):
+    """per-sequence softmax(QK^T/8 + mask)V against torch fp32 on the fp16-rounded inputs; a request's
+    output must not depend on its batch-mates (each sequence is also run alone and compared bit-wise)."""
+    import torch
+    heads, d = 12, 64
+    H = heads * d
+    rng = np.random.default_rng(len(lens) * 31 + lens[0])
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    T = int(cu[-1])
+    qkv = (rng.standard_normal((T, 3 * H)) * 0.7).astype(np.float16)
+    mask = np.ones(T, np.int32)
+    if masked:
+        mask[rng.random(T) < 0.2] = 0
+        mask[cu[:-1]] = 1    # keep at least one visible key per sequence
+    ref = np.zeros((T, H), np.float32)
+    q32 = torch.from_numpy(qkv.astype(np.float32))
+    for i, n in enumerate(lens):
+        s = int(cu[i])
+        blk = q32[s:s + n]
+        q, k, v = [blk[:, j * H:(j + 1) * H].reshape(n, heads, d).transpose(0, 1) for j in range(3)]
+        att = q @ k.transpose(1, 2) / 8.0
+        att = att.masked_fill(torch.from_numpy(mask[s:s + n] == 0)[None, None, :], float("-inf"))
+        ref[s:s + n] = (torch.softmax(att, -1) @ v).transpose(0, 1).reshape(n, H).numpy()
+    dq, dcu, dm = _dev(gpu_native, qkv), _dev(gpu_native, cu), _dev(gpu_native, mask)
+    dout = gpu_native.DeviceBuffer(T * H * 2)
+    try:
+        gpu_native.check(gpu_native.lib().b2s_op_attention(0, None, dq.ptr, dcu.ptr, dm.ptr if masked else None, dout.ptr,
+                                                           len(lens), max(lens), heads, d))
+        got = dout.download(np.float16, T * H).reshape(T, H)
+        # fp16 P and fp16 output rounding: ~1e-3 relative to the value range of V
+        np.testing.assert_allclose(got.astype(np.float32), ref, rtol=0, atol=4e-3 * np.abs(ref).max())
+        # batch independence: sequence i alone gives the same bits
+        for i, n in enumerate(lens[:2]):
+            s = int(cu[i])
+            one = _dev(gpu_native, np.ascontiguousarray(qkv[s:s + n]))
+            cu1 = _dev(gpu_native, np.array([0, n], np.int64))
+            m1 = _dev(gpu_native, np.ascontiguousarray(mask[s:s + n]))
+            o1 = gpu_native.DeviceBuffer(n * H * 2)
+            gpu_native.check(gpu_native.lib().b2s_op_attention(0, None, one.ptr, cu1.ptr, m1.ptr if masked else None, o1.ptr,
+                                                               1, n, heads, d))
+            assert np.array_equal(o1.download(np.float16, n * H).reshape(n, H), got[s:s + n])
+            for b in (one, cu1, m1, o1):
+                b.free()
+    finally:
+        for b in (dq, dcu, dm, dout):
+            b.free()
