@@ -215,7 +215,10 @@ void free_stream(Stream *s)
         if (s->d_out[i]) cudaFree(s->d_out[i]);
     }
     if (s->d_row_offsets) cudaFree(s->d_row_offsets);
-    if (s->scratch) cudaFree(s->scratch);
+    if (s->scratch) {
+        if (s->model) s->model->on_stream_destroy(s->scratch);
+        cudaFree(s->scratch);
+    }
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
 }
@@ -248,7 +251,11 @@ int submit_slot(Model *m, Stream *s, int slot_idx, int64_t n_rows, const int64_t
                                  cudaMemcpyHostToDevice, s->st));
     }
     for (int o = 0; o < info.n_outputs; ++o) d_out[o] = s->zero_copy_out ? (void *)sl.h_out[o] : s->d_out[o];
-    B2S_TRY(m->launch(s->st, n_rows, d_in, d_out, ragged ? s->d_row_offsets : nullptr, s->scratch, s->scratch_bytes));
+    LaunchInfo li;
+    li.h_row_offsets = ragged ? sl.h_row_offsets : nullptr;
+    li.max_rows = s->max_rows;
+    li.max_row_elems = s->max_row_elems;
+    B2S_TRY(m->launch(s->st, n_rows, d_in, d_out, ragged ? s->d_row_offsets : nullptr, s->scratch, s->scratch_bytes, li));
     if (!s->zero_copy_out) {
         for (int o = 0; o < info.n_outputs; ++o) {
             const size_t bytes = (size_t)n_rows * s->out_row_bytes[o];
@@ -368,6 +375,7 @@ int b2s_model_load(int device, int kind, const void *blob, size_t blob_bytes, co
     switch (kind) {
     case B2S_MODEL_FOREST: B2S_TRY(forest_model_create(device, blob, blob_bytes, &m)); break;
     case B2S_MODEL_LINEAR: B2S_TRY(linear_model_create(device, blob, blob_bytes, &m)); break;
+    case B2S_MODEL_GRAPH: B2S_TRY(graph_model_create(device, blob, blob_bytes, &m)); break;
     default: return fail(B2S_ERR_INVALID, "b2s_model_load: unknown model kind %d", kind);
     }
     Global &g = G();
@@ -533,13 +541,13 @@ int b2s_infer_batch(b2s_model_t model, b2s_stream_t stream, int32_t n_req, const
     if (!m || !s || s->model != m) return fail(B2S_ERR_INVALID, "b2s_infer_batch: bad model/stream handle");
     if (n_req <= 0 || !in || !out || !out_done) return fail(B2S_ERR_INVALID, "b2s_infer_batch: null or empty request list");
     const b2s_model_info &info = m->info;
-    for (int i = 0; i < info.n_inputs; ++i)
-        if (info.in_row_elems[i] < 0) return fail(B2S_ERR_INVALID, "b2s_infer_batch: variable-length models use the slot API");
+    bool ragged = false;
+    for (int i = 0; i < info.n_inputs; ++i) ragged = ragged || info.in_row_elems[i] < 0;
 
     // pass 1: validate and count rows (each request carries its own leading batch dim)
-    int64_t total_rows = 0;
+    int64_t total_rows = 0, total_elems = 0;
     for (int r = 0; r < n_req; ++r) {
-        int64_t rows = -1;
+        int64_t rows = -1, row_len = -1;
         for (int i = 0; i < info.n_inputs; ++i) {
             const b2s_tensor &t = in[(size_t)r * info.n_inputs + i];
             if (!t.data && t.ndim > 0) return fail(B2S_ERR_INVALID, "request %d input %d: null data", r, i);
@@ -551,19 +559,32 @@ int b2s_infer_batch(b2s_model_t model, b2s_stream_t stream, int32_t n_req, const
                 if (t.shape[d] < 0) return fail(B2S_ERR_INVALID, "request %d input %d: negative dim", r, i);
                 elems *= t.shape[d];
             }
-            const int64_t re = info.in_row_elems[i];
-            if (elems % re != 0)
-                return fail(B2S_ERR_INVALID, "request %d input %d: %lld elements is not a multiple of the model's %lld per row",
-                            r, i, (long long)elems, (long long)re);
-            const int64_t rr = elems / re;
+            int64_t rr;
+            if (info.in_row_elems[i] < 0) {  // variable length: [rows, len] (or [len] = one row)
+                rr = t.ndim >= 2 ? t.shape[0] : 1;
+                const int64_t len = rr > 0 ? elems / rr : 0;
+                if (len <= 0) return fail(B2S_ERR_INVALID, "request %d input %d: empty sequence", r, i);
+                if (row_len >= 0 && len != row_len) return fail(B2S_ERR_INVALID, "request %d: inputs disagree on sequence length", r);
+                row_len = len;
+            } else {
+                const int64_t re = info.in_row_elems[i];
+                if (elems % re != 0)
+                    return fail(B2S_ERR_INVALID, "request %d input %d: %lld elements is not a multiple of the model's %lld per row",
+                                r, i, (long long)elems, (long long)re);
+                rr = elems / re;
+            }
             if (rows >= 0 && rr != rows) return fail(B2S_ERR_INVALID, "request %d: inputs disagree on batch rows", r);
             rows = rr;
         }
         total_rows += rows;
+        if (ragged) total_elems += rows * row_len;
     }
     if (total_rows > s->max_rows)
         return fail(B2S_ERR_INVALID, "b2s_infer_batch: %lld rows exceed the stream's max_rows %lld",
                     (long long)total_rows, (long long)s->max_rows);
+    if (ragged && total_elems > s->max_rows * s->max_row_elems)
+        return fail(B2S_ERR_INVALID, "b2s_infer_batch: %lld tokens exceed the stream's capacity %lld",
+                    (long long)total_elems, (long long)(s->max_rows * s->max_row_elems));
     const int slot_idx = take_slot(s);
     if (slot_idx < 0) return fail(B2S_ERR_BUSY, "b2s_infer_batch: all %d staging slots are in flight", (int)s->slots.size());
     Slot &sl = s->slots[slot_idx];
@@ -573,15 +594,26 @@ int b2s_infer_batch(b2s_model_t model, b2s_stream_t stream, int32_t n_req, const
     sl.out_ptr.assign((size_t)n_req * info.n_outputs, nullptr);
     sl.out_row0.assign(n_req, 0);
     sl.out_rows.assign(n_req, 0);
-    int64_t row = 0;
+    int64_t row = 0, elem = 0;
+    if (ragged) sl.h_row_offsets[0] = 0;
     for (int r = 0; r < n_req; ++r) {
-        int64_t rows = 0;
+        int64_t rows = 0, row_len = 0;
         for (int i = 0; i < info.n_inputs; ++i) {
             const b2s_tensor &t = in[(size_t)r * info.n_inputs + i];
             int64_t elems = 1;
             for (int d = 0; d < t.ndim; ++d) elems *= t.shape[d];
-            rows = elems / info.in_row_elems[i];
-            memcpy(sl.h_in[i] + (size_t)row * s->in_row_bytes[i], t.data, (size_t)elems * dtype_size(t.dtype));
+            if (info.in_row_elems[i] < 0) {
+                rows = t.ndim >= 2 ? t.shape[0] : 1;
+                row_len = elems / rows;
+                memcpy(sl.h_in[i] + (size_t)elem * dtype_size(t.dtype), t.data, (size_t)elems * dtype_size(t.dtype));
+            } else {
+                rows = elems / info.in_row_elems[i];
+                memcpy(sl.h_in[i] + (size_t)row * s->in_row_bytes[i], t.data, (size_t)elems * dtype_size(t.dtype));
+            }
+        }
+        if (ragged) {
+            for (int64_t k = 0; k < rows; ++k) sl.h_row_offsets[row + k + 1] = elem + (k + 1) * row_len;
+            elem += rows * row_len;
         }
         sl.out_row0[r] = row;
         sl.out_rows[r] = rows;
@@ -605,7 +637,7 @@ int b2s_infer_batch(b2s_model_t model, b2s_stream_t stream, int32_t n_req, const
         }
         row += rows;
     }
-    const int rc = submit_slot(m, s, slot_idx, total_rows, nullptr);
+    const int rc = submit_slot(m, s, slot_idx, total_rows, ragged ? sl.h_row_offsets : nullptr);
     std::lock_guard<std::mutex> l(s->mu);
     if (rc != 0) {
         sl.state = SLOT_FREE;
@@ -732,7 +764,16 @@ int b2s_infer_device(b2s_model_t model, b2s_stream_t stream, int64_t n_rows, con
     if (!m || !s || s->model != m || !d_in || !d_out) return fail(B2S_ERR_INVALID, "b2s_infer_device: bad handle");
     if (n_rows < 0 || n_rows > s->max_rows) return fail(B2S_ERR_INVALID, "b2s_infer_device: n_rows %lld out of range", (long long)n_rows);
     B2S_CUDA(cudaSetDevice(s->device));
-    return m->launch(s->st, n_rows, d_in, d_out, d_row_offsets, s->scratch, s->scratch_bytes);
+    LaunchInfo li;
+    li.max_rows = s->max_rows;
+    li.max_row_elems = s->max_row_elems;
+    std::vector<int64_t> h_off;
+    if (d_row_offsets) {  // ragged model: the host needs the offsets too (token count, longest sequence)
+        h_off.resize((size_t)n_rows + 1);
+        B2S_CUDA(cudaMemcpy(h_off.data(), d_row_offsets, h_off.size() * 8, cudaMemcpyDeviceToHost));
+        li.h_row_offsets = h_off.data();
+    }
+    return m->launch(s->st, n_rows, d_in, d_out, d_row_offsets, s->scratch, s->scratch_bytes, li);
 }
 
 int b2s_device_malloc(int device, size_t bytes, void **out_ptr)

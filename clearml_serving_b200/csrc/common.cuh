@@ -46,6 +46,24 @@ inline size_t dtype_size(int dt)
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// what the host knows about a launch (ragged models need the offsets on the host as well)
+struct LaunchInfo {
+    const int64_t *h_row_offsets = nullptr;  // host copy of d_row_offsets (n_rows + 1) or null
+    int64_t max_rows = 0;                    // capacity of the stream the launch runs on
+    int64_t max_row_elems = 0;
+};
+
+// fused GEMM epilogue description (gemm.cu)
+struct GemmEpilogue {
+    const void *bias;      // [N] fp32 or null
+    const void *residual;  // [M, ldc] fp32 when out_f32 else 16-bit, or null
+    void *C;
+    int ldc;               // elements
+    int act;               // 0 none, 1 GELU(erf), 2 ReLU, 3 tanh
+    int out_f32;           // 1: C (and residual) fp32, 0: 16-bit like A/B
+    int is_bf16;
+};
+
 // ---- internal model interface: each model kind implements launch() on a stream -----------------
 struct Model {
     int device = 0;
@@ -57,12 +75,15 @@ struct Model {
     // once at stream creation and must be left zeroed where the kernels rely on it
     virtual int launch(cudaStream_t st, int64_t n_rows, const void *const *d_in,
                        void *const *d_out, const int64_t *d_row_offsets, void *scratch,
-                       size_t scratch_bytes) = 0;
+                       size_t scratch_bytes, const LaunchInfo &li) = 0;
+    // a stream that used `scratch` is going away: drop anything cached against it
+    virtual void on_stream_destroy(void *) {}
     // developer aid: copy 64 int64 of kernel phase stamps (model-specific meaning)
     virtual int debug_read(long long *) { return fail(B2S_ERR_INVALID, "no debug data for this model kind"); }
 };
 
 int forest_model_create(int device, const void *blob, size_t bytes, Model **out);
 int linear_model_create(int device, const void *blob, size_t bytes, Model **out);
+int graph_model_create(int device, const void *blob, size_t bytes, Model **out);
 
 }  // namespace b2s

@@ -343,7 +343,7 @@ struct ForestModel : Model {
     }
 
     int launch(cudaStream_t st, int64_t n_rows, const void *const *d_in, void *const *d_out,
-               const int64_t *, void *, size_t) override
+               const int64_t *, void *, size_t, const LaunchInfo &) override
     {
         if (n_rows <= 0) return 0;
         const float *X = static_cast<const float *>(d_in[0]);

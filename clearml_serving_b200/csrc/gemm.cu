@@ -26,16 +26,6 @@ using namespace sm100;
 
 enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
 
-struct GemmEpilogue {
-    const void *bias;      // [N] fp32 or null
-    const void *residual;  // [M, ldc] same dtype as C (16-bit) or null
-    void *C;
-    int ldc;               // elements
-    int act;
-    int out_f32;           // 1: C is fp32, 0: C is 16-bit (same format as A/B)
-    int is_bf16;
-};
-
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // 64 x 16-bit = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 192;
@@ -306,6 +296,18 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap
     return 0;
 }
 
+// tile width for an N-column weight (also the box height of its tensor map)
+int gemm_bn_for(int N) { return N <= 64 ? 64 : 128; }
+
+// GEMM with caller-provided tensor maps (graph executor: maps are cached per stream / per model)
+int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
+                 const GemmEpilogue &ep)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    if (gemm_bn_for(N) == 64) return launch_gemm<64, 6>(st, ta, tb, M, N, K, ep);
+    return launch_gemm<128, 6>(st, ta, tb, M, N, K, ep);
+}
+
 // C = epilogue(A[M,K] . B[N,K]^T).  A: lda elements per row, B: ldb elements per row.
 int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t ldb, int M, int N, int K,
             const GemmEpilogue &ep)
@@ -313,12 +315,8 @@ int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t 
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     CUtensorMap ta, tb;
     B2S_TRY(make_tmap_2d_kmajor(&ta, A, M, K, lda, GEMM_BM, ep.is_bf16));
-    if (N <= 64) {
-        B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, 64, ep.is_bf16));
-        return launch_gemm<64, 6>(st, ta, tb, M, N, K, ep);
-    }
-    B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, 128, ep.is_bf16));
-    return launch_gemm<128, 6>(st, ta, tb, M, N, K, ep);
+    B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, gemm_bn_for(N), ep.is_bf16));
+    return gemm_tn_maps(st, ta, tb, M, N, K, ep);
 }
 
 }  // namespace b2s

@@ -1,0 +1,328 @@
+// graph.cu -- B2S_MODEL_GRAPH: a small op-list executor for encoder-style DL models (BERT class).
+//
+// Stands in for what tritonserver does with the model file the reference ships to it
+// (clearml_serving/engines/triton/triton_helper.py:159-186 places model.pt / model.onnx, :378-385
+// selects the libtorch / ONNX-Runtime backend): the graph is lowered OFFLINE by
+// clearml_serving_b200/formats.py into a flat list of the hand-written sm_100a kernels of this
+// library -- no ONNX Runtime, no libtorch, no backend dispatch at run time.
+//
+// Execution model: tokens of all requests of a batch are PACKED (ragged) -- `row_offsets`
+// (cu_seqlens) delimits sequences -- so no FLOP is spent on padding and a request's result cannot
+// depend on its batch-mates.  Activations live in per-stream scratch buffers sized for the
+// stream's max tokens; weights stay resident in HBM as fp16 (GEMM operands) / fp32 (bias, LayerNorm).
+// TMA tensor maps are built once per (stream, op): the A operand of every GEMM is a fixed scratch
+// buffer whose row count is the stream's capacity (rows past the live batch are never stored).
+//
+// Blob layout ("B2SG"), little endian:
+//   header  {magic, version, n_tensors, n_buffers, n_ops, n_inputs, n_outputs, max_pos, out_buffer[4], in_dtype[4]}
+//   tensors n_tensors x {u32 dtype, u32 ndim, i64 shape[4], u64 offset, u64 nbytes}
+//   buffers n_buffers x {u32 dtype, u32 rows_kind (0 = per token, 1 = per sequence), i64 cols}
+//   ops     n_ops x {u32 opcode, i32 a[15], f32 f[4]}
+//   data    weights, each 256-byte aligned
+#include "common.cuh"
+
+#include <cuda.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace b2s {
+
+// kernels defined in gemm.cu / norm.cu / attention.cu
+int make_tmap_2d_kmajor(CUtensorMap *out, const void *base, int64_t rows, int64_t K, int64_t ld_elems, int box_rows,
+                        int is_bf16);
+int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
+                 const GemmEpilogue &ep);
+int gemm_bn_for(int N);
+int layernorm(cudaStream_t st, const float *in, int64_t rows, int H, const float *gamma, const float *beta, float eps,
+              void *out16, float *out32);
+int embed_layernorm(cudaStream_t st, const int32_t *ids, const int32_t *types, const int64_t *cu_seqlens, int n_seq,
+                    int64_t n_tokens, int H, const void *word, const void *pos, const void *type, int vocab, int max_pos,
+                    int n_types, const float *gamma, const float *beta, float eps, void *out16, float *out32);
+int gather_first(cudaStream_t st, const void *in, const int64_t *cu_seqlens, int n_seq, int H, void *out);
+int attention_varlen(cudaStream_t st, const void *qkv, const int64_t *cu_seqlens, const int32_t *key_mask, void *out,
+                     int n_seq, int max_seqlen, int heads, int head_dim);
+
+namespace {
+
+enum GraphOp { OP_EMBED_LN = 1, OP_LINEAR = 2, OP_LAYERNORM = 3, OP_ATTENTION = 4, OP_GATHER_FIRST = 5 };
+
+struct GHeader {
+    char magic[4];
+    uint32_t version, n_tensors, n_buffers, n_ops, n_inputs, n_outputs, max_pos;
+    int32_t out_buffer[4];
+    int32_t in_dtype[4];
+};
+static_assert(sizeof(GHeader) == 64, "graph header layout");
+struct GTensor {
+    uint32_t dtype, ndim;
+    int64_t shape[4];
+    uint64_t offset, nbytes;
+};
+static_assert(sizeof(GTensor) == 56, "graph tensor layout");
+struct GBuffer {
+    uint32_t dtype, rows_kind;
+    int64_t cols;
+};
+static_assert(sizeof(GBuffer) == 16, "graph buffer layout");
+struct GOp {
+    uint32_t opcode;
+    int32_t a[15];
+    float f[4];
+};
+static_assert(sizeof(GOp) == 80, "graph op layout");
+
+struct Plan {  // per-stream state: buffer addresses + cached A-operand tensor maps
+    std::vector<unsigned char *> buf;
+    std::vector<CUtensorMap> amap;  // one per op (only LINEAR ops use it)
+};
+
+struct GraphModel : Model {
+    GHeader h{};
+    std::vector<GTensor> tensors;
+    std::vector<GBuffer> buffers;
+    std::vector<GOp> ops;
+    std::vector<CUtensorMap> bmap;  // weight tensor maps, one per op
+    unsigned char *d_data = nullptr;
+    std::mutex mu;
+    std::map<void *, Plan> plans;   // keyed by the stream's scratch base
+
+    ~GraphModel() override
+    {
+        if (d_data) { cudaSetDevice(device); cudaFree(d_data); }
+    }
+    const void *tptr(int idx) const { return idx < 0 ? nullptr : d_data + tensors[idx].offset; }
+    void on_stream_destroy(void *scratch) override
+    {
+        std::lock_guard<std::mutex> l(mu);
+        plans.erase(scratch);
+    }
+
+    size_t buffer_bytes(const GBuffer &b, int64_t max_rows, int64_t max_tokens) const
+    {
+        const int64_t rows = b.rows_kind == 0 ? max_tokens : max_rows;
+        return (size_t)round_up(rows * b.cols * (int64_t)dtype_size(b.dtype), 1024) + 1024;
+    }
+    size_t scratch_bytes(int64_t max_rows, int64_t max_row_elems) const override
+    {
+        const int64_t max_tokens = max_rows * (max_row_elems > 0 ? max_row_elems : 1);
+        size_t total = 1024;
+        for (const GBuffer &b : buffers) total += buffer_bytes(b, max_rows, max_tokens);
+        return total;
+    }
+
+    int build_plan(Plan &pl, void *scratch, size_t scratch_sz, int64_t max_rows, int64_t max_tokens)
+    {
+        unsigned char *p = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~(uintptr_t)1023);
+        pl.buf.resize(buffers.size());
+        for (size_t i = 0; i < buffers.size(); ++i) {
+            pl.buf[i] = p;
+            p += buffer_bytes(buffers[i], max_rows, max_tokens);
+        }
+        if ((size_t)(p - static_cast<unsigned char *>(scratch)) > scratch_sz)
+            return fail(B2S_ERR_INVALID, "graph: stream scratch too small");
+        pl.amap.resize(ops.size());
+        for (size_t i = 0; i < ops.size(); ++i) {
+            const GOp &op = ops[i];
+            if (op.opcode != OP_LINEAR) continue;
+            const GBuffer &ab = buffers[op.a[0]];
+            const int64_t rows = ab.rows_kind == 0 ? max_tokens : max_rows;
+            B2S_TRY(make_tmap_2d_kmajor(&pl.amap[i], pl.buf[op.a[0]], rows, op.a[7], ab.cols, 128, 0));
+        }
+        return 0;
+    }
+
+    int launch(cudaStream_t st, int64_t n_rows, const void *const *d_in, void *const *d_out,
+               const int64_t *d_row_offsets, void *scratch, size_t scratch_sz, const LaunchInfo &li) override
+    {
+        if (n_rows <= 0) return 0;
+        if (!d_row_offsets || !li.h_row_offsets) return fail(B2S_ERR_INVALID, "graph: ragged batch needs row offsets");
+        const int64_t n_tokens = li.h_row_offsets[n_rows];
+        int max_seqlen = 0;
+        for (int64_t r = 0; r < n_rows; ++r) {
+            const int64_t s = li.h_row_offsets[r + 1] - li.h_row_offsets[r];
+            if (s <= 0) return fail(B2S_ERR_INVALID, "graph: empty sequence in batch");
+            if (s > (int64_t)h.max_pos) return fail(B2S_ERR_INVALID, "graph: sequence of %lld tokens exceeds the model's %u positions", (long long)s, h.max_pos);
+            if (s > max_seqlen) max_seqlen = (int)s;
+        }
+        Plan *pl;
+        {
+            std::lock_guard<std::mutex> l(mu);
+            auto it = plans.find(scratch);
+            if (it == plans.end()) {
+                Plan fresh;
+                B2S_TRY(build_plan(fresh, scratch, scratch_sz, li.max_rows, li.max_rows * (li.max_row_elems > 0 ? li.max_row_elems : 1)));
+                it = plans.emplace(scratch, std::move(fresh)).first;
+            }
+            pl = &it->second;
+        }
+        if (n_tokens > li.max_rows * (li.max_row_elems > 0 ? li.max_row_elems : 1))
+            return fail(B2S_ERR_INVALID, "graph: batch of %lld tokens exceeds the stream capacity", (long long)n_tokens);
+
+        for (size_t i = 0; i < ops.size(); ++i) {
+            const GOp &op = ops[i];
+            switch (op.opcode) {
+            case OP_EMBED_LN: {
+                // a: in_ids, in_types(-1), W_word, W_pos, W_type, gamma, beta, out16, out32, H, vocab, max_pos, n_types
+                B2S_TRY(embed_layernorm(st, static_cast<const int32_t *>(d_in[op.a[0]]),
+                                        op.a[1] >= 0 ? static_cast<const int32_t *>(d_in[op.a[1]]) : nullptr, d_row_offsets,
+                                        (int)n_rows, n_tokens, op.a[9], tptr(op.a[2]), tptr(op.a[3]), tptr(op.a[4]), op.a[10],
+                                        op.a[11], op.a[12], static_cast<const float *>(tptr(op.a[5])),
+                                        static_cast<const float *>(tptr(op.a[6])), op.f[0],
+                                        op.a[7] >= 0 ? pl->buf[op.a[7]] : nullptr,
+                                        op.a[8] >= 0 ? reinterpret_cast<float *>(pl->buf[op.a[8]]) : nullptr));
+                break;
+            }
+            case OP_LINEAR: {
+                // a: in_buf, W, bias(-1), residual_buf(-1), out_buf, act, N, K, out_f32
+                const GBuffer &ab = buffers[op.a[0]];
+                const int M = (int)(ab.rows_kind == 0 ? n_tokens : n_rows);
+                GemmEpilogue ep;
+                ep.bias = tptr(op.a[2]);
+                ep.residual = op.a[3] >= 0 ? pl->buf[op.a[3]] : nullptr;
+                const bool to_output = op.a[4] < 0;  // -1 - k  => model output k
+                ep.C = to_output ? d_out[-1 - op.a[4]] : pl->buf[op.a[4]];
+                ep.ldc = op.a[6];
+                ep.act = op.a[5];
+                ep.out_f32 = op.a[8];
+                ep.is_bf16 = 0;
+                B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap[i], M, op.a[6], op.a[7], ep));
+                break;
+            }
+            case OP_LAYERNORM: {
+                // a: in32_buf, gamma, beta, out16(-1), out32(-1), H
+                const GBuffer &ib = buffers[op.a[0]];
+                const int64_t rows = ib.rows_kind == 0 ? n_tokens : n_rows;
+                B2S_TRY(layernorm(st, reinterpret_cast<const float *>(pl->buf[op.a[0]]), rows, op.a[5],
+                                  static_cast<const float *>(tptr(op.a[1])), static_cast<const float *>(tptr(op.a[2])), op.f[0],
+                                  op.a[3] >= 0 ? pl->buf[op.a[3]] : nullptr,
+                                  op.a[4] >= 0 ? reinterpret_cast<float *>(pl->buf[op.a[4]]) : nullptr));
+                break;
+            }
+            case OP_ATTENTION: {
+                // a: qkv_buf, mask_input(-1), out_buf, heads, head_dim
+                B2S_TRY(attention_varlen(st, pl->buf[op.a[0]], d_row_offsets,
+                                         op.a[1] >= 0 ? static_cast<const int32_t *>(d_in[op.a[1]]) : nullptr, pl->buf[op.a[2]],
+                                         (int)n_rows, max_seqlen, op.a[3], op.a[4]));
+                break;
+            }
+            case OP_GATHER_FIRST: {
+                // a: in_buf, out_buf, H
+                B2S_TRY(gather_first(st, pl->buf[op.a[0]], d_row_offsets, (int)n_rows, op.a[2], pl->buf[op.a[1]]));
+                break;
+            }
+            default:
+                return fail(B2S_ERR_INVALID, "graph: unknown opcode %u", op.opcode);
+            }
+        }
+        return 0;
+    }
+};
+
+}  // namespace
+
+int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
+{
+    if (bytes < sizeof(GHeader)) return fail(B2S_ERR_INVALID, "graph blob too small");
+    GraphModel *m = new GraphModel();
+    m->device = device;
+    auto bail = [&](int code) {
+        delete m;
+        return code;
+    };
+    memcpy(&m->h, blob, sizeof(GHeader));
+    const GHeader &h = m->h;
+    if (memcmp(h.magic, "B2SG", 4) != 0 || h.version != 1) return bail(fail(B2S_ERR_INVALID, "graph blob: bad magic/version"));
+    if (h.n_inputs == 0 || h.n_inputs > 4 || h.n_outputs == 0 || h.n_outputs > 4 || h.n_ops == 0)
+        return bail(fail(B2S_ERR_INVALID, "graph blob: bad counts"));
+    const size_t table_bytes = (size_t)h.n_tensors * sizeof(GTensor) + (size_t)h.n_buffers * sizeof(GBuffer) + (size_t)h.n_ops * sizeof(GOp);
+    size_t data_off = (size_t)round_up((int64_t)(sizeof(GHeader) + table_bytes), 256);
+    if (bytes < data_off) return bail(fail(B2S_ERR_INVALID, "graph blob truncated (tables)"));
+    const unsigned char *p = static_cast<const unsigned char *>(blob) + sizeof(GHeader);
+    m->tensors.resize(h.n_tensors);
+    memcpy(m->tensors.data(), p, h.n_tensors * sizeof(GTensor));
+    p += h.n_tensors * sizeof(GTensor);
+    m->buffers.resize(h.n_buffers);
+    memcpy(m->buffers.data(), p, h.n_buffers * sizeof(GBuffer));
+    p += h.n_buffers * sizeof(GBuffer);
+    m->ops.resize(h.n_ops);
+    memcpy(m->ops.data(), p, h.n_ops * sizeof(GOp));
+    size_t data_bytes = 0;
+    for (const GTensor &t : m->tensors) {
+        if (t.offset % 256 != 0 || data_off + t.offset + t.nbytes > bytes)
+            return bail(fail(B2S_ERR_INVALID, "graph blob: tensor outside the data section"));
+        if (t.offset + t.nbytes > data_bytes) data_bytes = t.offset + t.nbytes;
+    }
+    // validate op operands
+    auto tok = [&](int idx, bool optional) { return (optional && idx < 0) || (idx >= 0 && idx < (int)h.n_tensors); };
+    auto bok = [&](int idx, bool optional) { return (optional && idx < 0) || (idx >= 0 && idx < (int)h.n_buffers); };
+    auto iok = [&](int idx, bool optional) { return (optional && idx < 0) || (idx >= 0 && idx < (int)h.n_inputs); };
+    for (const GOp &op : m->ops) {
+        bool ok = true;
+        switch (op.opcode) {
+        case OP_EMBED_LN:
+            ok = iok(op.a[0], false) && iok(op.a[1], true) && tok(op.a[2], false) && tok(op.a[3], false) && tok(op.a[4], false) &&
+                 tok(op.a[5], false) && tok(op.a[6], false) && bok(op.a[7], true) && bok(op.a[8], true);
+            break;
+        case OP_LINEAR:
+            ok = bok(op.a[0], false) && tok(op.a[1], false) && tok(op.a[2], true) && bok(op.a[3], true) &&
+                 (bok(op.a[4], false) || (op.a[4] < 0 && -1 - op.a[4] < (int)h.n_outputs)) && op.a[6] > 0 && op.a[7] > 0 &&
+                 op.a[7] % 8 == 0;
+            if (ok) {
+                const GTensor &w = m->tensors[op.a[1]];
+                ok = w.dtype == B2S_F16 && w.ndim == 2 && w.shape[0] == op.a[6] && w.shape[1] == op.a[7] &&
+                     m->buffers[op.a[0]].dtype == B2S_F16 && m->buffers[op.a[0]].cols == op.a[7];
+            }
+            break;
+        case OP_LAYERNORM:
+            ok = bok(op.a[0], false) && tok(op.a[1], false) && tok(op.a[2], false) && bok(op.a[3], true) && bok(op.a[4], true);
+            break;
+        case OP_ATTENTION:
+            ok = bok(op.a[0], false) && iok(op.a[1], true) && bok(op.a[2], false);
+            break;
+        case OP_GATHER_FIRST:
+            ok = bok(op.a[0], false) && bok(op.a[1], false);
+            break;
+        default:
+            ok = false;
+        }
+        if (!ok) return bail(fail(B2S_ERR_INVALID, "graph blob: malformed op (opcode %u)", op.opcode));
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->d_data), data_bytes ? data_bytes : 256);
+    if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(graph weights)"));
+    e = cudaMemcpy(m->d_data, static_cast<const unsigned char *>(blob) + data_off, data_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMemcpy(graph weights)"));
+    // weight tensor maps
+    m->bmap.resize(m->ops.size());
+    int64_t flops_fixed = 0;
+    for (size_t i = 0; i < m->ops.size(); ++i) {
+        const GOp &op = m->ops[i];
+        if (op.opcode != OP_LINEAR) continue;
+        const int rc = make_tmap_2d_kmajor(&m->bmap[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], gemm_bn_for(op.a[6]), 0);
+        if (rc != 0) return bail(rc);
+        flops_fixed += 2LL * op.a[6] * op.a[7];
+    }
+    b2s_model_info &info = m->info;
+    info.kind = B2S_MODEL_GRAPH;
+    info.n_inputs = (int32_t)h.n_inputs;
+    info.n_outputs = (int32_t)h.n_outputs;
+    for (uint32_t i = 0; i < h.n_inputs; ++i) {
+        info.in_dtype[i] = h.in_dtype[i];
+        info.in_row_elems[i] = -1;  // ragged: one variable-length row per sequence
+    }
+    for (uint32_t o = 0; o < h.n_outputs; ++o) {
+        const GBuffer &ob = m->buffers[h.out_buffer[o]];
+        info.out_dtype[o] = (int32_t)ob.dtype;
+        info.out_row_elems[o] = ob.cols;
+    }
+    info.weight_bytes = (int64_t)data_bytes;
+    info.algo_bytes_fixed = (int64_t)data_bytes;
+    info.algo_bytes_per_row = flops_fixed;  // GEMM FLOPs per token (linear part); see DESIGN.md
+    *out = m;
+    return 0;
+}
+
+}  // namespace b2s

@@ -56,7 +56,7 @@ struct LinearModel : Model {
     }
     size_t scratch_bytes(int64_t, int64_t) const override { return 256; }
     int launch(cudaStream_t st, int64_t n_rows, const void *const *d_in, void *const *d_out,
-               const int64_t *, void *, size_t) override
+               const int64_t *, void *, size_t, const LaunchInfo &) override
     {
         if (n_rows <= 0) return 0;
         const unsigned grid = (unsigned)((n_rows + 127) / 128);

@@ -259,11 +259,152 @@ def pack_sklearn(model):
     raise ValueError("b200 engine: unsupported sklearn model type '{}'".format(name))
 
 
+def pack_torch_module(module):
+    """A torch module the reference would have exported for Triton (TorchScript / ONNX): lowered here
+    instead.  Supported architectures: transformers BERT sequence classifiers."""
+    arch = type(module).__name__
+    if arch == "BertForSequenceClassification":
+        return pack_bert(module)
+    raise ValueError("b200 engine: torch architecture '{}' is not supported yet".format(arch))
+
+
 def load_model_file(path):
-    """Sniff the model file the reference would hand to xgboost / joblib and pack it."""
+    """Sniff the model file the reference would hand to xgboost / joblib / Triton and pack it."""
+    import os
+    if os.path.isdir(path) and os.path.exists(os.path.join(path, "config.json")):
+        # a transformers `save_pretrained` directory
+        from transformers import AutoModelForSequenceClassification
+        return pack_torch_module(AutoModelForSequenceClassification.from_pretrained(path).eval())
     with open(path, "rb") as f:
         head = f.read(16)
     if head.lstrip()[:1] == b"{":
         return pack_xgboost_json(path)
     import joblib  # noqa  (the reference's sklearn engine loads with joblib too)
     return pack_sklearn(joblib.load(path))
+
+
+# --------------------------------------------------------------------------------------------
+# DL graphs (B2S_MODEL_GRAPH): offline lowering of a torch module to the op list of csrc/graph.cu
+# --------------------------------------------------------------------------------------------
+
+OP_EMBED_LN, OP_LINEAR, OP_LAYERNORM, OP_ATTENTION, OP_GATHER_FIRST = 1, 2, 3, 4, 5
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+_DT = {"float32": 0, "float64": 1, "int32": 2, "int64": 3, "uint8": 4, "float16": 8}
+
+
+class GraphBuilder(object):
+    """Accumulates weights, activation buffers and ops, then serialises the "B2SG" blob."""
+
+    def __init__(self, in_dtypes, max_pos):
+        self.tensors, self.buffers, self.ops = [], [], []
+        self.in_dtypes = list(in_dtypes)
+        self.max_pos = int(max_pos)
+        self.outputs = []
+
+    def tensor(self, array, dtype):
+        a = np.ascontiguousarray(np.asarray(array, dtype=dtype))
+        self.tensors.append(a)
+        return len(self.tensors) - 1
+
+    def buffer(self, dtype, per_token, cols):
+        self.buffers.append((_DT[dtype], 0 if per_token else 1, int(cols)))
+        return len(self.buffers) - 1
+
+    def op(self, opcode, ints, floats=()):
+        a = list(ints) + [0] * (15 - len(ints))
+        f = list(floats) + [0.0] * (4 - len(floats))
+        self.ops.append((opcode, a, f))
+
+    def linear(self, in_buf, weight, bias, out_buf, act=ACT_NONE, residual=-1, out_f32=False):
+        w = np.asarray(weight)
+        n, k = w.shape
+        wi = self.tensor(w, np.float16)
+        bi = self.tensor(bias, np.float32) if bias is not None else -1
+        self.op(OP_LINEAR, [in_buf, wi, bi, residual, out_buf, act, n, k, 1 if out_f32 else 0])
+
+    def output(self, buf):
+        """marks `buf` as the next model output and returns the operand code ops use to write it"""
+        self.outputs.append(buf)
+        return -len(self.outputs)
+
+    def serialise(self):
+        n_t, n_b, n_o = len(self.tensors), len(self.buffers), len(self.ops)
+        out_buf = (self.outputs + [0, 0, 0, 0])[:4]
+        in_dt = ([_DT[d] for d in self.in_dtypes] + [0, 0, 0, 0])[:4]
+        header = struct.pack("<4s7I4i4i", b"B2SG", 1, n_t, n_b, n_o, len(self.in_dtypes), len(self.outputs),
+                             self.max_pos, *out_buf, *in_dt)
+        assert len(header) == 64
+        offsets, off = [], 0
+        for a in self.tensors:
+            offsets.append(off)
+            off += (a.nbytes + 255) // 256 * 256
+        tbl = b""
+        for a, o in zip(self.tensors, offsets):
+            shape = list(a.shape) + [1] * (4 - a.ndim)
+            tbl += struct.pack("<II4qQQ", _DT[str(a.dtype)], a.ndim, *shape, o, a.nbytes)
+        for (dt, kind, cols) in self.buffers:
+            tbl += struct.pack("<IIq", dt, kind, cols)
+        for (opc, a, f) in self.ops:
+            tbl += struct.pack("<I15i4f", opc, *a, *f)
+        head = header + tbl
+        pad = (-len(head)) % 256
+        data = bytearray(off)
+        for a, o in zip(self.tensors, offsets):
+            data[o:o + a.nbytes] = a.tobytes()
+        return head + b"\0" * pad + bytes(data)
+
+
+def pack_bert(model):
+    """transformers BertForSequenceClassification (or BertModel + classifier-less) -> PackedModel.
+    Inputs follow the reference's HF example (examples/huggingface/readme.md:113): int32
+    input_ids, token_type_ids, attention_mask, one variable-length row per sequence; output fp32
+    logits [batch, num_labels].  fp16 weights, fp32 biases / LayerNorm / residual stream."""
+    cfg = model.config
+    sd = {k: v.detach().cpu().float().numpy() for k, v in model.state_dict().items()}
+    prefix = "bert." if any(k.startswith("bert.") for k in sd) else ""
+    H, L, heads, I = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size
+    if H % heads or H // heads != 64:
+        raise ValueError("b200 engine: attention head_dim {} not supported (64 only)".format(H // heads))
+    if getattr(cfg, "hidden_act", "gelu") != "gelu":
+        raise ValueError("b200 engine: hidden_act '{}' not supported (gelu only)".format(cfg.hidden_act))
+    if getattr(cfg, "position_embedding_type", "absolute") != "absolute":
+        raise ValueError("b200 engine: only absolute position embeddings are supported")
+    eps = float(cfg.layer_norm_eps)
+    g = GraphBuilder(["int32", "int32", "int32"], cfg.max_position_embeddings)
+    h16, h32 = g.buffer("float16", True, H), g.buffer("float32", True, H)
+    h16b, h32b = g.buffer("float16", True, H), g.buffer("float32", True, H)
+    qkv, ctx = g.buffer("float16", True, 3 * H), g.buffer("float16", True, H)
+    pre32, ff = g.buffer("float32", True, H), g.buffer("float16", True, I)
+    e = prefix + "embeddings."
+    g.op(OP_EMBED_LN, [0, 1, g.tensor(sd[e + "word_embeddings.weight"], np.float16),
+                       g.tensor(sd[e + "position_embeddings.weight"], np.float16),
+                       g.tensor(sd[e + "token_type_embeddings.weight"], np.float16),
+                       g.tensor(sd[e + "LayerNorm.weight"], np.float32), g.tensor(sd[e + "LayerNorm.bias"], np.float32),
+                       h16, h32, H, cfg.vocab_size, cfg.max_position_embeddings, cfg.type_vocab_size], [eps])
+    for l in range(L):
+        p = "{}encoder.layer.{}.".format(prefix, l)
+        wqkv = np.concatenate([sd[p + "attention.self.query.weight"], sd[p + "attention.self.key.weight"],
+                               sd[p + "attention.self.value.weight"]], 0)
+        bqkv = np.concatenate([sd[p + "attention.self.query.bias"], sd[p + "attention.self.key.bias"],
+                               sd[p + "attention.self.value.bias"]], 0)
+        g.linear(h16, wqkv, bqkv, qkv)
+        g.op(OP_ATTENTION, [qkv, 2, ctx, heads, 64])
+        g.linear(ctx, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"], pre32,
+                 residual=h32, out_f32=True)
+        g.op(OP_LAYERNORM, [pre32, g.tensor(sd[p + "attention.output.LayerNorm.weight"], np.float32),
+                            g.tensor(sd[p + "attention.output.LayerNorm.bias"], np.float32), h16b, h32b, H], [eps])
+        g.linear(h16b, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"], ff, act=ACT_GELU)
+        g.linear(ff, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"], pre32, residual=h32b, out_f32=True)
+        g.op(OP_LAYERNORM, [pre32, g.tensor(sd[p + "output.LayerNorm.weight"], np.float32),
+                            g.tensor(sd[p + "output.LayerNorm.bias"], np.float32), h16, h32, H], [eps])
+    cls16, pool16 = g.buffer("float16", False, H), g.buffer("float16", False, H)
+    g.op(OP_GATHER_FIRST, [h16, cls16, H])
+    g.linear(cls16, sd[prefix + "pooler.dense.weight"], sd[prefix + "pooler.dense.bias"], pool16, act=ACT_TANH)
+    n_labels = sd["classifier.weight"].shape[0]
+    logits = g.buffer("float32", False, n_labels)
+    g.linear(pool16, sd["classifier.weight"], sd["classifier.bias"], g.output(logits), out_f32=True)
+    flops_per_token = 2.0 * L * (4 * H * H + 2 * H * I)
+    desc = dict(kind="graph", arch="bert", layers=L, hidden=H, heads=heads, intermediate=I, num_labels=int(n_labels),
+                max_row_elems=int(cfg.max_position_embeddings), input_dtype="int32", output_dtype="float32",
+                gemm_flops_per_token=flops_per_token, attn_flops_per_token_per_key=4.0 * L * H)
+    return PackedModel(native.MODEL_GRAPH, g.serialise(), desc)

@@ -254,6 +254,8 @@ class Stream(object):
                     t.shape[d] = a.shape[d]
                 if m.in_row_elems[i] > 0:
                     rows = a.size // m.in_row_elems[i]
+                else:  # variable length: [rows, len] (or [len] = one row)
+                    rows = a.shape[0] if a.ndim >= 2 else 1
             rows = rows or 0
             ro = []
             for o in range(m.n_outputs):

@@ -291,10 +291,15 @@ class B200EngineMixin(object):
         self._packed_description = packed.description
         self._policy = BatchPolicy.from_auxiliary_cfg(aux)
         name = str(ep.serving_url).replace("/", "_")
+        # variable-length models: per-row token capacity (aux `b200.max_seq_len`, else the model's own limit)
+        self._max_row_elems = int(packed.description.get("max_row_elems", 0))
+        if isinstance(aux, dict) and aux.get("b200.max_seq_len"):
+            self._max_row_elems = min(self._max_row_elems or (1 << 30), int(aux["b200.max_seq_len"]))
         replicas = []
         for dev in parse_devices(aux, self._default_device_index()):
             m = native.Model(packed.kind, packed.blob, device=dev)   # one full model copy per GPU
-            replicas.append(Replica(dev, m, DynamicBatcher(m, self._policy, name="{}@{}".format(name, dev))))
+            replicas.append(Replica(dev, m, DynamicBatcher(m, self._policy, name="{}@{}".format(name, dev),
+                                                           max_row_elems=self._max_row_elems)))
         self._replicas = ReplicaSet(replicas)
         self._native_model = replicas[0].model
         self._batcher = replicas[0].batcher
@@ -310,6 +315,8 @@ class B200EngineMixin(object):
             return formats.pack_xgboost_json(obj)
         if hasattr(obj, "predict"):
             return formats.pack_sklearn(obj)
+        if hasattr(obj, "state_dict") and hasattr(obj, "config"):   # a transformers torch module
+            return formats.pack_torch_module(obj)
         return None
 
     def _default_device_index(self):
@@ -354,7 +361,13 @@ class B200EngineMixin(object):
                                  "batch dimension, e.g. [[x0, x1, ...]]".format(a.ndim))
             r = a.shape[0]
             a = np.ascontiguousarray(a).reshape(r, -1)
-            if a.shape[1] != re_:
+            if re_ < 0:   # variable-length row (token sequence)
+                cap = getattr(self, "_max_row_elems", 0)
+                if a.shape[1] == 0 or (cap and a.shape[1] > cap):
+                    raise ValueError("b200 engine: sequence of {} tokens is outside (0, {}]".format(a.shape[1], cap))
+                if out and a.shape[1] != out[0].shape[1]:
+                    raise ValueError("b200 engine: inputs disagree on the sequence length")
+            elif a.shape[1] != re_:
                 raise ValueError("b200 engine: input {} has {} features per row, model expects {}".format(
                     i, a.shape[1], re_))
             if rows is not None and r != rows:

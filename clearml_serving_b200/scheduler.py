@@ -120,12 +120,15 @@ def _resolve_many(pairs):
 class DynamicBatcher(object):
     """Queue + scheduler of one endpoint in front of one native.Stream."""
 
-    def __init__(self, model, policy, name="endpoint", stream=None):
+    def __init__(self, model, policy, name="endpoint", stream=None, max_row_elems=0):
         self.model = model
         self.policy = policy
         self.name = name
+        self.max_row_elems = int(max_row_elems)
+        self.ragged = any(e < 0 for e in model.in_row_elems)
         # `stream` is injectable so the queueing logic can be unit-tested without a GPU
-        self.stream = stream if stream is not None else native.Stream(model, policy.max_batch_size, 0, policy.n_slots)
+        self.stream = stream if stream is not None else native.Stream(model, policy.max_batch_size, self.max_row_elems,
+                                                                      policy.n_slots)
         self._queue = collections.deque()
         self._queued_rows = 0
         self._cond = threading.Condition()
@@ -216,15 +219,32 @@ class DynamicBatcher(object):
             try:
                 slot = self._acquire_slot()
                 n_rows = 0
-                for i in range(m.n_inputs):
-                    parts = [r.inputs[i] for r in batch]
-                    n_rows = sum(p.shape[0] for p in parts)
-                    if len(parts) == 1:
-                        slot.inputs[i][:n_rows] = parts[0]
-                    else:
-                        np.concatenate(parts, axis=0, out=slot.inputs[i][:n_rows])
+                offsets = None
+                if self.ragged:
+                    # collate variable-length rows back to back (packed tokens) + cu_seqlens
+                    lens = []
+                    for r in batch:
+                        a = r.inputs[0]
+                        lens.extend([a.shape[1]] * a.shape[0])
+                    offsets = np.zeros(len(lens) + 1, dtype=np.int64)
+                    np.cumsum(lens, out=offsets[1:])
+                    n_rows, n_tok = len(lens), int(offsets[-1])
+                    for i in range(m.n_inputs):
+                        parts = [r.inputs[i].reshape(-1) for r in batch]
+                        if len(parts) == 1:
+                            slot.inputs[i][:n_tok] = parts[0]
+                        else:
+                            np.concatenate(parts, out=slot.inputs[i][:n_tok])
+                else:
+                    for i in range(m.n_inputs):
+                        parts = [r.inputs[i] for r in batch]
+                        n_rows = sum(p.shape[0] for p in parts)
+                        if len(parts) == 1:
+                            slot.inputs[i][:n_rows] = parts[0]
+                        else:
+                            np.concatenate(parts, axis=0, out=slot.inputs[i][:n_rows])
                 t_disp = time.perf_counter()
-                ev = self.stream.submit(slot, n_rows)
+                ev = self.stream.submit(slot, n_rows, offsets)
                 st = self.stats
                 st["batches"] += 1
                 st["requests"] += len(batch)
