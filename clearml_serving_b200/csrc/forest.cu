@@ -220,6 +220,233 @@ forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_row
 }
 
 // ---------------------------------------------------------------------------------------------
+// Kernel C (serving batches, fast path): like kernel B but the forest never pays a dependent L2 round
+// trip per tree level.  Measured on B200 (profiles/r01_forest_cluster_phase_timing.txt): a dependent
+// L2 access costs ~1000 SM cycles at 1.97 GHz, so 8 of them per tree dominated kernel B.  Here
+//   * each CTA of the cluster bulk-copies ITS slice of the forest (trees_per_cta consecutive trees,
+//     ~130 KB for 128 depth-6 trees) into shared memory with cp.async.bulk (one L2 latency, then
+//     full-rate streaming) and traverses out of shared memory (~40 cycles per level);
+//   * a row tile is 16 rows: lanes 0-15 / 16-31 of a warp walk two different trees, which halves the
+//     leaf matrix (T x 16) so that it fits next to the tree slice;
+//   * leaf values are pushed to rank 0 through distributed shared memory and each rank signals its
+//     own mbarrier in rank 0, so the ordered sum starts on rank 0's trees at once and the remaining
+//     pushes drain behind the 4-cycle-per-tree add chain instead of in front of it.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxSlices = 64;
+struct SliceTable {
+    uint32_t off[kMaxSlices + 1];  // node offset of the first tree of every trees_per_cta-group (+ end)
+};
+
+__device__ __forceinline__ void mbar_init_cta(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_cta(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cta(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster_acq(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                   "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+#define B2S_SPIN_LIMIT (1u << 26)
+
+template <bool F64, int WARPS, int U>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X, int64_t n_rows,
+                     void *__restrict__ out, int slice_cap_bytes, long long *__restrict__ dbg)
+{
+#define B2S_STAMP(k)                                                                    \
+    do {                                                                                \
+        if (dbg && blockIdx.x < 8 && threadIdx.x == 0) dbg[blockIdx.x * 8 + (k)] = clock64(); \
+    } while (0)
+    using acc_t = typename std::conditional<F64, double, float>::type;
+    constexpr int TPC = WARPS * 2 * U;          // trees per CTA per chunk
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row16 = lane & 15, half = lane >> 4;
+    const int F = p.n_features, T = p.n_trees;
+    const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
+    const int64_t r0 = (int64_t)(blockIdx.x / C) * 16;
+    const int rows_here = (int)min((int64_t)16, n_rows - r0);
+    const int chunk_trees = (int)C * TPC;
+
+    // smem carve-up
+    uint2 *snodes = reinterpret_cast<uint2 *>(smem);
+    acc_t *leafbuf = reinterpret_cast<acc_t *>(smem + slice_cap_bytes);                       // [chunk_trees][16]
+    float *xs = reinterpret_cast<float *>(smem + slice_cap_bytes + (size_t)chunk_trees * 16 * sizeof(acc_t));  // [F][17]
+    uint32_t *toff = reinterpret_cast<uint32_t *>(xs + (size_t)F * 17);                       // [TPC + 1]
+    uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(toff + TPC + 1) + 7) & ~(uintptr_t)7);
+    uint64_t *load_bar = bars;            // tree slice landed (this CTA)
+    uint64_t *chunk_bar = bars + 1;       // [C] in rank 0: rank r's leaf values landed
+
+    B2S_STAMP(0);
+    if (threadIdx.x == 0) {
+        mbar_init_cta(load_bar, 1);
+        for (uint32_t r = 0; r < C; ++r) mbar_init_cta(&chunk_bar[r], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_chunks = (T + chunk_trees - 1) / chunk_trees;
+    const uint32_t leaf_remote = map_to_rank(leafbuf, 0);
+    const uint32_t bar_remote = map_to_rank(&chunk_bar[rank], 0);
+    acc_t acc = F64 ? (acc_t)p.base : (acc_t)(float)p.base;
+
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int slice = ch * (int)C + (int)rank;                 // which trees_per_cta-group this CTA owns
+        const int t_lo = slice * TPC;
+        const int n_my = max(0, min(TPC, T - t_lo));               // trees of this CTA in this chunk
+        const uint32_t node_lo = st.off[min(slice, kMaxSlices)] & ~1u;   // 16-byte aligned bulk source
+        const uint32_t node_hi = (st.off[min(slice + 1, kMaxSlices)] + 1u) & ~1u;
+        if (threadIdx.x == 0 && n_my > 0) {
+            const uint32_t bytes = (node_hi - node_lo) * 8u;
+            mbar_expect_tx_cta(load_bar, bytes);
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(p.nodes + node_lo);
+            for (uint32_t o = 0; o < bytes; o += 32768u)
+                bulk_g2s(smem + o, src + o, min(32768u, bytes - o), load_bar);
+        }
+        // overlap with the bulk copy: per-tree offsets and (first chunk) the x tile
+        for (int i = threadIdx.x; i <= n_my; i += WARPS * 32) toff[i] = __ldg(p.tree_offset + t_lo + i) - node_lo;
+        if (ch == 0) {
+            const float *src = X + r0 * F;
+            for (int i = threadIdx.x; i < 16 * F; i += WARPS * 32) {
+                const int r = i / F, f = i - r * F;
+                xs[f * 17 + r] = (r < rows_here) ? __ldg(src + i) : 0.0f;
+            }
+            cluster_sync_all();   // mbarrier inits of rank 0 are visible before any remote arrive
+        }
+        __syncthreads();
+        if (n_my > 0) {
+            uint32_t spins = 0;
+            while (!mbar_try_wait_cta(load_bar, (uint32_t)(ch & 1))) {
+                if (++spins > B2S_SPIN_LIMIT) __trap();
+            }
+        }
+        B2S_STAMP(1);
+
+        // ---- traverse out of shared memory: this warp's 2*U trees, lane = (row16, half)
+        const int tl0 = warp * 2 * U + half;   // local tree index of slot u is tl0 + 2u
+        uint32_t base[U];
+        uint2 cur[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tl = tl0 + 2 * u;
+            base[u] = (tl < n_my) ? toff[tl] : 0u;
+            cur[u] = (tl < n_my) ? snodes[base[u]] : make_uint2(0u, 0u);
+        }
+        {
+            const int fb = p.feat_bits;
+            const uint32_t fmask = (1u << fb) - 1u;
+            for (int d = 0; d < p.max_depth; ++d) {
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t meta = cur[u].y;
+                    const uint32_t left = meta >> (fb + 1);
+                    if (left) {
+                        const float x = xs[(meta & fmask) * 17 + row16];
+                        const float thr = __uint_as_float(cur[u].x);
+                        const bool dl = (meta >> fb) & 1u;
+                        const bool go_left = (x != x) ? dl : (x < thr);
+                        cur[u] = snodes[base[u] + left + (go_left ? 0u : 1u)];
+                        any = true;
+                    }
+                }
+                if (!__any_sync(0xffffffffu, any)) break;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tl = tl0 + 2 * u;
+            if (tl < n_my) {
+                acc_t v;
+                if (F64) v = (acc_t)__ldg(p.leaf64 + cur[u].x);
+                else v = (acc_t)__uint_as_float(cur[u].x);
+                st_cluster(leaf_remote + (uint32_t)((((int)rank * TPC + tl) * 16 + row16) * sizeof(acc_t)), v);
+            }
+        }
+        // publish: all stores of this CTA, then one release-arrive on this rank's barrier in rank 0
+        asm volatile("fence.acq_rel.cluster;\n" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_arrive_remote_release(bar_remote);
+        B2S_STAMP(2);
+
+        // ---- ordered sum in rank 0: rank by rank as their leaf values land
+        if (rank == 0 && warp == 0) {
+            for (uint32_t r = 0; r < C; ++r) {
+                uint32_t spins = 0;
+                while (!mbar_try_wait_cluster_acq(&chunk_bar[r], (uint32_t)(ch & 1))) {
+                    if (++spins > B2S_SPIN_LIMIT) __trap();
+                }
+                if (r == 0) B2S_STAMP(3);
+                const int t_first = ch * chunk_trees + (int)r * TPC;
+                const int tcount = max(0, min(TPC, T - t_first));
+                const acc_t *buf = leafbuf + (size_t)r * TPC * 16 + row16;
+                // software-pipelined: the loads of group g+1 are in flight while group g is added
+                acc_t a[16], b[16];
+                const int ngroups = tcount / 16;
+                if (ngroups > 0) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) a[k] = buf[k * 16];
+                }
+                for (int g = 0; g < ngroups; g += 2) {
+                    if (g + 1 < ngroups) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) b[k] = buf[((g + 1) * 16 + k) * 16];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc = acc + a[k];
+                    if (g + 1 < ngroups) {
+                        if (g + 2 < ngroups) {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) a[k] = buf[((g + 2) * 16 + k) * 16];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) acc = acc + b[k];
+                    }
+                }
+                int t = ngroups * 16;
+                for (; t < tcount; ++t) acc = acc + buf[t * 16];
+            }
+            B2S_STAMP(4);
+        }
+        if (ch + 1 < n_chunks) cluster_sync_all();   // leaf matrix / tree slice are reused by the next chunk
+    }
+    if (rank == 0 && warp == 0 && half == 0 && row16 < rows_here) {
+        if (F64) reinterpret_cast<double *>(out)[r0 + row16] = (double)acc / p.divisor;
+        else reinterpret_cast<float *>(out)[r0 + row16] = (float)acc;
+    }
+#undef B2S_STAMP
+}
+
+// ---------------------------------------------------------------------------------------------
 // Kernel A: one row per thread, all trees in order (large batches; no scratch).
 // ---------------------------------------------------------------------------------------------
 template <bool F64, int BLOCK, int U>
@@ -277,6 +504,8 @@ forest_rows_kernel(ForestParams p, const float *__restrict__ X, int64_t n_rows,
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+constexpr int kStWarps = 16;               // staged kernel: 512 threads per CTA
+constexpr int kStU32 = 4, kStU64 = 2;      // => 128 / 64 trees per CTA per chunk
 constexpr int kClWarps = 32;               // 1024 threads per CTA, one CTA per SM
 constexpr int kClU32 = 4, kClU64 = 2;      // trees in flight per warp (fp32 / fp64 leaf matrix)
 constexpr int kRowsBlock = 128;
@@ -290,6 +519,11 @@ struct ForestModel : Model {
     bool f64 = false;
     int max_smem_optin = 0;
     long long *dbg_stamps = nullptr;  // device buffer [8 CTAs][8 phases], only with B2S_FOREST_TIMING=1
+    // staged (shared-memory resident) fast path
+    bool staged_ok = false;
+    SliceTable slices{};
+    int staged_C = 1, staged_slice_cap = 0;
+    size_t staged_smem = 0;
 
     ~ForestModel() override
     {
@@ -342,6 +576,27 @@ struct ForestModel : Model {
         return 0;
     }
 
+    template <bool F64, int U>
+    int launch_staged(cudaStream_t st, const float *X, int64_t n_rows, void *out)
+    {
+        const unsigned tiles = (unsigned)((n_rows + 15) / 16);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(tiles * staged_C, 1, 1);
+        cfg.blockDim = dim3(kStWarps * 32, 1, 1);
+        cfg.dynamicSmemBytes = staged_smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = staged_C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B2S_CUDA(cudaLaunchKernelEx(&cfg, forest_staged_kernel<F64, kStWarps, U>, p, slices, X, n_rows, out,
+                                    staged_slice_cap, dbg_stamps));
+        return 0;
+    }
+
     int launch(cudaStream_t st, int64_t n_rows, const void *const *d_in, void *const *d_out,
                const int64_t *, void *, size_t, const LaunchInfo &) override
     {
@@ -349,7 +604,10 @@ struct ForestModel : Model {
         const float *X = static_cast<const float *>(d_in[0]);
         void *out = d_out[0];
         const int F = p.n_features;
-        if (n_rows <= kClusterMaxRows) {
+        if (n_rows <= kClusterMaxRows && staged_ok) {
+            if (f64) B2S_TRY((launch_staged<true, kStU64>(st, X, n_rows, out)));
+            else B2S_TRY((launch_staged<false, kStU32>(st, X, n_rows, out)));
+        } else if (n_rows <= kClusterMaxRows) {
             if (f64) B2S_TRY((launch_cluster<true, kClU64>(st, X, n_rows, out)));
             else B2S_TRY((launch_cluster<false, kClU32>(st, X, n_rows, out)));
         } else {
@@ -425,15 +683,23 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
     ForestModel *m = new ForestModel();
     m->device = device;
     m->f64 = h.acc_mode == 1;
+    // device layout: [tree_offset | nodes (+16 B pad for 16-byte bulk copies) | leaf64], 256-byte aligned sections
+    const size_t d_off_nodes = (size_t)round_up((int64_t)off_bytes, 256);
+    const size_t d_off_leaf = (size_t)round_up((int64_t)(d_off_nodes + node_bytes + 16), 256);
+    const size_t d_total = d_off_leaf + leaf_bytes + 256;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, need - sizeof(h));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, d_total);
     if (e != cudaSuccess) { delete m; return fail_cuda(e, "cudaMalloc(forest)"); }
-    e = cudaMemcpy(m->d_blob, base + sizeof(h), need - sizeof(h), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { delete m; return fail_cuda(e, "cudaMemcpy(forest)"); }
     unsigned char *d = static_cast<unsigned char *>(m->d_blob);
+    e = cudaMemset(d, 0, d_total);
+    if (e == cudaSuccess) e = cudaMemcpy(d, toff, (size_t)(h.n_trees + 1) * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + d_off_nodes, nodes, node_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && leaf_bytes)
+        e = cudaMemcpy(d + d_off_leaf, base + sizeof(h) + off_bytes + node_bytes, leaf_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete m; return fail_cuda(e, "cudaMemcpy(forest)"); }
     m->p.tree_offset = reinterpret_cast<const uint32_t *>(d);
-    m->p.nodes = reinterpret_cast<const uint2 *>(d + off_bytes);
-    m->p.leaf64 = reinterpret_cast<const double *>(d + off_bytes + node_bytes);
+    m->p.nodes = reinterpret_cast<const uint2 *>(d + d_off_nodes);
+    m->p.leaf64 = reinterpret_cast<const double *>(d + d_off_leaf);
     m->p.n_trees = (int)h.n_trees;
     m->p.n_features = (int)h.n_features;
     m->p.feat_bits = fb;
@@ -455,6 +721,35 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
     cudaFuncSetAttribute(forest_rows_kernel<false, kRowsBlock, kRowsU>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     cudaFuncSetAttribute(forest_rows_kernel<true, kRowsBlock, kRowsU>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     m->max_smem_optin = want;
+    cudaFuncSetAttribute(forest_staged_kernel<false, kStWarps, kStU32>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    cudaFuncSetAttribute(forest_staged_kernel<true, kStWarps, kStU64>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    {   // can every CTA keep its slice of the forest in shared memory?
+        const int tpc = kStWarps * 2 * (m->f64 ? kStU64 : kStU32);
+        const int n_slices = ((int)h.n_trees + tpc - 1) / tpc;
+        const char *no_staged = getenv("B2S_FOREST_NO_STAGED");
+        if (n_slices <= kMaxSlices && !(no_staged && no_staged[0] == '1')) {
+            uint32_t max_nodes = 0;
+            for (int k = 0; k <= kMaxSlices; ++k) {
+                const uint32_t t = (uint32_t)k * (uint32_t)tpc;
+                m->slices.off[k] = toff[t < h.n_trees ? t : h.n_trees];
+            }
+            for (int k = 0; k < n_slices; ++k) {
+                const uint32_t lo = m->slices.off[k] & ~1u, hi = (m->slices.off[k + 1] + 1u) & ~1u;
+                if (hi - lo > max_nodes) max_nodes = hi - lo;
+            }
+            int C = 1;
+            while (C < 8 && C * tpc < (int)h.n_trees) C *= 2;
+            const size_t cap = (size_t)round_up((int64_t)max_nodes * 8 + 16, 128);
+            const size_t leaf = (size_t)C * tpc * 16 * (m->f64 ? 8 : 4);
+            const size_t smem = cap + leaf + (size_t)h.n_features * 17 * 4 + (size_t)(tpc + 1) * 4 + 16 + (size_t)(1 + C) * 8 + 128;
+            if (smem <= (size_t)want) {
+                m->staged_ok = true;
+                m->staged_C = C;
+                m->staged_slice_cap = (int)cap;
+                m->staged_smem = smem;
+            }
+        }
+    }
 
     b2s_model_info &info = m->info;
     info.kind = B2S_MODEL_FOREST;
@@ -464,7 +759,7 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
     info.out_dtype[0] = m->f64 ? B2S_F64 : B2S_F32;
     info.in_row_elems[0] = h.n_features;
     info.out_row_elems[0] = 1;
-    info.weight_bytes = (int64_t)(need - sizeof(h));
+    info.weight_bytes = (int64_t)d_total;
     info.algo_bytes_fixed = algo_fixed;
     info.algo_bytes_per_row = (int64_t)h.n_features * 4 + (m->f64 ? 8 : 4);
     *out = m;
