@@ -275,12 +275,25 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
                  ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
                    "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
+// shared::cta -> (remote) shared::cluster bulk copy through the async proxy; completes bytes on an
+// mbarrier that lives in the DESTINATION CTA
+__device__ __forceinline__ void bulk_s2s_cluster(uint32_t dst_cluster_addr, const void *smem_src, uint32_t bytes,
+                                                 uint32_t bar_cluster_addr)
+{
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst_cluster_addr), "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(bytes),
+                   "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
 #define B2S_SPIN_LIMIT (1u << 26)
 
 template <bool F64, int WARPS, int U>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X, int64_t n_rows,
-                     void *__restrict__ out, int slice_cap_bytes, long long *__restrict__ dbg)
+                     void *__restrict__ out, int slice_cap_bytes, int bulk_piece, long long *__restrict__ dbg)
 {
 #define B2S_STAMP(k)                                                                    \
     do {                                                                                \
@@ -305,6 +318,8 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
     uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(toff + TPC + 1) + 7) & ~(uintptr_t)7);
     uint64_t *load_bar = bars;            // tree slice landed (this CTA)
     uint64_t *chunk_bar = bars + 1;       // [C] in rank 0: rank r's leaf values landed
+    // this CTA's leaf values [TPC][16], staged locally and pushed to rank 0 with ONE bulk copy
+    acc_t *stage_leaf = reinterpret_cast<acc_t *>((reinterpret_cast<uintptr_t>(chunk_bar + 8) + 127) & ~(uintptr_t)127);
 
     B2S_STAMP(0);
     if (threadIdx.x == 0) {
@@ -325,12 +340,20 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
         const int n_my = max(0, min(TPC, T - t_lo));               // trees of this CTA in this chunk
         const uint32_t node_lo = st.off[min(slice, kMaxSlices)] & ~1u;   // 16-byte aligned bulk source
         const uint32_t node_hi = (st.off[min(slice + 1, kMaxSlices)] + 1u) & ~1u;
-        if (threadIdx.x == 0 && n_my > 0) {
+        if (warp == 0 && n_my > 0) {
             const uint32_t bytes = (node_hi - node_lo) * 8u;
-            mbar_expect_tx_cta(load_bar, bytes);
+            if (lane == 0) mbar_expect_tx_cta(load_bar, bytes);
+            __syncwarp();
             const unsigned char *src = reinterpret_cast<const unsigned char *>(p.nodes + node_lo);
-            for (uint32_t o = 0; o < bytes; o += 32768u)
-                bulk_g2s(smem + o, src + o, min(32768u, bytes - o), load_bar);
+            for (uint32_t o = (uint32_t)lane * (uint32_t)bulk_piece; o < bytes; o += 32u * (uint32_t)bulk_piece)
+                bulk_g2s(smem + o, src + o, min((uint32_t)bulk_piece, bytes - o), load_bar);
+        }
+        if (rank == 0 && threadIdx.x == 32) {   // arm the per-rank arrival barriers with the bytes each rank pushes
+            for (uint32_t r = 1; r < C; ++r) {
+                const int n_r = max(0, min(TPC, T - (ch * (int)C + (int)r) * TPC));
+                if (n_r > 0) mbar_expect_tx_cta(&chunk_bar[r], (uint32_t)(n_r * 16 * sizeof(acc_t)));
+                else mbar_arrive_cta(&chunk_bar[r]);
+            }
         }
         // overlap with the bulk copy: per-tree offsets and (first chunk) the x tile
         for (int i = threadIdx.x; i <= n_my; i += WARPS * 32) toff[i] = __ldg(p.tree_offset + t_lo + i) - node_lo;
@@ -389,13 +412,20 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
                 acc_t v;
                 if (F64) v = (acc_t)__ldg(p.leaf64 + cur[u].x);
                 else v = (acc_t)__uint_as_float(cur[u].x);
-                st_cluster(leaf_remote + (uint32_t)((((int)rank * TPC + tl) * 16 + row16) * sizeof(acc_t)), v);
+                if (rank == 0) leafbuf[tl * 16 + row16] = v;          // rank 0: straight into the leaf matrix
+                else stage_leaf[tl * 16 + row16] = v;                 // others: local staging
             }
         }
-        // publish: all stores of this CTA, then one release-arrive on this rank's barrier in rank 0
-        asm volatile("fence.acq_rel.cluster;\n" ::: "memory");
+        // publish: rank 0 arrives locally; every other rank pushes its block with one bulk DSMEM copy that
+        // completes bytes on its barrier in rank 0 (generic-proxy writes -> async-proxy read needs the fence)
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();
-        if (threadIdx.x == 0) mbar_arrive_remote_release(bar_remote);
+        if (threadIdx.x == 0) {
+            if (rank == 0) mbar_arrive_cta(&chunk_bar[0]);
+            else if (n_my > 0)
+                bulk_s2s_cluster(leaf_remote + (uint32_t)((size_t)rank * TPC * 16 * sizeof(acc_t)), stage_leaf,
+                                 (uint32_t)(n_my * 16 * sizeof(acc_t)), bar_remote);
+        }
         B2S_STAMP(2);
 
         // ---- ordered sum in rank 0: rank by rank as their leaf values land
@@ -592,8 +622,13 @@ struct ForestModel : Model {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        static const int bulk_piece = []() {
+            const char *e = getenv("B2S_FOREST_BULK_PIECE");
+            int v = e ? atoi(e) : 8192;
+            return (v >= 1024 && v % 16 == 0) ? v : 8192;
+        }();
         B2S_CUDA(cudaLaunchKernelEx(&cfg, forest_staged_kernel<F64, kStWarps, U>, p, slices, X, n_rows, out,
-                                    staged_slice_cap, dbg_stamps));
+                                    staged_slice_cap, bulk_piece, dbg_stamps));
         return 0;
     }
 
@@ -741,7 +776,8 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
             while (C < 8 && C * tpc < (int)h.n_trees) C *= 2;
             const size_t cap = (size_t)round_up((int64_t)max_nodes * 8 + 16, 128);
             const size_t leaf = (size_t)C * tpc * 16 * (m->f64 ? 8 : 4);
-            const size_t smem = cap + leaf + (size_t)h.n_features * 17 * 4 + (size_t)(tpc + 1) * 4 + 16 + (size_t)(1 + C) * 8 + 128;
+            const size_t smem = cap + leaf + (size_t)h.n_features * 17 * 4 + (size_t)(tpc + 1) * 4 + 16 + 9 * 8 + 256 +
+                                (size_t)tpc * 16 * (m->f64 ? 8 : 4);   // + local leaf staging block
             if (smem <= (size_t)want) {
                 m->staged_ok = true;
                 m->staged_C = C;

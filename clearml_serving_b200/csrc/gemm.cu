@@ -18,6 +18,8 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace b2s {
@@ -39,7 +41,125 @@ struct GemmSmem {
     static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU (erf form, as torch.nn.functional.gelu): erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far
+// below the fp16 rounding of the stored activation) -- one MUFU.RCP + one MUFU.EX2 instead of erff's
+// ~25-instruction polynomial, which made the epilogue the bottleneck of the FFN-up GEMM.
+__device__ __forceinline__ float gelu_erf(float x)
+{
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * exp2f(-z * z * 1.4426950408889634f);  // erf(|x|/sqrt2)
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+// Fused epilogue for 32 consecutive accumulator columns of one output row (fp32 bits in v[]):
+// + bias, activation, + residual, cast, one 64/128-byte contiguous store per thread.
+__device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int row, int col0, int M, int N,
+                                                 const uint32_t (&v)[32])
+{
+    const float *bias = static_cast<const float *>(ep.bias);
+    if (row < M && col0 < N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const int ncols = min(32, N - col0);
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) f[j] += __ldg(bias + col0 + j);
+        }
+        if (ep.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        } else if (ep.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        } else if (ep.act == ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+        }
+        const size_t off = (size_t)row * ep.ldc + col0;
+        if (ep.out_f32) {
+            float *C = static_cast<float *>(ep.C) + off;
+            if (ep.residual) {
+                const float *R = static_cast<const float *>(ep.residual) + off;
+                for (int j = 0; j < ncols; ++j) f[j] += R[j];
+            }
+            if (ncols == 32 && (off & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(C + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+                for (int j = 0; j < ncols; ++j) C[j] = f[j];
+            }
+        } else if (ep.is_bf16) {
+            __nv_bfloat16 *C = static_cast<__nv_bfloat16 *>(ep.C) + off;
+            if (ep.residual) {
+                const __nv_bfloat16 *R = static_cast<const __nv_bfloat16 *>(ep.residual) + off;
+                for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(R[j]);
+            }
+            if (ncols == 32 && (off & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t *>(&p0);
+                    u.y = *reinterpret_cast<uint32_t *>(&p1);
+                    u.z = *reinterpret_cast<uint32_t *>(&p2);
+                    u.w = *reinterpret_cast<uint32_t *>(&p3);
+                    *reinterpret_cast<uint4 *>(C + j) = u;
+                }
+            } else {
+                for (int j = 0; j < ncols; ++j) C[j] = __float2bfloat16_rn(f[j]);
+            }
+        } else {
+            __half *C = static_cast<__half *>(ep.C) + off;
+            if (ep.residual) {
+                const __half *R = static_cast<const __half *>(ep.residual) + off;
+                if (ncols == 32 && (off & 7) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 u = *reinterpret_cast<const uint4 *>(R + j);
+                        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float2 r2 = __half22float2(h[t]);
+                            f[j + 2 * t] += r2.x;
+                            f[j + 2 * t + 1] += r2.y;
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < ncols; ++j) f[j] += __half2float(R[j]);
+                }
+            }
+            if (ncols == 32 && (off & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    __half2 p0 = __floats2half2_rn(f[j], f[j + 1]);
+                    __half2 p1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+                    __half2 p2 = __floats2half2_rn(f[j + 4], f[j + 5]);
+                    __half2 p3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t *>(&p0);
+                    u.y = *reinterpret_cast<uint32_t *>(&p1);
+                    u.z = *reinterpret_cast<uint32_t *>(&p2);
+                    u.w = *reinterpret_cast<uint32_t *>(&p3);
+                    *reinterpret_cast<uint4 *>(C + j) = u;
+                }
+            } else {
+                for (int j = 0; j < ncols; ++j) C[j] = __float2half_rn(f[j]);
+            }
+        }
+    }
+}
+
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -124,109 +244,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int row = m_blk * GEMM_BM + q * 32 + lane;
-        const float *bias = static_cast<const float *>(ep.bias);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
             tmem_ld_wait();
-            const int col0 = n_blk * BN + c * 32;
-            if (row < M && col0 < N) {
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                const int ncols = min(32, N - col0);
-                if (bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncols) f[j] += __ldg(bias + col0 + j);
-                }
-                if (ep.act == ACT_GELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                } else if (ep.act == ACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-                } else if (ep.act == ACT_TANH) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-                }
-                const size_t off = (size_t)row * ep.ldc + col0;
-                if (ep.out_f32) {
-                    float *C = static_cast<float *>(ep.C) + off;
-                    if (ep.residual) {
-                        const float *R = static_cast<const float *>(ep.residual) + off;
-                        for (int j = 0; j < ncols; ++j) f[j] += R[j];
-                    }
-                    if (ncols == 32 && (off & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4 *>(C + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-                        for (int j = 0; j < ncols; ++j) C[j] = f[j];
-                    }
-                } else if (ep.is_bf16) {
-                    __nv_bfloat16 *C = static_cast<__nv_bfloat16 *>(ep.C) + off;
-                    if (ep.residual) {
-                        const __nv_bfloat16 *R = static_cast<const __nv_bfloat16 *>(ep.residual) + off;
-                        for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(R[j]);
-                    }
-                    if (ncols == 32 && (off & 7) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                            __nv_bfloat162 p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                            __nv_bfloat162 p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                            uint4 u;
-                            u.x = *reinterpret_cast<uint32_t *>(&p0);
-                            u.y = *reinterpret_cast<uint32_t *>(&p1);
-                            u.z = *reinterpret_cast<uint32_t *>(&p2);
-                            u.w = *reinterpret_cast<uint32_t *>(&p3);
-                            *reinterpret_cast<uint4 *>(C + j) = u;
-                        }
-                    } else {
-                        for (int j = 0; j < ncols; ++j) C[j] = __float2bfloat16_rn(f[j]);
-                    }
-                } else {
-                    __half *C = static_cast<__half *>(ep.C) + off;
-                    if (ep.residual) {
-                        const __half *R = static_cast<const __half *>(ep.residual) + off;
-                        if (ncols == 32 && (off & 7) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                const uint4 u = *reinterpret_cast<const uint4 *>(R + j);
-                                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const float2 r2 = __half22float2(h[t]);
-                                    f[j + 2 * t] += r2.x;
-                                    f[j + 2 * t + 1] += r2.y;
-                                }
-                            }
-                        } else {
-                            for (int j = 0; j < ncols; ++j) f[j] += __half2float(R[j]);
-                        }
-                    }
-                    if (ncols == 32 && (off & 7) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            __half2 p0 = __floats2half2_rn(f[j], f[j + 1]);
-                            __half2 p1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-                            __half2 p2 = __floats2half2_rn(f[j + 4], f[j + 5]);
-                            __half2 p3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-                            uint4 u;
-                            u.x = *reinterpret_cast<uint32_t *>(&p0);
-                            u.y = *reinterpret_cast<uint32_t *>(&p1);
-                            u.z = *reinterpret_cast<uint32_t *>(&p2);
-                            u.w = *reinterpret_cast<uint32_t *>(&p3);
-                            *reinterpret_cast<uint4 *>(C + j) = u;
-                        }
-                    } else {
-                        for (int j = 0; j < ncols; ++j) C[j] = __float2half_rn(f[j]);
-                    }
-                }
-            }
+            epilogue_store32(ep, row, n_blk * BN + c * 32, M, N, v);
         }
     }
 
@@ -235,6 +258,149 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel v2: persistent, 128 x 256 tiles, double-buffered TMEM accumulators.
+//   * grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... with m fastest,
+//     so the CTAs that run together share one 256-row weight panel (L2 reuse of B);
+//   * UMMA 128 x 256 x 16: per k-step A 4 KB + B 8 KB of shared-memory reads for 128 cycles of tensor
+//     work (the 128 x 128 shape of v1 is shared-memory-bandwidth bound at 128 B/clk);
+//   * TMEM holds two 256-column accumulators: the 8 epilogue warps drain tile i (tcgen05.ld, fused
+//     bias / GELU / residual, stores) while the MMA warp already accumulates tile i+1;
+//   * 4-stage TMA ring of 48 KB (A 16 KB + B 32 KB) per stage.
+// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM owner, 3 idle, 4-11 epilogue
+// (warp w drains TMEM lane quadrant w % 4, column half (w - 4) / 4).
+// ---------------------------------------------------------------------------------------------
+constexpr int G2_BN = 256;
+constexpr int G2_STAGES = 4;
+constexpr int G2_THREADS = 384;
+struct G2Smem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+    static constexpr int B_BYTES = G2_BN * GEMM_BK * 2;     // 32 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = G2_STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + (2 * G2_STAGES + 4) * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                          int M, int N, int K, GemmEpilogue ep)
+{
+    using S = G2Smem;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFFSET);
+    uint64_t *empty_bar = full_bar + G2_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + G2_STAGES;   // [2]
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + G2_BN - 1) / G2_BN;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_a);
+        prefetch_tensormap(&tmap_b);
+        for (int s = 0; s < G2_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 8);   // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                    unsigned char *sb = sa + S::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, n_blk * G2_BN);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_f16 = make_idesc_f16(GEMM_BM, G2_BN, 0);
+            constexpr uint32_t idesc_bf16 = make_idesc_f16(GEMM_BM, G2_BN, 1);
+            const uint32_t idesc = ep.is_bf16 ? idesc_bf16 : idesc_f16;
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * G2_BN);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                    unsigned char *sb = sa + S::A_BYTES;
+                    const uint64_t adesc = make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = make_sw128_kmajor_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16(d_tmem, desc_advance(adesc, k * 32), desc_advance(bdesc, k * 32), idesc,
+                                 (uint32_t)((kb | k) != 0));
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full_bar[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+            const int row = m_blk * GEMM_BM + q * 32 + lane;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * 128);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                if (c == 3) {   // last TMEM read of this warp: hand the accumulator back before the math
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                }
+                epilogue_store32(ep, row, n_blk * G2_BN + half * 128 + c * 32, M, N, v);
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -296,15 +462,43 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap
     return 0;
 }
 
+static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
+                                  const GemmEpilogue &ep)
+{
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    static int n_sms = 148;
+    std::call_once(once, []() {
+        attr_err = cudaFuncSetAttribute(gemm_tn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Smem::TOTAL);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+    });
+    if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(gemm v2)");
+    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + G2_BN - 1) / G2_BN);
+    const int grid = tiles < n_sms ? tiles : n_sms;
+    gemm_tn_persistent_kernel<<<grid, G2_THREADS, G2Smem::TOTAL, st>>>(ta, tb, M, N, K, ep);
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // tile width for an N-column weight (also the box height of its tensor map)
-int gemm_bn_for(int N) { return N <= 64 ? 64 : 128; }
+int gemm_bn_for(int N)
+{
+    static const bool v1_only = []() { const char *e = getenv("B2S_GEMM_V1"); return e && e[0] == '1'; }();
+    if (N <= 64) return 64;
+    return (N >= 256 && !v1_only) ? 256 : 128;
+}
 
 // GEMM with caller-provided tensor maps (graph executor: maps are cached per stream / per model)
 int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
                  const GemmEpilogue &ep)
 {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    if (gemm_bn_for(N) == 64) return launch_gemm<64, 6>(st, ta, tb, M, N, K, ep);
+    const int bn = gemm_bn_for(N);
+    if (bn == 64) return launch_gemm<64, 6>(st, ta, tb, M, N, K, ep);
+    if (bn == 256) return launch_gemm_persistent(st, ta, tb, M, N, K, ep);
     return launch_gemm<128, 6>(st, ta, tb, M, N, K, ep);
 }
 

@@ -43,7 +43,8 @@ def _ref_act(x, act):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 768), (256, 768, 768), (300, 2304, 768),
-                                    (1000, 3072, 768), (77, 768, 3072), (5, 2, 768), (130, 200, 72)])
+                                    (1000, 3072, 768), (77, 768, 3072), (5, 2, 768), (130, 200, 72), (260, 520, 136),
+                                    (4000, 256, 64), (20000, 768, 768)])
 def test_gemm_fp16_matches_fp32_reference(gpu_native, M, N, K):
     rng = np.random.default_rng(M * 7 + N)
     A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
