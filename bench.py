@@ -289,6 +289,115 @@ def _plugin_metrics(forest, device, seconds=2.0, lam=2000.0):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# second workload (BASELINE.json configs[3]): BERT-base fp16, mixed S in {16,64,128,256}, max_batch=64
+# ------------------------------------------------------------------------------------------------
+def _bert_flops(lens):
+    # 169.87e6*S + 36864*S^2 FLOP per sequence (linear part measured, + attention)
+    return float(sum(169.87e6 * s + 36864.0 * s * s for s in lens))
+
+
+def _bert_workload(native, device, steps, warmup, cpu_seconds):
+    import torch
+    from transformers import BertConfig, BertForSequenceClassification
+    from clearml_serving_b200 import formats
+    torch.manual_seed(0)
+    model_t = BertForSequenceClassification(BertConfig()).eval()
+    pm = formats.pack_bert(model_t)
+    model = native.Model(pm.kind, pm.blob, device=device)
+    B, SMAX = 64, 256
+    stream = native.Stream(model, B, SMAX, 2)
+    timer = native.Timer(stream)
+    rng = np.random.default_rng(1)
+    n_sets = 8
+    sets = []
+    for k in range(n_sets):
+        lens = rng.choice([16, 64, 128, 256], size=B)
+        reqs = []
+        for n in lens:
+            reqs.append([rng.integers(0, 30522, (1, n)).astype(np.int32), np.zeros((1, n), np.int32), np.ones((1, n), np.int32)])
+        sets.append((lens, reqs))
+    # device-resident copies
+    dsets = []
+    for lens, reqs in sets:
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        bufs = []
+        for i in range(3):
+            flat = np.concatenate([r[i].reshape(-1) for r in reqs])
+            b = native.DeviceBuffer(flat.nbytes, device); b.upload(flat); bufs.append(b)
+        doff = native.DeviceBuffer(off.nbytes, device); doff.upload(off)
+        dsets.append((bufs, doff))
+    d_out = native.DeviceBuffer(B * 2 * 4, device)
+    for w in range(max(warmup, 3)):
+        bufs, doff = dsets[w % n_sets]
+        stream.infer_device(B, [b.ptr for b in bufs], [d_out.ptr], doff.ptr)
+    stream.synchronize()
+    launches0 = native.launch_count()
+    total_ms, flops = 0.0, 0.0
+    for k in range(steps):
+        bufs, doff = dsets[k % n_sets]
+        stream.flush_l2()
+        timer.start()
+        stream.infer_device(B, [b.ptr for b in bufs], [d_out.ptr], doff.ptr)
+        timer.stop()
+        total_ms += timer.elapsed_ms()
+        flops += _bert_flops(sets[k % n_sets][0])
+    launches = native.launch_count() - launches0
+    # e2e through the C ABI with host tensors (64 requests x 3 inputs), 2 batches in flight
+    t0 = time.perf_counter()
+    inflight = []
+    for k in range(steps):
+        if len(inflight) == 2:
+            stream.wait(inflight.pop(0)[0])
+        ev, outs, keep = stream.infer_batch(sets[k % n_sets][1])
+        inflight.append((ev, outs, keep))
+    for it in inflight:
+        stream.wait(it[0])
+    e2e_s = time.perf_counter() - t0
+    # parity guard on one batch (full parity lives in tests/test_gpu_bert.py)
+    ev, outs, keep = stream.infer_batch(sets[0][1][:4])
+    stream.wait(ev)
+    with torch.no_grad():
+        ref = np.concatenate([model_t(input_ids=torch.from_numpy(r[0]).long(), token_type_ids=torch.from_numpy(r[1]).long(),
+                                      attention_mask=torch.from_numpy(r[2]).long()).logits.numpy() for r in sets[0][1][:4]])
+    got = np.concatenate([o[0] for o in outs])
+    rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+    # CPU arm: the same model in torch fp32 on the host cores, one request at a time (no batching in the reference)
+    n_cpu, t_cpu0 = 0, time.perf_counter()
+    with torch.no_grad():
+        while time.perf_counter() - t_cpu0 < cpu_seconds:
+            r = sets[0][1][n_cpu % B]
+            model_t(input_ids=torch.from_numpy(r[0]).long(), token_type_ids=torch.from_numpy(r[1]).long(),
+                    attention_mask=torch.from_numpy(r[2]).long())
+            n_cpu += 1
+    cpu_dt = time.perf_counter() - t_cpu0
+    peak = 1431.4
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            peak = float(json.load(f).get("bf16_tflops_sustained", peak))
+    achieved = flops / (total_ms * 1e-3) / 1e12
+    res = dict(workload="bert-base-fp16_mixedS16-256_maxbatch64_ragged", metric="sequences/sec",
+               value=B * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps, steps=steps,
+               e2e=dict(value=B * steps / e2e_s, unit="sequences/s", ms_per_step=e2e_s / steps * 1e3, in_flight=2,
+                        h2d_bytes_per_step=int(np.mean([sum(l) for l, _ in sets]) * 12), d2h_bytes_per_step=B * 8),
+               gpu_launches_per_step=launches / steps, parity_rel_err_vs_torch_cpu_fp32=rel,
+               roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                             peak_source="MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a step)",
+                             flops_per_step_mean=flops / steps),
+               cpu_baseline=dict(value=n_cpu / cpu_dt, unit="sequences/s", cores=int(torch.get_num_threads()), kind="port",
+                                 sample="{} single-sequence torch fp32 forwards in {:.1f}s".format(n_cpu, cpu_dt)))
+    timer.destroy()
+    for bufs, doff in dsets:
+        for b in bufs:
+            b.free()
+        doff.free()
+    d_out.free()
+    stream.destroy()
+    model.free()
+    return res
+
+
 def run_b200(args):
     rank, world, local, dist = _dist_setup(args.gpus)
     device = local
@@ -394,6 +503,13 @@ def run_b200(args):
         except Exception as ex:  # noqa
             plugin = dict(error=str(ex))
 
+    bert = None
+    if args.bert and rank == 0:
+        try:
+            bert = _bert_workload(native, device, max(10, min(args.steps, 40)), 3, min(args.cpu_seconds, 8.0))
+        except Exception as ex:  # noqa
+            bert = dict(error="{}: {}".format(type(ex).__name__, ex))
+
     if rank == 0:
         peak, peak_src = _peaks()
         algo = model.algo_bytes(MAX_BATCH)
@@ -416,8 +532,8 @@ def run_b200(args):
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                           traffic=_traffic_bytes(), algorithmic_bytes_per_launch=algo, peak_source=peak_src,
-                          kernel="forest_pairs_kernel<f32>", note="latency-bound at 64 rows: 1000-add fp32 chain"),
-            cpu_baseline=cpu, clocks=clk, plugin=plugin)
+                          kernel="forest_staged_kernel<f32>", note="latency-bound at 64 rows: 1000-add fp32 chain"),
+            cpu_baseline=cpu, clocks=clk, plugin=plugin, workloads=dict(bert_base=bert))
         print(json.dumps(line))
     timer.destroy()
     for b in d_in:
@@ -437,6 +553,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-plugin", action="store_true")
+    ap.add_argument("--no-bert", dest="bert", action="store_false", help="skip the BERT-base (configs[3]) section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
