@@ -124,6 +124,13 @@ struct Slot {
     unsigned char *h_in[kMaxIO] = {nullptr, nullptr, nullptr, nullptr};
     unsigned char *h_out[kMaxIO] = {nullptr, nullptr, nullptr, nullptr};
     int64_t *h_row_offsets = nullptr;
+    // each slot is an independent lane on the device: its own CUDA stream, staging buffers and model
+    // scratch, so consecutive batches of one endpoint overlap (copy / kernel / copy-back) on the GPU
+    cudaStream_t st = nullptr;
+    void *d_in[kMaxIO] = {nullptr, nullptr, nullptr, nullptr};
+    void *d_out[kMaxIO] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t *d_row_offsets = nullptr;
+    void *scratch = nullptr;
     // scatter plan of b2s_infer_batch
     bool scatter = false;
     int64_t n_rows = 0;
@@ -139,9 +146,7 @@ struct Stream {
     int64_t max_rows = 0, max_row_elems = 0;
     size_t in_bytes[kMaxIO] = {0, 0, 0, 0}, out_bytes[kMaxIO] = {0, 0, 0, 0};
     size_t in_row_bytes[kMaxIO] = {0, 0, 0, 0}, out_row_bytes[kMaxIO] = {0, 0, 0, 0};
-    void *d_in[kMaxIO] = {nullptr, nullptr, nullptr, nullptr};
-    void *d_out[kMaxIO] = {nullptr, nullptr, nullptr, nullptr};
-    int64_t *d_row_offsets = nullptr;
+    // `st` / `scratch` alias slot 0's (the lane b2s_infer_device, timers and the L2 flush run on)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     bool zero_copy_out = false;
@@ -201,25 +206,24 @@ void free_stream(Stream *s)
 {
     Global &g = G();
     cudaSetDevice(s->device);
-    if (s->st) cudaStreamSynchronize(s->st);
+    for (Slot &sl : s->slots)
+        if (sl.st) cudaStreamSynchronize(sl.st);
     for (Slot &sl : s->slots) {
         if (sl.ev) cudaEventDestroy(sl.ev);
         for (int i = 0; i < kMaxIO; ++i) {
             g.arena.release(sl.h_in[i], s->in_bytes[i]);
             g.arena.release(sl.h_out[i], s->out_bytes[i]);
+            if (sl.d_in[i]) cudaFree(sl.d_in[i]);
+            if (sl.d_out[i]) cudaFree(sl.d_out[i]);
         }
         g.arena.release(reinterpret_cast<unsigned char *>(sl.h_row_offsets), (size_t)(s->max_rows + 1) * 8);
+        if (sl.d_row_offsets) cudaFree(sl.d_row_offsets);
+        if (sl.scratch) {
+            if (s->model) s->model->on_stream_destroy(sl.scratch);
+            cudaFree(sl.scratch);
+        }
+        if (sl.st) cudaStreamDestroy(sl.st);
     }
-    for (int i = 0; i < kMaxIO; ++i) {
-        if (s->d_in[i]) cudaFree(s->d_in[i]);
-        if (s->d_out[i]) cudaFree(s->d_out[i]);
-    }
-    if (s->d_row_offsets) cudaFree(s->d_row_offsets);
-    if (s->scratch) {
-        if (s->model) s->model->on_stream_destroy(s->scratch);
-        cudaFree(s->scratch);
-    }
-    if (s->st) cudaStreamDestroy(s->st);
     delete s;
 }
 
@@ -242,27 +246,27 @@ int submit_slot(Model *m, Stream *s, int slot_idx, int64_t n_rows, const int64_t
             bytes = (size_t)n_rows * s->in_row_bytes[i];
         }
         if (bytes > s->in_bytes[i]) return fail(B2S_ERR_INVALID, "batch exceeds the stream's staging capacity");
-        if (bytes) B2S_CUDA(cudaMemcpyAsync(s->d_in[i], sl.h_in[i], bytes, cudaMemcpyHostToDevice, s->st));
-        d_in[i] = s->d_in[i];
+        if (bytes) B2S_CUDA(cudaMemcpyAsync(sl.d_in[i], sl.h_in[i], bytes, cudaMemcpyHostToDevice, sl.st));
+        d_in[i] = sl.d_in[i];
     }
     if (ragged) {
         if (row_offsets != sl.h_row_offsets) memcpy(sl.h_row_offsets, row_offsets, (size_t)(n_rows + 1) * 8);
-        B2S_CUDA(cudaMemcpyAsync(s->d_row_offsets, sl.h_row_offsets, (size_t)(n_rows + 1) * 8,
-                                 cudaMemcpyHostToDevice, s->st));
+        B2S_CUDA(cudaMemcpyAsync(sl.d_row_offsets, sl.h_row_offsets, (size_t)(n_rows + 1) * 8,
+                                 cudaMemcpyHostToDevice, sl.st));
     }
-    for (int o = 0; o < info.n_outputs; ++o) d_out[o] = s->zero_copy_out ? (void *)sl.h_out[o] : s->d_out[o];
+    for (int o = 0; o < info.n_outputs; ++o) d_out[o] = s->zero_copy_out ? (void *)sl.h_out[o] : sl.d_out[o];
     LaunchInfo li;
     li.h_row_offsets = ragged ? sl.h_row_offsets : nullptr;
     li.max_rows = s->max_rows;
     li.max_row_elems = s->max_row_elems;
-    B2S_TRY(m->launch(s->st, n_rows, d_in, d_out, ragged ? s->d_row_offsets : nullptr, s->scratch, s->scratch_bytes, li));
+    B2S_TRY(m->launch(sl.st, n_rows, d_in, d_out, ragged ? sl.d_row_offsets : nullptr, sl.scratch, s->scratch_bytes, li));
     if (!s->zero_copy_out) {
         for (int o = 0; o < info.n_outputs; ++o) {
             const size_t bytes = (size_t)n_rows * s->out_row_bytes[o];
-            if (bytes) B2S_CUDA(cudaMemcpyAsync(sl.h_out[o], s->d_out[o], bytes, cudaMemcpyDeviceToHost, s->st));
+            if (bytes) B2S_CUDA(cudaMemcpyAsync(sl.h_out[o], sl.d_out[o], bytes, cudaMemcpyDeviceToHost, sl.st));
         }
     }
-    B2S_CUDA(cudaEventRecord(sl.ev, s->st));
+    B2S_CUDA(cudaEventRecord(sl.ev, sl.st));
     sl.n_rows = n_rows;
     return 0;
 }
@@ -438,8 +442,7 @@ int b2s_stream_create(b2s_model_t model, int64_t max_rows, int64_t max_row_elems
         return code;
     };
     cudaError_t e = cudaSetDevice(s->device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
-    if (e != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
+    if (e != cudaSuccess) return bail(fail_cuda(e, "cudaSetDevice"));
     size_t total_out = 0;
     bool ragged = false;
     for (int i = 0; i < info.n_inputs; ++i) {
@@ -453,42 +456,46 @@ int b2s_stream_create(b2s_model_t model, int64_t max_rows, int64_t max_row_elems
             s->in_row_bytes[i] = (size_t)info.in_row_elems[i] * es;
             s->in_bytes[i] = (size_t)max_rows * s->in_row_bytes[i];
         }
-        e = cudaMalloc(&s->d_in[i], s->in_bytes[i] ? s->in_bytes[i] : 256);
-        if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(stream input)"));
     }
     for (int o = 0; o < info.n_outputs; ++o) {
         s->out_row_bytes[o] = (size_t)info.out_row_elems[o] * dtype_size(info.out_dtype[o]);
         s->out_bytes[o] = (size_t)max_rows * s->out_row_bytes[o];
         total_out += s->out_bytes[o];
-        e = cudaMalloc(&s->d_out[o], s->out_bytes[o] ? s->out_bytes[o] : 256);
-        if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(stream output)"));
     }
     const char *zc = getenv("B2S_ZEROCOPY_OUT");
     s->zero_copy_out = (total_out <= kZeroCopyOutMax) && !(zc && zc[0] == '0');
-    if (ragged) {
-        e = cudaMalloc(reinterpret_cast<void **>(&s->d_row_offsets), (size_t)(max_rows + 1) * 8);
-        if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(row offsets)"));
-    }
     s->scratch_bytes = m->scratch_bytes(max_rows, max_row_elems);
-    e = cudaMalloc(&s->scratch, s->scratch_bytes);
-    if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(stream scratch)"));
-    e = cudaMemset(s->scratch, 0, s->scratch_bytes);
-    if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMemset(stream scratch)"));
     s->slots.resize(n_slots);
     for (Slot &sl : s->slots) {
+        e = cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
         e = cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming);
         if (e != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
         for (int i = 0; i < info.n_inputs; ++i) {
+            e = cudaMalloc(&sl.d_in[i], s->in_bytes[i] ? s->in_bytes[i] : 256);
+            if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(slot input)"));
             sl.h_in[i] = g.arena.alloc(s->in_bytes[i]);
             if (!sl.h_in[i]) return bail(fail(B2S_ERR_OOM, "CUDA out of memory. pinned staging arena exhausted (input slot of %zu bytes)", s->in_bytes[i]));
         }
         for (int o = 0; o < info.n_outputs; ++o) {
+            e = cudaMalloc(&sl.d_out[o], s->out_bytes[o] ? s->out_bytes[o] : 256);
+            if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(slot output)"));
             sl.h_out[o] = g.arena.alloc(s->out_bytes[o]);
             if (!sl.h_out[o]) return bail(fail(B2S_ERR_OOM, "CUDA out of memory. pinned staging arena exhausted (output slot of %zu bytes)", s->out_bytes[o]));
         }
         sl.h_row_offsets = reinterpret_cast<int64_t *>(g.arena.alloc((size_t)(max_rows + 1) * 8));
         if (!sl.h_row_offsets) return bail(fail(B2S_ERR_OOM, "CUDA out of memory. pinned staging arena exhausted (row offsets)"));
+        if (ragged) {
+            e = cudaMalloc(reinterpret_cast<void **>(&sl.d_row_offsets), (size_t)(max_rows + 1) * 8);
+            if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(row offsets)"));
+        }
+        e = cudaMalloc(&sl.scratch, s->scratch_bytes);
+        if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMalloc(slot scratch)"));
+        e = cudaMemset(sl.scratch, 0, s->scratch_bytes);
+        if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMemset(slot scratch)"));
     }
+    s->st = s->slots[0].st;
+    s->scratch = s->slots[0].scratch;
     std::lock_guard<std::mutex> l(g.mu);
     g.streams.push_back(s);
     *out_stream = (b2s_stream_t)g.streams.size();
@@ -523,7 +530,7 @@ int b2s_stream_synchronize(b2s_stream_t stream)
     Stream *s = get_stream(stream);
     if (!s) return fail(B2S_ERR_INVALID, "b2s_stream_synchronize: bad handle");
     B2S_CUDA(cudaSetDevice(s->device));
-    B2S_CUDA(cudaStreamSynchronize(s->st));
+    for (Slot &sl : s->slots) B2S_CUDA(cudaStreamSynchronize(sl.st));
     return 0;
 }
 

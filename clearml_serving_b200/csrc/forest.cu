@@ -436,6 +436,8 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
                     if (++spins > B2S_SPIN_LIMIT) __trap();
                 }
                 if (r == 0) B2S_STAMP(3);
+                if (r == 1) B2S_STAMP(5);        // rank 1's block landed
+                if (r == C - 1) B2S_STAMP(6);    // last rank's block landed
                 const int t_first = ch * chunk_trees + (int)r * TPC;
                 const int tcount = max(0, min(TPC, T - t_first));
                 const acc_t *buf = leafbuf + (size_t)r * TPC * 16 + row16;

@@ -18,7 +18,34 @@ model = native.Model(pm.kind, pm.blob, 0)
 stream = native.Stream(model, 4096, 0, 2)
 timer = native.Timer(stream)
 rng = np.random.default_rng(0)
-for rows in (1, 32, 64, 256, 1024, 4096):
+def one_forest(n_trees):
+    f = orc.synth_xgb_forest(n_trees, 6, 32, seed=0)
+    pmm = formats.pack_forest(f, "xgb", base=0.5)
+    mm = native.Model(pmm.kind, pmm.blob, 0)
+    ss = native.Stream(mm, 64, 0, 2)
+    X = rng.standard_normal((64, 32)).astype(np.float32)
+    di = native.DeviceBuffer(X.nbytes); di.upload(X)
+    do = native.DeviceBuffer(64 * 4)
+    tt = native.Timer(ss)
+    for _ in range(5):
+        ss.infer_device(64, [di.ptr], [do.ptr])
+    tt.start()
+    for _ in range(50):
+        ss.infer_device(64, [di.ptr], [do.ptr])
+    tt.stop()
+    w = tt.elapsed_ms() / 50
+    b = (ctypes.c_longlong * 64)()
+    native.check(native.lib().b2s_debug_read(mm.handle, b))
+    s0 = np.array(b[:]).reshape(8, 8)[0]
+    print("trees=%d rows=64 warm50=%.2fus  cta0: load=%d traverse+publish=%d first_wait=%d sum=%d total=%d" % (
+        n_trees, w * 1e3, s0[1] - s0[0], s0[2] - s0[1], s0[3] - s0[2], s0[4] - s0[3], s0[4] - s0[0]))
+    di.free(); do.free(); ss.destroy(); mm.free()
+
+
+for nt in (16, 128, 256, 512):
+    one_forest(nt)
+
+for rows in (1, 64, 1024, 4096):
     X = rng.standard_normal((rows, 32)).astype(np.float32)
     d_in = native.DeviceBuffer(X.nbytes); d_in.upload(X)
     d_out = native.DeviceBuffer(rows * 4)
@@ -43,6 +70,7 @@ for rows in (1, 32, 64, 256, 1024, 4096):
         s = st[r]
         if s[0] == 0:
             continue
-        print("   cta%d: xtile=%d traverse=%d cluster_sync=%d sum=%d  total=%d cycles" % (
-            r, s[1] - s[0], s[2] - s[1], s[3] - s[2], (s[4] - s[3]) if s[4] else -1, (s[4] if s[4] else s[3]) - s[0]))
+        print("   cta%d: load=%d traverse+publish=%d first_wait=%d sum=%d (rank1 landed +%d, last rank landed +%d after first_wait) total=%d cycles" % (
+            r, s[1] - s[0], s[2] - s[1], s[3] - s[2], (s[4] - s[3]) if s[4] else -1, (s[5] - s[3]) if s[5] else -1,
+            (s[6] - s[3]) if s[6] else -1, (s[4] if s[4] else s[2]) - s[0]))
     d_in.free(); d_out.free()
