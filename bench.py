@@ -348,7 +348,8 @@ def _bert_workload(native, device, steps, warmup, cpu_seconds):
     inflight = []
     for k in range(steps):
         if len(inflight) == 2:
-            stream.wait(inflight.pop(0)[0])
+            item = inflight.pop(0)      # keep the output buffers alive until the scatter has run
+            stream.wait(item[0])
         ev, outs, keep = stream.infer_batch(sets[k % n_sets][1])
         inflight.append((ev, outs, keep))
     for it in inflight:

@@ -311,14 +311,17 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
     const int chunk_trees = (int)C * TPC;
 
     // smem carve-up
+    constexpr int VEC = 16 / (int)sizeof(acc_t);   // values per 128-bit shared-memory load
+    const int LD = chunk_trees + VEC;              // leaf-matrix row pitch: +16 B keeps 128-bit row reads conflict-free
+    constexpr int SLD = TPC + VEC;                 // pitch of the local staging block
     uint2 *snodes = reinterpret_cast<uint2 *>(smem);
-    acc_t *leafbuf = reinterpret_cast<acc_t *>(smem + slice_cap_bytes);                       // [chunk_trees][16]
-    float *xs = reinterpret_cast<float *>(smem + slice_cap_bytes + (size_t)chunk_trees * 16 * sizeof(acc_t));  // [F][17]
+    acc_t *leafbuf = reinterpret_cast<acc_t *>(smem + slice_cap_bytes);                       // [16 rows][LD]: row-major per ROW
+    float *xs = reinterpret_cast<float *>(smem + slice_cap_bytes + (size_t)16 * LD * sizeof(acc_t));  // [F][17]
     uint32_t *toff = reinterpret_cast<uint32_t *>(xs + (size_t)F * 17);                       // [TPC + 1]
     uint64_t *bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(toff + TPC + 1) + 7) & ~(uintptr_t)7);
     uint64_t *load_bar = bars;            // tree slice landed (this CTA)
     uint64_t *chunk_bar = bars + 1;       // [C] in rank 0: rank r's leaf values landed
-    // this CTA's leaf values [TPC][16], staged locally and pushed to rank 0 with ONE bulk copy
+    // this CTA's leaf values [16 rows][SLD], staged locally and pushed to rank 0 with one bulk copy per row
     acc_t *stage_leaf = reinterpret_cast<acc_t *>((reinterpret_cast<uintptr_t>(chunk_bar + 8) + 127) & ~(uintptr_t)127);
 
     B2S_STAMP(0);
@@ -328,6 +331,9 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
+    // split-phase cluster barrier: arrive now, wait only right before the first remote access, so the
+    // start-up skew between the CTAs of the cluster hides behind the tree-slice load and the traversal
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
 
     const int n_chunks = (T + chunk_trees - 1) / chunk_trees;
     const uint32_t leaf_remote = map_to_rank(leafbuf, 0);
@@ -351,7 +357,7 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
         if (rank == 0 && threadIdx.x == 32) {   // arm the per-rank arrival barriers with the bytes each rank pushes
             for (uint32_t r = 1; r < C; ++r) {
                 const int n_r = max(0, min(TPC, T - (ch * (int)C + (int)r) * TPC));
-                if (n_r > 0) mbar_expect_tx_cta(&chunk_bar[r], (uint32_t)(n_r * 16 * sizeof(acc_t)));
+                if (n_r > 0) mbar_expect_tx_cta(&chunk_bar[r], (uint32_t)(16 * TPC * sizeof(acc_t)));
                 else mbar_arrive_cta(&chunk_bar[r]);
             }
         }
@@ -363,7 +369,6 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
                 const int r = i / F, f = i - r * F;
                 xs[f * 17 + r] = (r < rows_here) ? __ldg(src + i) : 0.0f;
             }
-            cluster_sync_all();   // mbarrier inits of rank 0 are visible before any remote arrive
         }
         __syncthreads();
         if (n_my > 0) {
@@ -412,19 +417,20 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
                 acc_t v;
                 if (F64) v = (acc_t)__ldg(p.leaf64 + cur[u].x);
                 else v = (acc_t)__uint_as_float(cur[u].x);
-                if (rank == 0) leafbuf[tl * 16 + row16] = v;          // rank 0: straight into the leaf matrix
-                else stage_leaf[tl * 16 + row16] = v;                 // others: local staging
+                if (rank == 0) leafbuf[row16 * LD + tl] = v;          // rank 0: straight into the leaf matrix
+                else stage_leaf[row16 * SLD + tl] = v;                // others: local staging
             }
         }
         // publish: rank 0 arrives locally; every other rank pushes its block with one bulk DSMEM copy that
         // completes bytes on its barrier in rank 0 (generic-proxy writes -> async-proxy read needs the fence)
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if (ch == 0) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");  // peers started, barriers initialised
         __syncthreads();
-        if (threadIdx.x == 0) {
-            if (rank == 0) mbar_arrive_cta(&chunk_bar[0]);
-            else if (n_my > 0)
-                bulk_s2s_cluster(leaf_remote + (uint32_t)((size_t)rank * TPC * 16 * sizeof(acc_t)), stage_leaf,
-                                 (uint32_t)(n_my * 16 * sizeof(acc_t)), bar_remote);
+        if (rank == 0) {
+            if (threadIdx.x == 0) mbar_arrive_cta(&chunk_bar[0]);
+        } else if (warp == 0 && lane < 16 && n_my > 0) {   // one 16-byte-aligned row segment per lane
+            bulk_s2s_cluster(leaf_remote + (uint32_t)(((size_t)lane * LD + (size_t)rank * TPC) * sizeof(acc_t)),
+                             stage_leaf + (size_t)lane * SLD, (uint32_t)(TPC * sizeof(acc_t)), bar_remote);
         }
         B2S_STAMP(2);
 
@@ -440,32 +446,43 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
                 if (r == C - 1) B2S_STAMP(6);    // last rank's block landed
                 const int t_first = ch * chunk_trees + (int)r * TPC;
                 const int tcount = max(0, min(TPC, T - t_first));
-                const acc_t *buf = leafbuf + (size_t)r * TPC * 16 + row16;
-                // software-pipelined: the loads of group g+1 are in flight while group g is added
-                acc_t a[16], b[16];
-                const int ngroups = tcount / 16;
-                if (ngroups > 0) {
+                const acc_t *bp = leafbuf + (size_t)row16 * LD + (size_t)r * TPC;   // this lane's row, rank r's trees
+                if (tcount == TPC) {
+                    // straight-line, fully unrolled: 128-bit loads of block b+1 are issued among the dependent
+                    // adds of block b, so the chain runs at the 4-cycle FADD/DADD issue distance
+                    constexpr int BLK = 8;                 // vectors per block
+                    constexpr int NBLK = TPC / (VEC * BLK);
+                    typedef typename std::conditional<F64, double2, float4>::type vec_t;
+                    const vec_t *vp = reinterpret_cast<const vec_t *>(bp);
+                    vec_t cur[BLK], nxt[BLK];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) a[k] = buf[k * 16];
-                }
-                for (int g = 0; g < ngroups; g += 2) {
-                    if (g + 1 < ngroups) {
+                    for (int k = 0; k < BLK; ++k) cur[k] = vp[k];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) b[k] = buf[((g + 1) * 16 + k) * 16];
-                    }
+                    for (int blk = 0; blk < NBLK; ++blk) {
+                        if (blk + 1 < NBLK) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) acc = acc + a[k];
-                    if (g + 1 < ngroups) {
-                        if (g + 2 < ngroups) {
-#pragma unroll
-                            for (int k = 0; k < 16; ++k) a[k] = buf[((g + 2) * 16 + k) * 16];
+                            for (int k = 0; k < BLK; ++k) nxt[k] = vp[(blk + 1) * BLK + k];
                         }
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) acc = acc + b[k];
+                        for (int k = 0; k < BLK; ++k) {
+                            if (F64) {
+                                const double2 d = *reinterpret_cast<const double2 *>(&cur[k]);
+                                acc = acc + (acc_t)d.x;
+                                acc = acc + (acc_t)d.y;
+                            } else {
+                                const float4 f4 = *reinterpret_cast<const float4 *>(&cur[k]);
+                                acc = acc + (acc_t)f4.x;
+                                acc = acc + (acc_t)f4.y;
+                                acc = acc + (acc_t)f4.z;
+                                acc = acc + (acc_t)f4.w;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < BLK; ++k) cur[k] = nxt[k];
                     }
+                } else {
+                    for (int t = 0; t < tcount; ++t) acc = acc + bp[t];
                 }
-                int t = ngroups * 16;
-                for (; t < tcount; ++t) acc = acc + buf[t * 16];
             }
             B2S_STAMP(4);
         }
@@ -777,9 +794,10 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
             int C = 1;
             while (C < 8 && C * tpc < (int)h.n_trees) C *= 2;
             const size_t cap = (size_t)round_up((int64_t)max_nodes * 8 + 16, 128);
-            const size_t leaf = (size_t)C * tpc * 16 * (m->f64 ? 8 : 4);
+            const size_t esz = m->f64 ? 8 : 4, vec = 16 / esz;
+            const size_t leaf = (size_t)16 * ((size_t)C * tpc + vec) * esz;
             const size_t smem = cap + leaf + (size_t)h.n_features * 17 * 4 + (size_t)(tpc + 1) * 4 + 16 + 9 * 8 + 256 +
-                                (size_t)tpc * 16 * (m->f64 ? 8 : 4);   // + local leaf staging block
+                                (size_t)16 * ((size_t)tpc + vec) * esz;   // + local leaf staging block
             if (smem <= (size_t)want) {
                 m->staged_ok = true;
                 m->staged_C = C;
