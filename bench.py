@@ -103,6 +103,8 @@ class ClockSampler(object):
 
 
 def _dist_setup(n_gpus):
+    """One process per GPU (torchrun).  NCCL on the GPU box; B2S_DIST_BACKEND=gloo lets the same code
+    path run on CPU (tests/test_multi_rank_cpu.py, world_size 2)."""
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -110,24 +112,33 @@ def _dist_setup(n_gpus):
     if world > 1:
         import torch
         import torch.distributed as dist_mod
-        torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        backend = os.environ.get("B2S_DIST_BACKEND", "nccl")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist_mod.init_process_group(backend)
         dist = dist_mod
     return rank, world, local, dist
+
+
+def _dist_device(dist, local):
+    return "cuda:%d" % local if dist.get_backend() == "nccl" else "cpu"
 
 
 def _barrier_sync(dist, local):
     if dist is not None:
         import torch
         dist.barrier()
-        torch.cuda.synchronize(local)
+        if dist.get_backend() == "nccl":
+            torch.cuda.synchronize(local)
 
 
 def _max_over_ranks(dist, local, x):
     if dist is None:
         return float(x)
     import torch
-    t = torch.tensor([float(x)], device="cuda:%d" % local, dtype=torch.float64)
+    t = torch.tensor([float(x)], device=_dist_device(dist, local), dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
@@ -136,9 +147,14 @@ def _sum_over_ranks(dist, local, x):
     if dist is None:
         return float(x)
     import torch
-    t = torch.tensor([float(x)], device="cuda:%d" % local, dtype=torch.float64)
+    t = torch.tensor([float(x)], device=_dist_device(dist, local), dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def whole_job_value(world, units_per_rank_per_step, steps, max_seconds):
+    """`value` of the contract: units all ranks processed / the slowest rank's time (weak scaling)."""
+    return world * units_per_rank_per_step * steps / max_seconds
 
 
 def _make_model():
@@ -517,7 +533,7 @@ def run_b200(args):
         kernel_s = cold_ms * 1e-3 / K
         achieved = algo / kernel_s / 1e9
         cpu = _cpu_baseline(forest, args.cpu_seconds) if world == 1 else None
-        value = world * MAX_BATCH * K / (cold_ms * 1e-3)
+        value = whole_job_value(world, MAX_BATCH, K, cold_ms * 1e-3)
         line = dict(
             metric="requests/sec", value=value, unit="requests/s", n_gpus=world, steps=K, warmup=W,
             ms_per_step=cold_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,

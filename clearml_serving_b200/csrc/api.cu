@@ -51,6 +51,7 @@ namespace {
 constexpr int kMaxDevices = 16;
 constexpr int kMaxIO = 4;
 constexpr size_t kZeroCopyOutMax = 64 * 1024;
+constexpr size_t kZeroCopyInMax = 16 * 1024;
 
 // ---- shared pinned arena: first-fit free list with coalescing ---------------------------------
 struct Arena {
@@ -150,6 +151,7 @@ struct Stream {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     bool zero_copy_out = false;
+    bool zero_copy_in = false;   // small fixed-width inputs: kernels read the mapped pinned slot directly
     std::vector<Slot> slots;
     int next = 0;
     std::mutex mu;
@@ -246,8 +248,12 @@ int submit_slot(Model *m, Stream *s, int slot_idx, int64_t n_rows, const int64_t
             bytes = (size_t)n_rows * s->in_row_bytes[i];
         }
         if (bytes > s->in_bytes[i]) return fail(B2S_ERR_INVALID, "batch exceeds the stream's staging capacity");
-        if (bytes) B2S_CUDA(cudaMemcpyAsync(sl.d_in[i], sl.h_in[i], bytes, cudaMemcpyHostToDevice, sl.st));
-        d_in[i] = sl.d_in[i];
+        if (s->zero_copy_in && bytes <= kZeroCopyInMax) {
+            d_in[i] = sl.h_in[i];   // UVA: the mapped pinned slot is addressable from the device (one PCIe read, no copy op)
+        } else {
+            if (bytes) B2S_CUDA(cudaMemcpyAsync(sl.d_in[i], sl.h_in[i], bytes, cudaMemcpyHostToDevice, sl.st));
+            d_in[i] = sl.d_in[i];
+        }
     }
     if (ragged) {
         if (row_offsets != sl.h_row_offsets) memcpy(sl.h_row_offsets, row_offsets, (size_t)(n_rows + 1) * 8);
@@ -464,6 +470,8 @@ int b2s_stream_create(b2s_model_t model, int64_t max_rows, int64_t max_row_elems
     }
     const char *zc = getenv("B2S_ZEROCOPY_OUT");
     s->zero_copy_out = (total_out <= kZeroCopyOutMax) && !(zc && zc[0] == '0');
+    const char *zci = getenv("B2S_ZEROCOPY_IN");
+    s->zero_copy_in = !ragged && info.kind != B2S_MODEL_GRAPH && !(zci && zci[0] == '0');
     s->scratch_bytes = m->scratch_bytes(max_rows, max_row_elems);
     s->slots.resize(n_slots);
     for (Slot &sl : s->slots) {

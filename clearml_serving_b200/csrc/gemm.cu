@@ -273,22 +273,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // Warp roles (384 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM owner, 3 idle, 4-11 epilogue
 // (warp w drains TMEM lane quadrant w % 4, column half (w - 4) / 4).
 // ---------------------------------------------------------------------------------------------
-constexpr int G2_BN = 256;
-constexpr int G2_STAGES = 4;
 constexpr int G2_THREADS = 384;
+template <int G2_BN, int G2_STAGES>
 struct G2Smem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
-    static constexpr int B_BYTES = G2_BN * GEMM_BK * 2;     // 32 KB
+    static constexpr int B_BYTES = G2_BN * GEMM_BK * 2;     // 32 KB (BN 256) / 16 KB (BN 128)
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = G2_STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + (2 * G2_STAGES + 4) * 8 + 16 + 1024;
 };
 
+// BN = 256 (4 stages) for wide outputs; BN = 128 (6 stages) when 128 x 256 tiles would leave the last
+// wave of the persistent grid mostly empty (e.g. M = 7400 tokens, N = 768: 174 tiles on 148 SMs).
+template <int G2_BN, int G2_STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                           int M, int N, int K, GemmEpilogue ep)
 {
-    using S = G2Smem;
+    using S = G2Smem<G2_BN, G2_STAGES>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFFSET);
@@ -316,7 +318,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, 2 * G2_BN);   // two accumulators
         tmem_relinquish();
     }
     tc_fence_before();
@@ -379,18 +381,19 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const int row = m_blk * GEMM_BM + q * 32 + lane;
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * 128);
+            constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
-                if (c == 3) {   // last TMEM read of this warp: hand the accumulator back before the math
+                if (c == NCH - 1) {   // last TMEM read of this warp: hand the accumulator back before the math
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                epilogue_store32(ep, row, n_blk * G2_BN + half * 128 + c * 32, M, N, v);
+                epilogue_store32(ep, row, n_blk * G2_BN + half * HALF + c * 32, M, N, v);
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
@@ -400,7 +403,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, 2 * G2_BN);
     }
 }
 
@@ -462,44 +465,62 @@ static int launch_gemm(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap
     return 0;
 }
 
+static int g_num_sms()
+{
+    static int n = []() {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+
+template <int BN, int STAGES>
 static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
                                   const GemmEpilogue &ep)
 {
+    using S = G2Smem<BN, STAGES>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    static int n_sms = 148;
     std::call_once(once, []() {
-        attr_err = cudaFuncSetAttribute(gemm_tn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Smem::TOTAL);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_err = cudaFuncSetAttribute(gemm_tn_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     });
     if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(gemm v2)");
-    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + G2_BN - 1) / G2_BN);
-    const int grid = tiles < n_sms ? tiles : n_sms;
-    gemm_tn_persistent_kernel<<<grid, G2_THREADS, G2Smem::TOTAL, st>>>(ta, tb, M, N, K, ep);
+    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < g_num_sms() ? tiles : g_num_sms();
+    gemm_tn_persistent_kernel<BN, STAGES><<<grid, G2_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
 }
 
-// tile width for an N-column weight (also the box height of its tensor map)
-int gemm_bn_for(int N)
+// 128 x 256 tiles move 1.5x fewer operand bytes per flop than 128 x 128, but on a persistent grid the
+// cost is waves x tile time: pick the shape with the smaller estimate.
+bool gemm_prefer_bn256(int M, int N)
 {
-    static const bool v1_only = []() { const char *e = getenv("B2S_GEMM_V1"); return e && e[0] == '1'; }();
-    if (N <= 64) return 64;
-    return (N >= 256 && !v1_only) ? 256 : 128;
+    if (N < 256) return false;
+    const int sms = g_num_sms(), mt = (M + GEMM_BM - 1) / GEMM_BM;
+    const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+    const double e256 = (double)((t256 + sms - 1) / sms) * 2.0;
+    const double e128 = (double)((t128 + sms - 1) / sms) * 1.15;
+    return e256 <= e128;
 }
 
-// GEMM with caller-provided tensor maps (graph executor: maps are cached per stream / per model)
-int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
+// narrow tile width for an N-column weight (box height of its "small" tensor map)
+int gemm_bn_for(int N) { return N <= 64 ? 64 : 128; }
+
+// GEMM with caller-provided tensor maps (graph executor: maps are cached per stream / per model).
+// `tb` must have been built with box height `bn` (64, 128 or 256).
+int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, int M, int N, int K,
                  const GemmEpilogue &ep)
 {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
-    const int bn = gemm_bn_for(N);
+    static const bool v1_only = []() { const char *e = getenv("B2S_GEMM_V1"); return e && e[0] == '1'; }();
     if (bn == 64) return launch_gemm<64, 6>(st, ta, tb, M, N, K, ep);
-    if (bn == 256) return launch_gemm_persistent(st, ta, tb, M, N, K, ep);
-    return launch_gemm<128, 6>(st, ta, tb, M, N, K, ep);
+    if (bn == 256) return launch_gemm_persistent<256, 4>(st, ta, tb, M, N, K, ep);
+    if (v1_only) return launch_gemm<128, 6>(st, ta, tb, M, N, K, ep);
+    return launch_gemm_persistent<128, 6>(st, ta, tb, M, N, K, ep);
 }
 
 // C = epilogue(A[M,K] . B[N,K]^T).  A: lda elements per row, B: ldb elements per row.
@@ -508,9 +529,10 @@ int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t 
 {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     CUtensorMap ta, tb;
+    const int bn = N <= 64 ? 64 : (gemm_prefer_bn256(M, N) ? 256 : 128);
     B2S_TRY(make_tmap_2d_kmajor(&ta, A, M, K, lda, GEMM_BM, ep.is_bf16));
-    B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, gemm_bn_for(N), ep.is_bf16));
-    return gemm_tn_maps(st, ta, tb, M, N, K, ep);
+    B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, bn, ep.is_bf16));
+    return gemm_tn_maps(st, ta, tb, bn, M, N, K, ep);
 }
 
 }  // namespace b2s

@@ -33,9 +33,10 @@ namespace b2s {
 // kernels defined in gemm.cu / norm.cu / attention.cu
 int make_tmap_2d_kmajor(CUtensorMap *out, const void *base, int64_t rows, int64_t K, int64_t ld_elems, int box_rows,
                         int is_bf16);
-int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
+int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, int M, int N, int K,
                  const GemmEpilogue &ep);
 int gemm_bn_for(int N);
+bool gemm_prefer_bn256(int M, int N);
 int layernorm(cudaStream_t st, const float *in, int64_t rows, int H, const float *gamma, const float *beta, float eps,
               void *out16, float *out32);
 int embed_layernorm(cudaStream_t st, const int32_t *ids, const int32_t *types, const int64_t *cu_seqlens, int n_seq,
@@ -84,7 +85,8 @@ struct GraphModel : Model {
     std::vector<GTensor> tensors;
     std::vector<GBuffer> buffers;
     std::vector<GOp> ops;
-    std::vector<CUtensorMap> bmap;  // weight tensor maps, one per op
+    std::vector<CUtensorMap> bmap;     // weight tensor maps (narrow tiles: box 64 / 128), one per op
+    std::vector<CUtensorMap> bmap256;  // weight tensor maps for 128 x 256 tiles (N >= 256)
     unsigned char *d_data = nullptr;
     std::mutex mu;
     std::map<void *, Plan> plans;   // keyed by the stream's scratch base
@@ -188,7 +190,10 @@ struct GraphModel : Model {
                 ep.act = op.a[5];
                 ep.out_f32 = op.a[8];
                 ep.is_bf16 = 0;
-                B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap[i], M, op.a[6], op.a[7], ep));
+                if (gemm_prefer_bn256(M, op.a[6]))
+                    B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap256[i], 256, M, op.a[6], op.a[7], ep));
+                else
+                    B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap[i], gemm_bn_for(op.a[6]), M, op.a[6], op.a[7], ep));
                 break;
             }
             case OP_LAYERNORM: {
@@ -297,11 +302,14 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
     if (e != cudaSuccess) return bail(fail_cuda(e, "cudaMemcpy(graph weights)"));
     // weight tensor maps
     m->bmap.resize(m->ops.size());
+    m->bmap256.resize(m->ops.size());
     int64_t flops_fixed = 0;
     for (size_t i = 0; i < m->ops.size(); ++i) {
         const GOp &op = m->ops[i];
         if (op.opcode != OP_LINEAR) continue;
-        const int rc = make_tmap_2d_kmajor(&m->bmap[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], gemm_bn_for(op.a[6]), 0);
+        int rc = make_tmap_2d_kmajor(&m->bmap[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], gemm_bn_for(op.a[6]), 0);
+        if (rc == 0 && op.a[6] >= 256)
+            rc = make_tmap_2d_kmajor(&m->bmap256[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], 256, 0);
         if (rc != 0) return bail(rc);
         flops_fixed += 2LL * op.a[6] * op.a[7];
     }

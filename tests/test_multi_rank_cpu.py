@@ -1,0 +1,61 @@
+"""The N>1 path of bench.py on CPU: two processes, gloo backend (the GPU box runs the same helpers over
+NCCL).  Requests are independent, so ranks are replicas: no data-path collective, only the timing
+barrier, the max-over-ranks reduction and the whole-job aggregation are shared."""
+import os
+import subprocess
+import sys
+import textwrap
+
+from tests.conftest import ROOT
+
+
+def test_two_rank_gloo_timing_and_aggregation(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent('''
+        import json, os, sys, time
+        sys.path.insert(0, %r)
+        import bench
+        rank, world, local, dist = bench._dist_setup(2)
+        assert world == 2 and dist is not None and dist.get_backend() == "gloo"
+        bench._barrier_sync(dist, local)
+        # each rank is a replica serving its own 64-request batches; rank 1 is slower
+        my_seconds = 0.010 * (1 + rank)
+        mx = bench._max_over_ranks(dist, local, my_seconds)
+        total = bench._sum_over_ranks(dist, local, 100.0 * (rank + 1))
+        bench._barrier_sync(dist, local)
+        out = dict(rank=rank, mx=mx, total=total, value=bench.whole_job_value(world, 64, 10, mx))
+        print("RESULT " + json.dumps(out), flush=True)
+        dist.destroy_process_group()
+    ''' % ROOT))
+    env = dict(os.environ, B2S_DIST_BACKEND="gloo", MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", WORLD_SIZE="2")
+    procs = []
+    for r in range(2):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    import json
+    res = []
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        line = [l for l in o.splitlines() if l.startswith("RESULT ")][0]
+        res.append(json.loads(line[7:]))
+    for r in res:
+        assert abs(r["mx"] - 0.020) < 1e-12          # the slowest rank defines the step time
+        assert r["total"] == 300.0
+        assert abs(r["value"] - 2 * 64 * 10 / 0.020) < 1e-6
+
+
+def test_reference_arm_runs_on_rank0_only():
+    """`bench.py --impl reference` under a 2-rank launch: rank 0 prints the line, rank 1 exits 0 silently."""
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29732")
+    outs = []
+    for r in range(2):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                            "--steps", "20", "--warmup", "3"], env=e, capture_output=True, text=True, timeout=240)
+        assert p.returncode == 0, p.stderr
+        outs.append(p.stdout.strip())
+    import json
+    line = json.loads(outs[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and outs[1] == ""
