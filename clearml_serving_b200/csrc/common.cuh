@@ -62,6 +62,7 @@ struct GemmEpilogue {
     int act;               // 0 none, 1 GELU(erf), 2 ReLU, 3 tanh
     int out_f32;           // 1: C (and residual) fp32, 0: 16-bit like A/B
     int is_bf16;
+    int act_after;         // 1: activation applied AFTER the residual add (ResNet), 0: before (BERT)
 };
 
 // ---- internal model interface: each model kind implements launch() on a stream -----------------

@@ -1,0 +1,186 @@
+// conv.cu -- data-movement kernels that turn a convolutional network (ResNet class, BASELINE.json
+// configs[2]) into GEMMs on the tcgen05 kernel of gemm.cu (K6 of SURVEY.md 2.2, first form):
+//   * activations are NHWC fp16 with channels padded to a multiple of 8 (16-byte pixels), so a 1x1
+//     stride-1 convolution IS `gemm_tn` on the activation matrix [N*H*W, C] with the weight [Cout, C];
+//   * every other convolution (7x7 stem, 3x3, strided 1x1) gathers its receptive fields into a
+//     [N*OH*OW, KH*KW*C] matrix (im2col, 128-bit moves, zero padding folded in) and runs the same GEMM
+//     with BatchNorm folded into weight/bias and bias + ReLU (+ residual) fused in the epilogue;
+//   * max-pool / global average pool are plain coalesced NHWC kernels.
+// This is what tritonserver's libtorch backend does with cuDNN for the reference's pytorch endpoint
+// (clearml_serving/engines/triton/triton_helper.py:166-168,382-383; examples/pytorch).
+// The explicit im2col costs one extra write+read of the patch matrix (HBM-bound, ~50 MB per image for
+// ResNet-50); the implicit form (4-D TMA boxes feeding the UMMA mainloop directly) is the planned
+// replacement -- see DESIGN.md section 7.
+#include "common.cuh"
+
+#include <cuda_fp16.h>
+
+namespace b2s {
+
+// in: NCHW fp32 (in_dtype 0) or uint8 (in_dtype 4); out: NHWC fp16 with Cp >= C channels (zero padded)
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const void *__restrict__ in, int in_dtype, int64_t n_pix_total, int C, int HW, int Cp,
+                    __half *__restrict__ out)
+{
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // n*HW + hw
+    if (pix >= n_pix_total) return;
+    const int64_t n = pix / HW, hw = pix - n * HW;
+    __half *o = out + pix * Cp;
+    for (int c0 = 0; c0 < Cp; c0 += 8) {
+        __half v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            float f = 0.f;
+            if (c < C) {
+                const int64_t idx = (n * C + c) * HW + hw;
+                f = in_dtype == B2S_U8 ? (float)static_cast<const uint8_t *>(in)[idx] : static_cast<const float *>(in)[idx];
+            }
+            v[j] = __float2half_rn(f);
+        }
+        *reinterpret_cast<uint4 *>(o + c0) = *reinterpret_cast<const uint4 *>(v);
+    }
+}
+
+// out[row, (kh*KW + kw)*C + c] = in[n, oh*s - pad + kh, ow*s - pad + kw, c]  (0 outside), row = (n, oh, ow);
+// columns K..Kp-1 are zero.  One thread moves one 16-byte (8-channel) chunk.
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const __half *__restrict__ in, int64_t n_rows, int H, int W, int C, int KH, int KW, int stride, int pad,
+                   int OH, int OW, int Kp, __half *__restrict__ out)
+{
+    const int chunks = Kp >> 3;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * chunks) return;
+    const int64_t row = idx / chunks;
+    const int chunk = (int)(idx - row * chunks);
+    const int k = chunk << 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (k < KH * KW * C) {
+        const int tap = k / C, c = k - tap * C;
+        const int kh = tap / KW, kw = tap - kh * KW;
+        const int64_t n = row / ((int64_t)OH * OW);
+        const int rem = (int)(row - n * (int64_t)OH * OW);
+        const int oh = rem / OW, ow = rem - oh * OW;
+        const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+            v = *reinterpret_cast<const uint4 *>(in + ((n * H + ih) * (int64_t)W + iw) * C + c);
+    }
+    *reinterpret_cast<uint4 *>(out + row * Kp + k) = v;
+}
+
+// 3x3 stride-2 pad-1 max pooling, NHWC fp16, 8 channels per thread
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const __half *__restrict__ in, int64_t n_out_pix, int H, int W, int C, int OH, int OW,
+                    __half *__restrict__ out)
+{
+    const int cg = C >> 3;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_out_pix * cg) return;
+    const int64_t pix = idx / cg;
+    const int c = (int)(idx - pix * cg) << 3;
+    const int64_t n = pix / ((int64_t)OH * OW);
+    const int rem = (int)(pix - n * (int64_t)OH * OW);
+    const int oh = rem / OW, ow = rem - oh * OW;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int kh = 0; kh < 3; ++kh) {
+        const int ih = oh * 2 - 1 + kh;
+        if (ih < 0 || ih >= H) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+            const int iw = ow * 2 - 1 + kw;
+            if (iw < 0 || iw >= W) continue;
+            const uint4 u = *reinterpret_cast<const uint4 *>(in + ((n * H + ih) * (int64_t)W + iw) * C + c);
+            const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                m[2 * j] = fmaxf(m[2 * j], f.x);
+                m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+            }
+        }
+    }
+    __half v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __float2half_rn(m[j]);
+    *reinterpret_cast<uint4 *>(out + pix * C + c) = *reinterpret_cast<const uint4 *>(v);
+}
+
+// global average pool: [N, HW, C] fp16 -> [N, C] fp16 (fp32 accumulation in pixel order)
+__global__ void __launch_bounds__(256)
+avgpool_kernel(const __half *__restrict__ in, int64_t n_img, int HW, int C, __half *__restrict__ out)
+{
+    const int cg = C >> 3;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_img * cg) return;
+    const int64_t n = idx / cg;
+    const int c = (int)(idx - n * cg) << 3;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < HW; ++p) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(in + (n * HW + p) * (int64_t)C + c);
+        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            s[2 * j] += f.x;
+            s[2 * j + 1] += f.y;
+        }
+    }
+    __half v[8];
+    const float inv = 1.0f / (float)HW;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __float2half_rn(s[j] * inv);
+    *reinterpret_cast<uint4 *>(out + n * C + c) = *reinterpret_cast<const uint4 *>(v);
+}
+
+static unsigned blocks_for(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+int nchw_to_nhwc(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Cp, void *out)
+{
+    if (n_img <= 0) return 0;
+    if (Cp % 8 != 0 || Cp < C) return fail(B2S_ERR_INVALID, "nchw_to_nhwc: bad channel padding");
+    if (in_dtype != B2S_F32 && in_dtype != B2S_U8) return fail(B2S_ERR_INVALID, "nchw_to_nhwc: input must be float32 or uint8");
+    const int64_t pix = n_img * H * W;
+    nchw_to_nhwc_kernel<<<blocks_for(pix), 256, 0, st>>>(in, in_dtype, pix, C, H * W, Cp, static_cast<__half *>(out));
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int im2col_nhwc(cudaStream_t st, const void *in, int64_t n_img, int H, int W, int C, int KH, int KW, int stride, int pad,
+                int OH, int OW, int Kp, void *out)
+{
+    if (n_img <= 0) return 0;
+    if (C % 8 != 0 || Kp % 8 != 0 || Kp < KH * KW * C) return fail(B2S_ERR_INVALID, "im2col: channels / K padding must be multiples of 8");
+    const int64_t rows = n_img * OH * OW;
+    im2col_nhwc_kernel<<<blocks_for(rows * (Kp / 8)), 256, 0, st>>>(static_cast<const __half *>(in), rows, H, W, C, KH, KW,
+                                                                  stride, pad, OH, OW, Kp, static_cast<__half *>(out));
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int maxpool3x3s2(cudaStream_t st, const void *in, int64_t n_img, int H, int W, int C, int OH, int OW, void *out)
+{
+    if (n_img <= 0) return 0;
+    if (C % 8 != 0) return fail(B2S_ERR_INVALID, "maxpool: C must be a multiple of 8");
+    const int64_t pix = n_img * OH * OW;
+    maxpool3x3s2_kernel<<<blocks_for(pix * (C / 8)), 256, 0, st>>>(static_cast<const __half *>(in), pix, H, W, C, OH, OW,
+                                                                  static_cast<__half *>(out));
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int avgpool(cudaStream_t st, const void *in, int64_t n_img, int HW, int C, void *out)
+{
+    if (n_img <= 0) return 0;
+    if (C % 8 != 0) return fail(B2S_ERR_INVALID, "avgpool: C must be a multiple of 8");
+    avgpool_kernel<<<blocks_for(n_img * (C / 8)), 256, 0, st>>>(static_cast<const __half *>(in), n_img, HW, C,
+                                                               static_cast<__half *>(out));
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b2s

@@ -72,13 +72,14 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int row
             for (int j = 0; j < 32; ++j)
                 if (j < ncols) f[j] += __ldg(bias + col0 + j);
         }
-        if (ep.act == ACT_GELU) {
+        const int act_pre = ep.act_after ? ACT_NONE : ep.act;
+        if (act_pre == ACT_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        } else if (ep.act == ACT_RELU) {
+        } else if (act_pre == ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        } else if (ep.act == ACT_TANH) {
+        } else if (act_pre == ACT_TANH) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
         }
@@ -138,6 +139,10 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int row
                 } else {
                     for (int j = 0; j < ncols; ++j) f[j] += __half2float(R[j]);
                 }
+            }
+            if (ep.act_after && ep.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
             }
             if (ncols == 32 && (off & 7) == 0) {
 #pragma unroll
@@ -554,5 +559,6 @@ extern "C" B2S_API int b2s_op_gemm(int device, void *cuda_stream, const void *A,
     ep.act = act;
     ep.out_f32 = out_f32;
     ep.is_bf16 = is_bf16;
+    ep.act_after = 0;
     return gemm_tn(static_cast<cudaStream_t>(cuda_stream), A, K, B, K, M, N, K, ep);
 }

@@ -14,9 +14,10 @@
 // buffer whose row count is the stream's capacity (rows past the live batch are never stored).
 //
 // Blob layout ("B2SG"), little endian:
-//   header  {magic, version, n_tensors, n_buffers, n_ops, n_inputs, n_outputs, max_pos, out_buffer[4], in_dtype[4]}
+//   header  {magic, version, n_tensors, n_buffers, n_ops, n_inputs, n_outputs, max_pos, out_buffer[4], in_dtype[4],
+//            in_row_elems[4]}
 //   tensors n_tensors x {u32 dtype, u32 ndim, i64 shape[4], u64 offset, u64 nbytes}
-//   buffers n_buffers x {u32 dtype, u32 rows_kind (0 = per token, 1 = per sequence), i64 cols}
+//   buffers n_buffers x {u32 dtype, u32 rows_kind (0 = per token, k = k rows per batch item), i64 cols}
 //   ops     n_ops x {u32 opcode, i32 a[15], f32 f[4]}
 //   data    weights, each 256-byte aligned
 #include "common.cuh"
@@ -45,18 +46,28 @@ int embed_layernorm(cudaStream_t st, const int32_t *ids, const int32_t *types, c
 int gather_first(cudaStream_t st, const void *in, const int64_t *cu_seqlens, int n_seq, int H, void *out);
 int attention_varlen(cudaStream_t st, const void *qkv, const int64_t *cu_seqlens, const int32_t *key_mask, void *out,
                      int n_seq, int max_seqlen, int heads, int head_dim);
+// conv.cu
+int nchw_to_nhwc(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Cp, void *out);
+int im2col_nhwc(cudaStream_t st, const void *in, int64_t n_img, int H, int W, int C, int KH, int KW, int stride, int pad,
+                int OH, int OW, int Kp, void *out);
+int maxpool3x3s2(cudaStream_t st, const void *in, int64_t n_img, int H, int W, int C, int OH, int OW, void *out);
+int avgpool(cudaStream_t st, const void *in, int64_t n_img, int HW, int C, void *out);
 
 namespace {
 
-enum GraphOp { OP_EMBED_LN = 1, OP_LINEAR = 2, OP_LAYERNORM = 3, OP_ATTENTION = 4, OP_GATHER_FIRST = 5 };
+enum GraphOp {
+    OP_EMBED_LN = 1, OP_LINEAR = 2, OP_LAYERNORM = 3, OP_ATTENTION = 4, OP_GATHER_FIRST = 5,
+    OP_NCHW_TO_NHWC = 6, OP_IM2COL = 7, OP_MAXPOOL = 8, OP_AVGPOOL = 9
+};
 
 struct GHeader {
     char magic[4];
     uint32_t version, n_tensors, n_buffers, n_ops, n_inputs, n_outputs, max_pos;
     int32_t out_buffer[4];
     int32_t in_dtype[4];
+    int64_t in_row_elems[4];   // elements per batch row of input i, -1 = variable length (packed tokens)
 };
-static_assert(sizeof(GHeader) == 64, "graph header layout");
+static_assert(sizeof(GHeader) == 96, "graph header layout");
 struct GTensor {
     uint32_t dtype, ndim;
     int64_t shape[4];
@@ -64,7 +75,7 @@ struct GTensor {
 };
 static_assert(sizeof(GTensor) == 56, "graph tensor layout");
 struct GBuffer {
-    uint32_t dtype, rows_kind;
+    uint32_t dtype, rows_kind;   // rows_kind 0: one row per packed token; k >= 1: k rows per batch item
     int64_t cols;
 };
 static_assert(sizeof(GBuffer) == 16, "graph buffer layout");
@@ -90,6 +101,7 @@ struct GraphModel : Model {
     unsigned char *d_data = nullptr;
     std::mutex mu;
     std::map<void *, Plan> plans;   // keyed by the stream's scratch base
+    bool ragged = false;
 
     ~GraphModel() override
     {
@@ -104,7 +116,7 @@ struct GraphModel : Model {
 
     size_t buffer_bytes(const GBuffer &b, int64_t max_rows, int64_t max_tokens) const
     {
-        const int64_t rows = b.rows_kind == 0 ? max_tokens : max_rows;
+        const int64_t rows = b.rows_kind == 0 ? max_tokens : max_rows * (int64_t)b.rows_kind;
         return (size_t)round_up(rows * b.cols * (int64_t)dtype_size(b.dtype), 1024) + 1024;
     }
     size_t scratch_bytes(int64_t max_rows, int64_t max_row_elems) const override
@@ -130,7 +142,7 @@ struct GraphModel : Model {
             const GOp &op = ops[i];
             if (op.opcode != OP_LINEAR) continue;
             const GBuffer &ab = buffers[op.a[0]];
-            const int64_t rows = ab.rows_kind == 0 ? max_tokens : max_rows;
+            const int64_t rows = ab.rows_kind == 0 ? max_tokens : max_rows * (int64_t)ab.rows_kind;
             B2S_TRY(make_tmap_2d_kmajor(&pl.amap[i], pl.buf[op.a[0]], rows, op.a[7], ab.cols, 128, 0));
         }
         return 0;
@@ -140,14 +152,17 @@ struct GraphModel : Model {
                const int64_t *d_row_offsets, void *scratch, size_t scratch_sz, const LaunchInfo &li) override
     {
         if (n_rows <= 0) return 0;
-        if (!d_row_offsets || !li.h_row_offsets) return fail(B2S_ERR_INVALID, "graph: ragged batch needs row offsets");
-        const int64_t n_tokens = li.h_row_offsets[n_rows];
+        int64_t n_tokens = 0;
         int max_seqlen = 0;
-        for (int64_t r = 0; r < n_rows; ++r) {
-            const int64_t s = li.h_row_offsets[r + 1] - li.h_row_offsets[r];
-            if (s <= 0) return fail(B2S_ERR_INVALID, "graph: empty sequence in batch");
-            if (s > (int64_t)h.max_pos) return fail(B2S_ERR_INVALID, "graph: sequence of %lld tokens exceeds the model's %u positions", (long long)s, h.max_pos);
-            if (s > max_seqlen) max_seqlen = (int)s;
+        if (ragged) {
+            if (!d_row_offsets || !li.h_row_offsets) return fail(B2S_ERR_INVALID, "graph: ragged batch needs row offsets");
+            n_tokens = li.h_row_offsets[n_rows];
+            for (int64_t r = 0; r < n_rows; ++r) {
+                const int64_t s = li.h_row_offsets[r + 1] - li.h_row_offsets[r];
+                if (s <= 0) return fail(B2S_ERR_INVALID, "graph: empty sequence in batch");
+                if (s > (int64_t)h.max_pos) return fail(B2S_ERR_INVALID, "graph: sequence of %lld tokens exceeds the model's %u positions", (long long)s, h.max_pos);
+                if (s > max_seqlen) max_seqlen = (int)s;
+            }
         }
         Plan *pl;
         {
@@ -160,7 +175,7 @@ struct GraphModel : Model {
             }
             pl = &it->second;
         }
-        if (n_tokens > li.max_rows * (li.max_row_elems > 0 ? li.max_row_elems : 1))
+        if (ragged && n_tokens > li.max_rows * (li.max_row_elems > 0 ? li.max_row_elems : 1))
             return fail(B2S_ERR_INVALID, "graph: batch of %lld tokens exceeds the stream capacity", (long long)n_tokens);
 
         for (size_t i = 0; i < ops.size(); ++i) {
@@ -180,7 +195,7 @@ struct GraphModel : Model {
             case OP_LINEAR: {
                 // a: in_buf, W, bias(-1), residual_buf(-1), out_buf, act, N, K, out_f32
                 const GBuffer &ab = buffers[op.a[0]];
-                const int M = (int)(ab.rows_kind == 0 ? n_tokens : n_rows);
+                const int M = (int)(ab.rows_kind == 0 ? n_tokens : n_rows * (int64_t)ab.rows_kind);
                 GemmEpilogue ep;
                 ep.bias = tptr(op.a[2]);
                 ep.residual = op.a[3] >= 0 ? pl->buf[op.a[3]] : nullptr;
@@ -190,6 +205,7 @@ struct GraphModel : Model {
                 ep.act = op.a[5];
                 ep.out_f32 = op.a[8];
                 ep.is_bf16 = 0;
+                ep.act_after = op.a[9];
                 if (gemm_prefer_bn256(M, op.a[6]))
                     B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap256[i], 256, M, op.a[6], op.a[7], ep));
                 else
@@ -199,7 +215,7 @@ struct GraphModel : Model {
             case OP_LAYERNORM: {
                 // a: in32_buf, gamma, beta, out16(-1), out32(-1), H
                 const GBuffer &ib = buffers[op.a[0]];
-                const int64_t rows = ib.rows_kind == 0 ? n_tokens : n_rows;
+                const int64_t rows = ib.rows_kind == 0 ? n_tokens : n_rows * (int64_t)ib.rows_kind;
                 B2S_TRY(layernorm(st, reinterpret_cast<const float *>(pl->buf[op.a[0]]), rows, op.a[5],
                                   static_cast<const float *>(tptr(op.a[1])), static_cast<const float *>(tptr(op.a[2])), op.f[0],
                                   op.a[3] >= 0 ? pl->buf[op.a[3]] : nullptr,
@@ -218,6 +234,23 @@ struct GraphModel : Model {
                 B2S_TRY(gather_first(st, pl->buf[op.a[0]], d_row_offsets, (int)n_rows, op.a[2], pl->buf[op.a[1]]));
                 break;
             }
+            case OP_NCHW_TO_NHWC:
+                // a: in_input, out_buf, C, H, W, Cp
+                B2S_TRY(nchw_to_nhwc(st, d_in[op.a[0]], h.in_dtype[op.a[0]], n_rows, op.a[2], op.a[3], op.a[4], op.a[5], pl->buf[op.a[1]]));
+                break;
+            case OP_IM2COL:
+                // a: in_buf, out_buf, H, W, C, KH, KW, stride, pad, OH, OW, Kp
+                B2S_TRY(im2col_nhwc(st, pl->buf[op.a[0]], n_rows, op.a[2], op.a[3], op.a[4], op.a[5], op.a[6], op.a[7], op.a[8],
+                                    op.a[9], op.a[10], op.a[11], pl->buf[op.a[1]]));
+                break;
+            case OP_MAXPOOL:
+                // a: in_buf, out_buf, H, W, C, OH, OW
+                B2S_TRY(maxpool3x3s2(st, pl->buf[op.a[0]], n_rows, op.a[2], op.a[3], op.a[4], op.a[5], op.a[6], pl->buf[op.a[1]]));
+                break;
+            case OP_AVGPOOL:
+                // a: in_buf, out_buf, HW, C
+                B2S_TRY(avgpool(st, pl->buf[op.a[0]], n_rows, op.a[2], op.a[3], pl->buf[op.a[1]]));
+                break;
             default:
                 return fail(B2S_ERR_INVALID, "graph: unknown opcode %u", op.opcode);
             }
@@ -290,6 +323,24 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
         case OP_GATHER_FIRST:
             ok = bok(op.a[0], false) && bok(op.a[1], false);
             break;
+        case OP_NCHW_TO_NHWC:
+            ok = iok(op.a[0], false) && bok(op.a[1], false) && op.a[5] % 8 == 0 && op.a[5] >= op.a[2] &&
+                 m->buffers[op.a[1]].cols == op.a[5] && (int64_t)m->buffers[op.a[1]].rows_kind == (int64_t)op.a[3] * op.a[4];
+            break;
+        case OP_IM2COL:
+            ok = bok(op.a[0], false) && bok(op.a[1], false) && op.a[4] % 8 == 0 && op.a[11] % 8 == 0 &&
+                 op.a[11] >= op.a[5] * op.a[6] * op.a[4] && m->buffers[op.a[1]].cols == op.a[11] &&
+                 (int64_t)m->buffers[op.a[1]].rows_kind == (int64_t)op.a[9] * op.a[10] &&
+                 (int64_t)m->buffers[op.a[0]].rows_kind == (int64_t)op.a[2] * op.a[3] && m->buffers[op.a[0]].cols == op.a[4];
+            break;
+        case OP_MAXPOOL:
+            ok = bok(op.a[0], false) && bok(op.a[1], false) && op.a[4] % 8 == 0 &&
+                 (int64_t)m->buffers[op.a[1]].rows_kind == (int64_t)op.a[5] * op.a[6] && m->buffers[op.a[1]].cols == op.a[4];
+            break;
+        case OP_AVGPOOL:
+            ok = bok(op.a[0], false) && bok(op.a[1], false) && op.a[3] % 8 == 0 &&
+                 (int64_t)m->buffers[op.a[0]].rows_kind == (int64_t)op.a[2] && m->buffers[op.a[1]].rows_kind == 1;
+            break;
         default:
             ok = false;
         }
@@ -319,7 +370,8 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
     info.n_outputs = (int32_t)h.n_outputs;
     for (uint32_t i = 0; i < h.n_inputs; ++i) {
         info.in_dtype[i] = h.in_dtype[i];
-        info.in_row_elems[i] = -1;  // ragged: one variable-length row per sequence
+        info.in_row_elems[i] = h.in_row_elems[i];  // -1: one variable-length row per sequence
+        if (h.in_row_elems[i] < 0) m->ragged = true;
     }
     for (uint32_t o = 0; o < h.n_outputs; ++o) {
         const GBuffer &ob = m->buffers[h.out_buffer[o]];

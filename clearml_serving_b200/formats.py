@@ -265,6 +265,8 @@ def pack_torch_module(module):
     arch = type(module).__name__
     if arch == "BertForSequenceClassification":
         return pack_bert(module)
+    if arch == "ResNet":
+        return pack_resnet(module.eval())
     raise ValueError("b200 engine: torch architecture '{}' is not supported yet".format(arch))
 
 
@@ -295,9 +297,10 @@ _DT = {"float32": 0, "float64": 1, "int32": 2, "int64": 3, "uint8": 4, "float16"
 class GraphBuilder(object):
     """Accumulates weights, activation buffers and ops, then serialises the "B2SG" blob."""
 
-    def __init__(self, in_dtypes, max_pos):
+    def __init__(self, in_dtypes, max_pos, in_row_elems=None):
         self.tensors, self.buffers, self.ops = [], [], []
         self.in_dtypes = list(in_dtypes)
+        self.in_row_elems = list(in_row_elems) if in_row_elems is not None else [-1] * len(self.in_dtypes)
         self.max_pos = int(max_pos)
         self.outputs = []
 
@@ -306,8 +309,9 @@ class GraphBuilder(object):
         self.tensors.append(a)
         return len(self.tensors) - 1
 
-    def buffer(self, dtype, per_token, cols):
-        self.buffers.append((_DT[dtype], 0 if per_token else 1, int(cols)))
+    def buffer(self, dtype, per_token, cols, rows_per_item=1):
+        """per_token: one row per packed token (ragged models); else `rows_per_item` rows per batch item"""
+        self.buffers.append((_DT[dtype], 0 if per_token else int(rows_per_item), int(cols)))
         return len(self.buffers) - 1
 
     def op(self, opcode, ints, floats=()):
@@ -315,12 +319,12 @@ class GraphBuilder(object):
         f = list(floats) + [0.0] * (4 - len(floats))
         self.ops.append((opcode, a, f))
 
-    def linear(self, in_buf, weight, bias, out_buf, act=ACT_NONE, residual=-1, out_f32=False):
+    def linear(self, in_buf, weight, bias, out_buf, act=ACT_NONE, residual=-1, out_f32=False, act_after=False):
         w = np.asarray(weight)
         n, k = w.shape
         wi = self.tensor(w, np.float16)
         bi = self.tensor(bias, np.float32) if bias is not None else -1
-        self.op(OP_LINEAR, [in_buf, wi, bi, residual, out_buf, act, n, k, 1 if out_f32 else 0])
+        self.op(OP_LINEAR, [in_buf, wi, bi, residual, out_buf, act, n, k, 1 if out_f32 else 0, 1 if act_after else 0])
 
     def output(self, buf):
         """marks `buf` as the next model output and returns the operand code ops use to write it"""
@@ -331,9 +335,10 @@ class GraphBuilder(object):
         n_t, n_b, n_o = len(self.tensors), len(self.buffers), len(self.ops)
         out_buf = (self.outputs + [0, 0, 0, 0])[:4]
         in_dt = ([_DT[d] for d in self.in_dtypes] + [0, 0, 0, 0])[:4]
-        header = struct.pack("<4s7I4i4i", b"B2SG", 1, n_t, n_b, n_o, len(self.in_dtypes), len(self.outputs),
-                             self.max_pos, *out_buf, *in_dt)
-        assert len(header) == 64
+        in_re = (list(self.in_row_elems) + [0, 0, 0, 0])[:4]
+        header = struct.pack("<4s7I4i4i4q", b"B2SG", 1, n_t, n_b, n_o, len(self.in_dtypes), len(self.outputs),
+                             self.max_pos, *out_buf, *in_dt, *in_re)
+        assert len(header) == 96
         offsets, off = [], 0
         for a in self.tensors:
             offsets.append(off)
@@ -407,4 +412,114 @@ def pack_bert(model):
     desc = dict(kind="graph", arch="bert", layers=L, hidden=H, heads=heads, intermediate=I, num_labels=int(n_labels),
                 max_row_elems=int(cfg.max_position_embeddings), input_dtype="int32", output_dtype="float32",
                 gemm_flops_per_token=flops_per_token, attn_flops_per_token_per_key=4.0 * L * H)
+    return PackedModel(native.MODEL_GRAPH, g.serialise(), desc)
+
+
+OP_NCHW_TO_NHWC, OP_IM2COL, OP_MAXPOOL, OP_AVGPOOL = 6, 7, 8, 9
+
+
+def _fold_bn(conv_w, bn):
+    """conv (no bias) followed by eval-mode BatchNorm -> (weight', bias')"""
+    gamma = bn.weight.detach().double().numpy()
+    beta = bn.bias.detach().double().numpy()
+    mean = bn.running_mean.detach().double().numpy()
+    var = bn.running_var.detach().double().numpy()
+    scale = gamma / np.sqrt(var + bn.eps)
+    w = conv_w.detach().double().numpy() * scale[:, None, None, None]
+    return w, beta - mean * scale
+
+
+class _ConvNetLowering(object):
+    """Lowers torchvision-style conv / bn / relu / residual stacks onto GraphBuilder ops: NHWC fp16
+    activations (channels padded to 8), 1x1 stride-1 convs as direct GEMMs, everything else as
+    im2col + GEMM, BatchNorm folded, bias/ReLU/residual fused in the GEMM epilogue."""
+
+    def __init__(self, g):
+        self.g = g
+        self._pool = {}   # (rows_per_item, cols, tag) -> [buffers], round robin
+
+    def buf(self, rows_per_item, cols, tag="act", n=3):
+        key = (int(rows_per_item), int(cols), tag)
+        ring = self._pool.setdefault(key, dict(items=[], nxt=0))
+        if len(ring["items"]) < n:
+            ring["items"].append(self.g.buffer("float16", False, cols, rows_per_item=rows_per_item))
+            return ring["items"][-1]
+        b = ring["items"][ring["nxt"] % n]
+        ring["nxt"] += 1
+        return b
+
+    def conv_bn(self, x, H, W, Cin_p, conv, bn, relu=True, residual=-1):
+        g = self.g
+        KH, KW = conv.kernel_size
+        s, p = conv.stride[0], conv.padding[0]
+        if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] or conv.groups != 1 or conv.dilation != (1, 1):
+            raise ValueError("b200 engine: unsupported convolution configuration")
+        w, b = _fold_bn(conv.weight, bn) if bn is not None else (conv.weight.detach().double().numpy(),
+                                                                 np.zeros(conv.out_channels))
+        if conv.bias is not None:
+            b = b + conv.bias.detach().double().numpy()
+        Cout, Cin = w.shape[0], w.shape[1]
+        if Cout % 8:
+            raise ValueError("b200 engine: conv output channels must be a multiple of 8")
+        OH, OW = (H + 2 * p - KH) // s + 1, (W + 2 * p - KW) // s + 1
+        wk = np.zeros((Cout, KH, KW, Cin_p), np.float64)
+        wk[:, :, :, :Cin] = np.transpose(w, (0, 2, 3, 1))
+        K = KH * KW * Cin_p
+        wk = wk.reshape(Cout, K)
+        if KH == 1 and KW == 1 and s == 1 and p == 0:
+            a = x
+        else:
+            a = self.buf(OH * OW, K, tag="col", n=1)
+            g.op(OP_IM2COL, [x, a, H, W, Cin_p, KH, KW, s, p, OH, OW, K])
+        y = self.buf(OH * OW, Cout)
+        guard = 0
+        while y in (x, residual) and guard < 4:   # never write over a live operand
+            y = self.buf(OH * OW, Cout)
+            guard += 1
+        g.linear(a, wk, b, y, act=ACT_RELU if relu else ACT_NONE, residual=residual, act_after=residual >= 0)
+        return y, OH, OW, Cout
+
+
+def pack_resnet(model, input_dtype="float32", image_hw=(224, 224)):
+    """torchvision.models.resnet.ResNet (Bottleneck or BasicBlock) in eval mode -> PackedModel.
+    Input: NCHW images [batch, 3, H, W] float32 (what the reference's Triton client can send,
+    SURVEY.md F5) or uint8; output fp32 logits [batch, num_classes]."""
+    H, W = image_hw
+    g = GraphBuilder([input_dtype], 0, in_row_elems=[3 * H * W])
+    low = _ConvNetLowering(g)
+    x = g.buffer("float16", False, 8, rows_per_item=H * W)
+    g.op(OP_NCHW_TO_NHWC, [0, x, 3, H, W, 8])
+    x, H, W, C = low.conv_bn(x, H, W, 8, model.conv1, model.bn1, relu=True)
+    OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = low.buf(OH * OW, C)
+    g.op(OP_MAXPOOL, [x, y, H, W, C, OH, OW])
+    x, H, W = y, OH, OW
+    n_convs = 1
+    for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+        for blk in layer:
+            kind = type(blk).__name__
+            if blk.downsample is not None:
+                idn, _, _, _ = low.conv_bn(x, H, W, C, blk.downsample[0], blk.downsample[1], relu=False)
+                n_convs += 1
+            else:
+                idn = x
+            if kind == "Bottleneck":
+                t, h1, w1, c1 = low.conv_bn(x, H, W, C, blk.conv1, blk.bn1, relu=True)
+                t, h2, w2, c2 = low.conv_bn(t, h1, w1, c1, blk.conv2, blk.bn2, relu=True)
+                x, H, W, C = low.conv_bn(t, h2, w2, c2, blk.conv3, blk.bn3, relu=True, residual=idn)
+                n_convs += 3
+            elif kind == "BasicBlock":
+                t, h1, w1, c1 = low.conv_bn(x, H, W, C, blk.conv1, blk.bn1, relu=True)
+                x, H, W, C = low.conv_bn(t, h1, w1, c1, blk.conv2, blk.bn2, relu=True, residual=idn)
+                n_convs += 2
+            else:
+                raise ValueError("b200 engine: unsupported residual block '{}'".format(kind))
+    pooled = g.buffer("float16", False, C, rows_per_item=1)
+    g.op(OP_AVGPOOL, [x, pooled, H * W, C])
+    n_cls = model.fc.out_features
+    logits = g.buffer("float32", False, n_cls, rows_per_item=1)
+    g.linear(pooled, model.fc.weight.detach().double().numpy(), model.fc.bias.detach().double().numpy(),
+             g.output(logits), out_f32=True)
+    desc = dict(kind="graph", arch=type(model).__name__.lower(), convs=n_convs, num_classes=int(n_cls),
+                input_dtype=input_dtype, output_dtype="float32", image_hw=list(image_hw), max_row_elems=0)
     return PackedModel(native.MODEL_GRAPH, g.serialise(), desc)
