@@ -48,7 +48,7 @@ def _peaks():
 
 def _traffic_bytes():
     """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
-    p = os.path.join(ROOT, "profiles", "forest_pairs_traffic.json")
+    p = os.path.join(ROOT, "profiles", "forest_traffic.json")
     if os.path.exists(p):
         try:
             with open(p) as f:
@@ -415,6 +415,96 @@ def _bert_workload(native, device, steps, warmup, cpu_seconds):
     return res
 
 
+# ------------------------------------------------------------------------------------------------
+# third workload (BASELINE.json configs[2]): ResNet-50 fp16, 3x224x224, max_batch=128
+# ------------------------------------------------------------------------------------------------
+def _resnet_workload(native, device, steps, warmup, cpu_seconds):
+    import torch
+    import torchvision
+    from clearml_serving_b200 import formats
+    torch.manual_seed(0)
+    model_t = torchvision.models.resnet50(weights=None).eval()
+    with torch.no_grad():   # trained-looking BatchNorm statistics keep activations O(1) (see tests/test_gpu_resnet.py)
+        gen = torch.Generator().manual_seed(0)
+        for name, m in model_t.named_modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=gen) * 0.1)
+                m.running_var.copy_(torch.rand(m.num_features, generator=gen) + 0.5)
+                m.weight.copy_((torch.rand(m.num_features, generator=gen) * 0.5 + 0.75) * (0.3 if name.endswith("bn3") else 1.0))
+                m.bias.copy_(torch.randn(m.num_features, generator=gen) * 0.1)
+    pm = formats.pack_resnet(model_t)
+    model = native.Model(pm.kind, pm.blob, device=device)
+    B = 128
+    stream = native.Stream(model, B, 0, 2)
+    timer = native.Timer(stream)
+    rng = np.random.default_rng(1)
+    n_sets = 2
+    X = [rng.standard_normal((B, 3, 224, 224)).astype(np.float32) for _ in range(n_sets)]
+    d_in = []
+    for x in X:
+        b = native.DeviceBuffer(x.nbytes, device); b.upload(x); d_in.append(b)
+    d_out = native.DeviceBuffer(B * 1000 * 4, device)
+    for w in range(max(warmup, 3)):
+        stream.infer_device(B, [d_in[w % n_sets].ptr], [d_out.ptr])
+    stream.synchronize()
+    launches0 = native.launch_count()
+    total_ms = 0.0
+    for k in range(steps):
+        stream.flush_l2()
+        timer.start()
+        stream.infer_device(B, [d_in[k % n_sets].ptr], [d_out.ptr])
+        timer.stop()
+        total_ms += timer.elapsed_ms()
+    launches = native.launch_count() - launches0
+    got = d_out.download(np.float32, B * 1000).reshape(B, 1000)[:2]
+    with torch.no_grad():
+        ref = model_t(torch.from_numpy(X[(steps - 1) % n_sets][:2])).numpy()
+    rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+    # e2e: 128 single-image requests per step through the C ABI (77 MB of fp32 pixels host -> device)
+    reqs = [[[X[s][i:i + 1]] for i in range(B)] for s in range(n_sets)]
+    e2e_steps = max(3, min(steps, 8))
+    t0 = time.perf_counter()
+    inflight = []
+    for k in range(e2e_steps):
+        if len(inflight) == 2:
+            item = inflight.pop(0)
+            stream.wait(item[0])
+        inflight.append(stream.infer_batch(reqs[k % n_sets]))
+    for item in inflight:
+        stream.wait(item[0])
+    e2e_s = time.perf_counter() - t0
+    n_cpu, t_cpu0 = 0, time.perf_counter()
+    with torch.no_grad():
+        while time.perf_counter() - t_cpu0 < cpu_seconds:
+            model_t(torch.from_numpy(X[0][n_cpu % B:n_cpu % B + 1]))
+            n_cpu += 1
+    cpu_dt = time.perf_counter() - t_cpu0
+    peak = 1431.4
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            peak = float(json.load(f).get("bf16_tflops_sustained", peak))
+    flops_per_img = 8.178e9   # BASELINE.md section 3 (torch FlopCounterMode, 2*MAC)
+    achieved = flops_per_img * B * steps / (total_ms * 1e-3) / 1e12
+    res = dict(workload="resnet50-fp16_3x224x224_maxbatch128", metric="images/sec",
+               value=B * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps, steps=steps,
+               e2e=dict(value=B * e2e_steps / e2e_s, unit="images/s", ms_per_step=e2e_s / e2e_steps * 1e3, in_flight=2,
+                        h2d_bytes_per_step=B * 3 * 224 * 224 * 4, d2h_bytes_per_step=B * 4000),
+               gpu_launches_per_step=launches / steps, parity_rel_err_vs_torch_cpu_fp32=rel,
+               roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                             peak_source="MEASURED_PEAKS.json bf16_tflops_sustained", flops_per_image=flops_per_img,
+                             note="explicit im2col form: patch matrices add ~50 MB/image of HBM traffic"),
+               cpu_baseline=dict(value=n_cpu / cpu_dt, unit="images/s", cores=int(torch.get_num_threads()), kind="port",
+                                 sample="{} single-image torch fp32 forwards in {:.1f}s".format(n_cpu, cpu_dt)))
+    timer.destroy()
+    for b in d_in:
+        b.free()
+    d_out.free()
+    stream.destroy()
+    model.free()
+    return res
+
+
 def run_b200(args):
     rank, world, local, dist = _dist_setup(args.gpus)
     device = local
@@ -527,6 +617,13 @@ def run_b200(args):
         except Exception as ex:  # noqa
             bert = dict(error="{}: {}".format(type(ex).__name__, ex))
 
+    resnet = None
+    if args.resnet and rank == 0:
+        try:
+            resnet = _resnet_workload(native, device, max(5, min(args.steps, 20)), 3, min(args.cpu_seconds, 6.0))
+        except Exception as ex:  # noqa
+            resnet = dict(error="{}: {}".format(type(ex).__name__, ex))
+
     if rank == 0:
         peak, peak_src = _peaks()
         algo = model.algo_bytes(MAX_BATCH)
@@ -550,7 +647,7 @@ def run_b200(args):
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                           traffic=_traffic_bytes(), algorithmic_bytes_per_launch=algo, peak_source=peak_src,
                           kernel="forest_staged_kernel<f32>", note="latency-bound at 64 rows: 1000-add fp32 chain"),
-            cpu_baseline=cpu, clocks=clk, plugin=plugin, workloads=dict(bert_base=bert))
+            cpu_baseline=cpu, clocks=clk, plugin=plugin, workloads=dict(bert_base=bert, resnet50=resnet))
         print(json.dumps(line))
     timer.destroy()
     for b in d_in:
@@ -571,6 +668,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-plugin", action="store_true")
     ap.add_argument("--no-bert", dest="bert", action="store_false", help="skip the BERT-base (configs[3]) section")
+    ap.add_argument("--no-resnet", dest="resnet", action="store_false", help="skip the ResNet-50 (configs[2]) section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

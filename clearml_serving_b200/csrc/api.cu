@@ -53,66 +53,87 @@ constexpr int kMaxIO = 4;
 constexpr size_t kZeroCopyOutMax = 64 * 1024;
 constexpr size_t kZeroCopyInMax = 16 * 1024;
 
-// ---- shared pinned arena: first-fit free list with coalescing ---------------------------------
+// ---- shared pinned arena: first-fit free list with coalescing; grows by whole segments on demand
 struct Arena {
-    unsigned char *base = nullptr;
-    size_t size = 0;
-    std::map<size_t, size_t> free_blocks;  // offset -> length
+    std::vector<std::pair<unsigned char *, size_t>> segments;
+    std::map<uintptr_t, size_t> free_blocks;  // address -> length
+    size_t default_segment = (size_t)64 << 20;
     std::mutex mu;
 
-    int init(size_t bytes)
+    int add_segment(size_t bytes)
     {
-        if (base) return 0;
         void *p = nullptr;
         cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
         if (e != cudaSuccess) return fail_cuda(e, "cudaHostAlloc(pinned arena)");
-        base = static_cast<unsigned char *>(p);
-        size = bytes;
-        free_blocks.clear();
-        free_blocks[0] = bytes;
+        segments.emplace_back(static_cast<unsigned char *>(p), bytes);
+        free_blocks[reinterpret_cast<uintptr_t>(p)] = bytes;
         return 0;
+    }
+    int init(size_t bytes)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!segments.empty()) return 0;
+        default_segment = bytes;
+        return add_segment(bytes);
     }
     void destroy()
     {
-        if (base) cudaFreeHost(base);
-        base = nullptr;
-        size = 0;
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &sg : segments) cudaFreeHost(sg.first);
+        segments.clear();
         free_blocks.clear();
+    }
+    unsigned char *take(size_t bytes)
+    {
+        for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it) {
+            if (it->second >= bytes) {
+                const uintptr_t addr = it->first;
+                const size_t len = it->second;
+                free_blocks.erase(it);
+                if (len > bytes) free_blocks[addr + bytes] = len - bytes;
+                return reinterpret_cast<unsigned char *>(addr);
+            }
+        }
+        return nullptr;
     }
     unsigned char *alloc(size_t bytes)
     {
         bytes = (size_t)round_up((int64_t)(bytes ? bytes : 1), 256);
         std::lock_guard<std::mutex> g(mu);
-        for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it) {
-            if (it->second >= bytes) {
-                const size_t off = it->first, len = it->second;
-                free_blocks.erase(it);
-                if (len > bytes) free_blocks[off + bytes] = len - bytes;
-                return base + off;
-            }
+        unsigned char *p = take(bytes);
+        if (!p) {  // grow: endpoints with large inputs (images) need more than the initial segment
+            const size_t seg = bytes > default_segment ? bytes : default_segment;
+            if (add_segment(seg) != 0) return nullptr;
+            p = take(bytes);
         }
-        return nullptr;
+        return p;
     }
     void release(unsigned char *p, size_t bytes)
     {
         if (!p) return;
         bytes = (size_t)round_up((int64_t)(bytes ? bytes : 1), 256);
         std::lock_guard<std::mutex> g(mu);
-        size_t off = (size_t)(p - base);
-        auto next = free_blocks.lower_bound(off);
+        uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+        // coalesce only inside one segment
+        uintptr_t seg_lo = 0, seg_hi = 0;
+        for (auto &sg : segments) {
+            const uintptr_t lo = reinterpret_cast<uintptr_t>(sg.first);
+            if (addr >= lo && addr < lo + sg.second) { seg_lo = lo; seg_hi = lo + sg.second; }
+        }
+        auto next = free_blocks.lower_bound(addr);
         if (next != free_blocks.begin()) {
             auto prev = std::prev(next);
-            if (prev->first + prev->second == off) {
-                off = prev->first;
+            if (prev->first + prev->second == addr && prev->first >= seg_lo) {
+                addr = prev->first;
                 bytes += prev->second;
                 free_blocks.erase(prev);
             }
         }
-        if (next != free_blocks.end() && off + bytes == next->first) {
+        if (next != free_blocks.end() && addr + bytes == next->first && next->first < seg_hi) {
             bytes += next->second;
             free_blocks.erase(next);
         }
-        free_blocks[off] = bytes;
+        free_blocks[addr] = bytes;
     }
 };
 
