@@ -413,6 +413,146 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Kernel v3: v2 on CTA PAIRS sharing the weight tile.  BERT-class GEMMs (K = 768) are bound by the
+// L2 -> SM operand traffic of 1-CTA tiles (profiles/r01_ncu_gemm_tn_persistent.txt: tensor pipe 24 %
+// active, long-scoreboard stalls): a 128 x 256 tile moves A 16 KB + B 32 KB per 64-deep k-block.  Here
+// the two CTAs of a cluster compute vertically adjacent tiles (same 256 weight rows, different 128
+// activation rows); each loads its own A tile and HALF of the B tile, multicast into both CTAs' shared
+// memory, so a CTA pulls 32 KB instead of 48 KB per k-block.  A stage is free again only when BOTH MMA
+// warps are done with it (tcgen05.commit multicast onto both CTAs' empty barriers, count 2).
+// ---------------------------------------------------------------------------------------------
+template <int G2_STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_half,
+                    int M, int N, int K, GemmEpilogue ep)
+{
+    constexpr int G2_BN = 256;
+    using S = G2Smem<G2_BN, G2_STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFFSET);
+    uint64_t *empty_bar = full_bar + G2_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + G2_STAGES;
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + G2_BN - 1) / G2_BN;
+    const int m_pairs = (m_tiles + 1) / 2;
+    const int total = m_pairs * n_tiles;            // pair-tiles
+    const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_a);
+        prefetch_tensormap(&tmap_b_half);
+        for (int s = 0; s < G2_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 2);            // both CTAs of the pair release a stage
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 2 * G2_BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_arrive();   // peer barriers initialised / peer CTA resident before any multicast or remote arrive
+    cluster_wait();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = pair0; pt < total; pt += pair_stride) {
+                const int m_blk = 2 * (pt % m_pairs) + (int)rank, n_blk = pt / m_pairs;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                    unsigned char *sb = sa + S::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);   // own A + both halves of B
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d_multicast(sb + rank * (S::B_BYTES / 2), &tmap_b_half, &full_bar[stage], kb * GEMM_BK,
+                                          n_blk * G2_BN + (int)rank * (G2_BN / 2), (uint16_t)0x3);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_f16 = make_idesc_f16(GEMM_BM, G2_BN, 0);
+            constexpr uint32_t idesc_bf16 = make_idesc_f16(GEMM_BM, G2_BN, 1);
+            const uint32_t idesc = ep.is_bf16 ? idesc_bf16 : idesc_f16;
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int pt = pair0; pt < total; pt += pair_stride) {
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * G2_BN);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                    unsigned char *sb = sa + S::A_BYTES;
+                    const uint64_t adesc = make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = make_sw128_kmajor_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16(d_tmem, desc_advance(adesc, k * 32), desc_advance(bdesc, k * 32), idesc,
+                                 (uint32_t)((kb | k) != 0));
+                    umma_commit_multicast(&empty_bar[stage], (uint16_t)0x3);   // frees the stage in BOTH CTAs
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full_bar[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int pt = pair0; pt < total; pt += pair_stride) {
+            const int m_blk = 2 * (pt % m_pairs) + (int)rank, n_blk = pt / m_pairs;
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+            const int row = m_blk * GEMM_BM + q * 32 + lane;
+            constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                if (c == NCH - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                }
+                epilogue_store32(ep, row, n_blk * G2_BN + half * HALF + c * 32, M, N, v);
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_arrive();   // the peer may still multicast into this CTA's shared memory / arrive on its barriers
+    cluster_wait();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * G2_BN);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side: tensor maps via the driver entry point (no link-time libcuda dependency)
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -500,6 +640,32 @@ static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const 
     return 0;
 }
 
+static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb_half, int M, int N, int K,
+                            const GemmEpilogue &ep)
+{
+    using S = G2Smem<256, 4>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, []() {
+        attr_err = cudaFuncSetAttribute(gemm_tn_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    });
+    if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(gemm pair)");
+    const int m_pairs = (((M + GEMM_BM - 1) / GEMM_BM) + 1) / 2;
+    const int total = m_pairs * ((N + 255) / 256);
+    const int max_pairs = g_num_sms() / 2;
+    const int pairs = total < max_pairs ? total : max_pairs;
+    gemm_tn_pair_kernel<4><<<2 * pairs, G2_THREADS, S::TOTAL, st>>>(ta, tb_half, M, N, K, ep);
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool gemm_pair_enabled()
+{
+    static const bool on = []() { const char *e = getenv("B2S_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // 128 x 256 tiles move 1.5x fewer operand bytes per flop than 128 x 128, but on a persistent grid the
 // cost is waves x tile time: pick the shape with the smaller estimate.
 bool gemm_prefer_bn256(int M, int N)
@@ -517,6 +683,14 @@ int gemm_bn_for(int N) { return N <= 64 ? 64 : 128; }
 
 // GEMM with caller-provided tensor maps (graph executor: maps are cached per stream / per model).
 // `tb` must have been built with box height `bn` (64, 128 or 256).
+// 128 x 256 tiles on CTA pairs: `tb_half` is the weight map with box height 128
+int gemm_tn_maps_pair(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb_half, int M, int N, int K,
+                      const GemmEpilogue &ep)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return launch_gemm_pair(st, ta, tb_half, M, N, K, ep);
+}
+
 int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, int M, int N, int K,
                  const GemmEpilogue &ep)
 {
@@ -536,6 +710,10 @@ int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t 
     CUtensorMap ta, tb;
     const int bn = N <= 64 ? 64 : (gemm_prefer_bn256(M, N) ? 256 : 128);
     B2S_TRY(make_tmap_2d_kmajor(&ta, A, M, K, lda, GEMM_BM, ep.is_bf16));
+    if (bn == 256 && gemm_pair_enabled()) {
+        B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, 128, ep.is_bf16));
+        return gemm_tn_maps_pair(st, ta, tb, M, N, K, ep);
+    }
     B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, bn, ep.is_bf16));
     return gemm_tn_maps(st, ta, tb, bn, M, N, K, ep);
 }

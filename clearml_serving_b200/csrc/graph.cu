@@ -38,6 +38,9 @@ int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, 
                  const GemmEpilogue &ep);
 int gemm_bn_for(int N);
 bool gemm_prefer_bn256(int M, int N);
+bool gemm_pair_enabled();
+int gemm_tn_maps_pair(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb_half, int M, int N, int K,
+                      const GemmEpilogue &ep);
 int layernorm(cudaStream_t st, const float *in, int64_t rows, int H, const float *gamma, const float *beta, float eps,
               void *out16, float *out32);
 int embed_layernorm(cudaStream_t st, const int32_t *ids, const int32_t *types, const int64_t *cu_seqlens, int n_seq,
@@ -206,7 +209,9 @@ struct GraphModel : Model {
                 ep.out_f32 = op.a[8];
                 ep.is_bf16 = 0;
                 ep.act_after = op.a[9];
-                if (gemm_prefer_bn256(M, op.a[6]))
+                if (gemm_prefer_bn256(M, op.a[6]) && gemm_pair_enabled())
+                    B2S_TRY(gemm_tn_maps_pair(st, pl->amap[i], bmap[i], M, op.a[6], op.a[7], ep));   // bmap: box 128 = half tile
+                else if (gemm_prefer_bn256(M, op.a[6]))
                     B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap256[i], 256, M, op.a[6], op.a[7], ep));
                 else
                     B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap[i], gemm_bn_for(op.a[6]), M, op.a[6], op.a[7], ep));
