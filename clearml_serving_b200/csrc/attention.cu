@@ -58,14 +58,29 @@ __device__ __forceinline__ void load_tile(__half *dst, const __half *src, int64_
     }
 }
 
+// same, with cp.async (16-byte, zero-fill for rows >= valid): the copy of key block k+1 overlaps the MMAs of block k
+__device__ __forceinline__ void load_tile_async(__half *dst, const __half *src, int64_t ld_src, int valid_rows, int tid)
+{
+    for (int i = tid; i < 64 * 8; i += 128) {
+        const int r = i >> 3, c = (i & 7) * 8;
+        const bool ok = r < valid_rows;
+        const __half *g = src + (int64_t)(ok ? r : 0) * ld_src + c;
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + r * ATT_LD + c);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(g), "r"(ok ? 16 : 0) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(128)
 attention_varlen_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ cu_seqlens,
                         const int32_t *__restrict__ key_mask, __half *__restrict__ out, int heads, float scale_log2e)
 {
     __shared__ __align__(16) __half Qs[ATT_BQ * ATT_LD];
-    __shared__ __align__(16) __half Ks[ATT_BK * ATT_LD];
-    __shared__ __align__(16) __half Vs[ATT_BK * ATT_LD];
-    __shared__ float mask_bias[ATT_BK];
+    __shared__ __align__(16) __half Ks2[2][ATT_BK * ATT_LD];   // double-buffered key / value blocks
+    __shared__ __align__(16) __half Vs2[2][ATT_BK * ATT_LD];
+    __shared__ float mask_bias2[2][ATT_BK];
 
     const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
     const int64_t s0 = __ldg(cu_seqlens + b);
@@ -92,18 +107,27 @@ attention_varlen_kernel(const __half *__restrict__ qkv, const int64_t *__restric
     for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 
-    for (int k0 = 0; k0 < S; k0 += ATT_BK) {
+    auto issue_block = [&](int k0, int buf) {
         const int kv_valid = min(ATT_BK, S - k0);
-        __syncthreads();  // previous block fully consumed
-        load_tile(Ks, qkv + (s0 + k0) * ld + H + h * ATT_D, ld, kv_valid, tid);
-        load_tile(Vs, qkv + (s0 + k0) * ld + 2 * H + h * ATT_D, ld, kv_valid, tid);
+        load_tile_async(Ks2[buf], qkv + (s0 + k0) * ld + H + h * ATT_D, ld, kv_valid, tid);
+        load_tile_async(Vs2[buf], qkv + (s0 + k0) * ld + 2 * H + h * ATT_D, ld, kv_valid, tid);
         if (tid < ATT_BK) {
             float mb = 0.f;
             if (tid >= kv_valid) mb = -INFINITY;
             else if (key_mask && __ldg(key_mask + s0 + k0 + tid) == 0) mb = -INFINITY;
-            mask_bias[tid] = mb;
+            mask_bias2[buf][tid] = mb;
         }
+        cp_async_commit_group();
+    };
+    issue_block(0, 0);
+    int buf = 0;
+    for (int k0 = 0; k0 < S; k0 += ATT_BK, buf ^= 1) {
+        const bool more = k0 + ATT_BK < S;
+        if (more) issue_block(k0 + ATT_BK, buf ^ 1);   // prefetch the next block into the other buffer
+        if (more) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
         __syncthreads();
+        const __half *Ks = Ks2[buf], *Vs = Vs2[buf];
+        const float *mask_bias = mask_bias2[buf];
 
         // S = Q K^T for 16 rows x 64 keys
         float s[8][4];
@@ -178,6 +202,7 @@ attention_varlen_kernel(const __half *__restrict__ qkv, const int64_t *__restric
                 mma_16816(o[2 * np + 1], pa, vb[2], vb[3]);
             }
         }
+        __syncthreads();   // everyone is done with this buffer before the next prefetch overwrites it
     }
 
     // normalise and store: rows g and g+8 of this warp's 16-row slab

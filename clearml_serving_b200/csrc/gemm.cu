@@ -58,8 +58,13 @@ __device__ __forceinline__ float gelu_erf(float x)
 
 // Fused epilogue for 32 consecutive accumulator columns of one output row (fp32 bits in v[]):
 // + bias, activation, + residual, cast, one 64/128-byte contiguous store per thread.
+// `bv`: the 32 bias values of these columns already in registers (zero where there is no bias / past N), or
+// nullptr to fetch them here (v1 kernel).  Fetching 32 predicated scalars per chunk through L1 was the
+// bottleneck of the persistent kernels: the tile's own output stores keep evicting the bias lines from the
+// ~30 KB of L1 left beside 197 KB of shared memory, so every chunk paid L2 latency 32 times
+// (profiles/r01_ncu_gemm_tn_persistent.txt: long-scoreboard stalls on the FADDs behind LDG.E.CONSTANT).
 __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int row, int col0, int M, int N,
-                                                 const uint32_t (&v)[32])
+                                                 const uint32_t (&v)[32], const float *bv = nullptr)
 {
     const float *bias = static_cast<const float *>(ep.bias);
     if (row < M && col0 < N) {
@@ -67,7 +72,10 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int row
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         const int ncols = min(32, N - col0);
-        if (bias) {
+        if (bv) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += bv[j];
+        } else if (bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j < ncols) f[j] += __ldg(bias + col0 + j);
@@ -266,6 +274,34 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+// One coalesced 128-bit load per lane fetches the bias of the 128 columns a warp drains (lane l holds columns
+// 4l..4l+3); broadcast32() then hands every lane the 32 values of chunk c by warp shuffles.
+__device__ __forceinline__ float4 load_bias128(const float *bias, int col_base, int lane, int N)
+{
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) {
+        const int c = col_base + lane * 4;
+        if (c + 3 < N) b = __ldg(reinterpret_cast<const float4 *>(bias + c));
+        else {
+            if (c < N) b.x = __ldg(bias + c);
+            if (c + 1 < N) b.y = __ldg(bias + c + 1);
+            if (c + 2 < N) b.z = __ldg(bias + c + 2);
+        }
+    }
+    return b;
+}
+__device__ __forceinline__ void broadcast32(const float4 &b, int chunk, float (&bv)[32])
+{
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const int src = chunk * 8 + (j >> 2);
+        bv[j] = __shfl_sync(0xffffffffu, b.x, src);
+        bv[j + 1] = __shfl_sync(0xffffffffu, b.y, src);
+        bv[j + 2] = __shfl_sync(0xffffffffu, b.z, src);
+        bv[j + 3] = __shfl_sync(0xffffffffu, b.w, src);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel v2: persistent, 128 x 256 tiles, double-buffered TMEM accumulators.
 //   * grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... with m fastest,
@@ -388,17 +424,21 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             const int row = m_blk * GEMM_BM + q * 32 + lane;
             constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
+            // this warp's bias slice, fetched once per tile while the accumulator is still being produced
+            const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 uint32_t v[32];
+                float bv[32];
                 tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
+                broadcast32(b4, c, bv);
                 tmem_ld_wait();
                 if (c == NCH - 1) {   // last TMEM read of this warp: hand the accumulator back before the math
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                epilogue_store32(ep, row, n_blk * G2_BN + half * HALF + c * 32, M, N, v);
+                epilogue_store32(ep, row, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv);
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
@@ -526,17 +566,21 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int row = m_blk * GEMM_BM + q * 32 + lane;
             constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
+            // this warp's bias slice, fetched once per tile while the accumulator is still being produced
+            const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 uint32_t v[32];
+                float bv[32];
                 tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
+                broadcast32(b4, c, bv);
                 tmem_ld_wait();
                 if (c == NCH - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                epilogue_store32(ep, row, n_blk * G2_BN + half * HALF + c * 32, M, N, v);
+                epilogue_store32(ep, row, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv);
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }

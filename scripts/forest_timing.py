@@ -74,3 +74,30 @@ for rows in (1, 64, 1024, 4096):
             r, s[1] - s[0], s[2] - s[1], s[3] - s[2], (s[4] - s[3]) if s[4] else -1, (s[5] - s[3]) if s[5] else -1,
             (s[6] - s[3]) if s[6] else -1, (s[4] if s[4] else s[2]) - s[0]))
     d_in.free(); d_out.free()
+
+# ---- host-side split of the serial e2e latency: submit call vs wait call (64 one-row requests)
+import time
+stream2 = native.Stream(model, 64, 0, 4)
+X = rng.standard_normal((64, 32)).astype(np.float32)
+tin = (native.Tensor * 64)(); tout = (native.Tensor * 64)()
+ob = np.zeros((64, 1), np.float32)
+for r in range(64):
+    row = X[r:r + 1]
+    tin[r].data = row.ctypes.data; tin[r].dtype = 0; tin[r].ndim = 2; tin[r].shape[0], tin[r].shape[1] = 1, 32
+    tout[r].data = ob[r].ctypes.data
+lib = native.lib()
+ev = ctypes.c_uint64(0)
+for _ in range(50):
+    native.check(lib.b2s_infer_batch(model.handle, stream2.handle, 64, tin, tout, ctypes.byref(ev)))
+    native.check(lib.b2s_event_wait(ev.value))
+ts, tw = [], []
+for _ in range(500):
+    t0 = time.perf_counter()
+    native.check(lib.b2s_infer_batch(model.handle, stream2.handle, 64, tin, tout, ctypes.byref(ev)))
+    t1 = time.perf_counter()
+    native.check(lib.b2s_event_wait(ev.value))
+    t2 = time.perf_counter()
+    ts.append(t1 - t0); tw.append(t2 - t1)
+ts, tw = np.array(ts) * 1e6, np.array(tw) * 1e6
+print("serial e2e (64 requests): submit p50=%.1fus p99=%.1fus | wait p50=%.1fus p99=%.1fus | total p50=%.1fus" % (
+    np.percentile(ts, 50), np.percentile(ts, 99), np.percentile(tw, 50), np.percentile(tw, 99), np.percentile(ts + tw, 50)))
