@@ -96,7 +96,15 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int row
             float *C = static_cast<float *>(ep.C) + off;
             if (ep.residual) {
                 const float *R = static_cast<const float *>(ep.residual) + off;
-                for (int j = 0; j < ncols; ++j) f[j] += R[j];
+                if (ncols == 32 && (off & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(R + j);
+                        f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                    }
+                } else {
+                    for (int j = 0; j < ncols; ++j) f[j] += R[j];
+                }
             }
             if (ncols == 32 && (off & 3) == 0) {
 #pragma unroll

@@ -20,12 +20,16 @@ for (M, N, K) in shapes:
     bias = torch.randn(N, device="cuda")
     def mine():
         native.check(lib.b2s_op_gemm(0, None, A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, bias.data_ptr(), None, 1, 0, 0))
+    def mine_plain():
+        native.check(lib.b2s_op_gemm(0, None, A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, None, None, 0, 0, 0))
+    def mine_bias():
+        native.check(lib.b2s_op_gemm(0, None, A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, bias.data_ptr(), None, 0, 0, 0))
     def ref():
         return torch.nn.functional.gelu(torch.nn.functional.linear(A, B, bias.half()))
     def plain():
         return torch.nn.functional.linear(A, B)
     res = {}
-    for name, fn in (("b2s_gemm+bias+gelu", mine), ("torch linear+gelu", ref), ("torch linear only", plain)):
+    for name, fn in (("b2s plain", mine_plain), ("b2s +bias", mine_bias), ("b2s +bias+gelu", mine), ("torch linear+gelu", ref), ("torch linear only", plain)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
