@@ -56,131 +56,166 @@ __device__ __forceinline__ float gelu_erf(float x)
     return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+// Warp-cooperative store of a 32-row x 64-byte slab: every lane holds the 64 bytes (16 words) of ITS row;
+// written directly that is 32 rows x 16 B per store instruction, i.e. 32 half-filled 32-byte sectors.  Staged
+// through a 2.5 KB per-warp shared-memory scratch (80-byte pitch: conflict-free 128-bit accesses) four adjacent
+// lanes emit one row's 64 contiguous bytes, so each instruction writes 8 rows x 2 full sectors.
+constexpr int EPI_SCRATCH_WORDS = 32 * 20;
+__device__ __forceinline__ void warp_store_rows64(uint32_t *scratch, const uint32_t (&w)[16], unsigned char *gbase,
+                                                  size_t row_pitch_bytes, int rows_valid, int lane)
+{
+    uint4 *mine = reinterpret_cast<uint4 *>(scratch + lane * 20);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mine[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    __syncwarp();
+    const int seg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = (lane >> 2) + 8 * i;
+        const uint4 val = *reinterpret_cast<const uint4 *>(scratch + r * 20 + seg * 4);
+        if (r < rows_valid) *reinterpret_cast<uint4 *>(gbase + (size_t)r * row_pitch_bytes + seg * 16) = val;
+    }
+    __syncwarp();
+}
+
 // Fused epilogue for 32 consecutive accumulator columns of one output row (fp32 bits in v[]):
-// + bias, activation, + residual, cast, one 64/128-byte contiguous store per thread.
+// + bias, activation, + residual, cast, store.  `warp_row0` is the first output row of this warp's 32-row slab.
 // `bv`: the 32 bias values of these columns already in registers (zero where there is no bias / past N), or
 // nullptr to fetch them here (v1 kernel).  Fetching 32 predicated scalars per chunk through L1 was the
 // bottleneck of the persistent kernels: the tile's own output stores keep evicting the bias lines from the
 // ~30 KB of L1 left beside 197 KB of shared memory, so every chunk paid L2 latency 32 times
 // (profiles/r01_ncu_gemm_tn_persistent.txt: long-scoreboard stalls on the FADDs behind LDG.E.CONSTANT).
-__device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int row, int col0, int M, int N,
-                                                 const uint32_t (&v)[32], const float *bv = nullptr)
+// `scratch`: per-warp shared memory for the cooperative store, or nullptr for per-thread row stores.
+__device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int warp_row0, int lane, int col0, int M, int N,
+                                                 const uint32_t (&v)[32], const float *bv = nullptr,
+                                                 uint32_t *scratch = nullptr)
 {
+    if (col0 >= N) return;   // warp-uniform
+    const int row = warp_row0 + lane;
+    const bool row_ok = row < M;
+    const int ncols = min(32, N - col0);
+    const bool full = ncols == 32;
     const float *bias = static_cast<const float *>(ep.bias);
-    if (row < M && col0 < N) {
-        float f[32];
+    float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const int ncols = min(32, N - col0);
-        if (bv) {
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (bv) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += bv[j];
-        } else if (bias) {
+        for (int j = 0; j < 32; ++j) f[j] += bv[j];
+    } else if (bias && row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j < ncols) f[j] += __ldg(bias + col0 + j);
+        for (int j = 0; j < 32; ++j)
+            if (j < ncols) f[j] += __ldg(bias + col0 + j);
+    }
+    const int act_pre = ep.act_after ? ACT_NONE : ep.act;
+    if (act_pre == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    } else if (act_pre == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+    } else if (act_pre == ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+    }
+    const size_t off = (size_t)row * ep.ldc + col0;
+    const int rows_valid = min(32, max(0, M - warp_row0));
+    if (ep.out_f32) {
+        const bool vec = full && (ep.ldc & 3) == 0;
+        if (ep.residual && row_ok) {
+            const float *R = static_cast<const float *>(ep.residual) + off;
+            if (vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4 *>(R + j);
+                    f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                }
+            } else {
+                for (int j = 0; j < ncols; ++j) f[j] += R[j];
+            }
         }
-        const int act_pre = ep.act_after ? ACT_NONE : ep.act;
-        if (act_pre == ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        } else if (act_pre == ACT_RELU) {
+        if (ep.act_after && ep.act == ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        } else if (act_pre == ACT_TANH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
         }
-        const size_t off = (size_t)row * ep.ldc + col0;
-        if (ep.out_f32) {
-            float *C = static_cast<float *>(ep.C) + off;
-            if (ep.residual) {
-                const float *R = static_cast<const float *>(ep.residual) + off;
-                if (ncols == 32 && (off & 3) == 0) {
+        float *C = static_cast<float *>(ep.C);
+        if (vec && scratch) {   // two 64-byte halves per row
+            uint32_t w[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 r4 = *reinterpret_cast<const float4 *>(R + j);
-                        f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-                    }
-                } else {
-                    for (int j = 0; j < ncols; ++j) f[j] += R[j];
-                }
+            for (int hlf = 0; hlf < 2; ++hlf) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(f[hlf * 16 + j]);
+                warp_store_rows64(scratch, w, reinterpret_cast<unsigned char *>(C + (size_t)warp_row0 * ep.ldc + col0 + hlf * 16),
+                                  (size_t)ep.ldc * 4, rows_valid, lane);
             }
-            if (ncols == 32 && (off & 3) == 0) {
+        } else if (row_ok) {
+            if (vec) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4 *>(C + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    *reinterpret_cast<float4 *>(C + off + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
-                for (int j = 0; j < ncols; ++j) C[j] = f[j];
+                for (int j = 0; j < ncols; ++j) C[off + j] = f[j];
             }
-        } else if (ep.is_bf16) {
-            __nv_bfloat16 *C = static_cast<__nv_bfloat16 *>(ep.C) + off;
-            if (ep.residual) {
-                const __nv_bfloat16 *R = static_cast<const __nv_bfloat16 *>(ep.residual) + off;
-                for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(R[j]);
-            }
-            if (ncols == 32 && (off & 7) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t *>(&p0);
-                    u.y = *reinterpret_cast<uint32_t *>(&p1);
-                    u.z = *reinterpret_cast<uint32_t *>(&p2);
-                    u.w = *reinterpret_cast<uint32_t *>(&p3);
-                    *reinterpret_cast<uint4 *>(C + j) = u;
-                }
-            } else {
-                for (int j = 0; j < ncols; ++j) C[j] = __float2bfloat16_rn(f[j]);
-            }
+        }
+        return;
+    }
+    // 16-bit output (fp16 / bf16)
+    const bool vec = full && (ep.ldc & 7) == 0;
+    if (ep.residual && row_ok) {
+        if (ep.is_bf16) {
+            const __nv_bfloat16 *R = static_cast<const __nv_bfloat16 *>(ep.residual) + off;
+            for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(R[j]);
         } else {
-            __half *C = static_cast<__half *>(ep.C) + off;
-            if (ep.residual) {
-                const __half *R = static_cast<const __half *>(ep.residual) + off;
-                if (ncols == 32 && (off & 7) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const uint4 u = *reinterpret_cast<const uint4 *>(R + j);
-                        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float2 r2 = __half22float2(h[t]);
-                            f[j + 2 * t] += r2.x;
-                            f[j + 2 * t + 1] += r2.y;
-                        }
-                    }
-                } else {
-                    for (int j = 0; j < ncols; ++j) f[j] += __half2float(R[j]);
-                }
-            }
-            if (ep.act_after && ep.act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
-            if (ncols == 32 && (off & 7) == 0) {
+            const __half *R = static_cast<const __half *>(ep.residual) + off;
+            if (vec) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
-                    __half2 p0 = __floats2half2_rn(f[j], f[j + 1]);
-                    __half2 p1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-                    __half2 p2 = __floats2half2_rn(f[j + 4], f[j + 5]);
-                    __half2 p3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t *>(&p0);
-                    u.y = *reinterpret_cast<uint32_t *>(&p1);
-                    u.z = *reinterpret_cast<uint32_t *>(&p2);
-                    u.w = *reinterpret_cast<uint32_t *>(&p3);
-                    *reinterpret_cast<uint4 *>(C + j) = u;
+                    const uint4 u = *reinterpret_cast<const uint4 *>(R + j);
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 r2 = __half22float2(h[t]);
+                        f[j + 2 * t] += r2.x;
+                        f[j + 2 * t + 1] += r2.y;
+                    }
                 }
             } else {
-                for (int j = 0; j < ncols; ++j) C[j] = __float2half_rn(f[j]);
+                for (int j = 0; j < ncols; ++j) f[j] += __half2float(R[j]);
             }
         }
     }
+    if (ep.act_after && ep.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
+    uint32_t w[16];
+    if (ep.is_bf16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t *>(&p);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            __half2 p = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t *>(&p);
+        }
+    }
+    unsigned char *C = static_cast<unsigned char *>(ep.C);
+    if (vec && scratch) {
+        warp_store_rows64(scratch, w, C + ((size_t)warp_row0 * ep.ldc + col0) * 2, (size_t)ep.ldc * 2, rows_valid, lane);
+    } else if (row_ok) {
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4 *>(C + off * 2 + j * 4) = make_uint4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+        } else {
+            unsigned short *Cs = reinterpret_cast<unsigned short *>(C) + off;
+            for (int j = 0; j < ncols; ++j) Cs[j] = (unsigned short)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu));
+        }
+    }
 }
-
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -264,13 +299,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const int row = m_blk * GEMM_BM + q * 32 + lane;
+        const int warp_row0 = m_blk * GEMM_BM + q * 32;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
             tmem_ld_wait();
-            epilogue_store32(ep, row, n_blk * BN + c * 32, M, N, v);
+            epilogue_store32(ep, warp_row0, lane, n_blk * BN + c * 32, M, N, v);
         }
     }
 
@@ -329,7 +364,8 @@ struct G2Smem {
     static constexpr int B_BYTES = G2_BN * GEMM_BK * 2;     // 32 KB (BN 256) / 16 KB (BN 128)
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = G2_STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * G2_STAGES + 4) * 8 + 16 + 1024;
+    static constexpr int SCRATCH_OFFSET = BAR_OFFSET + 256;                       // 12 warps x 2.5 KB epilogue scratch
+    static constexpr int TOTAL = SCRATCH_OFFSET + 12 * 32 * 20 * 4 + 1024;        // + alignment slack
 };
 
 // BN = 256 (4 stages) for wide outputs; BN = 128 (6 stages) when 128 x 256 tiles would leave the last
@@ -347,6 +383,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     uint64_t *tmem_full_bar = empty_bar + G2_STAGES;   // [2]
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    uint32_t *epi_scratch = reinterpret_cast<uint32_t *>(smem + S::SCRATCH_OFFSET) + (threadIdx.x >> 5) * EPI_SCRATCH_WORDS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
@@ -429,7 +466,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
-            const int row = m_blk * GEMM_BM + q * 32 + lane;
+            const int warp_row0 = m_blk * GEMM_BM + q * 32;
             constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
@@ -446,7 +483,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                epilogue_store32(ep, row, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv);
+                epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv, epi_scratch);
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
@@ -483,6 +520,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t *tmem_full_bar = empty_bar + G2_STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    uint32_t *epi_scratch = reinterpret_cast<uint32_t *>(smem + S::SCRATCH_OFFSET) + (threadIdx.x >> 5) * EPI_SCRATCH_WORDS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -571,7 +609,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int m_blk = 2 * (pt % m_pairs) + (int)rank, n_blk = pt / m_pairs;
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
-            const int row = m_blk * GEMM_BM + q * 32 + lane;
+            const int warp_row0 = m_blk * GEMM_BM + q * 32;
             constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
@@ -588,7 +626,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                epilogue_store32(ep, row, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv);
+                epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv, epi_scratch);
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
