@@ -299,7 +299,8 @@ class B200EngineMixin(object):
         for dev in parse_devices(aux, self._default_device_index()):
             m = native.Model(packed.kind, packed.blob, device=dev)   # one full model copy per GPU
             replicas.append(Replica(dev, m, DynamicBatcher(m, self._policy, name="{}@{}".format(name, dev),
-                                                           max_row_elems=self._max_row_elems)))
+                                                           max_row_elems=self._max_row_elems,
+                                                           request_timeout_s=self._timeout)))
         self._replicas = ReplicaSet(replicas)
         self._native_model = replicas[0].model
         self._batcher = replicas[0].batcher
@@ -347,7 +348,8 @@ class B200EngineMixin(object):
         else:
             # no io spec on the endpoint (as with the sklearn / xgboost engines): the model decides
             list_data = [data] if m.n_inputs == 1 else data
-            arrays = [np.array(d, dtype=m.in_dtypes[i]) for i, d in enumerate(list_data)]
+            arrays = [d if (isinstance(d, np.ndarray) and d.dtype == m.in_dtypes[i]) else np.array(d, dtype=m.in_dtypes[i])
+                      for i, d in enumerate(list_data)]
         if len(arrays) != m.n_inputs:
             raise ValueError("b200 engine: model takes {} inputs, request carries {}".format(m.n_inputs, len(arrays)))
         rows = None
@@ -398,11 +400,8 @@ class B200EngineMixin(object):
         if self._preprocess is not None and hasattr(self._preprocess, "process"):
             return await self._preprocess.process(data, state, collect_custom_statistics_fn)
         arrays, rows = self._marshal(data)
-        fut = self._next_batcher().submit_async(arrays, rows)
-        try:
-            outs = await asyncio.wait_for(fut, timeout=self._timeout)
-        except asyncio.TimeoutError:
-            raise ValueError("b200 engine: request timed out after {}s".format(self._timeout))
+        # the deadline (self._timeout, preprocess_service.py:48-49) is enforced by the batcher on the queue age
+        outs = await self._next_batcher().submit_async(arrays, rows)
         return self._unmarshal(outs)
 
     def process_sync(self, data, timeout=None):

@@ -120,10 +120,13 @@ def _resolve_many(pairs):
 class DynamicBatcher(object):
     """Queue + scheduler of one endpoint in front of one native.Stream."""
 
-    def __init__(self, model, policy, name="endpoint", stream=None, max_row_elems=0):
+    def __init__(self, model, policy, name="endpoint", stream=None, max_row_elems=0, request_timeout_s=None):
         self.model = model
         self.policy = policy
         self.name = name
+        # a request that waited longer than this in the queue is failed instead of dispatched (the engine's
+        # per-request deadline, preprocess_service.py:48-49, without a timer object per request)
+        self.request_timeout_s = request_timeout_s
         self.max_row_elems = int(max_row_elems)
         self.ragged = any(e < 0 for e in model.in_row_elems)
         # `stream` is injectable so the queueing logic can be unit-tested without a GPU
@@ -199,10 +202,18 @@ class DynamicBatcher(object):
                 fits = [p for p in pol.preferred_batch_size if p <= self._queued_rows]
                 if fits:
                     limit = fits[-1]
+            expired = []
             while self._queue and rows + self._queue[0].rows <= limit:
                 r = self._queue.popleft()
+                if self.request_timeout_s is not None and time.perf_counter() - r.t_enq > self.request_timeout_s:
+                    self._queued_rows -= r.rows
+                    expired.append(r)
+                    continue
                 rows += r.rows
                 batch.append(r)
+            if expired:
+                self._fail(expired, ValueError("b200 engine: request timed out after {}s in the queue".format(
+                    self.request_timeout_s)))
             if not batch and self._queue:  # head does not fit a preferred size: take it alone
                 r = self._queue.popleft()
                 rows += r.rows
@@ -282,10 +293,13 @@ class DynamicBatcher(object):
                 ev, slot, batch = self._inflight.popleft()
             try:
                 self.stream.wait(ev)
+                # one copy per output per batch out of the pinned slot; requests get row views of it
+                n_rows = sum(r.rows for r in batch)
+                outs = [slot.outputs[o][:n_rows].copy() for o in range(m.n_outputs)]
                 row = 0
                 results = []
                 for r in batch:
-                    results.append([slot.outputs[o][row:row + r.rows].copy() for o in range(m.n_outputs)])
+                    results.append([out[row:row + r.rows] for out in outs])
                     row += r.rows
                 self.stream.release(slot)
                 with self._inflight_cond:
