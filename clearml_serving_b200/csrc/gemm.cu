@@ -471,21 +471,19 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
             const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
-            // software pipeline: the TMEM read of chunk c+1 is in flight while chunk c goes through the epilogue math
-            uint32_t vbuf[2][32];
-            tmem_ld_32x32(t_addr, vbuf[0]);
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
+                uint32_t v[32];
                 float bv[32];
+                tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
                 broadcast32(b4, c, bv);
                 tmem_ld_wait();
-                if (c + 1 < NCH) tmem_ld_32x32(t_addr + (uint32_t)((c + 1) * 32), vbuf[(c + 1) & 1]);
-                if (c == NCH - 1) {   // last TMEM read of this warp has landed: hand the accumulator back before the math
+                if (c == NCH - 1) {   // last TMEM read of this warp: hand the accumulator back before the math
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, vbuf[c & 1], bv, epi_scratch);
+                epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv, epi_scratch);
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
@@ -616,20 +614,19 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
             const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
-            uint32_t vbuf[2][32];   // software pipeline, as in gemm_tn_persistent_kernel
-            tmem_ld_32x32(t_addr, vbuf[0]);
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
+                uint32_t v[32];
                 float bv[32];
+                tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
                 broadcast32(b4, c, bv);
                 tmem_ld_wait();
-                if (c + 1 < NCH) tmem_ld_32x32(t_addr + (uint32_t)((c + 1) * 32), vbuf[(c + 1) & 1]);
                 if (c == NCH - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, vbuf[c & 1], bv, epi_scratch);
+                epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv, epi_scratch);
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
