@@ -1,0 +1,225 @@
+// skinny.cu -- weight-streaming GEMM for the decode step of the LLM endpoint (BASELINE.json configs[4];
+// the reference hands this endpoint to vLLM: clearml_serving/serving/preprocess_service.py:1097-1348):
+//     Y[m, n] += sum_k X[m, k] * W[n, k]         W: [N_out, K] bf16 K-major (nn.Linear weight as stored)
+//                                                X: [M <= 32, K] bf16 (one row per running sequence)
+//                                                Y: [32, N_out] fp32, accumulated in place
+// A decode step multiplies every weight of the model by at most max_batch (32) activation rows: the op is
+// bound by streaming W from HBM once (2 bytes per weight, 32 FMAs each), so the kernel is organised around
+// keeping every SM's share of that stream in flight, not around tensor-pipe utilisation:
+//   * operands are swapped: the WEIGHT tile (128 rows x 64 k) is the UMMA "A" operand and X the 32-wide "B"
+//     operand, so one tcgen05.mma 128x32x16 consumes a full 128-row weight slab with no padding of the batch
+//     to 128 rows;
+//   * stream-K: the (weight tile, k-block) units of the whole GEMM are dealt evenly to one persistent CTA per
+//     SM, each CTA owning a CONTIGUOUS range, so all 148 SMs pull the same number of bytes whatever N_out is
+//     (a 4096 x 2048 projection has only 32 row tiles); a CTA's range covers at most a few (tile, k-range)
+//     segments, each accumulated in TMEM (double-buffered) and added into Y with red.global.add.f32 (a warp's
+//     32 lanes hold 32 consecutive n of one batch row: every reduction instruction is one coalesced 128-byte line);
+//   * a 10-stage TMA ring (20 KB per stage: W 16 KB + X 4 KB) keeps ~200 KB per SM in flight.
+// The consumer kernels (llm.cu) read Y and zero it again, so no separate memset is needed.
+// Roofline: HBM; algorithmic bytes = 2 * N_out * K (the weight), X and Y are L2-resident.
+#include "common.cuh"
+#include "sm100.cuh"
+
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+namespace b2s {
+
+using namespace sm100;
+
+int make_tmap_2d_kmajor(CUtensorMap *out, const void *base, int64_t rows, int64_t K, int64_t ld_elems,
+                        int box_rows, int is_bf16);
+
+constexpr int SK_BM = 128;       // weight rows per tile (UMMA M)
+constexpr int SK_BN = 32;        // activation rows (UMMA N)
+constexpr int SK_BK = 64;
+constexpr int SK_STAGES = 10;
+constexpr int SK_THREADS = 256;  // warp 0 TMA, 1 MMA, 2 TMEM owner, 3 idle, 4-7 epilogue
+
+struct SkSmem {
+    static constexpr int A_BYTES = SK_BM * SK_BK * 2;   // 16 KB
+    static constexpr int B_BYTES = SK_BN * SK_BK * 2;   // 4 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = SK_STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+};
+
+__device__ __forceinline__ void red_add(float *addr, float a)
+{
+    asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(a) : "memory");
+}
+
+__global__ void __launch_bounds__(SK_THREADS, 1)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                   float *__restrict__ y, int n_out, int m_rows, int num_k, int total_units)
+{
+    using S = SkSmem;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFFSET);
+    uint64_t *empty_bar = full_bar + SK_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + SK_STAGES;   // [2]
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // contiguous unit range of this CTA (unit = tile * num_k + kb)
+    const int u0 = (int)(((int64_t)total_units * blockIdx.x) / gridDim.x);
+    const int u1 = (int)(((int64_t)total_units * (blockIdx.x + 1)) / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_w);
+        prefetch_tensormap(&tmap_x);
+        for (int s = 0; s < SK_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 2 * SK_BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int u = u0; u < u1; ++u) {
+                const int tile = u / num_k, kb = u - tile * num_k;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                tma_load_2d(sa, &tmap_w, &full_bar[stage], kb * SK_BK, tile * SK_BM);
+                tma_load_2d(sa + S::A_BYTES, &tmap_x, &full_bar[stage], kb * SK_BK, 0);
+                if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(SK_BM, SK_BN, 1);   // bf16 operands
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            int u = u0;
+            while (u < u1) {
+                const int tile = u / num_k;
+                const int seg_end = min(u1, (tile + 1) * num_k);
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * SK_BN);
+                for (int first = u; u < seg_end; ++u) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                    const uint64_t adesc = make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = make_sw128_kmajor_desc(sa + S::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < SK_BK / 16; ++k)
+                        umma_f16(d_tmem, desc_advance(adesc, k * 32), desc_advance(bdesc, k * 32), idesc,
+                                 (uint32_t)((u != first) || (k != 0)));
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == SK_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full_bar[as]);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        int u = u0;
+        while (u < u1) {
+            const int tile = u / num_k;
+            u = min(u1, (tile + 1) * num_k);
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * SK_BN), v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            const int n = tile * SK_BM + q * 32 + lane;
+            if (n < n_out) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < m_rows) red_add(y + (size_t)j * n_out + n, __uint_as_float(v[j]));
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * SK_BN);
+    }
+}
+
+static int sk_num_sms()
+{
+    static int n = []() {
+        int dev = 0, v = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+
+// tensor maps for one (weight, activation buffer) pair; both are cached by the caller (CUDA-graph friendly)
+int skinny_make_maps(CUtensorMap *tw, CUtensorMap *tx, const void *W, int64_t n_out, int64_t K, const void *X, int64_t x_rows)
+{
+    if (K % 8 != 0) return fail(B2S_ERR_INVALID, "skinny gemm: K must be a multiple of 8");
+    if (x_rows > SK_BN) return fail(B2S_ERR_INVALID, "skinny gemm: at most %d activation rows", SK_BN);
+    B2S_TRY(make_tmap_2d_kmajor(tw, W, n_out, K, K, SK_BM, 1));
+    B2S_TRY(make_tmap_2d_kmajor(tx, X, x_rows, K, K, SK_BN, 1));
+    return 0;
+}
+
+int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows)
+{
+    if (n_out <= 0 || K <= 0) return 0;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, []() {
+        attr_err = cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SkSmem::TOTAL);
+    });
+    if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(skinny gemm)");
+    const int num_k = (K + SK_BK - 1) / SK_BK;
+    const int tiles = (n_out + SK_BM - 1) / SK_BM;
+    const int64_t units = (int64_t)tiles * num_k;
+    if (units > INT32_MAX) return fail(B2S_ERR_INVALID, "skinny gemm: problem too large");
+    // at least 4 k-blocks per CTA so tiny problems do not pay 148 prologues for nothing
+    int grid = sk_num_sms();
+    if (units < (int64_t)grid * 4) grid = (int)((units + 3) / 4);
+    skinny_gemm_kernel<<<grid, SK_THREADS, SkSmem::TOTAL, st>>>(tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units);
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b2s
+
+// C ABI (operator level, device pointers): y[m][n_out] fp32 += X[m,K] . W[n_out,K]^T ; y must be zeroed by the
+// caller before the first accumulation.
+extern "C" B2S_API int b2s_op_skinny_gemm(int device, void *cuda_stream, const void *W, const void *X, float *y,
+                                           int n_out, int K, int m)
+{
+    using namespace b2s;
+    B2S_CUDA(cudaSetDevice(device));
+    CUtensorMap tw, tx;
+    B2S_TRY(skinny_make_maps(&tw, &tx, W, n_out, K, X, m));
+    return skinny_gemm_maps(static_cast<cudaStream_t>(cuda_stream), tw, tx, y, n_out, K, m);
+}
