@@ -1,0 +1,1028 @@
+// llm.cu -- decoder-only transformer executor (Llama family) for the tensor-parallel LLM endpoint of
+// BASELINE.json configs[4].  In the reference this endpoint is `VllmPreprocessRequest`
+// (clearml_serving/serving/preprocess_service.py:1097-1348), a thin wrapper that hands prompts to vLLM; here the
+// model runs on the library's own kernels:
+//   prefill : RMSNorm -> QKV GEMM (tcgen05, gemm.cu) -> RoPE + KV-cache write -> causal GQA attention
+//             (llm_attention.cu) -> O GEMM -> [TP all-reduce] + residual + RMSNorm -> gate/up GEMM -> SwiGLU ->
+//             down GEMM -> [TP all-reduce] + residual + RMSNorm ... -> lm_head -> greedy argmax
+//   decode  : the same chain for <= 32 running sequences, every projection on the weight-streaming stream-K
+//             kernel of skinny.cu; one decode step is captured in a CUDA graph (context lengths, positions and
+//             the step counter live in device memory, so the same graph replays for every step).
+// Tensor parallelism (Megatron split: QKV / gate / up by output rows, O / down by input columns, lm_head by
+// vocabulary) runs as ONE PROCESS PER GPU.  The row-parallel partial sums are exchanged through peer memory
+// (cudaIpc handles swapped by the host side over torch.distributed): the kernel that consumes a partial sum --
+// residual add + RMSNorm -- reads the peer's half directly over NVLink and adds it on the fly, so the
+// all-reduce is fused into its consumer and no NCCL call sits on the data path.  With two ranks each direction
+// of the link carries exactly the bytes a reduce-scatter + all-gather would.
+// Synchronisation: a monotonically increasing step counter `gen` in device memory and one flag word per
+// exchange point; a rank publishes flag[k] = gen + 1 in the PEER's memory once its partial for point k is
+// complete and spins (bounded) on its own flag[k].  Partial buffers alternate between two copies so a buffer
+// is only rewritten after the peer has signalled the NEXT exchange point, i.e. finished reading it.
+//
+// Layouts: weights bf16 [out, in] as nn.Linear stores them; residual stream fp32 [T, H]; KV cache per layer
+// K, V = [slot][kv_head][max_ctx][128] bf16; decode accumulators fp32 [32, N].
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace b2s {
+
+int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t ldb, int M, int N, int K,
+            const GemmEpilogue &ep);
+int skinny_make_maps(CUtensorMap *tw, CUtensorMap *tx, const void *W, int64_t n_out, int64_t K, const void *X, int64_t x_rows);
+int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows);
+int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *kc, const void *vc, const int32_t *cu_seqlens,
+                     const int32_t *slots, void *out, int ld_out, int n_seq, int max_seqlen, int hq_r, int kvh_r,
+                     int max_ctx, float scale);
+int llm_attn_decode(cudaStream_t st, const void *q, int ld_q, const void *kc, const void *vc, const int32_t *ctx_len,
+                    const int32_t *slots, void *out, int ld_out, int n_seq, int hq_r, int kvh_r, int max_ctx, float scale);
+
+constexpr int LLM_MAXB = 32;          // decode batch (rows of the skinny GEMM)
+constexpr int LLM_HD = 128;           // head dim
+constexpr int LLM_FLAGS = 512;
+
+// ------------------------------------------------------------------------------------------------
+// deterministic on-device initialisation: value(tensor, row, col) is a pure integer function of the GLOBAL
+// coordinates, so every tensor-parallel layout of the same model holds the same numbers (and numpy can
+// reproduce them bit for bit: tests/test_llm_host.py)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t llm_mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// Irwin-Hall(4) of 16-bit uniforms: mean 0, std 1 after scaling; exact in fp32
+__host__ __device__ inline float llm_init_value(uint64_t seed, uint32_t tensor_id, uint32_t row, uint32_t col, float std)
+{
+    const uint64_t r = llm_mix64(seed ^ ((uint64_t)tensor_id << 48) ^ ((uint64_t)row << 24) ^ (uint64_t)col);
+    const int32_t s = (int32_t)(r & 0xFFFF) + (int32_t)((r >> 16) & 0xFFFF) + (int32_t)((r >> 32) & 0xFFFF) +
+                      (int32_t)((r >> 48) & 0xFFFF) - 2 * 65535;
+    return (float)s * (std * (1.7320508f / 65536.0f));   // Var[sum of 4 U(0,65536)] = 65536^2 / 3
+}
+
+__global__ void __launch_bounds__(256)
+llm_fill_kernel(__nv_bfloat16 *__restrict__ w, int64_t rows, int64_t cols, uint64_t seed, uint32_t tensor_id,
+                uint32_t row0, uint32_t col0, float std)
+{
+    const int64_t n = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        w[i] = __float2bfloat16_rn(llm_init_value(seed, tensor_id, row0 + (uint32_t)r, col0 + (uint32_t)c, std));
+    }
+}
+__global__ void __launch_bounds__(256) llm_fill_const_kernel(float *__restrict__ w, int64_t n, float v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer-memory primitives
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// peer data must never be served from this SM's L1 (the same addresses are rewritten every step)
+__device__ __forceinline__ uint4 ld_peer_v4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ld_peer_v2(const void *p)
+{
+    uint2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+// Exchange point k of the current step: tell the peer our partial is complete, wait until its is.  All threads
+// of the CTA call this; returns after a __syncthreads().  `gen` is read from device memory (stable during a step).
+__device__ __forceinline__ void tp_exchange_point(uint32_t *my_flags, uint32_t *peer_flags, const uint32_t *gen, int k)
+{
+    if (peer_flags == nullptr) return;
+    if (threadIdx.x == 0) {
+        const uint32_t want = *reinterpret_cast<const volatile uint32_t *>(gen) + 1u;
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(peer_flags + k, want);
+        }
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(my_flags + k) - want) < 0) {
+            if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a lost peer must not hang the GPU
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float *red /*[8]*/)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding gather + first RMSNorm.  One CTA (256 threads) per token; H <= 8192, H % 4 == 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+llm_embed_rms_kernel(const int32_t *__restrict__ tokens, const __nv_bfloat16 *__restrict__ embed, const float *__restrict__ w,
+                     float *__restrict__ h, __nv_bfloat16 *__restrict__ xn, int H, int vocab, float eps)
+{
+    __shared__ float red[8];
+    const int t = blockIdx.x;
+    int tok = __ldg(tokens + t);
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+    const __nv_bfloat16 *e = embed + (int64_t)tok * H;
+    float4 v[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = (it * 256 + threadIdx.x) * 4;
+        if (i < H) {
+            const uint2 u = *reinterpret_cast<const uint2 *>(e + i);
+            const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
+            const float2 a = __bfloat1622float2(p[0]), c = __bfloat1622float2(p[1]);
+            v[it] = make_float4(a.x, a.y, c.x, c.y);
+            *reinterpret_cast<float4 *>(h + (int64_t)t * H + i) = v[it];
+            ss += a.x * a.x + a.y * a.y + c.x * c.x + c.y * c.y;
+        }
+    }
+    const float inv = rsqrtf(block_sum_256(ss, red) / (float)H + eps);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = (it * 256 + threadIdx.x) * 4;
+        if (i < H) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(w + i));
+            __nv_bfloat162 o0 = __floats2bfloat162_rn(v[it].x * inv * g.x, v[it].y * inv * g.y);
+            __nv_bfloat162 o1 = __floats2bfloat162_rn(v[it].z * inv * g.z, v[it].w * inv * g.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t *>(&o0);
+            u.y = *reinterpret_cast<uint32_t *>(&o1);
+            *reinterpret_cast<uint2 *>(xn + (int64_t)t * H + i) = u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// [TP all-reduce of a row-parallel partial] + residual add + RMSNorm, fused.  One CTA per token.
+//   F32 = false (prefill): partial is bf16 [T, H];   F32 = true (decode): partial is fp32 [32, H] accumulated by
+//   the skinny GEMM; the OLDER decode partial buffer (`zero_buf`) is cleared for the GEMM after next.
+// h += mine + peer;  xn = bf16( h * rsqrt(mean(h^2) + eps) * w )
+// ------------------------------------------------------------------------------------------------
+template <bool F32>
+__global__ void __launch_bounds__(256)
+llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *zero_buf, uint32_t *my_flags, uint32_t *peer_flags,
+                      const uint32_t *gen, int k, const float *__restrict__ w, float *__restrict__ h,
+                      __nv_bfloat16 *__restrict__ xn, int H, float eps)
+{
+    __shared__ float red[8];
+    tp_exchange_point(my_flags, peer_flags, gen, k);
+    const int t = blockIdx.x;
+    float4 v[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = (it * 256 + threadIdx.x) * 4;
+        if (i < H) {
+            float4 a;
+            if (F32) {
+                a = *reinterpret_cast<const float4 *>(static_cast<const float *>(mine) + (int64_t)t * H + i);
+                if (peer) {
+                    const uint4 u = ld_peer_v4(static_cast<const float *>(peer) + (int64_t)t * H + i);
+                    a.x += __uint_as_float(u.x); a.y += __uint_as_float(u.y);
+                    a.z += __uint_as_float(u.z); a.w += __uint_as_float(u.w);
+                }
+                if (zero_buf) *reinterpret_cast<float4 *>(zero_buf + (int64_t)t * H + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const uint2 u = *reinterpret_cast<const uint2 *>(static_cast<const __nv_bfloat16 *>(mine) + (int64_t)t * H + i);
+                const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
+                const float2 m0 = __bfloat1622float2(p[0]), m1 = __bfloat1622float2(p[1]);
+                a = make_float4(m0.x, m0.y, m1.x, m1.y);
+                if (peer) {
+                    const uint2 q = ld_peer_v2(static_cast<const __nv_bfloat16 *>(peer) + (int64_t)t * H + i);
+                    const __nv_bfloat162 *pq = reinterpret_cast<const __nv_bfloat162 *>(&q);
+                    const float2 q0 = __bfloat1622float2(pq[0]), q1 = __bfloat1622float2(pq[1]);
+                    a.x += q0.x; a.y += q0.y; a.z += q1.x; a.w += q1.y;
+                }
+            }
+            float4 r = *reinterpret_cast<const float4 *>(h + (int64_t)t * H + i);
+            r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+            *reinterpret_cast<float4 *>(h + (int64_t)t * H + i) = r;
+            v[it] = r;
+            ss += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+        }
+    }
+    const float inv = rsqrtf(block_sum_256(ss, red) / (float)H + eps);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = (it * 256 + threadIdx.x) * 4;
+        if (i < H) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(w + i));
+            __nv_bfloat162 o0 = __floats2bfloat162_rn(v[it].x * inv * g.x, v[it].y * inv * g.y);
+            __nv_bfloat162 o1 = __floats2bfloat162_rn(v[it].z * inv * g.z, v[it].w * inv * g.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t *>(&o0);
+            u.y = *reinterpret_cast<uint32_t *>(&o1);
+            *reinterpret_cast<uint2 *>(xn + (int64_t)t * H + i) = u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE (rotate-half convention: pairs (i, i + 64)) on q and k, K/V append to the cache.  One CTA per token.
+//   prefill: qkv bf16 [T, QKV] -- q rotated in place, position = tok_pos[t], slot = slots[tok_seq[t]]
+//   decode : src fp32 [32, QKV] (skinny GEMM accumulator, cleared here), q -> bf16 [32, hq*128],
+//            position = ctx_len[b], slot = slots[b]
+// ------------------------------------------------------------------------------------------------
+template <bool DEC>
+__global__ void __launch_bounds__(256)
+llm_rope_cache_kernel(void *__restrict__ qkv_src, __nv_bfloat16 *__restrict__ q_out, __nv_bfloat16 *__restrict__ kc,
+                      __nv_bfloat16 *__restrict__ vc, const int32_t *__restrict__ tok_seq, const int32_t *__restrict__ tok_pos,
+                      const int32_t *__restrict__ slots, const float *__restrict__ rope_cos, const float *__restrict__ rope_sin,
+                      int hq_r, int kvh_r, int max_ctx)
+{
+    const int t = blockIdx.x;
+    const int QKV = (hq_r + 2 * kvh_r) * LLM_HD;
+    const int seq = DEC ? t : __ldg(tok_seq + t);
+    int pos = __ldg(tok_pos + (DEC ? seq : t));
+    pos = pos < max_ctx ? pos : max_ctx - 1;
+    const int slot = __ldg(slots + seq);
+    const float *cs = rope_cos + (int64_t)pos * 64, *sn = rope_sin + (int64_t)pos * 64;
+    float *srcf = DEC ? static_cast<float *>(qkv_src) + (int64_t)t * QKV : nullptr;
+    __nv_bfloat16 *srcb = DEC ? nullptr : static_cast<__nv_bfloat16 *>(qkv_src) + (int64_t)t * QKV;
+    // q and k heads: (head, pair)
+    const int n_rot = (hq_r + kvh_r) * 64;
+    for (int idx = threadIdx.x; idx < n_rot; idx += 256) {
+        const int head = idx >> 6, i = idx & 63;
+        const int c0 = head * LLM_HD + i;   // q heads first, then k heads: contiguous in the QKV row
+        float x1, x2;
+        if (DEC) { x1 = srcf[c0]; x2 = srcf[c0 + 64]; srcf[c0] = 0.f; srcf[c0 + 64] = 0.f; }
+        else { x1 = __bfloat162float(srcb[c0]); x2 = __bfloat162float(srcb[c0 + 64]); }
+        const float c = cs[i], s = sn[i];
+        const __nv_bfloat16 o1 = __float2bfloat16_rn(x1 * c - x2 * s), o2 = __float2bfloat16_rn(x2 * c + x1 * s);
+        if (head < hq_r) {
+            __nv_bfloat16 *dst = DEC ? q_out + (int64_t)t * hq_r * LLM_HD : srcb;
+            dst[c0] = o1;
+            dst[c0 + 64] = o2;
+        } else {
+            const int kh = head - hq_r;
+            __nv_bfloat16 *dst = kc + (((int64_t)slot * kvh_r + kh) * max_ctx + pos) * LLM_HD;
+            dst[i] = o1;
+            dst[i + 64] = o2;
+        }
+    }
+    const int v0 = (hq_r + kvh_r) * LLM_HD;
+    for (int idx = threadIdx.x; idx < kvh_r * LLM_HD; idx += 256) {
+        const int kh = idx >> 7, d = idx & 127;
+        __nv_bfloat16 val;
+        if (DEC) { val = __float2bfloat16_rn(srcf[v0 + idx]); srcf[v0 + idx] = 0.f; }
+        else val = srcb[v0 + idx];
+        vc[(((int64_t)slot * kvh_r + kh) * max_ctx + pos) * LLM_HD + d] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SwiGLU: act = silu(gate) * up.  gate = columns [0, I), up = columns [I, 2I) of the fused projection.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
+
+template <bool DEC>
+__global__ void __launch_bounds__(256)
+llm_swiglu_kernel(void *__restrict__ gu, __nv_bfloat16 *__restrict__ act, int64_t rows, int I)
+{
+    const int64_t n4 = rows * (I / 4);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / (I / 4);
+        const int c = (int)(idx - r * (I / 4)) * 4;
+        float4 g, u;
+        if (DEC) {
+            float *row = static_cast<float *>(gu) + r * 2 * I;
+            g = *reinterpret_cast<float4 *>(row + c);
+            u = *reinterpret_cast<float4 *>(row + I + c);
+            *reinterpret_cast<float4 *>(row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(row + I + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const __nv_bfloat16 *row = static_cast<const __nv_bfloat16 *>(gu) + r * 2 * I;
+            const uint2 a = *reinterpret_cast<const uint2 *>(row + c), b = *reinterpret_cast<const uint2 *>(row + I + c);
+            const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&a), *pb = reinterpret_cast<const __nv_bfloat162 *>(&b);
+            const float2 a0 = __bfloat1622float2(pa[0]), a1 = __bfloat1622float2(pa[1]);
+            const float2 b0 = __bfloat1622float2(pb[0]), b1 = __bfloat1622float2(pb[1]);
+            g = make_float4(a0.x, a0.y, a1.x, a1.y);
+            u = make_float4(b0.x, b0.y, b1.x, b1.y);
+        }
+        __nv_bfloat162 o0 = __floats2bfloat162_rn(silu_mul(g.x, u.x), silu_mul(g.y, u.y));
+        __nv_bfloat162 o1 = __floats2bfloat162_rn(silu_mul(g.z, u.z), silu_mul(g.w, u.w));
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t *>(&o0);
+        o.y = *reinterpret_cast<uint32_t *>(&o1);
+        *reinterpret_cast<uint2 *>(act + r * I + c) = o;
+    }
+}
+
+// last token of every sequence -> the 32-row activation block the lm_head GEMM reads
+__global__ void __launch_bounds__(256)
+llm_gather_last_kernel(const __nv_bfloat16 *__restrict__ xn, const int32_t *__restrict__ cu_seqlens, __nv_bfloat16 *__restrict__ xlast, int H)
+{
+    const int b = blockIdx.x;
+    const int64_t t = __ldg(cu_seqlens + b + 1) - 1;
+    for (int i = threadIdx.x * 8; i < H; i += 256 * 8)
+        *reinterpret_cast<uint4 *>(xlast + (int64_t)b * H + i) = *reinterpret_cast<const uint4 *>(xn + t * H + i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy sampling over the vocabulary shard + cross-rank exchange.  One CTA per sequence.
+// logits fp32 [32, V_r] (skinny GEMM accumulator, cleared here; optionally copied to `keep` first).
+// ------------------------------------------------------------------------------------------------
+struct AmaxSlot { float val; int32_t idx; };
+
+__global__ void __launch_bounds__(256)
+llm_argmax_kernel(float *__restrict__ logits, float *__restrict__ keep, int V_r, int v_offset, AmaxSlot *my_slots, AmaxSlot *peer_slots,
+                  uint32_t *my_flags, uint32_t *peer_flags, const uint32_t *gen, int k, int32_t *__restrict__ next_tok,
+                  int32_t *__restrict__ out_tokens, const int32_t *__restrict__ out_pos, int max_new)
+{
+    __shared__ float s_val[256];
+    __shared__ int s_idx[256];
+    const int b = blockIdx.x;
+    float *row = logits + (int64_t)b * V_r;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < V_r; i += 256) {
+        const float v = row[i];
+        if (keep) keep[(int64_t)b * V_r + i] = v;
+        row[i] = 0.f;
+        if (v > best) { best = v; bi = i; }   // strided scan: first maximum per thread
+    }
+    s_val[threadIdx.x] = best;
+    s_idx[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const float v2 = s_val[threadIdx.x + o];
+            const int i2 = s_idx[threadIdx.x + o];
+            if (v2 > s_val[threadIdx.x] || (v2 == s_val[threadIdx.x] && i2 < s_idx[threadIdx.x])) {
+                s_val[threadIdx.x] = v2;
+                s_idx[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t g = *reinterpret_cast<const volatile uint32_t *>(gen);
+    const int par = (int)(g & 1u) * LLM_MAXB;
+    float val = s_val[0];
+    int idx = s_idx[0] + v_offset;
+    if (peer_flags) {
+        // every CTA publishes its own (val, idx) into the peer's slot table, then ONE flag per step is raised by
+        // the last CTA to get there (grid-wide counter in my_flags[LLM_FLAGS - 1])
+        if (threadIdx.x == 0) {
+            AmaxSlot s;
+            s.val = val;
+            s.idx = idx;
+            *reinterpret_cast<volatile float *>(&peer_slots[par + b].val) = s.val;
+            *reinterpret_cast<volatile int32_t *>(&peer_slots[par + b].idx) = s.idx;
+            __threadfence_system();
+            const uint32_t done = atomicAdd(&my_flags[LLM_FLAGS - 1], 1u);
+            if (done == gridDim.x - 1) {
+                my_flags[LLM_FLAGS - 1] = 0u;
+                __threadfence_system();
+                st_release_sys(peer_flags + k, g + 1u);
+            }
+            const long long t0 = clock64();
+            while ((int32_t)(ld_acquire_sys(my_flags + k) - (g + 1u)) < 0) {
+                if (clock64() - t0 > 20000000000ll) __trap();
+                __nanosleep(64);
+            }
+            const float pv = *reinterpret_cast<volatile float *>(&my_slots[par + b].val);
+            const int pi = *reinterpret_cast<volatile int32_t *>(&my_slots[par + b].idx);
+            if (pv > val || (pv == val && pi < idx)) { val = pv; idx = pi; }
+            s_idx[0] = idx;
+        }
+        __syncthreads();
+        idx = s_idx[0];
+    }
+    if (threadIdx.x == 0) {
+        next_tok[b] = idx;
+        const int p = out_pos[b];
+        if (p < max_new) out_tokens[(int64_t)b * max_new + p] = idx;
+    }
+}
+
+// end of a step: the step counter advances; decode steps also advance context lengths / output positions
+__global__ void llm_step_end_kernel(uint32_t *gen, int32_t *ctx_len, int32_t *out_pos, int n_seq, int is_decode)
+{
+    const int b = threadIdx.x;
+    if (b < n_seq) {
+        if (is_decode) ctx_len[b] += 1;
+        out_pos[b] += 1;
+    }
+    if (b == 0) *gen += 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct LlmLayer {
+    __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr;
+    float *ln1 = nullptr, *ln2 = nullptr;
+    CUtensorMap m_qkv_w, m_o_w, m_gu_w, m_down_w;   // skinny-GEMM weight maps
+};
+
+struct Llm {
+    b2s_llm_config cfg{};
+    int device = 0;
+    int hq_r = 0, kvh_r = 0, qkv_n = 0, I_r = 0, V_r = 0, H = 0;
+    int64_t max_tokens = 0;
+    std::vector<LlmLayer> layers;
+    __nv_bfloat16 *embed = nullptr, *lm_head = nullptr;
+    float *final_norm = nullptr, *rope_cos = nullptr, *rope_sin = nullptr;
+    __nv_bfloat16 *kcache = nullptr, *vcache = nullptr;
+    int64_t kv_layer_stride = 0;
+    // activations
+    float *h = nullptr;
+    __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr, *xlast = nullptr, *qdec = nullptr;
+    float *ws_qkv = nullptr, *ws_gu = nullptr, *ws_logits = nullptr, *keep_logits = nullptr;
+    // exchange block (one allocation, exported through cudaIpc)
+    unsigned char *comm = nullptr, *peer_comm = nullptr;
+    size_t comm_bytes = 0, off_amax = 0, off_pdec[2] = {0, 0}, off_ppre[2] = {0, 0};
+    // step state
+    int32_t *d_tokens = nullptr, *d_tok_seq = nullptr, *d_tok_pos = nullptr, *d_cu = nullptr, *d_slots = nullptr,
+            *d_ctx_len = nullptr, *d_next_tok = nullptr, *d_out_tokens = nullptr, *d_out_pos = nullptr;
+    uint32_t *d_gen = nullptr;
+    int32_t *h_stage = nullptr;   // pinned staging for token metadata
+    int max_new_cap = 0;
+    int n_seq = 0;                // sequences of the current wave
+    CUtensorMap m_x_xn, m_x_attn, m_x_act, m_x_last, m_lm_w;
+    std::map<int, cudaGraphExec_t> decode_graphs;   // by n_seq
+    std::map<int, int> decode_graph_launches;
+    std::vector<void *> allocs;
+    cudaStream_t stream = nullptr;        // every step of this model runs on its own stream
+    cudaEvent_t events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+    uint32_t *flags(unsigned char *base) const { return reinterpret_cast<uint32_t *>(base); }
+    AmaxSlot *amax(unsigned char *base) const { return reinterpret_cast<AmaxSlot *>(base + off_amax); }
+
+    ~Llm()
+    {
+        cudaSetDevice(device);
+        for (auto &g : decode_graphs) cudaGraphExecDestroy(g.second);
+        if (peer_comm) cudaIpcCloseMemHandle(peer_comm);
+        for (void *p : allocs) cudaFree(p);
+        if (h_stage) cudaFreeHost(h_stage);
+        for (cudaEvent_t e : events) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+template <typename T>
+static int llm_alloc(Llm *m, T **out, size_t count, bool zero = true)
+{
+    void *p = nullptr;
+    const size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(llm)");
+    m->allocs.push_back(p);
+    if (zero) B2S_CUDA(cudaMemset(p, 0, bytes ? bytes : 16));
+    *out = static_cast<T *>(p);
+    return 0;
+}
+
+static int llm_create(int device, const b2s_llm_config *c, Llm **out)
+{
+    if (!c || !out) return fail(B2S_ERR_INVALID, "llm_create: null argument");
+    if (c->head_dim != LLM_HD) return fail(B2S_ERR_INVALID, "llm: head_dim must be 128");
+    if (c->tp_size != 1 && c->tp_size != 2) return fail(B2S_ERR_INVALID, "llm: tensor_parallel must be 1 or 2");
+    if (c->tp_rank < 0 || c->tp_rank >= c->tp_size) return fail(B2S_ERR_INVALID, "llm: bad tp_rank");
+    if (c->n_heads % c->tp_size || c->n_kv_heads % c->tp_size || c->inter % (64 * c->tp_size) || c->vocab % c->tp_size)
+        return fail(B2S_ERR_INVALID, "llm: heads / kv heads / intermediate / vocab must divide by tensor_parallel");
+    if (c->n_heads % c->n_kv_heads) return fail(B2S_ERR_INVALID, "llm: n_heads must be a multiple of n_kv_heads");
+    if (c->hidden % 64 || c->hidden > 8192) return fail(B2S_ERR_INVALID, "llm: hidden must be a multiple of 64, <= 8192");
+    if (c->max_batch < 1 || c->max_batch > LLM_MAXB) return fail(B2S_ERR_INVALID, "llm: max_batch must be 1..32");
+    if (c->max_ctx < 16 || c->max_tokens < c->max_batch) return fail(B2S_ERR_INVALID, "llm: bad max_ctx / max_tokens");
+    B2S_CUDA(cudaSetDevice(device));
+    Llm *m = new Llm();
+    m->cfg = *c;
+    m->device = device;
+    m->H = c->hidden;
+    m->hq_r = c->n_heads / c->tp_size;
+    m->kvh_r = c->n_kv_heads / c->tp_size;
+    m->qkv_n = (m->hq_r + 2 * m->kvh_r) * LLM_HD;
+    m->I_r = c->inter / c->tp_size;
+    m->V_r = c->vocab / c->tp_size;
+    m->max_tokens = c->max_tokens;
+    m->max_new_cap = c->max_ctx;
+    const int H = m->H, L = c->n_layers;
+    const int64_t T = m->max_tokens;
+    int rc = 0;
+#define LA(ptr, count) if ((rc = llm_alloc(m, &(ptr), (size_t)(count))) != 0) { delete m; return rc; }
+    LA(m->embed, (int64_t)c->vocab * H);
+    LA(m->lm_head, (int64_t)m->V_r * H);
+    LA(m->final_norm, H);
+    LA(m->rope_cos, (int64_t)c->max_ctx * 64);
+    LA(m->rope_sin, (int64_t)c->max_ctx * 64);
+    m->layers.resize(L);
+    for (int l = 0; l < L; ++l) {
+        LlmLayer &y = m->layers[l];
+        LA(y.wqkv, (int64_t)m->qkv_n * H);
+        LA(y.wo, (int64_t)H * m->hq_r * LLM_HD);
+        LA(y.wgu, (int64_t)2 * m->I_r * H);
+        LA(y.wdown, (int64_t)H * m->I_r);
+        LA(y.ln1, H);
+        LA(y.ln2, H);
+    }
+    m->kv_layer_stride = (int64_t)c->max_batch * m->kvh_r * c->max_ctx * LLM_HD;
+    LA(m->kcache, m->kv_layer_stride * L);
+    LA(m->vcache, m->kv_layer_stride * L);
+    const int64_t Tp = T > LLM_MAXB ? T : LLM_MAXB;
+    LA(m->h, Tp * H);
+    LA(m->xn, Tp * H);
+    LA(m->qkv, Tp * m->qkv_n);
+    LA(m->attn, Tp * m->hq_r * LLM_HD);
+    LA(m->gu, Tp * 2 * m->I_r);
+    LA(m->act, Tp * m->I_r);
+    LA(m->xlast, (int64_t)LLM_MAXB * H);
+    LA(m->qdec, (int64_t)LLM_MAXB * m->hq_r * LLM_HD);
+    LA(m->ws_qkv, (int64_t)LLM_MAXB * m->qkv_n);
+    LA(m->ws_gu, (int64_t)LLM_MAXB * 2 * m->I_r);
+    LA(m->ws_logits, (int64_t)LLM_MAXB * m->V_r);
+    // exchange block
+    m->off_amax = LLM_FLAGS * 4;
+    size_t off = m->off_amax + 2 * LLM_MAXB * sizeof(AmaxSlot);
+    off = (size_t)round_up((int64_t)off, 256);
+    for (int i = 0; i < 2; ++i) { m->off_pdec[i] = off; off += (size_t)LLM_MAXB * H * 4; }
+    for (int i = 0; i < 2; ++i) { m->off_ppre[i] = off; off += (size_t)Tp * H * 2; }
+    m->comm_bytes = off;
+    LA(m->comm, off);
+    LA(m->d_tokens, Tp);
+    LA(m->d_tok_seq, Tp);
+    LA(m->d_tok_pos, Tp);
+    LA(m->d_cu, LLM_MAXB + 1);
+    LA(m->d_slots, LLM_MAXB);
+    LA(m->d_ctx_len, LLM_MAXB);
+    LA(m->d_next_tok, LLM_MAXB);
+    LA(m->d_out_pos, LLM_MAXB);
+    LA(m->d_out_tokens, (int64_t)LLM_MAXB * m->max_new_cap);
+    LA(m->d_gen, 4);
+#undef LA
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&m->h_stage), (size_t)(3 * Tp + 4 * LLM_MAXB + 8) * 4);
+    if (e != cudaSuccess) { delete m; return fail_cuda(e, "cudaMallocHost(llm staging)"); }
+    // RoPE table (fp32, as torch computes inv_freq / cos / sin in fp32)
+    {
+        std::vector<float> cs((size_t)c->max_ctx * 64), sn((size_t)c->max_ctx * 64);
+        for (int i = 0; i < 64; ++i) {
+            const float inv_freq = 1.0f / powf(c->rope_theta, (float)(2 * i) / (float)LLM_HD);
+            for (int p = 0; p < c->max_ctx; ++p) {
+                const float ang = (float)p * inv_freq;
+                cs[(size_t)p * 64 + i] = (float)cos((double)ang);
+                sn[(size_t)p * 64 + i] = (float)sin((double)ang);
+            }
+        }
+        cudaMemcpy(m->rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(m->rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice);
+    }
+    // norm weights default to 1 (nn.Module init); everything else zero until loaded / initialised
+    llm_fill_const_kernel<<<8, 256>>>(m->final_norm, H, 1.0f);
+    for (int l = 0; l < L; ++l) {
+        llm_fill_const_kernel<<<8, 256>>>(m->layers[l].ln1, H, 1.0f);
+        llm_fill_const_kernel<<<8, 256>>>(m->layers[l].ln2, H, 1.0f);
+    }
+    // tensor maps of the decode path (fixed buffers: graph-capturable)
+    for (int l = 0; l < L && rc == 0; ++l) {
+        LlmLayer &y = m->layers[l];
+        rc = skinny_make_maps(&y.m_qkv_w, &m->m_x_xn, y.wqkv, m->qkv_n, H, m->xn, LLM_MAXB);
+        if (!rc) rc = skinny_make_maps(&y.m_o_w, &m->m_x_attn, y.wo, H, m->hq_r * LLM_HD, m->attn, LLM_MAXB);
+        if (!rc) rc = skinny_make_maps(&y.m_gu_w, &m->m_x_xn, y.wgu, 2 * m->I_r, H, m->xn, LLM_MAXB);
+        if (!rc) rc = skinny_make_maps(&y.m_down_w, &m->m_x_act, y.wdown, H, m->I_r, m->act, LLM_MAXB);
+    }
+    if (!rc) rc = skinny_make_maps(&m->m_lm_w, &m->m_x_last, m->lm_head, m->V_r, H, m->xlast, LLM_MAXB);
+    if (rc) { delete m; return rc; }
+    e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&m->events[i]);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete m; return fail_cuda(e, "llm_create"); }
+    *out = m;
+    return 0;
+}
+
+static int llm_find_tensor(Llm *m, const char *name, int layer, void **ptr, int64_t *rows, int64_t *cols, int *elem)
+{
+    const std::string n(name ? name : "");
+    const int H = m->H;
+    *elem = 2;
+    if (n == "embed") { *ptr = m->embed; *rows = m->cfg.vocab; *cols = H; return 0; }
+    if (n == "lm_head") { *ptr = m->lm_head; *rows = m->V_r; *cols = H; return 0; }
+    if (n == "final_norm") { *ptr = m->final_norm; *rows = 1; *cols = H; *elem = 4; return 0; }
+    if (layer < 0 || layer >= m->cfg.n_layers) return fail(B2S_ERR_INVALID, "llm tensor '%s': layer %d out of range", name, layer);
+    LlmLayer &y = m->layers[layer];
+    if (n == "wqkv") { *ptr = y.wqkv; *rows = m->qkv_n; *cols = H; return 0; }
+    if (n == "wo") { *ptr = y.wo; *rows = H; *cols = m->hq_r * LLM_HD; return 0; }
+    if (n == "wgu") { *ptr = y.wgu; *rows = 2 * m->I_r; *cols = H; return 0; }
+    if (n == "wdown") { *ptr = y.wdown; *rows = H; *cols = m->I_r; return 0; }
+    if (n == "ln1") { *ptr = y.ln1; *rows = 1; *cols = H; *elem = 4; return 0; }
+    if (n == "ln2") { *ptr = y.ln2; *rows = 1; *cols = H; *elem = 4; return 0; }
+    return fail(B2S_ERR_INVALID, "llm: unknown tensor '%s'", name);
+}
+
+static void llm_fill(__nv_bfloat16 *w, int64_t rows, int64_t cols, uint64_t seed, uint32_t id, uint32_t row0, uint32_t col0, float std)
+{
+    llm_fill_kernel<<<1184, 256>>>(w, rows, cols, seed, id, row0, col0, std);
+    count_launch();
+}
+
+// tensor ids of the deterministic initialiser: 0 embed, 1 lm_head, 16 + 8 * layer + {0 q, 1 k, 2 v, 3 o, 4 gate, 5 up, 6 down}
+static int llm_init_random(Llm *m, uint64_t seed, float std)
+{
+    B2S_CUDA(cudaSetDevice(m->device));
+    const int H = m->H, r = m->cfg.tp_rank;
+    llm_fill(m->embed, m->cfg.vocab, H, seed, 0, 0, 0, std);
+    llm_fill(m->lm_head, m->V_r, H, seed, 1, (uint32_t)(r * m->V_r), 0, std);
+    for (int l = 0; l < m->cfg.n_layers; ++l) {
+        LlmLayer &y = m->layers[l];
+        const uint32_t id = 16 + 8 * (uint32_t)l;
+        const int qr = m->hq_r * LLM_HD, kr = m->kvh_r * LLM_HD;
+        llm_fill(y.wqkv, qr, H, seed, id + 0, (uint32_t)(r * qr), 0, std);
+        llm_fill(y.wqkv + (int64_t)qr * H, kr, H, seed, id + 1, (uint32_t)(r * kr), 0, std);
+        llm_fill(y.wqkv + (int64_t)(qr + kr) * H, kr, H, seed, id + 2, (uint32_t)(r * kr), 0, std);
+        llm_fill(y.wo, H, qr, seed, id + 3, 0, (uint32_t)(r * qr), std);
+        llm_fill(y.wgu, m->I_r, H, seed, id + 4, (uint32_t)(r * m->I_r), 0, std);
+        llm_fill(y.wgu + (int64_t)m->I_r * H, m->I_r, H, seed, id + 5, (uint32_t)(r * m->I_r), 0, std);
+        llm_fill(y.wdown, H, m->I_r, seed, id + 6, 0, (uint32_t)(r * m->I_r), std);
+    }
+    B2S_CUDA(cudaGetLastError());
+    B2S_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+static int llm_gemm_bf16(cudaStream_t st, const void *A, int64_t lda, const void *W, int M, int N, int K, void *C)
+{
+    GemmEpilogue ep;
+    ep.bias = nullptr;
+    ep.residual = nullptr;
+    ep.C = C;
+    ep.ldc = N;
+    ep.act = 0;
+    ep.out_f32 = 0;
+    ep.is_bf16 = 1;
+    ep.act_after = 0;
+    return gemm_tn(st, A, lda, W, K, M, N, K, ep);
+}
+
+static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens, const int32_t *offsets)
+{
+    B2S_CUDA(cudaSetDevice(m->device));
+    if (n_seq < 1 || n_seq > m->cfg.max_batch) return fail(B2S_ERR_INVALID, "llm prefill: n_seq %d outside 1..%d", n_seq, m->cfg.max_batch);
+    const int64_t T = offsets[n_seq];
+    if (offsets[0] != 0 || T < n_seq || T > m->max_tokens)
+        return fail(B2S_ERR_INVALID, "llm prefill: %lld prompt tokens exceed max_tokens %lld", (long long)T, (long long)m->max_tokens);
+    int max_len = 0;
+    // stage token metadata: tokens | tok_seq | tok_pos | cu | slots | ctx_len | out_pos
+    B2S_CUDA(cudaStreamSynchronize(st));   // staging buffer reuse
+    int32_t *s_tok = m->h_stage, *s_seq = s_tok + T, *s_pos = s_seq + T, *s_cu = s_pos + T, *s_slots = s_cu + LLM_MAXB + 1,
+            *s_ctx = s_slots + LLM_MAXB, *s_opos = s_ctx + LLM_MAXB;
+    for (int b = 0; b < n_seq; ++b) {
+        const int len = offsets[b + 1] - offsets[b];
+        if (len < 1 || len >= m->cfg.max_ctx) return fail(B2S_ERR_INVALID, "llm prefill: prompt %d has %d tokens (1..%d)", b, len, m->cfg.max_ctx - 1);
+        max_len = len > max_len ? len : max_len;
+        for (int i = 0; i < len; ++i) {
+            s_tok[offsets[b] + i] = tokens[offsets[b] + i];
+            s_seq[offsets[b] + i] = b;
+            s_pos[offsets[b] + i] = i;
+        }
+        s_cu[b] = offsets[b];
+        s_slots[b] = b;
+        s_ctx[b] = len;
+        s_opos[b] = 0;
+    }
+    s_cu[n_seq] = (int32_t)T;
+    for (int b = n_seq; b < LLM_MAXB; ++b) { s_cu[b + 1] = (int32_t)T; s_slots[b] = 0; s_ctx[b] = 0; s_opos[b] = 0; }
+    B2S_CUDA(cudaMemcpyAsync(m->d_tokens, s_tok, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_tok_seq, s_seq, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_tok_pos, s_pos, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_cu, s_cu, (LLM_MAXB + 1) * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_slots, s_slots, LLM_MAXB * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_ctx_len, s_ctx, LLM_MAXB * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_out_pos, s_opos, LLM_MAXB * 4, cudaMemcpyHostToDevice, st));
+    m->n_seq = n_seq;
+
+    const int H = m->H, L = m->cfg.n_layers, Ti = (int)T;
+    const float scale = 1.0f / sqrtf((float)LLM_HD);
+    uint32_t *myf = m->flags(m->comm), *peerf = m->peer_comm ? m->flags(m->peer_comm) : nullptr;
+    llm_embed_rms_kernel<<<Ti, 256, 0, st>>>(m->d_tokens, m->embed, m->layers[0].ln1, m->h, m->xn, H, m->cfg.vocab, m->cfg.rms_eps);
+    count_launch();
+    int k = 0;
+    for (int l = 0; l < L; ++l) {
+        LlmLayer &y = m->layers[l];
+        __nv_bfloat16 *kc = m->kcache + m->kv_layer_stride * l, *vc = m->vcache + m->kv_layer_stride * l;
+        B2S_TRY(llm_gemm_bf16(st, m->xn, H, y.wqkv, Ti, m->qkv_n, H, m->qkv));
+        llm_rope_cache_kernel<false><<<Ti, 256, 0, st>>>(m->qkv, nullptr, kc, vc, m->d_tok_seq, m->d_tok_pos, m->d_slots,
+                                                         m->rope_cos, m->rope_sin, m->hq_r, m->kvh_r, m->cfg.max_ctx);
+        count_launch();
+        B2S_TRY(llm_attn_prefill(st, m->qkv, m->qkv_n, kc, vc, m->d_cu, m->d_slots, m->attn, m->hq_r * LLM_HD, n_seq, max_len,
+                                 m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
+        for (int half = 0; half < 2; ++half, ++k) {
+            void *mine = m->comm + m->off_ppre[k & 1];
+            const void *peer = m->peer_comm ? m->peer_comm + m->off_ppre[k & 1] : nullptr;
+            if (half == 0) {
+                B2S_TRY(llm_gemm_bf16(st, m->attn, m->hq_r * LLM_HD, y.wo, Ti, H, m->hq_r * LLM_HD, mine));
+            } else {
+                B2S_TRY(llm_gemm_bf16(st, m->xn, H, y.wgu, Ti, 2 * m->I_r, H, m->gu));
+                llm_swiglu_kernel<false><<<1184, 256, 0, st>>>(m->gu, m->act, T, m->I_r);
+                count_launch();
+                B2S_TRY(llm_gemm_bf16(st, m->act, m->I_r, y.wdown, Ti, H, m->I_r, mine));
+            }
+            const float *w = half == 0 ? y.ln2 : (l + 1 < L ? m->layers[l + 1].ln1 : m->final_norm);
+            llm_reduce_rms_kernel<false><<<Ti, 256, 0, st>>>(mine, peer, nullptr, myf, peerf, m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps);
+            count_launch();
+        }
+    }
+    llm_gather_last_kernel<<<n_seq, 256, 0, st>>>(m->xn, m->d_cu, m->xlast, H);
+    count_launch();
+    B2S_TRY(skinny_gemm_maps(st, m->m_lm_w, m->m_x_last, m->ws_logits, m->V_r, H, n_seq));
+    llm_argmax_kernel<<<n_seq, 256, 0, st>>>(m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r, m->amax(m->comm),
+                                             m->peer_comm ? m->amax(m->peer_comm) : nullptr, myf, peerf, m->d_gen, k, m->d_next_tok,
+                                             m->d_out_tokens, m->d_out_pos, m->max_new_cap);
+    llm_step_end_kernel<<<1, 32, 0, st>>>(m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 0);
+    count_launch(2);
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// one decode step for the current wave (enqueue only)
+static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch)
+{
+    const int H = m->H, L = m->cfg.n_layers, n_seq = m->n_seq;
+    const float scale = 1.0f / sqrtf((float)LLM_HD);
+    uint32_t *myf = m->flags(m->comm), *peerf = m->peer_comm ? m->flags(m->peer_comm) : nullptr;
+    int nl = 0;
+    llm_embed_rms_kernel<<<n_seq, 256, 0, st>>>(m->d_next_tok, m->embed, m->layers[0].ln1, m->h, m->xn, H, m->cfg.vocab, m->cfg.rms_eps);
+    ++nl;
+    int k = 0;
+    for (int l = 0; l < L; ++l) {
+        LlmLayer &y = m->layers[l];
+        __nv_bfloat16 *kc = m->kcache + m->kv_layer_stride * l, *vc = m->vcache + m->kv_layer_stride * l;
+        B2S_TRY(skinny_gemm_maps(st, y.m_qkv_w, m->m_x_xn, m->ws_qkv, m->qkv_n, H, n_seq));
+        llm_rope_cache_kernel<true><<<n_seq, 256, 0, st>>>(m->ws_qkv, m->qdec, kc, vc, nullptr, m->d_ctx_len, m->d_slots, m->rope_cos,
+                                                        m->rope_sin, m->hq_r, m->kvh_r, m->cfg.max_ctx);
+        B2S_TRY(llm_attn_decode(st, m->qdec, m->hq_r * LLM_HD, kc, vc, m->d_ctx_len, m->d_slots, m->attn, m->hq_r * LLM_HD, n_seq,
+                                m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
+        nl += 3;
+        for (int half = 0; half < 2; ++half, ++k) {
+            float *mine = reinterpret_cast<float *>(m->comm + m->off_pdec[k & 1]);
+            float *older = reinterpret_cast<float *>(m->comm + m->off_pdec[(k & 1) ^ 1]);
+            const void *peer = m->peer_comm ? m->peer_comm + m->off_pdec[k & 1] : nullptr;
+            if (half == 0) {
+                B2S_TRY(skinny_gemm_maps(st, y.m_o_w, m->m_x_attn, mine, H, m->hq_r * LLM_HD, n_seq));
+                ++nl;
+            } else {
+                B2S_TRY(skinny_gemm_maps(st, y.m_gu_w, m->m_x_xn, m->ws_gu, 2 * m->I_r, H, n_seq));
+                llm_swiglu_kernel<true><<<(n_seq * (m->I_r / 4) + 255) / 256, 256, 0, st>>>(m->ws_gu, m->act, n_seq, m->I_r);
+                B2S_TRY(skinny_gemm_maps(st, y.m_down_w, m->m_x_act, mine, H, m->I_r, n_seq));
+                nl += 3;
+            }
+            const float *w = half == 0 ? y.ln2 : (l + 1 < L ? m->layers[l + 1].ln1 : m->final_norm);
+            llm_reduce_rms_kernel<true><<<n_seq, 256, 0, st>>>(mine, peer, older, myf, peerf, m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps);
+            ++nl;
+        }
+    }
+    // xn rows 0..n_seq-1 are the final-normed hidden states: lm_head reads them through the xn map
+    B2S_TRY(skinny_gemm_maps(st, m->m_lm_w, m->m_x_xn, m->ws_logits, m->V_r, H, n_seq));
+    llm_argmax_kernel<<<n_seq, 256, 0, st>>>(m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r, m->amax(m->comm),
+                                             m->peer_comm ? m->amax(m->peer_comm) : nullptr, myf, peerf, m->d_gen, k, m->d_next_tok,
+                                             m->d_out_tokens, m->d_out_pos, m->max_new_cap);
+    llm_step_end_kernel<<<1, 32, 0, st>>>(m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 1);
+    nl += 3;
+    B2S_CUDA(cudaGetLastError());
+    *n_launch = nl;
+    return 0;
+}
+
+static int llm_decode(Llm *m, cudaStream_t st, int n_steps, int use_graph)
+{
+    B2S_CUDA(cudaSetDevice(m->device));
+    if (m->n_seq < 1) return fail(B2S_ERR_INVALID, "llm decode: no prefilled wave");
+    if (n_steps < 0) return fail(B2S_ERR_INVALID, "llm decode: negative step count");
+    if (!use_graph) {
+        for (int s = 0; s < n_steps; ++s) {
+            int nl = 0;
+            B2S_TRY(llm_decode_enqueue(m, st, &nl));
+            count_launch((uint64_t)nl);
+        }
+        return 0;
+    }
+    auto it = m->decode_graphs.find(m->n_seq);
+    if (it == m->decode_graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        int nl = 0;
+        B2S_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = llm_decode_enqueue(m, st, &nl);
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture(llm decode)");
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaGraphInstantiate(llm decode)");
+        m->decode_graphs[m->n_seq] = exec;
+        m->decode_graph_launches[m->n_seq] = nl;
+        it = m->decode_graphs.find(m->n_seq);
+    }
+    const int nl = m->decode_graph_launches[m->n_seq];
+    for (int s = 0; s < n_steps; ++s) {
+        B2S_CUDA(cudaGraphLaunch(it->second, st));
+        count_launch((uint64_t)nl);
+    }
+    return 0;
+}
+
+}  // namespace b2s
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using b2s::Llm;
+
+extern "C" {
+
+B2S_API int b2s_llm_create(int device, const b2s_llm_config *cfg, b2s_llm **out)
+{
+    Llm *m = nullptr;
+    const int rc = b2s::llm_create(device, cfg, &m);
+    if (rc == 0) *out = reinterpret_cast<b2s_llm *>(m);
+    return rc;
+}
+
+B2S_API int b2s_llm_free(b2s_llm *llm)
+{
+    delete reinterpret_cast<Llm *>(llm);
+    return 0;
+}
+
+B2S_API int b2s_llm_init_random(b2s_llm *llm, uint64_t seed, float std)
+{
+    if (!llm) return b2s::fail(B2S_ERR_INVALID, "null llm");
+    return b2s::llm_init_random(reinterpret_cast<Llm *>(llm), seed, std);
+}
+
+// device pointer + shape of one (per-rank) weight tensor; elem_bytes 2 = bf16, 4 = fp32
+B2S_API int b2s_llm_tensor(b2s_llm *llm, const char *name, int layer, void **dptr, int64_t *rows, int64_t *cols, int *elem_bytes)
+{
+    if (!llm || !dptr || !rows || !cols || !elem_bytes) return b2s::fail(B2S_ERR_INVALID, "null argument");
+    return b2s::llm_find_tensor(reinterpret_cast<Llm *>(llm), name, layer, dptr, rows, cols, elem_bytes);
+}
+
+B2S_API int b2s_llm_comm_export(b2s_llm *llm, unsigned char *handle64, uint64_t *bytes)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || !handle64) return fail(B2S_ERR_INVALID, "null argument");
+    B2S_CUDA(cudaSetDevice(m->device));
+    cudaIpcMemHandle_t hnd;
+    B2S_CUDA(cudaIpcGetMemHandle(&hnd, m->comm));
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &hnd, 64);
+    if (bytes) *bytes = m->comm_bytes;
+    return 0;
+}
+
+B2S_API int b2s_llm_comm_attach(b2s_llm *llm, const unsigned char *peer_handle64)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || !peer_handle64) return fail(B2S_ERR_INVALID, "null argument");
+    if (m->cfg.tp_size != 2) return fail(B2S_ERR_INVALID, "llm: comm_attach needs tensor_parallel = 2");
+    if (m->peer_comm) return fail(B2S_ERR_INVALID, "llm: peer already attached");
+    B2S_CUDA(cudaSetDevice(m->device));
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, peer_handle64, 64);
+    void *p = nullptr;
+    B2S_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    m->peer_comm = static_cast<unsigned char *>(p);
+    return 0;
+}
+
+B2S_API int b2s_llm_prefill(b2s_llm *llm, int n_seq, const int32_t *tokens, const int32_t *offsets)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || !tokens || !offsets) return fail(B2S_ERR_INVALID, "null argument");
+    if (m->cfg.tp_size == 2 && !m->peer_comm) return fail(B2S_ERR_INVALID, "llm: tensor-parallel peer not attached");
+    return llm_prefill(m, m->stream, n_seq, tokens, offsets);
+}
+
+B2S_API int b2s_llm_decode(b2s_llm *llm, int n_steps, int use_graph)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m) return fail(B2S_ERR_INVALID, "null argument");
+    return llm_decode(m, m->stream, n_steps, use_graph);
+}
+
+// generated tokens of the current wave: out[n_seq][n] (first n per sequence); synchronises the stream
+B2S_API int b2s_llm_get_tokens(b2s_llm *llm, int32_t *out, int n)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || !out) return fail(B2S_ERR_INVALID, "null argument");
+    if (n < 0 || n > m->max_new_cap) return fail(B2S_ERR_INVALID, "llm: at most %d generated tokens are kept", m->max_new_cap);
+    B2S_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    B2S_CUDA(cudaMemcpy2DAsync(out, (size_t)n * 4, m->d_out_tokens, (size_t)m->max_new_cap * 4, (size_t)n * 4, (size_t)m->n_seq,
+                               cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// parity aid: keep a copy of the last step's logits shard ([n_seq][vocab / tp] fp32)
+B2S_API int b2s_llm_keep_logits(b2s_llm *llm, int on)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m) return fail(B2S_ERR_INVALID, "null argument");
+    B2S_CUDA(cudaSetDevice(m->device));
+    if (on && !m->keep_logits) {
+        B2S_TRY(llm_alloc(m, &m->keep_logits, (size_t)LLM_MAXB * m->V_r));
+        for (auto &g : m->decode_graphs) cudaGraphExecDestroy(g.second);   // graphs baked the old pointer
+        m->decode_graphs.clear();
+    }
+    return 0;
+}
+
+B2S_API int b2s_llm_get_logits(b2s_llm *llm, float *out)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || !out) return fail(B2S_ERR_INVALID, "null argument");
+    if (!m->keep_logits) return fail(B2S_ERR_INVALID, "llm: call b2s_llm_keep_logits(llm, 1) first");
+    B2S_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    B2S_CUDA(cudaMemcpyAsync(out, m->keep_logits, (size_t)m->n_seq * m->V_r * 4, cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// stream control: synchronise; record one of 8 CUDA events on the model's stream; device time between two of them
+B2S_API int b2s_llm_synchronize(b2s_llm *llm)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m) return fail(B2S_ERR_INVALID, "null argument");
+    B2S_CUDA(cudaSetDevice(m->device));
+    B2S_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+B2S_API int b2s_llm_event_record(b2s_llm *llm, int which)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || which < 0 || which >= 8) return fail(B2S_ERR_INVALID, "llm event index must be 0..7");
+    B2S_CUDA(cudaSetDevice(m->device));
+    B2S_CUDA(cudaEventRecord(m->events[which], m->stream));
+    return 0;
+}
+
+B2S_API int b2s_llm_elapsed_ms(b2s_llm *llm, int from, int to, float *ms)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || !ms || from < 0 || from >= 8 || to < 0 || to >= 8) return fail(B2S_ERR_INVALID, "llm event index must be 0..7");
+    B2S_CUDA(cudaSetDevice(m->device));
+    B2S_CUDA(cudaEventSynchronize(m->events[to]));
+    B2S_CUDA(cudaEventElapsedTime(ms, m->events[from], m->events[to]));
+    return 0;
+}
+
+B2S_API int b2s_llm_flush_l2(b2s_llm *llm)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m) return fail(B2S_ERR_INVALID, "null argument");
+    B2S_CUDA(cudaSetDevice(m->device));
+    // the activation scratch of the gate/up projection is larger than L2 whenever max_tokens >= 4096
+    B2S_CUDA(cudaMemsetAsync(m->gu, 0, (size_t)(m->max_tokens > LLM_MAXB ? m->max_tokens : LLM_MAXB) * 2 * m->I_r * 2, m->stream));
+    return 0;
+}
+
+}  // extern "C"

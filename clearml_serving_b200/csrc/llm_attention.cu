@@ -260,7 +260,7 @@ llm_attn_decode_kernel(const __nv_bfloat16 *__restrict__ q, int ld_q, const __nv
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) o[gi][0] = o[gi][1] = o[gi][2] = o[gi][3] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;   // softmax state of head (lane % G), replicated over the lanes sharing it
-    const int my_head = lane % G, my_key = lane / G;
+    const int my_key = lane / G;
 
     for (int k0 = warp * KB; k0 < n_ctx; k0 += LD_WARPS * KB) {
         float part[32];

@@ -44,6 +44,14 @@ class ModelInfo(ctypes.Structure):
                 ("algo_bytes_per_row", ctypes.c_int64)]
 
 
+class LlmConfig(ctypes.Structure):
+    _fields_ = [("vocab", ctypes.c_int32), ("hidden", ctypes.c_int32), ("inter", ctypes.c_int32),
+                ("n_layers", ctypes.c_int32), ("n_heads", ctypes.c_int32), ("n_kv_heads", ctypes.c_int32),
+                ("head_dim", ctypes.c_int32), ("max_batch", ctypes.c_int32), ("max_ctx", ctypes.c_int32),
+                ("max_tokens", ctypes.c_int32), ("tp_size", ctypes.c_int32), ("tp_rank", ctypes.c_int32),
+                ("rope_theta", ctypes.c_float), ("rms_eps", ctypes.c_float)]
+
+
 class B2SError(ValueError):
     """Raised for every non-zero status. A ValueError so the reference's REST layer maps it to 422
     (clearml_serving/serving/main.py:155-161) -- and a message containing "CUDA out of memory. "
@@ -96,6 +104,22 @@ PROTOTYPES = [
     ("b2s_op_embed_layernorm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp,
                                     ctypes.c_float, _vp, _vp]),
     ("b2s_op_attention", _i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    ("b2s_llm_create", _i, [_i, _P(LlmConfig), _P(_vp)]),
+    ("b2s_llm_free", _i, [_vp]),
+    ("b2s_llm_init_random", _i, [_vp, _u64, ctypes.c_float]),
+    ("b2s_llm_tensor", _i, [_vp, ctypes.c_char_p, _i, _P(_vp), _P(_i64), _P(_i64), _P(_i)]),
+    ("b2s_llm_comm_export", _i, [_vp, _vp, _P(_u64)]),
+    ("b2s_llm_comm_attach", _i, [_vp, _vp]),
+    ("b2s_llm_prefill", _i, [_vp, _i, _vp, _vp]),
+    ("b2s_llm_decode", _i, [_vp, _i, _i]),
+    ("b2s_llm_get_tokens", _i, [_vp, _vp, _i]),
+    ("b2s_llm_keep_logits", _i, [_vp, _i]),
+    ("b2s_llm_get_logits", _i, [_vp, _vp]),
+    ("b2s_llm_synchronize", _i, [_vp]),
+    ("b2s_llm_event_record", _i, [_vp, _i]),
+    ("b2s_llm_elapsed_ms", _i, [_vp, _i, _i, _P(ctypes.c_float)]),
+    ("b2s_llm_flush_l2", _i, [_vp]),
+    ("b2s_op_skinny_gemm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i]),
 ]
 
 _lib = None
@@ -397,3 +421,106 @@ class DeviceBuffer(object):
         if self.ptr:
             lib().b2s_device_free(self.device, self.ptr)
             self.ptr = 0
+
+
+class Llm(object):
+    """Decoder-only LLM executor (b2s_llm_* of include/b200serve.h).  One instance = one tensor-parallel rank."""
+
+    def __init__(self, device=0, vocab=0, hidden=0, inter=0, n_layers=0, n_heads=0, n_kv_heads=0, head_dim=128,
+                 max_batch=32, max_ctx=1024, max_tokens=None, tp_size=1, tp_rank=0, rope_theta=500000.0, rms_eps=1e-5):
+        ensure_init(device)
+        self.device = int(device)
+        if max_tokens is None:
+            max_tokens = max_batch * max_ctx
+        self.cfg = LlmConfig(vocab, hidden, inter, n_layers, n_heads, n_kv_heads, head_dim, max_batch, max_ctx,
+                             int(max_tokens), tp_size, tp_rank, rope_theta, rms_eps)
+        h = ctypes.c_void_p(0)
+        check(lib().b2s_llm_create(self.device, ctypes.byref(self.cfg), ctypes.byref(h)))
+        self.handle = h
+        self.vocab_shard = vocab // tp_size
+        self.n_seq = 0
+
+    def init_random(self, seed=0, std=0.02):
+        check(lib().b2s_llm_init_random(self.handle, int(seed), float(std)))
+
+    def tensor(self, name, layer=0):
+        """-> (device pointer, rows, cols, numpy dtype of the host image: uint16 for bf16 / float32)"""
+        ptr, rows, cols, eb = ctypes.c_void_p(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+        check(lib().b2s_llm_tensor(self.handle, name.encode(), int(layer), ctypes.byref(ptr), ctypes.byref(rows),
+                                   ctypes.byref(cols), ctypes.byref(eb)))
+        return ptr.value, rows.value, cols.value, (np.uint16 if eb.value == 2 else np.float32)
+
+    def load_tensor(self, name, layer, host):
+        """host: uint16 (bf16 bit patterns) or float32 array of exactly this rank's shard shape"""
+        ptr, rows, cols, dt = self.tensor(name, layer)
+        a = np.ascontiguousarray(host, dtype=dt).reshape(-1)
+        if a.size != rows * cols:
+            raise B2SError(B2S_ERR_INVALID, "llm tensor {}[{}]: expected {} x {} elements, got {}".format(
+                name, layer, rows, cols, a.size))
+        check(lib().b2s_memcpy_h2d(self.device, ptr, a.ctypes.data, a.nbytes))
+
+    def read_tensor(self, name, layer=0):
+        ptr, rows, cols, dt = self.tensor(name, layer)
+        out = np.empty((rows, cols), dtype=dt)
+        check(lib().b2s_memcpy_d2h(self.device, out.ctypes.data, ptr, out.nbytes))
+        return out
+
+    def comm_export(self):
+        buf = (ctypes.c_ubyte * 64)()
+        n = ctypes.c_uint64(0)
+        check(lib().b2s_llm_comm_export(self.handle, buf, ctypes.byref(n)))
+        return bytes(buf)
+
+    def comm_attach(self, peer_handle):
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(bytes(peer_handle))
+        check(lib().b2s_llm_comm_attach(self.handle, buf))
+
+    def prefill(self, prompts):
+        """prompts: list of int sequences (token ids); enqueues the prompt wave + the first sampled token"""
+        offs = np.zeros(len(prompts) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(p) for p in prompts])
+        toks = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32).reshape(-1) for p in prompts]))
+        check(lib().b2s_llm_prefill(self.handle, len(prompts), toks.ctypes.data, offs.ctypes.data))
+        self.n_seq = len(prompts)
+
+    def decode(self, n_steps, use_graph=True):
+        check(lib().b2s_llm_decode(self.handle, int(n_steps), 1 if use_graph else 0))
+
+    def tokens(self, n):
+        out = np.empty((self.n_seq, int(n)), dtype=np.int32)
+        check(lib().b2s_llm_get_tokens(self.handle, out.ctypes.data, int(n)))
+        return out
+
+    def keep_logits(self, on=True):
+        check(lib().b2s_llm_keep_logits(self.handle, 1 if on else 0))
+
+    def logits(self):
+        out = np.empty((self.n_seq, self.vocab_shard), dtype=np.float32)
+        check(lib().b2s_llm_get_logits(self.handle, out.ctypes.data))
+        return out
+
+    def synchronize(self):
+        check(lib().b2s_llm_synchronize(self.handle))
+
+    def record(self, which):
+        check(lib().b2s_llm_event_record(self.handle, int(which)))
+
+    def elapsed_ms(self, a, b):
+        ms = ctypes.c_float(0)
+        check(lib().b2s_llm_elapsed_ms(self.handle, int(a), int(b), ctypes.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        check(lib().b2s_llm_flush_l2(self.handle))
+
+    def free(self):
+        if self.handle:
+            lib().b2s_llm_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                lib().b2s_llm_free(self.handle)
+        except Exception:  # noqa
+            pass

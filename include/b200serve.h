@@ -211,6 +211,54 @@ B2S_API int b2s_op_attention(int device, void *cuda_stream, const void *qkv, con
                              const int32_t *key_mask, void *out, int n_seq, int max_seqlen, int heads,
                              int head_dim);
 
+/* ---- decoder-only LLM endpoint (BASELINE.json configs[4]) -------------------------------------------
+ * Replaces the vLLM engine the reference wraps in `VllmPreprocessRequest`
+ * (clearml_serving/serving/preprocess_service.py:1097-1348; engine args from `auxiliary_cfg`,
+ * examples/vllm/preprocess.py): a Llama-family model (RMSNorm, RoPE, grouped-query attention, SwiGLU) with
+ * a slot-based KV cache, greedy sampling, and optional 2-way tensor parallelism as ONE PROCESS PER GPU.
+ * The two ranks exchange row-parallel partial sums through peer memory: each exports a handle with
+ * b2s_llm_comm_export(), the host side swaps the 64 bytes (torch.distributed / any channel) and calls
+ * b2s_llm_comm_attach() on both before the first step; both ranks then issue the same call sequence.
+ * Every call enqueues on the model's own CUDA stream and returns; b2s_llm_get_tokens synchronises. */
+typedef struct b2s_llm b2s_llm;
+typedef struct b2s_llm_config {
+    int32_t vocab, hidden, inter, n_layers, n_heads, n_kv_heads, head_dim; /* head_dim must be 128 */
+    int32_t max_batch;   /* KV slots = sequences per wave, <= 32 */
+    int32_t max_ctx;     /* positions per slot (prompt + generated) */
+    int32_t max_tokens;  /* prompt tokens of one prefill wave (workspace size) */
+    int32_t tp_size, tp_rank; /* 1 or 2 */
+    float rope_theta, rms_eps;
+} b2s_llm_config;
+
+B2S_API int b2s_llm_create(int device, const b2s_llm_config *cfg, b2s_llm **out);
+B2S_API int b2s_llm_free(b2s_llm *llm);
+/* deterministic on-device initialisation N(0, std) of every projection / embedding (configs[4] "random-init");
+ * a pure function of (seed, tensor, global row, global col): all tensor-parallel layouts hold the same model */
+B2S_API int b2s_llm_init_random(b2s_llm *llm, uint64_t seed, float std);
+/* device pointer + shape of this rank's shard of a weight: "embed", "lm_head", "final_norm" (layer ignored),
+ * "wqkv" [(hq+2hkv)*128/tp, H], "wo" [H, hq*128/tp], "wgu" [2*I/tp, H] (gate rows then up rows),
+ * "wdown" [H, I/tp], "ln1", "ln2"; elem_bytes 2 = bf16, 4 = fp32.  Upload with b2s_memcpy_h2d. */
+B2S_API int b2s_llm_tensor(b2s_llm *llm, const char *name, int layer, void **dptr, int64_t *rows, int64_t *cols,
+                           int *elem_bytes);
+B2S_API int b2s_llm_comm_export(b2s_llm *llm, unsigned char *handle64, uint64_t *bytes);
+B2S_API int b2s_llm_comm_attach(b2s_llm *llm, const unsigned char *peer_handle64);
+/* prompt wave: tokens[offsets[n_seq]] int32 (host), offsets[n_seq + 1]; sequence b takes KV slot b; samples
+ * the first generated token of every sequence */
+B2S_API int b2s_llm_prefill(b2s_llm *llm, int n_seq, const int32_t *tokens, const int32_t *offsets);
+/* n_steps greedy decode steps for the current wave (use_graph: replay one captured CUDA graph per step) */
+B2S_API int b2s_llm_decode(b2s_llm *llm, int n_steps, int use_graph);
+/* out[n_seq][n] int32 (host): the first n generated tokens of each sequence; synchronises */
+B2S_API int b2s_llm_get_tokens(b2s_llm *llm, int32_t *out, int n);
+B2S_API int b2s_llm_keep_logits(b2s_llm *llm, int on);
+B2S_API int b2s_llm_get_logits(b2s_llm *llm, float *out); /* [n_seq][vocab / tp] fp32 of the last step */
+B2S_API int b2s_llm_synchronize(b2s_llm *llm);
+B2S_API int b2s_llm_event_record(b2s_llm *llm, int which);             /* which in 0..7 */
+B2S_API int b2s_llm_elapsed_ms(b2s_llm *llm, int from, int to, float *ms);
+B2S_API int b2s_llm_flush_l2(b2s_llm *llm);
+/* y[m][n_out] fp32 += X[m<=32, K] . W[n_out, K]^T (bf16 operands): the weight-streaming decode GEMM */
+B2S_API int b2s_op_skinny_gemm(int device, void *cuda_stream, const void *W, const void *X, float *y, int n_out,
+                               int K, int m);
+
 #ifdef __cplusplus
 }
 #endif
