@@ -22,10 +22,12 @@
 // Layouts: weights bf16 [out, in] as nn.Linear stores them; residual stream fp32 [T, H]; KV cache per layer
 // K, V = [slot][kv_head][max_ctx][128] bf16; decode accumulators fp32 [32, N].
 #include "common.cuh"
+#include "sm100.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -41,8 +43,9 @@ int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &
 int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *kc, const void *vc, const int32_t *cu_seqlens,
                      const int32_t *slots, void *out, int ld_out, int n_seq, int max_seqlen, int hq_r, int kvh_r,
                      int max_ctx, float scale);
-int llm_attn_decode(cudaStream_t st, const void *q, int ld_q, const void *kc, const void *vc, const int32_t *ctx_len,
-                    const int32_t *slots, void *out, int ld_out, int n_seq, int hq_r, int kvh_r, int max_ctx, float scale);
+int llm_attn_decode(cudaStream_t st, float *ws_qkv, void *kc, void *vc, const int32_t *ctx_len, const int32_t *slots,
+                    const float *rope_cos, const float *rope_sin, void *out, int ld_out, int n_seq, int hq_r, int kvh_r,
+                    int max_ctx, float scale);
 
 constexpr int LLM_MAXB = 32;          // decode batch (rows of the skinny GEMM)
 constexpr int LLM_HD = 128;           // head dim
@@ -153,6 +156,8 @@ llm_embed_rms_kernel(const int32_t *__restrict__ tokens, const __nv_bfloat16 *__
                      float *__restrict__ h, __nv_bfloat16 *__restrict__ xn, int H, int vocab, float eps)
 {
     __shared__ float red[8];
+    sm100::griddep_launch_dependents();   // the projection that follows may start prefetching its weights
+    sm100::griddep_wait();                // no-op unless launched as a programmatic dependent
     const int t = blockIdx.x;
     int tok = __ldg(tokens + t);
     tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
@@ -200,6 +205,8 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
                       __nv_bfloat16 *__restrict__ xn, int H, float eps)
 {
     __shared__ float red[8];
+    sm100::griddep_launch_dependents();
+    sm100::griddep_wait();
     tp_exchange_point(my_flags, peer_flags, gen, k);
     const int t = blockIdx.x;
     float4 v[8];
@@ -255,42 +262,34 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
 // ------------------------------------------------------------------------------------------------
 // RoPE (rotate-half convention: pairs (i, i + 64)) on q and k, K/V append to the cache.  One CTA per token.
 //   prefill: qkv bf16 [T, QKV] -- q rotated in place, position = tok_pos[t], slot = slots[tok_seq[t]]
-//   decode : src fp32 [32, QKV] (skinny GEMM accumulator, cleared here), q -> bf16 [32, hq*128],
-//            position = ctx_len[b], slot = slots[b]
+//   decode : fused into the attention kernel's prologue (llm_attention.cu)
 // ------------------------------------------------------------------------------------------------
-template <bool DEC>
 __global__ void __launch_bounds__(256)
-llm_rope_cache_kernel(void *__restrict__ qkv_src, __nv_bfloat16 *__restrict__ q_out, __nv_bfloat16 *__restrict__ kc,
-                      __nv_bfloat16 *__restrict__ vc, const int32_t *__restrict__ tok_seq, const int32_t *__restrict__ tok_pos,
-                      const int32_t *__restrict__ slots, const float *__restrict__ rope_cos, const float *__restrict__ rope_sin,
-                      int hq_r, int kvh_r, int max_ctx)
+llm_rope_cache_prefill_kernel(__nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ kc, __nv_bfloat16 *__restrict__ vc,
+                              const int32_t *__restrict__ tok_seq, const int32_t *__restrict__ tok_pos,
+                              const int32_t *__restrict__ slots, const float *__restrict__ rope_cos,
+                              const float *__restrict__ rope_sin, int hq_r, int kvh_r, int max_ctx)
 {
     const int t = blockIdx.x;
     const int QKV = (hq_r + 2 * kvh_r) * LLM_HD;
-    const int seq = DEC ? t : __ldg(tok_seq + t);
-    int pos = __ldg(tok_pos + (DEC ? seq : t));
+    const int seq = __ldg(tok_seq + t);
+    int pos = __ldg(tok_pos + t);
     pos = pos < max_ctx ? pos : max_ctx - 1;
     const int slot = __ldg(slots + seq);
     const float *cs = rope_cos + (int64_t)pos * 64, *sn = rope_sin + (int64_t)pos * 64;
-    float *srcf = DEC ? static_cast<float *>(qkv_src) + (int64_t)t * QKV : nullptr;
-    __nv_bfloat16 *srcb = DEC ? nullptr : static_cast<__nv_bfloat16 *>(qkv_src) + (int64_t)t * QKV;
-    // q and k heads: (head, pair)
-    const int n_rot = (hq_r + kvh_r) * 64;
+    __nv_bfloat16 *srcb = qkv + (int64_t)t * QKV;
+    const int n_rot = (hq_r + kvh_r) * 64;   // q heads first, then k heads: contiguous in the QKV row
     for (int idx = threadIdx.x; idx < n_rot; idx += 256) {
         const int head = idx >> 6, i = idx & 63;
-        const int c0 = head * LLM_HD + i;   // q heads first, then k heads: contiguous in the QKV row
-        float x1, x2;
-        if (DEC) { x1 = srcf[c0]; x2 = srcf[c0 + 64]; srcf[c0] = 0.f; srcf[c0 + 64] = 0.f; }
-        else { x1 = __bfloat162float(srcb[c0]); x2 = __bfloat162float(srcb[c0 + 64]); }
-        const float c = cs[i], s = sn[i];
-        const __nv_bfloat16 o1 = __float2bfloat16_rn(x1 * c - x2 * s), o2 = __float2bfloat16_rn(x2 * c + x1 * s);
+        const int c0 = head * LLM_HD + i;
+        const float x1 = __bfloat162float(srcb[c0]), x2 = __bfloat162float(srcb[c0 + 64]);
+        const float c = cs[i], sv = sn[i];
+        const __nv_bfloat16 o1 = __float2bfloat16_rn(x1 * c - x2 * sv), o2 = __float2bfloat16_rn(x2 * c + x1 * sv);
         if (head < hq_r) {
-            __nv_bfloat16 *dst = DEC ? q_out + (int64_t)t * hq_r * LLM_HD : srcb;
-            dst[c0] = o1;
-            dst[c0 + 64] = o2;
+            srcb[c0] = o1;
+            srcb[c0 + 64] = o2;
         } else {
-            const int kh = head - hq_r;
-            __nv_bfloat16 *dst = kc + (((int64_t)slot * kvh_r + kh) * max_ctx + pos) * LLM_HD;
+            __nv_bfloat16 *dst = kc + (((int64_t)slot * kvh_r + (head - hq_r)) * max_ctx + pos) * LLM_HD;
             dst[i] = o1;
             dst[i + 64] = o2;
         }
@@ -298,10 +297,7 @@ llm_rope_cache_kernel(void *__restrict__ qkv_src, __nv_bfloat16 *__restrict__ q_
     const int v0 = (hq_r + kvh_r) * LLM_HD;
     for (int idx = threadIdx.x; idx < kvh_r * LLM_HD; idx += 256) {
         const int kh = idx >> 7, d = idx & 127;
-        __nv_bfloat16 val;
-        if (DEC) { val = __float2bfloat16_rn(srcf[v0 + idx]); srcf[v0 + idx] = 0.f; }
-        else val = srcb[v0 + idx];
-        vc[(((int64_t)slot * kvh_r + kh) * max_ctx + pos) * LLM_HD + d] = val;
+        vc[(((int64_t)slot * kvh_r + kh) * max_ctx + pos) * LLM_HD + d] = srcb[v0 + idx];
     }
 }
 
@@ -314,6 +310,8 @@ template <bool DEC>
 __global__ void __launch_bounds__(256)
 llm_swiglu_kernel(void *__restrict__ gu, __nv_bfloat16 *__restrict__ act, int64_t rows, int I)
 {
+    sm100::griddep_launch_dependents();
+    sm100::griddep_wait();
     const int64_t n4 = rows * (I / 4);
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = idx / (I / 4);
@@ -366,6 +364,8 @@ llm_argmax_kernel(float *__restrict__ logits, float *__restrict__ keep, int V_r,
 {
     __shared__ float s_val[256];
     __shared__ int s_idx[256];
+    sm100::griddep_launch_dependents();
+    sm100::griddep_wait();
     const int b = blockIdx.x;
     float *row = logits + (int64_t)b * V_r;
     float best = -INFINITY;
@@ -433,6 +433,8 @@ llm_argmax_kernel(float *__restrict__ logits, float *__restrict__ keep, int V_r,
 // end of a step: the step counter advances; decode steps also advance context lengths / output positions
 __global__ void llm_step_end_kernel(uint32_t *gen, int32_t *ctx_len, int32_t *out_pos, int n_seq, int is_decode)
 {
+    sm100::griddep_launch_dependents();
+    sm100::griddep_wait();
     const int b = threadIdx.x;
     if (b < n_seq) {
         if (is_decode) ctx_len[b] += 1;
@@ -462,7 +464,7 @@ struct Llm {
     int64_t kv_layer_stride = 0;
     // activations
     float *h = nullptr;
-    __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr, *xlast = nullptr, *qdec = nullptr;
+    __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr, *xlast = nullptr;
     float *ws_qkv = nullptr, *ws_gu = nullptr, *ws_logits = nullptr, *keep_logits = nullptr;
     // exchange block (one allocation, exported through cudaIpc)
     unsigned char *comm = nullptr, *peer_comm = nullptr;
@@ -563,7 +565,6 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     LA(m->gu, Tp * 2 * m->I_r);
     LA(m->act, Tp * m->I_r);
     LA(m->xlast, (int64_t)LLM_MAXB * H);
-    LA(m->qdec, (int64_t)LLM_MAXB * m->hq_r * LLM_HD);
     LA(m->ws_qkv, (int64_t)LLM_MAXB * m->qkv_n);
     LA(m->ws_gu, (int64_t)LLM_MAXB * 2 * m->I_r);
     LA(m->ws_logits, (int64_t)LLM_MAXB * m->V_r);
@@ -736,8 +737,8 @@ static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens
         LlmLayer &y = m->layers[l];
         __nv_bfloat16 *kc = m->kcache + m->kv_layer_stride * l, *vc = m->vcache + m->kv_layer_stride * l;
         B2S_TRY(llm_gemm_bf16(st, m->xn, H, y.wqkv, Ti, m->qkv_n, H, m->qkv));
-        llm_rope_cache_kernel<false><<<Ti, 256, 0, st>>>(m->qkv, nullptr, kc, vc, m->d_tok_seq, m->d_tok_pos, m->d_slots,
-                                                         m->rope_cos, m->rope_sin, m->hq_r, m->kvh_r, m->cfg.max_ctx);
+        llm_rope_cache_prefill_kernel<<<Ti, 256, 0, st>>>(m->qkv, kc, vc, m->d_tok_seq, m->d_tok_pos, m->d_slots, m->rope_cos,
+                                                          m->rope_sin, m->hq_r, m->kvh_r, m->cfg.max_ctx);
         count_launch();
         B2S_TRY(llm_attn_prefill(st, m->qkv, m->qkv_n, kc, vc, m->d_cu, m->d_slots, m->attn, m->hq_r * LLM_HD, n_seq, max_len,
                                  m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
@@ -769,53 +770,112 @@ static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens
     return 0;
 }
 
-// one decode step for the current wave (enqueue only)
-static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch)
+// Launch as a programmatic dependent of the previous kernel in the stream: the grid may be scheduled before its
+// predecessor has drained (every decode kernel begins with griddepcontrol.wait), which takes the launch latency
+// of the ~9 small kernels per layer off the step's critical path.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args)
 {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = []() { const char *e = getenv("B2S_LLM_PDL"); return !(e && e[0] == '0'); }();
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// developer aid (b2s_llm_decode(..., use_graph = 2)): CUDA events between the kernels of eagerly launched steps
+struct LlmTiming {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> label;
+    size_t used = 0;
+    void mark(cudaStream_t st, int what)
+    {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+            label.push_back(0);
+        }
+        label[used] = what;
+        cudaEventRecord(ev[used++], st);
+    }
+};
+static const char *const LLM_TIMING_NAMES[] = {"start", "embed_rms", "qkv_gemm", "rope_cache", "attention", "o_gemm", "reduce_rms(attn)",
+                                               "gate_up_gemm", "swiglu", "down_gemm", "reduce_rms(mlp)", "lm_head_gemm", "argmax", "step_end"};
+
+// one decode step for the current wave (enqueue only)
+static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming *tm = nullptr)
+{
+#define LLM_MARK(id) do { if (tm) tm->mark(st, (id)); } while (0)
+    LLM_MARK(0);
     const int H = m->H, L = m->cfg.n_layers, n_seq = m->n_seq;
     const float scale = 1.0f / sqrtf((float)LLM_HD);
     uint32_t *myf = m->flags(m->comm), *peerf = m->peer_comm ? m->flags(m->peer_comm) : nullptr;
     int nl = 0;
-    llm_embed_rms_kernel<<<n_seq, 256, 0, st>>>(m->d_next_tok, m->embed, m->layers[0].ln1, m->h, m->xn, H, m->cfg.vocab, m->cfg.rms_eps);
+    // developer aid: B2S_LLM_SKIP bitmask drops kernels from the step (results are then meaningless) so that the
+    // in-pipeline cost of each one can be read off the step time: 1 attention, 2 reduce_rms, 4 swiglu, 8 qkv,
+    // 16 o, 32 gate/up, 64 down, 128 lm_head + argmax
+    static const int skip = []() { const char *e = getenv("B2S_LLM_SKIP"); return e ? atoi(e) : 0; }();
+    B2S_CUDA(launch_dependent(llm_embed_rms_kernel, dim3(n_seq), dim3(256), st, m->d_next_tok, m->embed, m->layers[0].ln1, m->h, m->xn, H,
+                              m->cfg.vocab, m->cfg.rms_eps));
     ++nl;
+    LLM_MARK(1);
     int k = 0;
     for (int l = 0; l < L; ++l) {
         LlmLayer &y = m->layers[l];
         __nv_bfloat16 *kc = m->kcache + m->kv_layer_stride * l, *vc = m->vcache + m->kv_layer_stride * l;
-        B2S_TRY(skinny_gemm_maps(st, y.m_qkv_w, m->m_x_xn, m->ws_qkv, m->qkv_n, H, n_seq));
-        llm_rope_cache_kernel<true><<<n_seq, 256, 0, st>>>(m->ws_qkv, m->qdec, kc, vc, nullptr, m->d_ctx_len, m->d_slots, m->rope_cos,
-                                                        m->rope_sin, m->hq_r, m->kvh_r, m->cfg.max_ctx);
-        B2S_TRY(llm_attn_decode(st, m->qdec, m->hq_r * LLM_HD, kc, vc, m->d_ctx_len, m->d_slots, m->attn, m->hq_r * LLM_HD, n_seq,
-                                m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
-        nl += 3;
+        if (!(skip & 8)) B2S_TRY(skinny_gemm_maps(st, y.m_qkv_w, m->m_x_xn, m->ws_qkv, m->qkv_n, H, n_seq));
+        LLM_MARK(2);
+        if (!(skip & 1)) B2S_TRY(llm_attn_decode(st, m->ws_qkv, kc, vc, m->d_ctx_len, m->d_slots, m->rope_cos, m->rope_sin, m->attn, m->hq_r * LLM_HD,
+                                n_seq, m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
+        LLM_MARK(4);
+        nl += 2;
         for (int half = 0; half < 2; ++half, ++k) {
             float *mine = reinterpret_cast<float *>(m->comm + m->off_pdec[k & 1]);
             float *older = reinterpret_cast<float *>(m->comm + m->off_pdec[(k & 1) ^ 1]);
             const void *peer = m->peer_comm ? m->peer_comm + m->off_pdec[k & 1] : nullptr;
             if (half == 0) {
-                B2S_TRY(skinny_gemm_maps(st, y.m_o_w, m->m_x_attn, mine, H, m->hq_r * LLM_HD, n_seq));
+                if (!(skip & 16)) B2S_TRY(skinny_gemm_maps(st, y.m_o_w, m->m_x_attn, mine, H, m->hq_r * LLM_HD, n_seq));
+                LLM_MARK(5);
                 ++nl;
             } else {
-                B2S_TRY(skinny_gemm_maps(st, y.m_gu_w, m->m_x_xn, m->ws_gu, 2 * m->I_r, H, n_seq));
-                llm_swiglu_kernel<true><<<(n_seq * (m->I_r / 4) + 255) / 256, 256, 0, st>>>(m->ws_gu, m->act, n_seq, m->I_r);
-                B2S_TRY(skinny_gemm_maps(st, y.m_down_w, m->m_x_act, mine, H, m->I_r, n_seq));
+                if (!(skip & 32)) B2S_TRY(skinny_gemm_maps(st, y.m_gu_w, m->m_x_xn, m->ws_gu, 2 * m->I_r, H, n_seq));
+                LLM_MARK(7);
+                if (!(skip & 4)) B2S_CUDA(launch_dependent(llm_swiglu_kernel<true>, dim3((n_seq * (m->I_r / 4) + 255) / 256), dim3(256), st, m->ws_gu, m->act,
+                                          (int64_t)n_seq, m->I_r));
+                LLM_MARK(8);
+                if (!(skip & 64)) B2S_TRY(skinny_gemm_maps(st, y.m_down_w, m->m_x_act, mine, H, m->I_r, n_seq));
+                LLM_MARK(9);
                 nl += 3;
             }
             const float *w = half == 0 ? y.ln2 : (l + 1 < L ? m->layers[l + 1].ln1 : m->final_norm);
-            llm_reduce_rms_kernel<true><<<n_seq, 256, 0, st>>>(mine, peer, older, myf, peerf, m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps);
+            if (!(skip & 2)) B2S_CUDA(launch_dependent(llm_reduce_rms_kernel<true>, dim3(n_seq), dim3(256), st, (const void *)mine, peer, older, myf, peerf,
+                                      (const uint32_t *)m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps));
+            LLM_MARK(half == 0 ? 6 : 10);
             ++nl;
         }
     }
     // xn rows 0..n_seq-1 are the final-normed hidden states: lm_head reads them through the xn map
-    B2S_TRY(skinny_gemm_maps(st, m->m_lm_w, m->m_x_xn, m->ws_logits, m->V_r, H, n_seq));
-    llm_argmax_kernel<<<n_seq, 256, 0, st>>>(m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r, m->amax(m->comm),
-                                             m->peer_comm ? m->amax(m->peer_comm) : nullptr, myf, peerf, m->d_gen, k, m->d_next_tok,
-                                             m->d_out_tokens, m->d_out_pos, m->max_new_cap);
-    llm_step_end_kernel<<<1, 32, 0, st>>>(m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 1);
+    if (!(skip & 128)) B2S_TRY(skinny_gemm_maps(st, m->m_lm_w, m->m_x_xn, m->ws_logits, m->V_r, H, n_seq));
+    LLM_MARK(11);
+    if (!(skip & 128)) B2S_CUDA(launch_dependent(llm_argmax_kernel, dim3(n_seq), dim3(256), st, m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r,
+                              m->amax(m->comm), m->peer_comm ? m->amax(m->peer_comm) : (AmaxSlot *)nullptr, myf, peerf,
+                              (const uint32_t *)m->d_gen, k, m->d_next_tok, m->d_out_tokens, (const int32_t *)m->d_out_pos, m->max_new_cap));
+    LLM_MARK(12);
+    B2S_CUDA(launch_dependent(llm_step_end_kernel, dim3(1), dim3(32), st, m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 1));
+    LLM_MARK(13);
     nl += 3;
     B2S_CUDA(cudaGetLastError());
     *n_launch = nl;
     return 0;
+#undef LLM_MARK
 }
 
 static int llm_decode(Llm *m, cudaStream_t st, int n_steps, int use_graph)
@@ -823,6 +883,33 @@ static int llm_decode(Llm *m, cudaStream_t st, int n_steps, int use_graph)
     B2S_CUDA(cudaSetDevice(m->device));
     if (m->n_seq < 1) return fail(B2S_ERR_INVALID, "llm decode: no prefilled wave");
     if (n_steps < 0) return fail(B2S_ERR_INVALID, "llm decode: negative step count");
+    if (use_graph == 2) {   // per-kernel device times of eagerly launched steps, printed to stderr
+        double tot[14] = {0}, all = 0;
+        int cnt[14] = {0};
+        LlmTiming tm;
+        for (int s = 0; s < n_steps; ++s) {
+            int nl = 0;
+            tm.used = 0;
+            B2S_TRY(llm_decode_enqueue(m, st, &nl, &tm));
+            count_launch((uint64_t)nl);
+            B2S_CUDA(cudaStreamSynchronize(st));
+            if (s == 0) continue;   // first step warms up
+            for (size_t i = 1; i < tm.used; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, tm.ev[i - 1], tm.ev[i]);
+                tot[tm.label[i]] += ms;
+                cnt[tm.label[i]] += 1;
+                all += ms;
+            }
+        }
+        const int steps = n_steps > 1 ? n_steps - 1 : 1;
+        fprintf(stderr, "llm decode timing (eager, %d steps, n_seq %d): %.3f ms/step\n", steps, m->n_seq, all / steps);
+        for (int i = 1; i < 14; ++i)
+            if (cnt[i]) fprintf(stderr, "  %-18s n/step=%4d avg=%8.2f us  per-step=%8.1f us (%4.1f%%)\n", LLM_TIMING_NAMES[i], cnt[i] / steps,
+                                1e3 * tot[i] / cnt[i], 1e3 * tot[i] / steps, 100.0 * tot[i] / all);
+        for (cudaEvent_t e : tm.ev) cudaEventDestroy(e);
+        return 0;
+    }
     if (!use_graph) {
         for (int s = 0; s < n_steps; ++s) {
             int nl = 0;

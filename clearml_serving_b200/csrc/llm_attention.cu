@@ -10,10 +10,10 @@
 //    the online softmax in registers; only key blocks at or below the diagonal are visited.
 //    FLOPs: 4 * 128 * S^2 / 2 per (sequence, q head).  ~1 % of the prefill FLOPs of Llama-3-8B at S=512, so
 //    it stays on the legacy tensor path; the tcgen05 budget is in the GEMMs.
-//  * decode: one CTA = (sequence, kv head), 8 warps; warp w walks key batches w, w+8, ... straight from global
-//    memory (each lane owns 4 of the 128 dims: one coalesced 256-byte row per load), scores of a batch of
-//    32/G keys x G q-heads are reduced with a 31-shuffle transpose-reduction, and the 8 partial softmax states
-//    are merged through shared memory.  HBM-bound: 512 bytes per cached token per kv head.
+//  * decode: one CTA = (sequence, kv head); the G query heads of the group are the rows of one 16-row MMA tile,
+//    keys stream through a 3-stage cp.async ring, RoPE + KV append are fused into the prologue (see below).
+//    A first CUDA-core version (one lane per 4 dims, shuffle reductions) was issue-bound at ~25 us per layer
+//    for 32 x 8 x 576 cached keys; HBM-bound target: 512 bytes per cached token per kv head.
 #include "common.cuh"
 
 #include <cuda_bf16.h>
@@ -227,139 +227,224 @@ int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *k
 }
 
 // ------------------------------------------------------------------------------------------------ decode
-constexpr int LD_WARPS = 8;
+// One CTA = (sequence, kv head), 4 warps.  Fused prologue: the q heads of the group and the new token's k / v
+// are taken straight from the fp32 accumulator of the QKV projection (cleared here), RoPE is applied, k / v are
+// appended to the cache.  The G query heads form the rows of ONE 16-row MMA tile (rows >= G are zero); cached
+// keys stream through a 3-stage cp.async ring in blocks of 64, warp w owning keys 16w..16w+15 of every block
+// (S = QK^T: 16 mma.sync, O += PV: 16 mma.sync per warp and block), and the four per-warp online-softmax
+// states are merged through shared memory at the end.
+constexpr int LDM_STAGES = 3;
+constexpr int LDM_TILE = LA_BK * LA_LD;                                      // elements of one K or V tile
+constexpr int LDM_SMEM = (16 * LA_LD + LDM_STAGES * 2 * LDM_TILE) * 2;       // Q + ring of (K, V)
 
-template <int G>
-__global__ void __launch_bounds__(LD_WARPS * 32)
-llm_attn_decode_kernel(const __nv_bfloat16 *__restrict__ q, int ld_q, const __nv_bfloat16 *__restrict__ kc,
-                       const __nv_bfloat16 *__restrict__ vc, const int32_t *__restrict__ ctx_len,
-                       const int32_t *__restrict__ slots, __nv_bfloat16 *__restrict__ out, int ld_out, int kvh_r,
-                       int max_ctx, float scale_log2e)
+__global__ void __launch_bounds__(128)
+llm_attn_decode_kernel(float *__restrict__ ws_qkv, __nv_bfloat16 *__restrict__ kc, __nv_bfloat16 *__restrict__ vc,
+                       const int32_t *__restrict__ ctx_len, const int32_t *__restrict__ slots,
+                       const float *__restrict__ rope_cos, const float *__restrict__ rope_sin,
+                       __nv_bfloat16 *__restrict__ out, int ld_out, int hq_r, int kvh_r, int max_ctx, float scale_log2e)
 {
-    constexpr int KB = 32 / G;   // keys per batch: KB * G (key, head) pairs = one per lane after the reduction
-    __shared__ float sm_m[LD_WARPS][G], sm_l[LD_WARPS][G];
-    __shared__ __align__(16) float sm_o[LD_WARPS][G][LA_D];
+    extern __shared__ __align__(16) unsigned char la_smem[];
+    __nv_bfloat16 *Qs = reinterpret_cast<__nv_bfloat16 *>(la_smem);
+    __nv_bfloat16 *ring = Qs + 16 * LA_LD;
 
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");                 // QKV projection complete
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");    // the O projection may prefetch its weights
     const int b = blockIdx.x, kvh = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_ctx = min(__ldg(ctx_len + b) + 1, max_ctx);   // cached tokens + the one appended this step
+    const int G = hq_r / kvh_r;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int QKV = (hq_r + 2 * kvh_r) * LA_D;
+    int pos = __ldg(ctx_len + b);
+    pos = pos < max_ctx ? pos : max_ctx - 1;
+    const int n_ctx = pos + 1;
     const int slot = __ldg(slots + b);
-    const __nv_bfloat16 *Kg = kc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D + lane * 4;
-    const __nv_bfloat16 *Vg = vc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D + lane * 4;
+    __nv_bfloat16 *Kg = kc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D;
+    __nv_bfloat16 *Vg = vc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D;
 
-    float qr[G][4];
-#pragma unroll
-    for (int gi = 0; gi < G; ++gi) {
-        const uint2 u = *reinterpret_cast<const uint2 *>(q + (int64_t)b * ld_q + (kvh * G + gi) * LA_D + lane * 4);
-        const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
-        const float2 a = __bfloat1622float2(p[0]), c = __bfloat1622float2(p[1]);
-        qr[gi][0] = a.x * scale_log2e; qr[gi][1] = a.y * scale_log2e;
-        qr[gi][2] = c.x * scale_log2e; qr[gi][3] = c.y * scale_log2e;
-    }
-    float o[G][4];
-#pragma unroll
-    for (int gi = 0; gi < G; ++gi) o[gi][0] = o[gi][1] = o[gi][2] = o[gi][3] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;   // softmax state of head (lane % G), replicated over the lanes sharing it
-    const int my_key = lane / G;
-
-    for (int k0 = warp * KB; k0 < n_ctx; k0 += LD_WARPS * KB) {
-        float part[32];
-        uint2 vraw[KB];
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-            const int key = min(k0 + kb, n_ctx - 1);
-            const uint2 u = __ldg(reinterpret_cast<const uint2 *>(Kg + (int64_t)key * LA_D));
-            vraw[kb] = __ldg(reinterpret_cast<const uint2 *>(Vg + (int64_t)key * LA_D));
-            const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
-            const float2 a = __bfloat1622float2(p[0]), c = __bfloat1622float2(p[1]);
-#pragma unroll
-            for (int gi = 0; gi < G; ++gi)
-                part[kb * G + gi] = fmaf(qr[gi][0], a.x, fmaf(qr[gi][1], a.y, fmaf(qr[gi][2], c.x, qr[gi][3] * c.y)));
+    // ---- prologue: RoPE on q (-> Qs) and k (-> cache), v -> cache, accumulator cleared
+    float *row = ws_qkv + (int64_t)b * QKV;
+    for (int idx = tid; idx < 16 * 64; idx += 128) {
+        const int r = idx >> 6, i = idx & 63;
+        __nv_bfloat16 o1 = __float2bfloat16_rn(0.f), o2 = o1;
+        if (r < G) {
+            float *src = row + (kvh * G + r) * LA_D;
+            const float x1 = src[i], x2 = src[i + 64];
+            src[i] = 0.f;
+            src[i + 64] = 0.f;
+            const float c = __ldg(rope_cos + (int64_t)pos * 64 + i), sv = __ldg(rope_sin + (int64_t)pos * 64 + i);
+            o1 = __float2bfloat16_rn(x1 * c - x2 * sv);
+            o2 = __float2bfloat16_rn(x2 * c + x1 * sv);
         }
-        // transpose-reduce: 32 partials on 32 lanes -> lane j holds the full dot product of pair j
+        Qs[r * LA_LD + i] = o1;
+        Qs[r * LA_LD + i + 64] = o2;
+    }
+    if (tid < 64) {
+        float *src = row + (hq_r + kvh) * LA_D;
+        const float x1 = src[tid], x2 = src[tid + 64];
+        src[tid] = 0.f;
+        src[tid + 64] = 0.f;
+        const float c = __ldg(rope_cos + (int64_t)pos * 64 + tid), sv = __ldg(rope_sin + (int64_t)pos * 64 + tid);
+        Kg[(int64_t)pos * LA_D + tid] = __float2bfloat16_rn(x1 * c - x2 * sv);
+        Kg[(int64_t)pos * LA_D + tid + 64] = __float2bfloat16_rn(x2 * c + x1 * sv);
+    } else {
+        const int i = tid - 64;
+        float *src = row + (hq_r + kvh_r + kvh) * LA_D;
+        const float x1 = src[i], x2 = src[i + 64];
+        src[i] = 0.f;
+        src[i + 64] = 0.f;
+        Vg[(int64_t)pos * LA_D + i] = __float2bfloat16_rn(x1);
+        Vg[(int64_t)pos * LA_D + i + 64] = __float2bfloat16_rn(x2);
+    }
+    __syncthreads();   // Qs complete; the appended K/V row is ordered before this CTA's tile loads
+
+    const int n_blocks = (n_ctx + LA_BK - 1) / LA_BK;
+    auto issue_block = [&](int blk) {
+        if (blk < n_blocks) {
+            const int k0 = blk * LA_BK;
+            __nv_bfloat16 *dst = ring + (blk % LDM_STAGES) * 2 * LDM_TILE;
+            la_load_tile_async(dst, Kg + (int64_t)k0 * LA_D, LA_D, min(LA_BK, n_ctx - k0), tid);
+            la_load_tile_async(dst + LDM_TILE, Vg + (int64_t)k0 * LA_D, LA_D, min(LA_BK, n_ctx - k0), tid);
+        }
+        la_commit();   // (possibly empty) group: keeps the wait_group arithmetic uniform
+    };
+    issue_block(0);
+    issue_block(1);
+
+    uint32_t qa[8][4];
 #pragma unroll
-        for (int w = 16; w >= 1; w >>= 1) {
-            const bool upper = (lane & w) != 0;
+    for (int kk = 0; kk < 8; ++kk)
+        la_ldmatrix_x4(qa[kk], Qs + (lane & 15) * LA_LD + kk * 16 + (lane >> 4) * 8);
+    float o[16][4];
 #pragma unroll
-            for (int i = 0; i < w; ++i) {
-                const float send = upper ? part[i] : part[i + w];
-                const float keep = upper ? part[i + w] : part[i];
-                part[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    for (int n = 0; n < 16; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        issue_block(blk + 2);
+        la_wait<2>();
+        __syncthreads();
+        const __nv_bfloat16 *Ks = ring + (blk % LDM_STAGES) * 2 * LDM_TILE, *Vs = Ks + LDM_TILE;
+        const int key0 = blk * LA_BK + warp * 16;   // this warp's 16 keys
+        if (key0 < n_ctx) {
+            float s[2][4];
+            s[0][0] = s[0][1] = s[0][2] = s[0][3] = s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                uint32_t kb[4];
+                la_ldmatrix_x4(kb, Ks + (warp * 16 + (lane & 7) + (lane >> 4) * 8) * LA_LD + kk * 16 + ((lane >> 3) & 1) * 8);
+                la_mma_bf16(s[0], qa[kk], kb[0], kb[1]);
+                la_mma_bf16(s[1], qa[kk], kb[2], kb[3]);
+            }
+            float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const int key = key0 + n * 8 + 2 * t;
+                s[n][0] = key < n_ctx ? s[n][0] * scale_log2e : -INFINITY;
+                s[n][1] = key + 1 < n_ctx ? s[n][1] * scale_log2e : -INFINITY;
+                s[n][2] = key < n_ctx ? s[n][2] * scale_log2e : -INFINITY;
+                s[n][3] = key + 1 < n_ctx ? s[n][3] * scale_log2e : -INFINITY;
+                mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
+            }
+            float corr[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+                const float m_new = fmaxf(m_run[r], mx[r]);   // finite: key0 < n_ctx
+                corr[r] = exp2f(m_run[r] - m_new);
+                m_run[r] = m_new;
+            }
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                s[n][0] = exp2f(s[n][0] - m_run[0]);
+                s[n][1] = exp2f(s[n][1] - m_run[0]);
+                s[n][2] = exp2f(s[n][2] - m_run[1]);
+                s[n][3] = exp2f(s[n][3] - m_run[1]);
+                rs[0] += s[n][0] + s[n][1];
+                rs[1] += s[n][2] + s[n][3];
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+                rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+                l_run[r] = l_run[r] * corr[r] + rs[r];
+            }
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+                o[n][0] *= corr[0]; o[n][1] *= corr[0];
+                o[n][2] *= corr[1]; o[n][3] *= corr[1];
+            }
+            uint32_t pa[4];
+            pa[0] = la_pack_bf16(s[0][0], s[0][1]);
+            pa[1] = la_pack_bf16(s[0][2], s[0][3]);
+            pa[2] = la_pack_bf16(s[1][0], s[1][1]);
+            pa[3] = la_pack_bf16(s[1][2], s[1][3]);
+#pragma unroll
+            for (int np = 0; np < 8; ++np) {
+                uint32_t vb[4];
+                la_ldmatrix_x4_trans(vb, Vs + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LA_LD + np * 16 + (lane >> 4) * 8);
+                la_mma_bf16(o[2 * np], pa, vb[0], vb[1]);
+                la_mma_bf16(o[2 * np + 1], pa, vb[2], vb[3]);
             }
         }
-        float sc = (k0 + my_key < n_ctx) ? part[0] : -INFINITY;
-        // per-head max / sum over the KB keys of the batch (lanes with equal lane % G)
-        float mx = sc;
-#pragma unroll
-        for (int off = G; off < 32; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        const float m_new = fmaxf(m_run, mx);            // finite: key k0 of the batch is always valid
-        const float corr = exp2f(m_run - m_new);         // 0 on the first batch (m_run = -inf)
-        const float p = exp2f(sc - m_new);
-        float ps = p;
-#pragma unroll
-        for (int off = G; off < 32; off <<= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
-        l_run = l_run * corr + ps;
-        m_run = m_new;
-#pragma unroll
-        for (int gi = 0; gi < G; ++gi) {
-            const float cg = __shfl_sync(0xffffffffu, corr, gi);
-            o[gi][0] *= cg; o[gi][1] *= cg; o[gi][2] *= cg; o[gi][3] *= cg;
-        }
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-            const __nv_bfloat162 *pv = reinterpret_cast<const __nv_bfloat162 *>(&vraw[kb]);
-            const float2 a = __bfloat1622float2(pv[0]), c = __bfloat1622float2(pv[1]);
-#pragma unroll
-            for (int gi = 0; gi < G; ++gi) {
-                const float pg = __shfl_sync(0xffffffffu, p, kb * G + gi);
-                o[gi][0] = fmaf(pg, a.x, o[gi][0]); o[gi][1] = fmaf(pg, a.y, o[gi][1]);
-                o[gi][2] = fmaf(pg, c.x, o[gi][2]); o[gi][3] = fmaf(pg, c.y, o[gi][3]);
-            }
-        }
+        __syncthreads();   // all warps done with this stage before it is refilled
     }
-    if (lane < G) { sm_m[warp][lane] = m_run; sm_l[warp][lane] = l_run; }
+
+    // ---- merge the four per-warp states (only rows g < G are real)
+    float *sm_m = reinterpret_cast<float *>(ring);        // [4][8]
+    float *sm_l = sm_m + 32;                              // [4][8]
+    float *sm_o = sm_l + 32;                              // [4][8][128]
+    if (t == 0) { sm_m[warp * 8 + g] = m_run[0]; sm_l[warp * 8 + g] = l_run[0]; }
 #pragma unroll
-    for (int gi = 0; gi < G; ++gi)
-        *reinterpret_cast<float4 *>(&sm_o[warp][gi][lane * 4]) = make_float4(o[gi][0], o[gi][1], o[gi][2], o[gi][3]);
+    for (int n = 0; n < 16; ++n)
+        *reinterpret_cast<float2 *>(sm_o + ((warp * 8 + g) * LA_D + n * 8 + 2 * t)) = make_float2(o[n][0], o[n][1]);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < G * LA_D; idx += LD_WARPS * 32) {
-        const int gi = idx / LA_D, d = idx - gi * LA_D;
+    for (int idx = tid; idx < G * LA_D; idx += 128) {
+        const int r = idx >> 7, d = idx & 127;
         float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < LD_WARPS; ++w) M = fmaxf(M, sm_m[w][gi]);
+        for (int w = 0; w < 4; ++w) M = fmaxf(M, sm_m[w * 8 + r]);
         float num = 0.f, den = 0.f;
 #pragma unroll
-        for (int w = 0; w < LD_WARPS; ++w) {
-            const float mw = sm_m[w][gi];
+        for (int w = 0; w < 4; ++w) {
+            const float mw = sm_m[w * 8 + r];
             const float wgt = (mw == -INFINITY) ? 0.f : exp2f(mw - M);
-            num = fmaf(wgt, sm_o[w][gi][d], num);
-            den = fmaf(wgt, sm_l[w][gi], den);
+            num = fmaf(wgt, sm_o[(w * 8 + r) * LA_D + d], num);
+            den = fmaf(wgt, sm_l[w * 8 + r], den);
         }
-        out[(int64_t)b * ld_out + (kvh * G + gi) * LA_D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+        out[(int64_t)b * ld_out + (kvh * G + r) * LA_D + d] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
     }
 }
 
-int llm_attn_decode(cudaStream_t st, const void *q, int ld_q, const void *kc, const void *vc, const int32_t *ctx_len,
-                    const int32_t *slots, void *out, int ld_out, int n_seq, int hq_r, int kvh_r, int max_ctx, float scale)
+// decode attention fused with RoPE + KV append: reads (and clears) the fp32 QKV accumulator [32, (hq+2hkv)*128]
+int llm_attn_decode(cudaStream_t st, float *ws_qkv, void *kc, void *vc, const int32_t *ctx_len, const int32_t *slots,
+                    const float *rope_cos, const float *rope_sin, void *out, int ld_out, int n_seq, int hq_r, int kvh_r,
+                    int max_ctx, float scale)
 {
     if (n_seq <= 0) return 0;
     const int G = hq_r / kvh_r;
-    dim3 grid(n_seq, kvh_r);
-    const float sl = scale * 1.4426950408889634f;
-#define B2S_LAUNCH_DEC(GG)                                                                                             \
-    llm_attn_decode_kernel<GG><<<grid, LD_WARPS * 32, 0, st>>>(static_cast<const __nv_bfloat16 *>(q), ld_q,            \
-        static_cast<const __nv_bfloat16 *>(kc), static_cast<const __nv_bfloat16 *>(vc), ctx_len, slots,               \
-        static_cast<__nv_bfloat16 *>(out), ld_out, kvh_r, max_ctx, sl)
-    switch (G) {
-    case 1: B2S_LAUNCH_DEC(1); break;
-    case 2: B2S_LAUNCH_DEC(2); break;
-    case 4: B2S_LAUNCH_DEC(4); break;
-    case 8: B2S_LAUNCH_DEC(8); break;
-    default: return fail(B2S_ERR_INVALID, "llm attention: query group size %d not supported (1, 2, 4, 8)", G);
-    }
-#undef B2S_LAUNCH_DEC
+    if (G < 1 || G > 8 || G * kvh_r != hq_r) return fail(B2S_ERR_INVALID, "llm attention: query group size %d not supported (1..8)", G);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, []() {
+        attr_err = cudaFuncSetAttribute(llm_attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LDM_SMEM);
+    });
+    if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(llm decode attention)");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_seq, (unsigned)kvh_r);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = LDM_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2S_CUDA(cudaLaunchKernelEx(&cfg, llm_attn_decode_kernel, ws_qkv, static_cast<__nv_bfloat16 *>(kc), static_cast<__nv_bfloat16 *>(vc),
+                                ctx_len, slots, rope_cos, rope_sin, static_cast<__nv_bfloat16 *>(out), ld_out, hq_r, kvh_r, max_ctx,
+                                scale * 1.4426950408889634f));
     count_launch();
-    B2S_CUDA(cudaGetLastError());
     return 0;
 }
 

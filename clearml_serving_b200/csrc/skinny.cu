@@ -14,13 +14,19 @@
 //     (a 4096 x 2048 projection has only 32 row tiles); a CTA's range covers at most a few (tile, k-range)
 //     segments, each accumulated in TMEM (double-buffered) and added into Y with red.global.add.f32 (a warp's
 //     32 lanes hold 32 consecutive n of one batch row: every reduction instruction is one coalesced 128-byte line);
-//   * a 10-stage TMA ring (20 KB per stage: W 16 KB + X 4 KB) keeps ~200 KB per SM in flight.
+//   * a 10-stage TMA ring (20 KB per stage: W 16 KB + X 4 KB) keeps ~200 KB per SM in flight;
+//   * programmatic dependent launch: the kernel may start while its predecessor (a small normalisation /
+//     attention kernel) still runs -- the producer fills the whole ring with WEIGHT tiles first and only then
+//     waits for the predecessor (griddepcontrol.wait) before it requests the activation tiles, so barrier
+//     set-up, TMEM allocation and the first 23 MB of the weight stream are off the critical path.
 // The consumer kernels (llm.cu) read Y and zero it again, so no separate memset is needed.
 // Roofline: HBM; algorithmic bytes = 2 * N_out * K (the weight), X and Y are L2-resident.
 #include "common.cuh"
 #include "sm100.cuh"
 
 #include <cuda_bf16.h>
+
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -63,6 +69,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
+    griddep_launch_dependents();   // the (small) kernel after this one may get resident early; it waits for us
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // contiguous unit range of this CTA (unit = tile * num_k + kb)
     const int u0 = (int)(((int64_t)total_units * blockIdx.x) / gridDim.x);
@@ -92,9 +99,22 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int u = u0; u < u1; ++u) {
+            // The weight does not depend on the kernel that precedes this one in the stream (only X does): with a
+            // programmatic dependent launch the ring is filled with weight tiles while that kernel still runs.
+            const int pre = min(u1 - u0, SK_STAGES);
+            for (int i = 0; i < pre; ++i) {
+                const int u = u0 + i, tile = u / num_k, kb = u - tile * num_k;
+                mbar_arrive_expect_tx(&full_bar[i], S::STAGE_BYTES);
+                tma_load_2d(smem + i * S::STAGE_BYTES, &tmap_w, &full_bar[i], kb * SK_BK, tile * SK_BM);
+            }
+            griddep_wait();
+            for (int i = 0; i < pre; ++i) {
+                const int u = u0 + i, tile = u / num_k, kb = u - tile * num_k;
+                tma_load_2d(smem + i * S::STAGE_BYTES + S::A_BYTES, &tmap_x, &full_bar[i], kb * SK_BK, 0);
+            }
+            int stage = pre == SK_STAGES ? 0 : pre;
+            uint32_t phase = pre == SK_STAGES ? 1 : 0;
+            for (int u = u0 + pre; u < u1; ++u) {
                 const int tile = u / num_k, kb = u - tile * num_k;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 unsigned char *sa = smem + stage * S::STAGE_BYTES;
@@ -204,7 +224,18 @@ int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &
     // at least 4 k-blocks per CTA so tiny problems do not pay 148 prologues for nothing
     int grid = sk_num_sms();
     if (units < (int64_t)grid * 4) grid = (int)((units + 3) / 4);
-    skinny_gemm_kernel<<<grid, SK_THREADS, SkSmem::TOTAL, st>>>(tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = SkSmem::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = []() { const char *e = getenv("B2S_SKINNY_PDL"); return !(e && e[0] == '0'); }();
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    B2S_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel, tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units));
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;

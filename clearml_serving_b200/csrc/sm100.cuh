@@ -24,6 +24,14 @@ __device__ __forceinline__ bool elect_one()
     return pred != 0;
 }
 
+// ---------------------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream is still running; griddep_wait() blocks the calling thread until that predecessor has completed
+// and its memory is visible.  griddep_launch_dependents() in the predecessor lets the successor's CTAs be
+// scheduled as soon as every CTA of the predecessor has issued it (instead of at its completion).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

@@ -484,7 +484,7 @@ class Llm(object):
         self.n_seq = len(prompts)
 
     def decode(self, n_steps, use_graph=True):
-        check(lib().b2s_llm_decode(self.handle, int(n_steps), 1 if use_graph else 0))
+        check(lib().b2s_llm_decode(self.handle, int(n_steps), int(use_graph)))   # 0 eager, 1 CUDA graph, 2 eager + per-kernel timing
 
     def tokens(self, n):
         out = np.empty((self.n_seq, int(n)), dtype=np.int32)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--gen", type=int, default=128)
     ap.add_argument("--waves", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--timing", action="store_true", help="per-kernel device times of eager decode steps (stderr)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -48,6 +49,10 @@ def main():
         m.record(2)
         toks = m.tokens(a.gen)
         res.append((m.elapsed_ms(0, 1), m.elapsed_ms(1, 2)))
+    if a.timing:
+        m.prefill(prompts)
+        m.decode(12, use_graph=2)
+        m.synchronize()
     pre, dec = np.median([r[0] for r in res[1:] or res]), np.median([r[1] for r in res[1:] or res])
     tp = 2 if world == 2 else 1
     step_ms = dec / (a.gen - 1)
