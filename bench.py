@@ -505,6 +505,82 @@ def _resnet_workload(native, device, steps, warmup, cpu_seconds):
     return res
 
 
+def _llama_workload(native, rank, world, local, dist, waves=3):
+    """BASELINE.json configs[4]: Llama-3-8B bf16 random-init, prompt 512, 128 new tokens, max_batch 32, greedy.
+    One GPU: TP 1.  N >= 2 (torchrun): ranks (2i, 2i+1) form tensor-parallel pairs exchanging partial sums through
+    peer memory; pairs are independent replicas.  Device-timed (CUDA events on the model's stream), max over ranks."""
+    from clearml_serving_b200 import llm as L
+    spec = L.LlamaSpec.llama3_8b()
+    batch, prompt_len, gen = 32, 512, 128
+    tp = 2 if world >= 2 else 1
+    group = None
+    if tp == 2:
+        if world % 2:
+            return dict(error="tensor-parallel pairs need an even number of GPUs")
+        for i in range(world // 2):   # every rank creates every pair group, in the same order
+            g = dist.new_group(ranks=[2 * i, 2 * i + 1], backend="gloo")
+            if rank // 2 == i:
+                group = g
+    eng = L.LlmEngine(spec, device=local, max_batch=batch, max_ctx=prompt_len + gen + 16, max_tokens=batch * prompt_len,
+                      tp_size=tp, tp_rank=rank % 2 if tp == 2 else 0, tp_group=group)
+    eng.init_random(seed=0, std=0.02)
+    rng = np.random.default_rng(1)
+    prompts = [rng.integers(0, spec.vocab_size, prompt_len) for _ in range(batch)]
+    m = eng.llm
+    launches0 = native.launch_count()
+    res, e2e = [], []
+    for w in range(waves):
+        _barrier_sync(dist, local)
+        m.flush_l2()
+        m.record(0)
+        m.prefill(prompts)
+        m.record(1)
+        m.decode(gen - 1, use_graph=True)
+        m.record(2)
+        toks = m.tokens(gen)
+        res.append((m.elapsed_ms(0, 1), m.elapsed_ms(1, 2)))
+    launches = (native.launch_count() - launches0) // waves
+    for w in range(2):   # end to end through the Python engine: host token ids in, host token ids out (wall clock)
+        _barrier_sync(dist, local)
+        t0 = time.perf_counter()
+        out = eng.generate(prompts, gen)
+        e2e.append(time.perf_counter() - t0)
+    if not np.array_equal(out, toks):
+        m.synchronize()
+    pre = _max_over_ranks(dist, local, float(np.median([r[0] for r in res[1:]])))
+    dec = _max_over_ranks(dist, local, float(np.median([r[1] for r in res[1:]])))
+    e2e_s = _max_over_ranks(dist, local, min(e2e))
+    if tp == 2:
+        dist.barrier()
+    eng.close()
+    replicas = world // tp
+    step_ms = dec / (gen - 1)
+    wbytes = (spec.n_params() - spec.vocab_size * spec.hidden_size) * 2 / tp
+    kv_bytes = batch * (prompt_len + gen / 2) * spec.num_hidden_layers * 2 * spec.num_key_value_heads * spec.head_dim * 2 / tp
+    pre_flops = batch * prompt_len * spec.flops_per_token() / tp
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa
+        pass
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1431.4) or 1431.4)   # kernels timed inside a long step
+    hbm_peak, _ = _peaks()
+    return dict(
+        workload="Llama-3-8B bf16 random-init (on-device deterministic init), prompt 512 + 128 new tokens, 32 sequences per wave, greedy",
+        parallelism="tp{} x {} replica(s)".format(tp, replicas), metric="requests/sec",
+        value=replicas * batch / ((pre + dec) * 1e-3), gen_tokens_per_s=replicas * batch * gen / ((pre + dec) * 1e-3),
+        prefill_ms=pre, decode_ms=dec, decode_step_ms=step_ms, gpu_launches_per_wave=int(launches),
+        e2e=dict(value=replicas * batch / e2e_s, unit="requests/s", path="LlmEngine.generate(host token ids) -> host token ids, wall clock",
+                 h2d_bytes_per_step=batch * prompt_len * 4, d2h_bytes_per_step=batch * gen * 4),
+        roofline=dict(prefill=dict(bound="tensor", achieved=pre_flops / (pre * 1e-3) / 1e12, peak=tf_peak, unit="TFLOP/s",
+                                   frac=pre_flops / (pre * 1e-3) / 1e12 / tf_peak),
+                      decode=dict(bound="hbm", achieved=(wbytes + kv_bytes) / (step_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
+                                  frac=(wbytes + kv_bytes) / (step_ms * 1e-3) / 1e9 / hbm_peak,
+                                  algorithmic_bytes_per_step=int(wbytes + kv_bytes))),
+        cpu_baseline=None, cpu_baseline_note="the reference has no CPU path for this endpoint (it wraps vLLM)",
+        waves_ms=[[round(x, 2) for x in r] for r in res])
+
+
 def run_b200(args):
     rank, world, local, dist = _dist_setup(args.gpus)
     device = local
@@ -624,6 +700,15 @@ def run_b200(args):
         except Exception as ex:  # noqa
             resnet = dict(error="{}: {}".format(type(ex).__name__, ex))
 
+    llama = None
+    if args.llama:
+        try:
+            llama = _llama_workload(native, rank, world, local, dist)
+        except Exception as ex:  # noqa
+            llama = dict(error="{}: {}".format(type(ex).__name__, ex))
+            if world > 1:
+                raise
+
     if rank == 0:
         peak, peak_src = _peaks()
         algo = model.algo_bytes(MAX_BATCH)
@@ -647,7 +732,7 @@ def run_b200(args):
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                           traffic=_traffic_bytes(), algorithmic_bytes_per_launch=algo, peak_source=peak_src,
                           kernel="forest_staged_kernel<f32>", note="latency-bound at 64 rows: 1000-add fp32 chain"),
-            cpu_baseline=cpu, clocks=clk, plugin=plugin, workloads=dict(bert_base=bert, resnet50=resnet))
+            cpu_baseline=cpu, clocks=clk, plugin=plugin, workloads=dict(bert_base=bert, resnet50=resnet, llama3_8b=llama))
         print(json.dumps(line))
     timer.destroy()
     for b in d_in:
@@ -669,6 +754,7 @@ def main():
     ap.add_argument("--no-plugin", action="store_true")
     ap.add_argument("--no-bert", dest="bert", action="store_false", help="skip the BERT-base (configs[3]) section")
     ap.add_argument("--no-resnet", dest="resnet", action="store_false", help="skip the ResNet-50 (configs[2]) section")
+    ap.add_argument("--no-llama", dest="llama", action="store_false", help="skip the Llama-3-8B (configs[4]) section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,7 +14,7 @@
 //     (a 4096 x 2048 projection has only 32 row tiles); a CTA's range covers at most a few (tile, k-range)
 //     segments, each accumulated in TMEM (double-buffered) and added into Y with red.global.add.f32 (a warp's
 //     32 lanes hold 32 consecutive n of one batch row: every reduction instruction is one coalesced 128-byte line);
-//   * a 10-stage TMA ring (20 KB per stage: W 16 KB + X 4 KB) keeps ~200 KB per SM in flight;
+//   * TMA rings of 20 KB stages (W 16 KB + X 4 KB), two CTAs x 5 stages per SM, keep ~200 KB per SM in flight;
 //   * programmatic dependent launch: the kernel may start while its predecessor (a small normalisation /
 //     attention kernel) still runs -- the producer fills the whole ring with WEIGHT tiles first and only then
 //     waits for the predecessor (griddepcontrol.wait) before it requests the activation tiles, so barrier
@@ -40,9 +40,9 @@ int make_tmap_2d_kmajor(CUtensorMap *out, const void *base, int64_t rows, int64_
 constexpr int SK_BM = 128;       // weight rows per tile (UMMA M)
 constexpr int SK_BN = 32;        // activation rows (UMMA N)
 constexpr int SK_BK = 64;
-constexpr int SK_STAGES = 10;
 constexpr int SK_THREADS = 256;  // warp 0 TMA, 1 MMA, 2 TMEM owner, 3 idle, 4-7 epilogue
 
+template <int SK_STAGES>
 struct SkSmem {
     static constexpr int A_BYTES = SK_BM * SK_BK * 2;   // 16 KB
     static constexpr int B_BYTES = SK_BN * SK_BK * 2;   // 4 KB
@@ -56,11 +56,15 @@ __device__ __forceinline__ void red_add(float *addr, float a)
     asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(a) : "memory");
 }
 
-__global__ void __launch_bounds__(SK_THREADS, 1)
+// SK_STAGES = 10: one CTA per SM; SK_STAGES = 5: two CTAs per SM (same bytes in flight per SM) -- the second
+// form lets the CTAs of the NEXT projection move in, and start streaming their weights, as soon as half an SM
+// frees up at the tail of the current one.
+template <int SK_STAGES>
+__global__ void __launch_bounds__(SK_THREADS, SK_STAGES > 5 ? 1 : 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                    float *__restrict__ y, int n_out, int m_rows, int num_k, int total_units)
 {
-    using S = SkSmem;
+    using S = SkSmem<SK_STAGES>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFFSET);
@@ -208,26 +212,24 @@ int skinny_make_maps(CUtensorMap *tw, CUtensorMap *tx, const void *W, int64_t n_
     return 0;
 }
 
-int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows)
+template <int STAGES>
+static int skinny_launch(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int m_rows, int num_k,
+                         int64_t units, int ctas_per_sm)
 {
-    if (n_out <= 0 || K <= 0) return 0;
+    using S = SkSmem<STAGES>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, []() {
-        attr_err = cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SkSmem::TOTAL);
+        attr_err = cudaFuncSetAttribute(skinny_gemm_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     });
     if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(skinny gemm)");
-    const int num_k = (K + SK_BK - 1) / SK_BK;
-    const int tiles = (n_out + SK_BM - 1) / SK_BM;
-    const int64_t units = (int64_t)tiles * num_k;
-    if (units > INT32_MAX) return fail(B2S_ERR_INVALID, "skinny gemm: problem too large");
-    // at least 4 k-blocks per CTA so tiny problems do not pay 148 prologues for nothing
-    int grid = sk_num_sms();
+    // at least 4 k-blocks per CTA so tiny problems do not pay hundreds of prologues for nothing
+    int grid = sk_num_sms() * ctas_per_sm;
     if (units < (int64_t)grid * 4) grid = (int)((units + 3) / 4);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(SK_THREADS);
-    cfg.dynamicSmemBytes = SkSmem::TOTAL;
+    cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -235,10 +237,21 @@ int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &
     static const bool pdl = []() { const char *e = getenv("B2S_SKINNY_PDL"); return !(e && e[0] == '0'); }();
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    B2S_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel, tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units));
+    B2S_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<STAGES>, tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units));
     count_launch();
-    B2S_CUDA(cudaGetLastError());
     return 0;
+}
+
+int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows)
+{
+    if (n_out <= 0 || K <= 0) return 0;
+    const int num_k = (K + SK_BK - 1) / SK_BK;
+    const int tiles = (n_out + SK_BM - 1) / SK_BM;
+    const int64_t units = (int64_t)tiles * num_k;
+    if (units > INT32_MAX) return fail(B2S_ERR_INVALID, "skinny gemm: problem too large");
+    static const int per_sm = []() { const char *e = getenv("B2S_SKINNY_CTAS"); return (e && e[0] == '1') ? 1 : 2; }();
+    return per_sm == 1 ? skinny_launch<10>(st, tw, tx, y, n_out, m_rows, num_k, units, 1)
+                       : skinny_launch<5>(st, tw, tx, y, n_out, m_rows, num_k, units, 2);
 }
 
 }  // namespace b2s
