@@ -261,6 +261,21 @@ llm_attn_decode_kernel(float *__restrict__ ws_qkv, __nv_bfloat16 *__restrict__ k
     __nv_bfloat16 *Kg = kc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D;
     __nv_bfloat16 *Vg = vc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D;
 
+    const int n_blocks = (n_ctx + LA_BK - 1) / LA_BK;
+    auto issue_block = [&](int blk) {
+        if (blk < n_blocks) {
+            const int k0 = blk * LA_BK;
+            __nv_bfloat16 *dst = ring + (blk % LDM_STAGES) * 2 * LDM_TILE;
+            la_load_tile_async(dst, Kg + (int64_t)k0 * LA_D, LA_D, min(LA_BK, n_ctx - k0), tid);
+            la_load_tile_async(dst + LDM_TILE, Vg + (int64_t)k0 * LA_D, LA_D, min(LA_BK, n_ctx - k0), tid);
+        }
+        la_commit();   // (possibly empty) group: keeps the wait_group arithmetic uniform
+    };
+    // Blocks 0 and 1 hold only OLD cache rows unless the row appended below falls into them: request them before
+    // the RoPE prologue so its three dependent round trips overlap the first HBM fetches.
+    const bool early = pos >= 2 * LA_BK;
+    if (early) { issue_block(0); issue_block(1); }
+
     // ---- prologue: RoPE on q (-> Qs) and k (-> cache), v -> cache, accumulator cleared
     float *row = ws_qkv + (int64_t)b * QKV;
     for (int idx = tid; idx < 16 * 64; idx += 128) {
@@ -297,18 +312,7 @@ llm_attn_decode_kernel(float *__restrict__ ws_qkv, __nv_bfloat16 *__restrict__ k
     }
     __syncthreads();   // Qs complete; the appended K/V row is ordered before this CTA's tile loads
 
-    const int n_blocks = (n_ctx + LA_BK - 1) / LA_BK;
-    auto issue_block = [&](int blk) {
-        if (blk < n_blocks) {
-            const int k0 = blk * LA_BK;
-            __nv_bfloat16 *dst = ring + (blk % LDM_STAGES) * 2 * LDM_TILE;
-            la_load_tile_async(dst, Kg + (int64_t)k0 * LA_D, LA_D, min(LA_BK, n_ctx - k0), tid);
-            la_load_tile_async(dst + LDM_TILE, Vg + (int64_t)k0 * LA_D, LA_D, min(LA_BK, n_ctx - k0), tid);
-        }
-        la_commit();   // (possibly empty) group: keeps the wait_group arithmetic uniform
-    };
-    issue_block(0);
-    issue_block(1);
+    if (!early) { issue_block(0); issue_block(1); }
 
     uint32_t qa[8][4];
 #pragma unroll

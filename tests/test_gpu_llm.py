@@ -108,6 +108,34 @@ def test_tiny_llama_matches_transformers_golden(native, use_graph):
         m.free()
 
 
+def test_long_and_mixed_contexts_match_oracle(native):
+    # contexts past 128 tokens take the early-prefetch path of the decode attention; mixed lengths in one wave
+    from oracle import llm_oracle
+    sd = L.random_state_dict(SPEC, seed=21, std=0.05)
+    rng = np.random.default_rng(9)
+    prompts = [rng.integers(0, SPEC.vocab_size, n) for n in (150, 3, 127, 200)]
+    n_new = 5
+    m = _tiny(native, max_batch=4, max_ctx=256)
+    try:
+        for (name, layer), arr in L.shard_state_dict(sd, SPEC).items():
+            m.load_tensor(name, layer, arr)
+        m.keep_logits(True)
+        m.prefill(prompts)
+        refs = [llm_oracle.greedy_generate(sd, SPEC, p, n_new) for p in prompts]
+        alive = [True] * len(prompts)
+        for step in range(n_new):
+            if step:
+                m.decode(1, use_graph=True)
+            lg = m.logits()
+            toks = m.tokens(step + 1)[:, step]
+            for i in range(len(prompts)):
+                if alive[i]:
+                    alive[i] = _check_step(lg[i], refs[i][1][step], int(toks[i]), int(refs[i][0][step]), "seq {} step {}".format(i, step))
+        assert sum(alive) >= len(prompts) - 1
+    finally:
+        m.free()
+
+
 def test_waves_are_independent_and_slots_reusable(native):
     # a sequence's tokens must not depend on its batch-mates or on what used the KV slot before
     from oracle import llm_oracle

@@ -1,0 +1,187 @@
+"""CPU tests of the LLM endpoint's serving side: the wave scheduler and the OpenAI-shaped engine surface
+(reference: VllmPreprocessRequest, clearml_serving/serving/preprocess_service.py:1097-1348; route
+serving/main.py:217-231).  The engine underneath is a host double -- no GPU, no product fallback."""
+import asyncio
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from clearml_serving_b200 import llm_service as S
+from clearml_serving_b200.endpoints import ModelEndpoint
+from clearml_serving_b200.model_request_processor import ModelRequestProcessor
+from clearml_serving_b200.preprocess_service import BasePreprocessRequest
+
+
+class FakeLlm(object):
+    """generate() -> token j of sequence i = (sum(prompt_i) + j) % 1000; records wave sizes"""
+
+    def __init__(self, max_batch=4, max_ctx=64, latency_s=0.0, vocab=1000):
+        self.max_batch, self.max_ctx, self.latency_s = max_batch, max_ctx, latency_s
+        self.waves = []
+        self.closed = False
+
+        class _Spec(object):
+            vocab_size = vocab
+        self.spec = _Spec()
+
+    def generate(self, prompts, n):
+        assert len(prompts) <= self.max_batch
+        self.waves.append((len(prompts), n))
+        time.sleep(self.latency_s)
+        return np.array([[(int(np.sum(p)) + j) % 1000 for j in range(n)] for p in prompts], dtype=np.int32)
+
+    def close(self):
+        self.closed = True
+
+
+def test_wave_batcher_groups_and_truncates():
+    eng = FakeLlm(max_batch=4, latency_s=0.02)
+    b = S.WaveBatcher(eng, max_batch=4, max_queue_delay_us=30000)
+    try:
+        futs = [b.submit(np.array([i, 1]), 2 + i % 3) for i in range(10)]
+        outs = [f.result(timeout=10) for f in futs]
+        for i, o in enumerate(outs):
+            assert o.tolist() == [(i + 1 + j) % 1000 for j in range(2 + i % 3)]
+        assert sum(n for n, _ in eng.waves) == 10 and max(n for n, _ in eng.waves) <= 4
+        assert len(eng.waves) <= 4                         # 10 requests in waves of <= 4, not 10 waves of 1
+        assert b.stats["requests"] == 10 and b.stats["waves"] == len(eng.waves)
+    finally:
+        b.close()
+
+
+def test_wave_batcher_timeout_dispatches_partial_wave_and_propagates_errors():
+    eng = FakeLlm(max_batch=8)
+    b = S.WaveBatcher(eng, max_batch=8, max_queue_delay_us=20000)
+    try:
+        t0 = time.perf_counter()
+        assert b.submit(np.array([5]), 3).result(timeout=5).tolist() == [5, 6, 7]
+        assert time.perf_counter() - t0 < 1.0 and eng.waves == [(1, 3)]
+
+        def boom(prompts, n):
+            raise ValueError("CUDA out of memory. injected")
+        eng.generate = boom
+        with pytest.raises(ValueError, match="CUDA out of memory. "):     # the text the reference restarts on
+            b.submit(np.array([1]), 1).result(timeout=5)
+    finally:
+        b.close()
+    with pytest.raises(RuntimeError):
+        b.submit(np.array([1]), 1)
+
+
+def _engine(monkeypatch, tokenizer=None, max_batch=4):
+    fake = FakeLlm(max_batch=max_batch)
+    monkeypatch.setattr(S, "build_engine", lambda cfg, model_path=None, device=0, tp_rank=0, tp_group=None: fake)
+    ep = ModelEndpoint(engine_type="b200_llm", serving_url="llama", auxiliary_cfg={
+        "b200.llm": {"architecture": "llama3-8b", "load_format": "dummy", "max_batch": max_batch},
+        "dynamic_batching": {"max_queue_delay_microseconds": 5000}})
+    eng = S.B200LlmPreprocessRequest(ep)
+    eng._tokenizer = tokenizer
+    return eng, fake
+
+
+def test_engine_is_registered_with_reference_flags():
+    cls = BasePreprocessRequest.get_engine_cls("b200_llm")
+    assert cls is S.B200LlmPreprocessRequest
+    assert cls.is_preprocess_async and cls.is_process_async and cls.is_postprocess_async     # ps.py:1099-1101
+    for name in ("v1_completions", "v1_chat_completions", "v1_models", "version", "tokenize", "detokenize"):
+        assert asyncio.iscoroutinefunction(getattr(cls, name))
+
+
+def test_completions_token_ids_batch_and_usage(monkeypatch):
+    eng, fake = _engine(monkeypatch)
+    try:
+        stats = []
+        r = asyncio.run(eng.v1_completions({"request": {"model": "llama", "prompt": [[1, 2, 3], [10]], "max_tokens": 3}}, {}, stats.append))
+        assert r["object"] == "text_completion" and r["model"] == "llama"
+        assert [c["token_ids"] for c in r["choices"]] == [[6, 7, 8], [10, 11, 12]]
+        assert [c["index"] for c in r["choices"]] == [0, 1] and all(c["finish_reason"] == "length" for c in r["choices"])
+        assert r["usage"] == {"prompt_tokens": 4, "completion_tokens": 6, "total_tokens": 10}
+        assert stats == [{"prompt_tokens": 4, "completion_tokens": 6}]
+        assert fake.waves == [(2, 3)]                      # both prompts rode one wave
+        one = asyncio.run(eng.v1_completions({"prompt": [4, 4], "max_tokens": 1}, {}, None))
+        assert one["choices"][0]["token_ids"] == [8]
+    finally:
+        eng.unload()
+    assert fake.closed
+
+
+def test_completions_rejects_bad_requests(monkeypatch):
+    eng, _ = _engine(monkeypatch)
+    try:
+        for body in ({"prompt": "hello", "max_tokens": 2},                 # text without a tokenizer
+                     {"max_tokens": 2},                                    # no prompt
+                     {"prompt": [1, 2], "max_tokens": 0},
+                     {"prompt": [1, 200000], "max_tokens": 1},             # id outside the vocabulary
+                     {"prompt": list(range(60)), "max_tokens": 10}):       # exceeds max_model_len 64
+            with pytest.raises(ValueError):
+                asyncio.run(eng.v1_completions(body, {}, None))
+        with pytest.raises(ValueError):
+            asyncio.run(eng.v1_chat_completions({"messages": [{"role": "user", "content": "hi"}]}, {}, None))
+    finally:
+        eng.unload()
+
+
+class _Tok(object):
+    def encode(self, s):
+        return [ord(c) % 256 for c in s]
+
+    def decode(self, ids):
+        return "".join(chr(65 + i % 26) for i in ids)
+
+    def apply_chat_template(self, messages, add_generation_prompt=True, tokenize=True):
+        return self.encode("|".join(m["content"] for m in messages))
+
+
+def test_text_and_chat_with_user_tokenizer(monkeypatch):
+    eng, _ = _engine(monkeypatch, tokenizer=_Tok())
+    try:
+        r = asyncio.run(eng.v1_completions({"prompt": "ab", "max_tokens": 2}, {}, None))
+        first = (97 + 98) % 1000
+        assert r["choices"][0]["token_ids"] == [first, first + 1] and r["choices"][0]["text"] == _Tok().decode([first, first + 1])
+        c = asyncio.run(eng.v1_chat_completions({"messages": [{"role": "user", "content": "a"}], "max_tokens": 1}, {}, None))
+        assert c["object"] == "chat.completion" and c["choices"][0]["message"]["role"] == "assistant"
+        t = asyncio.run(eng.tokenize({"prompt": "ab"}, {}, None))
+        assert t["tokens"] == [97, 98] and t["count"] == 2
+        assert asyncio.run(eng.detokenize({"tokens": [0, 1]}, {}, None)) == {"prompt": "AB"}
+        assert asyncio.run(eng.v1_models(None, {}, None))["data"][0]["id"] == "llama"
+    finally:
+        eng.unload()
+
+
+def test_openai_route_end_to_end(monkeypatch):
+    from starlette.testclient import TestClient
+    from clearml_serving_b200.main import create_app
+    eng, fake = _engine(monkeypatch)
+    p = ModelRequestProcessor()
+    p._endpoints["llama"] = eng.model_endpoint
+    p._engine_processor_lookup["llama"] = eng
+    client = TestClient(create_app(p), raise_server_exceptions=False)
+    try:
+        ok = client.post("/serve/openai/v1/completions", json={"model": "llama", "prompt": [1, 2], "max_tokens": 2})
+        assert ok.status_code == 200 and ok.json()["choices"][0]["token_ids"] == [3, 4]
+        plain = client.post("/serve/llama", json={"prompt": [7], "max_tokens": 1})
+        assert plain.status_code == 200 and plain.json()["choices"][0]["token_ids"] == [7]
+        bad = client.post("/serve/openai/v1/completions", json={"model": "llama", "prompt": "text", "max_tokens": 2})
+        assert bad.status_code == 422                                       # ValueError -> 422 (main.py:155-161)
+        missing = client.post("/serve/openai/v1/completions", json={"model": "nope", "prompt": [1]})
+        assert missing.status_code == 404
+        wrong_type = client.post("/serve/openai/v1/completions", content=b"x", headers={"Content-Type": "text/plain"})
+        assert wrong_type.status_code == 415                                # main.py:208-215
+    finally:
+        p.shutdown()
+
+
+def test_concurrent_clients_share_waves(monkeypatch):
+    eng, fake = _engine(monkeypatch, max_batch=4)
+    fake.latency_s = 0.02
+
+    async def run():
+        return await asyncio.gather(*[eng.v1_completions({"prompt": [i], "max_tokens": 2}, {}, None) for i in range(8)])
+    try:
+        rs = asyncio.run(run())
+        assert [r["choices"][0]["token_ids"] for r in rs] == [[i, i + 1] for i in range(8)]
+        assert len(fake.waves) <= 4 and sum(n for n, _ in fake.waves) == 8
+    finally:
+        eng.unload()

@@ -59,3 +59,53 @@ def test_reference_arm_runs_on_rank0_only():
     line = json.loads(outs[0])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and outs[1] == ""
+
+
+def test_tensor_parallel_leader_and_follower_replay_the_same_calls(tmp_path):
+    """LLM endpoint, tensor_parallel_size 2 (host logic on CPU, gloo): rank 0 (the serving process) announces every
+    engine call, rank 1 replays it with identical arguments, so both ranks would issue the same kernel sequence;
+    the pair's gloo sub-group is the one bench.py builds for ranks (2i, 2i+1)."""
+    script = tmp_path / "tp_worker.py"
+    script.write_text(textwrap.dedent('''
+        import json, os, sys
+        sys.path.insert(0, %r)
+        import numpy as np
+        import torch.distributed as dist
+        from clearml_serving_b200 import llm_service as S
+
+        class Rec(object):
+            def __init__(self):
+                self.calls, self.closed = [], False
+            def generate(self, prompts, n):
+                self.calls.append(([np.asarray(p).tolist() for p in prompts], int(n)))
+                return np.zeros((len(prompts), n), np.int32)
+            def close(self):
+                self.closed = True
+
+        dist.init_process_group("gloo")
+        rank = dist.get_rank()
+        group = dist.new_group(ranks=[0, 1], backend="gloo")
+        eng = Rec()
+        if rank == 0:
+            lead = S.TensorParallelLeader(eng, group)
+            lead.generate([[1, 2, 3], [4]], 5)
+            lead.generate([[9] * 7], 2)
+            lead.close()
+        else:
+            S.follower_loop(eng, group)
+        print("RESULT " + json.dumps(dict(rank=rank, calls=eng.calls, closed=eng.closed)), flush=True)
+        dist.destroy_process_group()
+    ''' % ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29733", WORLD_SIZE="2")
+    procs = []
+    for r in range(2):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    import json
+    res = []
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        res.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT ")][0][7:]))
+    assert res[0]["calls"] == res[1]["calls"] == [[[[1, 2, 3], [4]], 5], [[[9] * 7], 2]]
+    assert res[0]["closed"] and res[1]["closed"]
