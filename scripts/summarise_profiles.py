@@ -48,7 +48,7 @@ def launches():
     print("launch list:", len(rows), "launches,", len(agg), "kernels")
 
 
-def full(name):
+def full(name, cmd="python bench.py --steps 10 --warmup 3 --no-plugin"):
     rep = os.path.join(SRC, "ncu_%s.ncu-rep" % name)
     if not os.path.exists(rep):
         return None
@@ -62,7 +62,7 @@ def full(name):
         if h in KEYS or h == "Kernel Name":
             out[h] = dict(unit=units[i], values=[r[i] for r in rows[2:]])
     with open(os.path.join(OUT, "%s_ncu_%s.txt" % (tag, name)), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:%s (python bench.py --steps 10 --warmup 3 --no-plugin)\n" % name)
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:%s (%s)\n" % (name, cmd))
         for k, v in out.items():
             f.write("%-80s %-14s %s\n" % (k, v["unit"], " | ".join(x[:60] for x in v["values"])))
     return out
@@ -89,5 +89,16 @@ def main():
                 print("traffic:", ex)
 
 
+def llm():
+    """captures made by scripts/gpu_llm_ncu.sh"""
+    cmd = "python scripts/llm_bench.py --layers 2 --waves 1 --gen 4 --no-graph: Llama-3-8B shapes, TP 1, batch 32, prompt 512"
+    for name in ("skinny_gemm", "llm_attn_decode", "llm_attn_prefill", "llm_reduce_rms", "gemm_tn_pair"):
+        print(name, "ok" if full(name, cmd) else "missing")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "llm":
+        os.makedirs(OUT, exist_ok=True)
+        llm()
+        sys.exit(0)
     main()

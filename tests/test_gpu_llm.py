@@ -179,3 +179,34 @@ def test_tensor_parallel_pair_matches_single_gpu(native):
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=540)
     out = r.stdout.decode(errors="replace")
     assert r.returncode == 0 and "TP2 OK" in out, out[-4000:]
+
+
+def test_plugin_completions_match_direct_engine(native):
+    """the reference-facing surface: /openai/v1/completions on a b200_llm endpoint returns exactly what the engine
+    generates for the same prompts (dummy weights, architecture from auxiliary_cfg as the vLLM engine args are)"""
+    import asyncio
+    from clearml_serving_b200 import llm_service as S
+    from clearml_serving_b200.endpoints import ModelEndpoint
+    arch = dict(vocab_size=SPEC.vocab_size, hidden_size=SPEC.hidden_size, intermediate_size=SPEC.intermediate_size,
+                num_hidden_layers=SPEC.num_hidden_layers, num_attention_heads=SPEC.num_attention_heads,
+                num_key_value_heads=SPEC.num_key_value_heads, head_dim=128, rope_theta=SPEC.rope_theta, rms_norm_eps=SPEC.rms_norm_eps)
+    ep = ModelEndpoint(engine_type="b200_llm", serving_url="tiny", auxiliary_cfg={
+        "b200.llm": {"architecture": arch, "load_format": "dummy", "seed": 5, "init_std": 0.05, "max_batch": 4, "max_model_len": 128},
+        "dynamic_batching": {"max_queue_delay_microseconds": 20000}})
+    rng = np.random.default_rng(2)
+    prompts = [rng.integers(0, SPEC.vocab_size, n).tolist() for n in (6, 31, 12)]
+    eng = S.B200LlmPreprocessRequest(ep)
+    try:
+        async def run():
+            return await asyncio.gather(*[eng.v1_completions({"model": "tiny", "prompt": p, "max_tokens": 5}, {}, None) for p in prompts])
+        got = [r["choices"][0]["token_ids"] for r in asyncio.run(run())]
+        assert eng.engine_stats()["waves"] == 1 and eng.engine_stats()["requests"] == 3      # one wave for the three clients
+    finally:
+        eng.unload()
+    direct = L.LlmEngine(SPEC, device=0, max_batch=4, max_ctx=128)
+    try:
+        direct.init_random(seed=5, std=0.05)
+        want = direct.generate(prompts, 5)
+    finally:
+        direct.close()
+    assert got == want.tolist()
