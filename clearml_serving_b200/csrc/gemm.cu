@@ -26,7 +26,7 @@ namespace b2s {
 
 using namespace sm100;
 
-enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
+enum GemmAct { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_SWIGLU = 4 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // 64 x 16-bit = one 128-byte swizzle row
@@ -217,6 +217,33 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
     }
 }
 
+// SwiGLU epilogue (LLM gate/up projection): the weight rows are interleaved in blocks of 32 -- fused columns
+// [64j, 64j+32) are gate_{32j..32j+31}, [64j+32, 64j+64) the matching up columns -- so two consecutive 32-column
+// accumulator chunks of a warp hold (gate, up) of the same 32 outputs: out = silu(gate) * up, written as one
+// 64-byte row segment into C[M, N/2] (16-bit).  `col0_gate` is the fused column of the gate chunk.
+__device__ __forceinline__ void epilogue_swiglu32(const GemmEpilogue &ep, int warp_row0, int lane, int col0_gate, int M, int N,
+                                                  const uint32_t (&g)[32], const uint32_t (&u)[32], uint32_t *scratch)
+{
+    if (col0_gate + 32 >= N) return;   // warp-uniform; N is a multiple of 64 (checked on the host)
+    const int rows_valid = min(32, max(0, M - warp_row0));
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
+        const float a0 = g0 / (1.0f + __expf(-g0)) * __uint_as_float(u[2 * j]);
+        const float a1 = g1 / (1.0f + __expf(-g1)) * __uint_as_float(u[2 * j + 1]);
+        if (ep.is_bf16) {
+            __nv_bfloat162 p = __floats2bfloat162_rn(a0, a1);
+            w[j] = *reinterpret_cast<uint32_t *>(&p);
+        } else {
+            __half2 p = __floats2half2_rn(a0, a1);
+            w[j] = *reinterpret_cast<uint32_t *>(&p);
+        }
+    }
+    unsigned char *C = static_cast<unsigned char *>(ep.C);
+    warp_store_rows64(scratch, w, C + ((size_t)warp_row0 * ep.ldc + (col0_gate >> 1)) * 2, (size_t)ep.ldc * 2, rows_valid, lane);
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -345,6 +372,23 @@ __device__ __forceinline__ void broadcast32(const float4 &b, int chunk, float (&
     }
 }
 
+// Tile order of the persistent kernels.  With m fastest over ALL m-tiles a sweep of one weight panel touches
+// the whole activation matrix: for the LLM prefill (M = 16384, K = 4096: 134 MB of A) that does not fit in
+// L2 and every panel re-read A from DRAM (ncu: 9.6 GB of DRAM reads for a 0.37 GB problem,
+// profiles/r01_ncu_gemm_tn_pair.txt).  Tiles are therefore walked in groups of `gm` m-tiles (a ~32 MB slab of A,
+// chosen on the host): inside a group m is fastest, so the CTAs running together share a few weight panels and
+// the slab stays L2-resident while all weight panels stream past it once.
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int gm, int &m_blk, int &n_blk)
+{
+    const int per_group = gm * n_tiles;
+    const int g = t / per_group;
+    const int m0 = g * gm;
+    const int gsz = min(gm, m_tiles - m0);
+    const int r = t - g * per_group;
+    n_blk = r / gsz;
+    m_blk = m0 + (r - n_blk * gsz);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel v2: persistent, 128 x 256 tiles, double-buffered TMEM accumulators.
 //   * grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... with m fastest,
@@ -373,7 +417,7 @@ struct G2Smem {
 template <int G2_BN, int G2_STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                          int M, int N, int K, GemmEpilogue ep)
+                          int M, int N, int K, GemmEpilogue ep, int group_m)
 {
     using S = G2Smem<G2_BN, G2_STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -417,7 +461,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+                int m_blk, n_blk;
+                tile_coords(tile, m_tiles, n_tiles, group_m, m_blk, n_blk);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * S::STAGE_BYTES;
@@ -463,7 +508,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+            int m_blk, n_blk;
+            tile_coords(tile, m_tiles, n_tiles, group_m, m_blk, n_blk);
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const int warp_row0 = m_blk * GEMM_BM + q * 32;
@@ -471,6 +517,23 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
             const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+            if (ep.act == ACT_SWIGLU) {   // (gate, up) chunk pairs, see epilogue_swiglu32
+                if constexpr (NCH >= 2) {
+#pragma unroll 1
+                    for (int c = 0; c < NCH; c += 2) {
+                        uint32_t g[32], u[32];
+                        tmem_ld_32x32(t_addr + (uint32_t)(c * 32), g);
+                        tmem_ld_32x32(t_addr + (uint32_t)(c * 32 + 32), u);
+                        tmem_ld_wait();
+                        if (c == NCH - 2) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                        }
+                        epilogue_swiglu32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, g, u, epi_scratch);
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 uint32_t v[32];
@@ -484,6 +547,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
                 epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv, epi_scratch);
+            }
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
@@ -509,7 +573,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 template <int G2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_half,
-                    int M, int N, int K, GemmEpilogue ep)
+                    int M, int N, int K, GemmEpilogue ep, int group_mp)
 {
     constexpr int G2_BN = 256;
     using S = G2Smem<G2_BN, G2_STAGES>;
@@ -559,7 +623,9 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             for (int pt = pair0; pt < total; pt += pair_stride) {
-                const int m_blk = 2 * (pt % m_pairs) + (int)rank, n_blk = pt / m_pairs;
+                int mp, n_blk;
+                tile_coords(pt, m_pairs, n_tiles, group_mp, mp, n_blk);
+                const int m_blk = 2 * mp + (int)rank;
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * S::STAGE_BYTES;
@@ -606,7 +672,9 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int as = 0;
         uint32_t aphase = 0;
         for (int pt = pair0; pt < total; pt += pair_stride) {
-            const int m_blk = 2 * (pt % m_pairs) + (int)rank, n_blk = pt / m_pairs;
+            int mp, n_blk;
+            tile_coords(pt, m_pairs, n_tiles, group_mp, mp, n_blk);
+            const int m_blk = 2 * mp + (int)rank;
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const int warp_row0 = m_blk * GEMM_BM + q * 32;
@@ -614,6 +682,23 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
             const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+            if (ep.act == ACT_SWIGLU) {   // (gate, up) chunk pairs, see epilogue_swiglu32
+                if constexpr (NCH >= 2) {
+#pragma unroll 1
+                    for (int c = 0; c < NCH; c += 2) {
+                        uint32_t g[32], u[32];
+                        tmem_ld_32x32(t_addr + (uint32_t)(c * 32), g);
+                        tmem_ld_32x32(t_addr + (uint32_t)(c * 32 + 32), u);
+                        tmem_ld_wait();
+                        if (c == NCH - 2) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+                        }
+                        epilogue_swiglu32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, g, u, epi_scratch);
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 uint32_t v[32];
@@ -627,6 +712,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
                 epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv, epi_scratch);
+            }
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
@@ -711,6 +797,17 @@ static int g_num_sms()
     return n;
 }
 
+// m-tiles per group of the persistent tile walk: a slab of A of about 32 MB (all of A when it is smaller)
+static int gemm_group_m(int M, int K)
+{
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    static const int64_t slab = []() { const char *e = getenv("B2S_GEMM_SLAB_MB"); return (int64_t)(e ? atoi(e) : 32) << 20; }();
+    int64_t gm = slab / ((int64_t)GEMM_BM * K * 2);
+    if (gm < 2) gm = 2;
+    gm &= ~(int64_t)1;   // even: the pair kernel walks pairs of m-tiles
+    return gm >= m_tiles ? (m_tiles + 1) & ~1 : (int)gm;
+}
+
 template <int BN, int STAGES>
 static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
                                   const GemmEpilogue &ep)
@@ -724,7 +821,7 @@ static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const 
     if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(gemm v2)");
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     const int grid = tiles < g_num_sms() ? tiles : g_num_sms();
-    gemm_tn_persistent_kernel<BN, STAGES><<<grid, G2_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep);
+    gemm_tn_persistent_kernel<BN, STAGES><<<grid, G2_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep, gemm_group_m(M, K));
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
@@ -744,7 +841,7 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtens
     const int total = m_pairs * ((N + 255) / 256);
     const int max_pairs = g_num_sms() / 2;
     const int pairs = total < max_pairs ? total : max_pairs;
-    gemm_tn_pair_kernel<4><<<2 * pairs, G2_THREADS, S::TOTAL, st>>>(ta, tb_half, M, N, K, ep);
+    gemm_tn_pair_kernel<4><<<2 * pairs, G2_THREADS, S::TOTAL, st>>>(ta, tb_half, M, N, K, ep, gemm_group_m(M, K) / 2);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
@@ -786,9 +883,14 @@ int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, 
 {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     static const bool v1_only = []() { const char *e = getenv("B2S_GEMM_V1"); return e && e[0] == '1'; }();
-    if (bn == 64) return launch_gemm<64, 6>(st, ta, tb, M, N, K, ep);
+    // narrow outputs (ResNet stem / layer 1: N = 64 with M in the millions of pixels): same persistent kernel,
+    // 128 x 64 tiles, 8-stage ring; the non-persistent v1 form stays for tiny problems (classifier heads)
+    if (bn == 64) {
+        if (v1_only || (int64_t)M * N < (int64_t)1 << 16) return launch_gemm<64, 6>(st, ta, tb, M, N, K, ep);
+        return launch_gemm_persistent<64, 8>(st, ta, tb, M, N, K, ep);
+    }
     if (bn == 256) return launch_gemm_persistent<256, 4>(st, ta, tb, M, N, K, ep);
-    if (v1_only) return launch_gemm<128, 6>(st, ta, tb, M, N, K, ep);
+    if (v1_only && ep.act != ACT_SWIGLU) return launch_gemm<128, 6>(st, ta, tb, M, N, K, ep);
     return launch_gemm_persistent<128, 6>(st, ta, tb, M, N, K, ep);
 }
 
@@ -797,6 +899,8 @@ int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t 
             const GemmEpilogue &ep)
 {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
+    if (ep.act == ACT_SWIGLU && (N % 64 != 0 || N < 128 || ep.out_f32 || ep.bias || ep.residual || (ep.ldc & 7)))
+        return fail(B2S_ERR_INVALID, "gemm: SwiGLU epilogue needs N %% 64 == 0, N >= 128, 16-bit output, no bias / residual");
     CUtensorMap ta, tb;
     const int bn = N <= 64 ? 64 : (gemm_prefer_bn256(M, N) ? 256 : 128);
     B2S_TRY(make_tmap_2d_kmajor(&ta, A, M, K, lda, GEMM_BM, ep.is_bf16));

@@ -82,6 +82,20 @@ llm_fill_kernel(__nv_bfloat16 *__restrict__ w, int64_t rows, int64_t cols, uint6
         w[i] = __float2bfloat16_rn(llm_init_value(seed, tensor_id, row0 + (uint32_t)r, col0 + (uint32_t)c, std));
     }
 }
+// fused gate/up weight [2 * I_r, H]: fused row 64j + w is gate row 32j + w (w < 32) or up row 32j + w - 32
+__global__ void __launch_bounds__(256)
+llm_fill_gate_up_kernel(__nv_bfloat16 *__restrict__ w, int64_t I_r, int64_t cols, uint64_t seed, uint32_t id_gate, uint32_t id_up,
+                        uint32_t row0, float std)
+{
+    const int64_t n = 2 * I_r * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        const int64_t blk = r >> 6, within = r & 63;
+        const bool up = within >= 32;
+        const uint32_t src_row = row0 + (uint32_t)(blk * 32 + (within & 31));
+        w[i] = __float2bfloat16_rn(llm_init_value(seed, up ? id_up : id_gate, src_row, (uint32_t)c, std));
+    }
+}
 __global__ void __launch_bounds__(256) llm_fill_const_kernel(float *__restrict__ w, int64_t n, float v)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) w[i] = v;
@@ -302,36 +316,26 @@ llm_rope_cache_prefill_kernel(__nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__
 }
 
 // ------------------------------------------------------------------------------------------------
-// SwiGLU: act = silu(gate) * up.  gate = columns [0, I), up = columns [I, 2I) of the fused projection.
+// SwiGLU: act = silu(gate) * up.  The fused gate/up weight interleaves its rows in blocks of 32 (fused columns
+// [64j, 64j+32) = gate_{32j..}, [64j+32, 64j+64) = up_{32j..}) so that the prefill GEMM can apply SwiGLU in its
+// epilogue (gemm.cu, epilogue_swiglu32).  This kernel is the decode form: it reads (and clears) the fp32
+// accumulator [32, 2I] of the skinny GEMM.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
 
-template <bool DEC>
 __global__ void __launch_bounds__(256)
-llm_swiglu_kernel(void *__restrict__ gu, __nv_bfloat16 *__restrict__ act, int64_t rows, int I)
+llm_swiglu_decode_kernel(float *__restrict__ gu, __nv_bfloat16 *__restrict__ act, int64_t rows, int I)
 {
     sm100::griddep_launch_dependents();
     sm100::griddep_wait();
     const int64_t n4 = rows * (I / 4);
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = idx / (I / 4);
-        const int c = (int)(idx - r * (I / 4)) * 4;
-        float4 g, u;
-        if (DEC) {
-            float *row = static_cast<float *>(gu) + r * 2 * I;
-            g = *reinterpret_cast<float4 *>(row + c);
-            u = *reinterpret_cast<float4 *>(row + I + c);
-            *reinterpret_cast<float4 *>(row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4 *>(row + I + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            const __nv_bfloat16 *row = static_cast<const __nv_bfloat16 *>(gu) + r * 2 * I;
-            const uint2 a = *reinterpret_cast<const uint2 *>(row + c), b = *reinterpret_cast<const uint2 *>(row + I + c);
-            const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&a), *pb = reinterpret_cast<const __nv_bfloat162 *>(&b);
-            const float2 a0 = __bfloat1622float2(pa[0]), a1 = __bfloat1622float2(pa[1]);
-            const float2 b0 = __bfloat1622float2(pb[0]), b1 = __bfloat1622float2(pb[1]);
-            g = make_float4(a0.x, a0.y, a1.x, a1.y);
-            u = make_float4(b0.x, b0.y, b1.x, b1.y);
-        }
+        const int c = (int)(idx - r * (I / 4)) * 4;                 // output column (multiple of 4)
+        float *gp = gu + r * 2 * I + (c >> 5) * 64 + (c & 31);     // gate; up is 32 columns further
+        const float4 g = *reinterpret_cast<float4 *>(gp), u = *reinterpret_cast<float4 *>(gp + 32);
+        *reinterpret_cast<float4 *>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(gp + 32) = make_float4(0.f, 0.f, 0.f, 0.f);
         __nv_bfloat162 o0 = __floats2bfloat162_rn(silu_mul(g.x, u.x), silu_mul(g.y, u.y));
         __nv_bfloat162 o1 = __floats2bfloat162_rn(silu_mul(g.z, u.z), silu_mul(g.w, u.w));
         uint2 o;
@@ -562,7 +566,7 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     LA(m->xn, Tp * H);
     LA(m->qkv, Tp * m->qkv_n);
     LA(m->attn, Tp * m->hq_r * LLM_HD);
-    LA(m->gu, Tp * 2 * m->I_r);
+    LA(m->gu, (int64_t)128 << 20);   // 256 MiB of bf16: L2-flush scratch (the gate/up product itself never exists in memory)
     LA(m->act, Tp * m->I_r);
     LA(m->xlast, (int64_t)LLM_MAXB * H);
     LA(m->ws_qkv, (int64_t)LLM_MAXB * m->qkv_n);
@@ -667,8 +671,8 @@ static int llm_init_random(Llm *m, uint64_t seed, float std)
         llm_fill(y.wqkv + (int64_t)qr * H, kr, H, seed, id + 1, (uint32_t)(r * kr), 0, std);
         llm_fill(y.wqkv + (int64_t)(qr + kr) * H, kr, H, seed, id + 2, (uint32_t)(r * kr), 0, std);
         llm_fill(y.wo, H, qr, seed, id + 3, 0, (uint32_t)(r * qr), std);
-        llm_fill(y.wgu, m->I_r, H, seed, id + 4, (uint32_t)(r * m->I_r), 0, std);
-        llm_fill(y.wgu + (int64_t)m->I_r * H, m->I_r, H, seed, id + 5, (uint32_t)(r * m->I_r), 0, std);
+        llm_fill_gate_up_kernel<<<1184, 256>>>(y.wgu, m->I_r, H, seed, id + 4, id + 5, (uint32_t)(r * m->I_r), std);
+        count_launch();
         llm_fill(y.wdown, H, m->I_r, seed, id + 6, 0, (uint32_t)(r * m->I_r), std);
     }
     B2S_CUDA(cudaGetLastError());
@@ -676,14 +680,14 @@ static int llm_init_random(Llm *m, uint64_t seed, float std)
     return 0;
 }
 
-static int llm_gemm_bf16(cudaStream_t st, const void *A, int64_t lda, const void *W, int M, int N, int K, void *C)
+static int llm_gemm_bf16(cudaStream_t st, const void *A, int64_t lda, const void *W, int M, int N, int K, void *C, bool swiglu = false)
 {
     GemmEpilogue ep;
     ep.bias = nullptr;
     ep.residual = nullptr;
     ep.C = C;
-    ep.ldc = N;
-    ep.act = 0;
+    ep.ldc = swiglu ? N / 2 : N;
+    ep.act = swiglu ? 4 : 0;   // ACT_SWIGLU: C is [M, N / 2]
     ep.out_f32 = 0;
     ep.is_bf16 = 1;
     ep.act_after = 0;
@@ -748,9 +752,7 @@ static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens
             if (half == 0) {
                 B2S_TRY(llm_gemm_bf16(st, m->attn, m->hq_r * LLM_HD, y.wo, Ti, H, m->hq_r * LLM_HD, mine));
             } else {
-                B2S_TRY(llm_gemm_bf16(st, m->xn, H, y.wgu, Ti, 2 * m->I_r, H, m->gu));
-                llm_swiglu_kernel<false><<<1184, 256, 0, st>>>(m->gu, m->act, T, m->I_r);
-                count_launch();
+                B2S_TRY(llm_gemm_bf16(st, m->xn, H, y.wgu, Ti, 2 * m->I_r, H, m->act, true));   // SwiGLU in the epilogue
                 B2S_TRY(llm_gemm_bf16(st, m->act, m->I_r, y.wdown, Ti, H, m->I_r, mine));
             }
             const float *w = half == 0 ? y.ln2 : (l + 1 < L ? m->layers[l + 1].ln1 : m->final_norm);
@@ -848,7 +850,7 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
             } else {
                 if (!(skip & 32)) B2S_TRY(skinny_gemm_maps(st, y.m_gu_w, m->m_x_xn, m->ws_gu, 2 * m->I_r, H, n_seq));
                 LLM_MARK(7);
-                if (!(skip & 4)) B2S_CUDA(launch_dependent(llm_swiglu_kernel<true>, dim3((n_seq * (m->I_r / 4) + 255) / 256), dim3(256), st, m->ws_gu, m->act,
+                if (!(skip & 4)) B2S_CUDA(launch_dependent(llm_swiglu_decode_kernel, dim3((n_seq * (m->I_r / 4) + 255) / 256), dim3(256), st, m->ws_gu, m->act,
                                           (int64_t)n_seq, m->I_r));
                 LLM_MARK(8);
                 if (!(skip & 64)) B2S_TRY(skinny_gemm_maps(st, y.m_down_w, m->m_x_act, mine, H, m->I_r, n_seq));
@@ -1107,8 +1109,7 @@ B2S_API int b2s_llm_flush_l2(b2s_llm *llm)
     Llm *m = reinterpret_cast<Llm *>(llm);
     if (!m) return fail(B2S_ERR_INVALID, "null argument");
     B2S_CUDA(cudaSetDevice(m->device));
-    // the activation scratch of the gate/up projection is larger than L2 whenever max_tokens >= 4096
-    B2S_CUDA(cudaMemsetAsync(m->gu, 0, (size_t)(m->max_tokens > LLM_MAXB ? m->max_tokens : LLM_MAXB) * 2 * m->I_r * 2, m->stream));
+    B2S_CUDA(cudaMemsetAsync(m->gu, 0, (size_t)256 << 20, m->stream));   // larger than the 126 MB L2
     return 0;
 }
 

@@ -123,9 +123,25 @@ def _np(x):
     return np.asarray(x, dtype=np.float32)
 
 
+def interleave_gate_up(g, u):
+    """[I, H] gate and up -> fused [2I, H] with rows interleaved in blocks of 32 (gate block, up block, ...): two
+    consecutive 32-column chunks of the fused projection are (gate, up) of the same 32 outputs, which is what lets
+    the GEMM epilogue apply SwiGLU before anything is written (csrc/gemm.cu epilogue_swiglu32)"""
+    i, h = g.shape
+    assert i % 32 == 0 and u.shape == g.shape
+    return np.stack([g.reshape(i // 32, 32, h), u.reshape(i // 32, 32, h)], axis=1).reshape(2 * i, h)
+
+
+def split_gate_up(fused):
+    i2, h = fused.shape
+    blocks = fused.reshape(i2 // 64, 2, 32, h)
+    return blocks[:, 0].reshape(i2 // 2, h), blocks[:, 1].reshape(i2 // 2, h)
+
+
 def shard_state_dict(sd, spec, tp_size=1, tp_rank=0):
     """HF-named weights -> {(name, layer): array} for this rank, in the layouts b2s_llm_tensor documents:
-    QKV / gate / up split by OUTPUT rows (whole heads), O / down by INPUT columns, lm_head by vocabulary rows;
+    QKV / gate / up split by OUTPUT rows (whole heads; gate and up fused and interleaved, see interleave_gate_up),
+    O / down by INPUT columns, lm_head by vocabulary rows;
     bf16 tensors as uint16 bit patterns, norm weights float32."""
     hd = spec.head_dim
     hq, hk = spec.num_attention_heads // tp_size, spec.num_key_value_heads // tp_size
@@ -144,7 +160,7 @@ def shard_state_dict(sd, spec, tp_size=1, tp_rank=0):
         out[("wo", l)] = to_bf16_bits(_np(sd[p + "self_attn.o_proj.weight"])[:, r * hq * hd:(r + 1) * hq * hd])
         g = _np(sd[p + "mlp.gate_proj.weight"])[r * ir:(r + 1) * ir]
         u = _np(sd[p + "mlp.up_proj.weight"])[r * ir:(r + 1) * ir]
-        out[("wgu", l)] = to_bf16_bits(np.concatenate([g, u], axis=0))
+        out[("wgu", l)] = to_bf16_bits(interleave_gate_up(g, u))
         out[("wdown", l)] = to_bf16_bits(_np(sd[p + "mlp.down_proj.weight"])[:, r * ir:(r + 1) * ir])
         out[("ln1", l)] = _np(sd[p + "input_layernorm.weight"])
         out[("ln2", l)] = _np(sd[p + "post_attention_layernorm.weight"])

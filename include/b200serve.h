@@ -236,7 +236,8 @@ B2S_API int b2s_llm_free(b2s_llm *llm);
  * a pure function of (seed, tensor, global row, global col): all tensor-parallel layouts hold the same model */
 B2S_API int b2s_llm_init_random(b2s_llm *llm, uint64_t seed, float std);
 /* device pointer + shape of this rank's shard of a weight: "embed", "lm_head", "final_norm" (layer ignored),
- * "wqkv" [(hq+2hkv)*128/tp, H], "wo" [H, hq*128/tp], "wgu" [2*I/tp, H] (gate rows then up rows),
+ * "wqkv" [(hq+2hkv)*128/tp, H], "wo" [H, hq*128/tp], "wgu" [2*I/tp, H] (gate and up rows interleaved in
+ * blocks of 32: fused row 64j+w = gate row 32j+w for w < 32, up row 32j+w-32 otherwise),
  * "wdown" [H, I/tp], "ln1", "ln2"; elem_bytes 2 = bf16, 4 = fp32.  Upload with b2s_memcpy_h2d. */
 B2S_API int b2s_llm_tensor(b2s_llm *llm, const char *name, int layer, void **dptr, int64_t *rows, int64_t *cols,
                            int *elem_bytes);

@@ -54,9 +54,12 @@ def test_tensor_parallel_shards_reassemble():
         v = np.concatenate([a[("wqkv", l)][(hq + hk) * hd:], b[("wqkv", l)][(hq + hk) * hd:]])
         assert np.array_equal(np.concatenate([q, k, v]), s1[("wqkv", l)])
         assert np.array_equal(np.concatenate([a[("wo", l)], b[("wo", l)]], axis=1), s1[("wo", l)])
-        g = np.concatenate([a[("wgu", l)][:ir], b[("wgu", l)][:ir]])
-        u = np.concatenate([a[("wgu", l)][ir:], b[("wgu", l)][ir:]])
-        assert np.array_equal(np.concatenate([g, u]), s1[("wgu", l)])
+        (ga, ua), (gb, ub) = L.split_gate_up(a[("wgu", l)]), L.split_gate_up(b[("wgu", l)])
+        g1, u1 = L.split_gate_up(s1[("wgu", l)])
+        assert np.array_equal(np.concatenate([ga, gb]), g1) and np.array_equal(np.concatenate([ua, ub]), u1)
+        assert np.array_equal(g1, L.to_bf16_bits(sd["model.layers.%d.mlp.gate_proj.weight" % l]))
+        assert np.array_equal(L.interleave_gate_up(g1, u1), s1[("wgu", l)])
+        assert np.array_equal(s1[("wgu", l)][32:64], L.to_bf16_bits(sd["model.layers.%d.mlp.up_proj.weight" % l][:32]))
         assert np.array_equal(np.concatenate([a[("wdown", l)], b[("wdown", l)]], axis=1), s1[("wdown", l)])
     assert np.array_equal(np.concatenate([a[("lm_head", 0)], b[("lm_head", 0)]]), s1[("lm_head", 0)])
     assert np.array_equal(a[("embed", 0)], s1[("embed", 0)])
