@@ -65,6 +65,17 @@ struct GemmEpilogue {
     int act_after;         // 1: activation applied AFTER the residual add (ResNet), 0: before (BERT)
 };
 
+// Implicit-GEMM convolution geometry (gemm.cu): when `taps` > 0 the A operand of the GEMM is not a matrix in
+// memory but the im2col view of an NHWC activation tensor, fetched tile by tile with im2col-mode TMA.
+// GEMM row m = output pixel (n, p, q) in NHW order; GEMM k = (r * KS + s) * Cin + c.
+struct ConvGeom {
+    int taps = 0;      // KS * KS, 0 = plain GEMM
+    int KS = 1;
+    int cblocks = 1;   // Cin / 64: k-blocks per filter tap
+    int OH = 1, OW = 1;
+    int stride = 1, pad = 0;
+};
+
 // ---- internal model interface: each model kind implements launch() on a stream -----------------
 struct Model {
     int device = 0;

@@ -56,6 +56,13 @@ __device__ __forceinline__ float gelu_erf(float x)
     return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+// tanh(x) = 1 - 2 / (exp(2x) + 1): branch-free (tanhf's range split costs a divergent branch per element);
+// |err| ~ 1e-6, far below the 16-bit rounding of the stored activation; saturates correctly at +-inf
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f);
+}
+
 // Warp-cooperative store of a 32-row x 64-byte slab: every lane holds the 64 bytes (16 words) of ITS row;
 // written directly that is 32 rows x 16 B per store instruction, i.e. 32 half-filled 32-byte sectors.  Staged
 // through a 2.5 KB per-warp shared-memory scratch (80-byte pitch: conflict-free 128-bit accesses) four adjacent
@@ -116,7 +123,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
     } else if (act_pre == ACT_TANH) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+        for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
     }
     const size_t off = (size_t)row * ep.ldc + col0;
     const int rows_valid = min(32, max(0, M - warp_row0));
@@ -131,7 +138,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
                     f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
                 }
             } else {
-                for (int j = 0; j < ncols; ++j) f[j] += R[j];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncols) f[j] += R[j];
             }
         }
         if (ep.act_after && ep.act == ACT_RELU) {
@@ -154,7 +163,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4 *>(C + off + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
-                for (int j = 0; j < ncols; ++j) C[off + j] = f[j];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncols) C[off + j] = f[j];
             }
         }
         return;
@@ -164,7 +175,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
     if (ep.residual && row_ok) {
         if (ep.is_bf16) {
             const __nv_bfloat16 *R = static_cast<const __nv_bfloat16 *>(ep.residual) + off;
-            for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(R[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) f[j] += __bfloat162float(R[j]);
         } else {
             const __half *R = static_cast<const __half *>(ep.residual) + off;
             if (vec) {
@@ -180,7 +193,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
                     }
                 }
             } else {
-                for (int j = 0; j < ncols; ++j) f[j] += __half2float(R[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncols) f[j] += __half2float(R[j]);
             }
         }
     }
@@ -212,7 +227,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
                 *reinterpret_cast<uint4 *>(C + off * 2 + j * 4) = make_uint4(w[j], w[j + 1], w[j + 2], w[j + 3]);
         } else {
             unsigned short *Cs = reinterpret_cast<unsigned short *>(C) + off;
-            for (int j = 0; j < ncols; ++j) Cs[j] = (unsigned short)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu));
+#pragma unroll
+            for (int j = 0; j < 32; ++j)   // static indices + predicates: a dynamic index would put w[] / f[] in local memory
+                if (j < ncols) Cs[j] = (unsigned short)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu));
         }
     }
 }
@@ -389,6 +406,35 @@ __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int
     m_blk = m0 + (r - n_blk * gsz);
 }
 
+// A-operand fetch of the persistent kernels.  Plain GEMM: a [128 x 64] box of the activation matrix.  Implicit-GEMM
+// convolution (cg.taps > 0): the same 16 KB tile -- 128 consecutive output pixels x 64 input channels of ONE filter
+// tap -- is gathered by im2col-mode TMA straight from the NHWC activation tensor (zero fill outside the image is
+// the padding), so no patch matrix is ever written to or read from HBM.
+struct ConvTileOrigin { int w, h, n; };
+__device__ __forceinline__ ConvTileOrigin conv_tile_origin(const ConvGeom &cg, int m_blk)
+{
+    ConvTileOrigin o{0, 0, 0};
+    if (cg.taps) {
+        const int m0 = m_blk * GEMM_BM, hw = cg.OH * cg.OW;
+        o.n = m0 / hw;
+        const int rem = m0 - o.n * hw, p = rem / cg.OW, q = rem - p * cg.OW;
+        o.w = q * cg.stride - cg.pad;
+        o.h = p * cg.stride - cg.pad;
+    }
+    return o;
+}
+__device__ __forceinline__ void load_a_tile(void *sa, const CUtensorMap *tmap_a, uint64_t *bar, const ConvGeom &cg,
+                                            const ConvTileOrigin &o, int kb, int m_blk)
+{
+    if (cg.taps) {
+        const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
+        const int r = tap / cg.KS, s_ = tap - r * cg.KS;
+        tma_load_im2col_4d(sa, tmap_a, bar, cb * GEMM_BK, o.w, o.h, o.n, (uint16_t)s_, (uint16_t)r);
+    } else {
+        tma_load_2d(sa, tmap_a, bar, kb * GEMM_BK, m_blk * GEMM_BM);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel v2: persistent, 128 x 256 tiles, double-buffered TMEM accumulators.
 //   * grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x, +gridDim.x, ... with m fastest,
@@ -417,7 +463,7 @@ struct G2Smem {
 template <int G2_BN, int G2_STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                          int M, int N, int K, GemmEpilogue ep, int group_m)
+                          int M, int N, int K, GemmEpilogue ep, int group_m, ConvGeom cg)
 {
     using S = G2Smem<G2_BN, G2_STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -463,12 +509,13 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int m_blk, n_blk;
                 tile_coords(tile, m_tiles, n_tiles, group_m, m_blk, n_blk);
+                const ConvTileOrigin org = conv_tile_origin(cg, m_blk);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * S::STAGE_BYTES;
                     unsigned char *sb = sa + S::A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    load_a_tile(sa, &tmap_a, &full_bar[stage], cg, org, kb, m_blk);
                     tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, n_blk * G2_BN);
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -573,7 +620,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 template <int G2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_half,
-                    int M, int N, int K, GemmEpilogue ep, int group_mp)
+                    int M, int N, int K, GemmEpilogue ep, int group_mp, ConvGeom cg)
 {
     constexpr int G2_BN = 256;
     using S = G2Smem<G2_BN, G2_STAGES>;
@@ -626,12 +673,13 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 int mp, n_blk;
                 tile_coords(pt, m_pairs, n_tiles, group_mp, mp, n_blk);
                 const int m_blk = 2 * mp + (int)rank;
+                const ConvTileOrigin org = conv_tile_origin(cg, m_blk);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * S::STAGE_BYTES;
                     unsigned char *sb = sa + S::A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);   // own A + both halves of B
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    load_a_tile(sa, &tmap_a, &full_bar[stage], cg, org, kb, m_blk);
                     tma_load_2d_multicast(sb + rank * (S::B_BYTES / 2), &tmap_b_half, &full_bar[stage], kb * GEMM_BK,
                                           n_blk * G2_BN + (int)rank * (G2_BN / 2), (uint16_t)0x3);
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
@@ -810,7 +858,7 @@ static int gemm_group_m(int M, int K)
 
 template <int BN, int STAGES>
 static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int M, int N, int K,
-                                  const GemmEpilogue &ep)
+                                  const GemmEpilogue &ep, const ConvGeom &cg = ConvGeom())
 {
     using S = G2Smem<BN, STAGES>;
     static std::once_flag once;
@@ -821,14 +869,16 @@ static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const 
     if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(gemm v2)");
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
     const int grid = tiles < g_num_sms() ? tiles : g_num_sms();
-    gemm_tn_persistent_kernel<BN, STAGES><<<grid, G2_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep, gemm_group_m(M, K));
+    // the L2 slab of a convolution is the activation tensor itself (K / taps channels per pixel), not the patch matrix
+    const int group_m = gemm_group_m(M, cg.taps ? K / cg.taps : K);
+    gemm_tn_persistent_kernel<BN, STAGES><<<grid, G2_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep, group_m, cg);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
 }
 
 static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb_half, int M, int N, int K,
-                            const GemmEpilogue &ep)
+                            const GemmEpilogue &ep, const ConvGeom &cg = ConvGeom())
 {
     using S = G2Smem<256, 4>;
     static std::once_flag once;
@@ -841,7 +891,8 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtens
     const int total = m_pairs * ((N + 255) / 256);
     const int max_pairs = g_num_sms() / 2;
     const int pairs = total < max_pairs ? total : max_pairs;
-    gemm_tn_pair_kernel<4><<<2 * pairs, G2_THREADS, S::TOTAL, st>>>(ta, tb_half, M, N, K, ep, gemm_group_m(M, K) / 2);
+    const int group_mp = gemm_group_m(M, cg.taps ? K / cg.taps : K) / 2;
+    gemm_tn_pair_kernel<4><<<2 * pairs, G2_THREADS, S::TOTAL, st>>>(ta, tb_half, M, N, K, ep, group_mp, cg);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
@@ -894,6 +945,81 @@ int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, 
     return launch_gemm_persistent<128, 6>(st, ta, tb, M, N, K, ep);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution (kernel K6 of SURVEY.md 2.2): im2col-mode tensor map over NHWC activations
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+
+static PFN_encodeIm2col get_encode_im2col()
+{
+    static PFN_encodeIm2col fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeIm2col>(p);
+    });
+    return fn;
+}
+
+// Activations x[n_img, H, W, C] fp16 (C % 64 == 0), KS x KS filter, `stride`, `pad`: one load = 128 consecutive
+// output pixels (NHW order) x 64 channels of one tap, 128-byte swizzle (the layout make_sw128_kmajor_desc expects).
+// The bounding box of filter base positions is [-pad, dim + pad - (KS - 1)) per spatial dim, walked with `stride`.
+int make_tmap_im2col_nhwc(CUtensorMap *out, const void *base, int64_t n_img, int H, int W, int C, int KS, int stride, int pad)
+{
+    PFN_encodeIm2col enc = get_encode_im2col();
+    if (!enc) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeIm2col driver entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || C % GEMM_BK != 0)
+        return fail(B2S_ERR_INVALID, "conv: activations must be 16-byte aligned with channels a multiple of 64");
+    if (KS < 1 || KS > 7 || stride < 1 || stride > 8 || pad < 0 || pad > 7)
+        return fail(B2S_ERR_INVALID, "conv: unsupported filter geometry (KS %d stride %d pad %d)", KS, stride, pad);
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+    cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - (KS - 1), pad - (KS - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), gdim, gstride, lower, upper,
+                     (cuuint32_t)GEMM_BK, (cuuint32_t)GEMM_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeIm2col failed with %d", (int)r);
+    // drivers up to CUDA 13.1 set a descriptor bit for tensors below 128 KiB that im2col loads must not carry
+    int drv = 0;
+    if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (int64_t)n_img * H * W * C * 2 < 131072)
+        reinterpret_cast<uint64_t *>(out)[1] &= ~(1ull << 21);
+    return 0;
+}
+
+ConvGeom make_conv_geom(int H, int W, int C, int KS, int stride, int pad)
+{
+    ConvGeom cg;
+    cg.taps = KS * KS;
+    cg.KS = KS;
+    cg.cblocks = C / GEMM_BK;
+    cg.OH = (H + 2 * pad - KS) / stride + 1;
+    cg.OW = (W + 2 * pad - KS) / stride + 1;
+    cg.stride = stride;
+    cg.pad = pad;
+    return cg;
+}
+
+// Convolution as GEMM with caller-provided maps: `ta` from make_tmap_im2col_nhwc, `tb` over the weight
+// [Cout, KS*KS*C] with box height `bn` (64 / 128 / 256; 128 = half tile of the CTA-pair kernel when `pair`).
+int conv_implicit_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, bool pair, int M, int N, int K,
+                       const GemmEpilogue &ep, const ConvGeom &cg)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    if (cg.taps <= 0 || K != cg.taps * cg.cblocks * GEMM_BK) return fail(B2S_ERR_INVALID, "conv: K does not match the filter geometry");
+    if (pair) return launch_gemm_pair(st, ta, tb, M, N, K, ep, cg);
+    if (bn == 64) return launch_gemm_persistent<64, 8>(st, ta, tb, M, N, K, ep, cg);
+    if (bn == 256) return launch_gemm_persistent<256, 4>(st, ta, tb, M, N, K, ep, cg);
+    return launch_gemm_persistent<128, 6>(st, ta, tb, M, N, K, ep, cg);
+}
+
 // C = epilogue(A[M,K] . B[N,K]^T).  A: lda elements per row, B: ldb elements per row.
 int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t ldb, int M, int N, int K,
             const GemmEpilogue &ep)
@@ -933,4 +1059,35 @@ extern "C" B2S_API int b2s_op_gemm(int device, void *cuda_stream, const void *A,
     ep.is_bf16 = is_bf16;
     ep.act_after = 0;
     return gemm_tn(static_cast<cudaStream_t>(cuda_stream), A, K, B, K, M, N, K, ep);
+}
+
+/* y[n_img, OH, OW, Cout] = act(conv(x[n_img, H, W, C], w[Cout, KS, KS, C]) + bias) (+ residual, activation after the
+ * add when act_after): implicit GEMM, no patch matrix (see conv_implicit_maps). */
+extern "C" B2S_API int b2s_op_conv(int device, void *cuda_stream, const void *x, int64_t n_img, int H, int W, int C,
+                                    const void *w, int Cout, int KS, int stride, int pad, const float *bias,
+                                    const void *residual, void *y, int act, int act_after)
+{
+    using namespace b2s;
+    B2S_CUDA(cudaSetDevice(device));
+    if (n_img <= 0) return 0;
+    const ConvGeom cg = make_conv_geom(H, W, C, KS, stride, pad);
+    const int64_t M64 = n_img * cg.OH * cg.OW;
+    if (M64 > 0x7fffffff) return fail(B2S_ERR_INVALID, "conv: too many output pixels");
+    const int M = (int)M64, K = KS * KS * C;
+    GemmEpilogue ep;
+    ep.bias = bias;
+    ep.residual = residual;
+    ep.C = y;
+    ep.ldc = Cout;
+    ep.act = act;
+    ep.out_f32 = 0;
+    ep.is_bf16 = 0;
+    ep.act_after = act_after;
+    CUtensorMap ta, tb;
+    B2S_TRY(make_tmap_im2col_nhwc(&ta, x, n_img, H, W, C, KS, stride, pad));
+    const bool bn256 = gemm_prefer_bn256(M, Cout);
+    const bool pair = bn256 && gemm_pair_enabled();
+    const int bn = Cout <= 64 ? 64 : (bn256 && !pair ? 256 : 128);
+    B2S_TRY(make_tmap_2d_kmajor(&tb, w, Cout, K, K, bn, 0));
+    return conv_implicit_maps(static_cast<cudaStream_t>(cuda_stream), ta, tb, bn, pair, M, Cout, K, ep, cg);
 }

@@ -49,6 +49,10 @@ int embed_layernorm(cudaStream_t st, const int32_t *ids, const int32_t *types, c
 int gather_first(cudaStream_t st, const void *in, const int64_t *cu_seqlens, int n_seq, int H, void *out);
 int attention_varlen(cudaStream_t st, const void *qkv, const int64_t *cu_seqlens, const int32_t *key_mask, void *out,
                      int n_seq, int max_seqlen, int heads, int head_dim);
+int make_tmap_im2col_nhwc(CUtensorMap *out, const void *base, int64_t n_img, int H, int W, int C, int KS, int stride, int pad);
+ConvGeom make_conv_geom(int H, int W, int C, int KS, int stride, int pad);
+int conv_implicit_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, bool pair, int M, int N, int K,
+                       const GemmEpilogue &ep, const ConvGeom &cg);
 // conv.cu
 int nchw_to_nhwc(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Cp, void *out);
 int im2col_nhwc(cudaStream_t st, const void *in, int64_t n_img, int H, int W, int C, int KH, int KW, int stride, int pad,
@@ -60,7 +64,7 @@ namespace {
 
 enum GraphOp {
     OP_EMBED_LN = 1, OP_LINEAR = 2, OP_LAYERNORM = 3, OP_ATTENTION = 4, OP_GATHER_FIRST = 5,
-    OP_NCHW_TO_NHWC = 6, OP_IM2COL = 7, OP_MAXPOOL = 8, OP_AVGPOOL = 9
+    OP_NCHW_TO_NHWC = 6, OP_IM2COL = 7, OP_MAXPOOL = 8, OP_AVGPOOL = 9, OP_CONV = 10
 };
 
 struct GHeader {
@@ -143,6 +147,11 @@ struct GraphModel : Model {
         pl.amap.resize(ops.size());
         for (size_t i = 0; i < ops.size(); ++i) {
             const GOp &op = ops[i];
+            if (op.opcode == OP_CONV) {   // im2col view of the NHWC input buffer, `max_rows` images
+                B2S_TRY(make_tmap_im2col_nhwc(&pl.amap[i], pl.buf[op.a[0]], max_rows, op.a[8], op.a[9], op.a[10], op.a[11],
+                                              op.a[12], op.a[13]));
+                continue;
+            }
             if (op.opcode != OP_LINEAR) continue;
             const GBuffer &ab = buffers[op.a[0]];
             const int64_t rows = ab.rows_kind == 0 ? max_tokens : max_rows * (int64_t)ab.rows_kind;
@@ -215,6 +224,28 @@ struct GraphModel : Model {
                     B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap256[i], 256, M, op.a[6], op.a[7], ep));
                 else
                     B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap[i], gemm_bn_for(op.a[6]), M, op.a[6], op.a[7], ep));
+                break;
+            }
+            case OP_CONV: {
+                // a: in_buf, W, bias(-1), residual_buf(-1), out_buf, act, N, K, H, W, Cin, KS, stride, pad, act_after
+                const ConvGeom cg = make_conv_geom(op.a[8], op.a[9], op.a[10], op.a[11], op.a[12], op.a[13]);
+                const int M = (int)(n_rows * (int64_t)cg.OH * cg.OW);
+                GemmEpilogue ep;
+                ep.bias = tptr(op.a[2]);
+                ep.residual = op.a[3] >= 0 ? pl->buf[op.a[3]] : nullptr;
+                ep.C = pl->buf[op.a[4]];
+                ep.ldc = op.a[6];
+                ep.act = op.a[5];
+                ep.out_f32 = 0;
+                ep.is_bf16 = 0;
+                ep.act_after = op.a[14];
+                const bool bn256 = gemm_prefer_bn256(M, op.a[6]);
+                if (bn256 && gemm_pair_enabled())
+                    B2S_TRY(conv_implicit_maps(st, pl->amap[i], bmap[i], 128, true, M, op.a[6], op.a[7], ep, cg));
+                else if (bn256)
+                    B2S_TRY(conv_implicit_maps(st, pl->amap[i], bmap256[i], 256, false, M, op.a[6], op.a[7], ep, cg));
+                else
+                    B2S_TRY(conv_implicit_maps(st, pl->amap[i], bmap[i], gemm_bn_for(op.a[6]), false, M, op.a[6], op.a[7], ep, cg));
                 break;
             }
             case OP_LAYERNORM: {
@@ -319,6 +350,24 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
                      m->buffers[op.a[0]].dtype == B2S_F16 && m->buffers[op.a[0]].cols == op.a[7];
             }
             break;
+        case OP_CONV: {
+            ok = bok(op.a[0], false) && tok(op.a[1], false) && tok(op.a[2], true) && bok(op.a[3], true) && bok(op.a[4], false) &&
+                 op.a[6] > 0 && op.a[6] % 8 == 0 && op.a[10] > 0 && op.a[10] % 64 == 0 && op.a[11] >= 1 && op.a[11] <= 7 &&
+                 op.a[12] >= 1 && op.a[13] >= 0 && op.a[7] == op.a[11] * op.a[11] * op.a[10];
+            if (ok) {
+                const GTensor &w = m->tensors[op.a[1]];
+                const int OH = (op.a[8] + 2 * op.a[13] - op.a[11]) / op.a[12] + 1, OW = (op.a[9] + 2 * op.a[13] - op.a[11]) / op.a[12] + 1;
+                const GBuffer &ib = m->buffers[op.a[0]], &ob = m->buffers[op.a[4]];
+                ok = w.dtype == B2S_F16 && w.ndim == 2 && w.shape[0] == op.a[6] && w.shape[1] == op.a[7] && ib.dtype == B2S_F16 &&
+                     ib.cols == op.a[10] && (int64_t)ib.rows_kind == (int64_t)op.a[8] * op.a[9] && ob.dtype == B2S_F16 &&
+                     ob.cols == op.a[6] && (int64_t)ob.rows_kind == (int64_t)OH * OW;
+                if (ok && op.a[3] >= 0) {
+                    const GBuffer &rb = m->buffers[op.a[3]];
+                    ok = rb.dtype == B2S_F16 && rb.cols == op.a[6] && rb.rows_kind == ob.rows_kind;
+                }
+            }
+            break;
+        }
         case OP_LAYERNORM:
             ok = bok(op.a[0], false) && tok(op.a[1], false) && tok(op.a[2], false) && bok(op.a[3], true) && bok(op.a[4], true);
             break;
@@ -362,7 +411,7 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
     int64_t flops_fixed = 0;
     for (size_t i = 0; i < m->ops.size(); ++i) {
         const GOp &op = m->ops[i];
-        if (op.opcode != OP_LINEAR) continue;
+        if (op.opcode != OP_LINEAR && op.opcode != OP_CONV) continue;
         int rc = make_tmap_2d_kmajor(&m->bmap[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], gemm_bn_for(op.a[6]), 0);
         if (rc == 0 && op.a[6] >= 256)
             rc = make_tmap_2d_kmajor(&m->bmap256[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], 256, 0);

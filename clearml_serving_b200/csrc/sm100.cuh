@@ -111,6 +111,22 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// 4-D im2col-mode load (implicit-GEMM convolution over NHWC activations): the tensor map describes the
+// activation tensor (c, w, h, n) plus the bounding box of filter BASE positions; (c0, w, h, n) is the base pixel
+// of the first of `pixelsPerColumn` output positions (the hardware walks w, then h, then n inside the bounding
+// box with the map's traversal strides) and (off_w, off_h) is the filter tap added to every base pixel.
+// Positions outside the tensor are zero-filled: that is the convolution's padding.
+__device__ __forceinline__ void tma_load_im2col_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(w), "r"(h),
+        "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols)
 {

@@ -415,7 +415,7 @@ def pack_bert(model):
     return PackedModel(native.MODEL_GRAPH, g.serialise(), desc)
 
 
-OP_NCHW_TO_NHWC, OP_IM2COL, OP_MAXPOOL, OP_AVGPOOL = 6, 7, 8, 9
+OP_NCHW_TO_NHWC, OP_IM2COL, OP_MAXPOOL, OP_AVGPOOL, OP_CONV = 6, 7, 8, 9, 10
 
 
 def _fold_bn(conv_w, bn):
@@ -434,8 +434,9 @@ class _ConvNetLowering(object):
     activations (channels padded to 8), 1x1 stride-1 convs as direct GEMMs, everything else as
     im2col + GEMM, BatchNorm folded, bias/ReLU/residual fused in the GEMM epilogue."""
 
-    def __init__(self, g):
+    def __init__(self, g, implicit=True):
         self.g = g
+        self.implicit = implicit   # False: every KxK / strided conv as explicit im2col + GEMM (comparison form)
         self._pool = {}   # (rows_per_item, cols, tag) -> [buffers], round robin
 
     def buf(self, rows_per_item, cols, tag="act", n=3):
@@ -466,9 +467,12 @@ class _ConvNetLowering(object):
         wk[:, :, :, :Cin] = np.transpose(w, (0, 2, 3, 1))
         K = KH * KW * Cin_p
         wk = wk.reshape(Cout, K)
-        if KH == 1 and KW == 1 and s == 1 and p == 0:
+        direct = KH == 1 and KW == 1 and s == 1 and p == 0
+        # implicit GEMM (im2col-mode TMA) needs whole 64-channel k-blocks per filter tap; the 3-channel stem does not
+        implicit = self.implicit and not direct and KH == KW and Cin_p % 64 == 0
+        if direct:
             a = x
-        else:
+        elif not implicit:
             a = self.buf(OH * OW, K, tag="col", n=1)
             g.op(OP_IM2COL, [x, a, H, W, Cin_p, KH, KW, s, p, OH, OW, K])
         y = self.buf(OH * OW, Cout)
@@ -476,17 +480,26 @@ class _ConvNetLowering(object):
         while y in (x, residual) and guard < 4:   # never write over a live operand
             y = self.buf(OH * OW, Cout)
             guard += 1
-        g.linear(a, wk, b, y, act=ACT_RELU if relu else ACT_NONE, residual=residual, act_after=residual >= 0)
+        act = ACT_RELU if relu else ACT_NONE
+        if implicit:
+            wi = g.tensor(wk, np.float16)
+            bi = g.tensor(b, np.float32)
+            g.op(OP_CONV, [x, wi, bi, residual, y, act, Cout, K, H, W, Cin_p, KH, s, p, 1 if residual >= 0 else 0])
+        else:
+            g.linear(a, wk, b, y, act=act, residual=residual, act_after=residual >= 0)
         return y, OH, OW, Cout
 
 
-def pack_resnet(model, input_dtype="float32", image_hw=(224, 224)):
+def pack_resnet(model, input_dtype="float32", image_hw=(224, 224), implicit_conv=None):
     """torchvision.models.resnet.ResNet (Bottleneck or BasicBlock) in eval mode -> PackedModel.
     Input: NCHW images [batch, 3, H, W] float32 (what the reference's Triton client can send,
     SURVEY.md F5) or uint8; output fp32 logits [batch, num_classes]."""
     H, W = image_hw
     g = GraphBuilder([input_dtype], 0, in_row_elems=[3 * H * W])
-    low = _ConvNetLowering(g)
+    if implicit_conv is None:
+        import os
+        implicit_conv = os.environ.get("B2S_CONV_IMPLICIT", "1") != "0"
+    low = _ConvNetLowering(g, implicit=implicit_conv)
     x = g.buffer("float16", False, 8, rows_per_item=H * W)
     g.op(OP_NCHW_TO_NHWC, [0, x, 3, H, W, 8])
     x, H, W, C = low.conv_bn(x, H, W, 8, model.conv1, model.bn1, relu=True)
@@ -521,5 +534,6 @@ def pack_resnet(model, input_dtype="float32", image_hw=(224, 224)):
     g.linear(pooled, model.fc.weight.detach().double().numpy(), model.fc.bias.detach().double().numpy(),
              g.output(logits), out_f32=True)
     desc = dict(kind="graph", arch=type(model).__name__.lower(), convs=n_convs, num_classes=int(n_cls),
-                input_dtype=input_dtype, output_dtype="float32", image_hw=list(image_hw), max_row_elems=0)
+                input_dtype=input_dtype, output_dtype="float32", image_hw=list(image_hw), max_row_elems=0,
+                implicit_conv=bool(implicit_conv))
     return PackedModel(native.MODEL_GRAPH, g.serialise(), desc)

@@ -193,6 +193,14 @@ B2S_API int b2s_timer_destroy(b2s_timer_t timer);
 B2S_API int b2s_op_gemm(int device, void *cuda_stream, const void *A, const void *B, void *C, int M, int N,
                         int K, const float *bias, const void *residual, int act, int is_bf16, int out_f32);
 
+/* y[n_img,OH,OW,Cout] = act(conv2d(x[n_img,H,W,C], w[Cout,KS,KS,C]) + bias[Cout]) (+ residual[n_img,OH,OW,Cout], with the
+ * activation after the add when act_after): fp16 NHWC activations (C % 64 == 0), square filter, symmetric
+ * stride / zero padding.  Implicit GEMM: the A tiles are gathered by im2col-mode TMA, no patch matrix exists.
+ * Stands in for the cuDNN convolutions of tritonserver's backends (triton_helper.py:378-385, examples/pytorch). */
+B2S_API int b2s_op_conv(int device, void *cuda_stream, const void *x, int64_t n_img, int H, int W, int C,
+                        const void *w, int Cout, int KS, int stride, int pad, const float *bias,
+                        const void *residual, void *y, int act, int act_after);
+
 /* LayerNorm over the last dim of fp32 in[rows,H] (torch.nn.LayerNorm numerics): writes an fp16 copy
  * (next GEMM operand) and/or an fp32 copy (residual stream); either output may be NULL. */
 B2S_API int b2s_op_layernorm(int device, void *cuda_stream, const float *in, int64_t rows, int H,

@@ -70,6 +70,60 @@ def test_gemm_fused_epilogue(gpu_native, act):
     np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
 
 
+# ---------------------------------------------------------------- implicit-GEMM convolution
+def _conv(native, x, w, bias, stride, pad, residual=None, act=0, act_after=0):
+    n, H, W, C = x.shape
+    Cout, KS = w.shape[0], w.shape[1]
+    OH, OW = (H + 2 * pad - KS) // stride + 1, (W + 2 * pad - KS) // stride + 1
+    bufs = [native.DeviceBuffer(a.nbytes) for a in (x, w, bias)]
+    for b, a in zip(bufs, (x, w, bias)):
+        b.upload(a)
+    dy = native.DeviceBuffer(n * OH * OW * Cout * 2)
+    dres = None
+    if residual is not None:
+        dres = native.DeviceBuffer(residual.nbytes); dres.upload(residual)
+    try:
+        native.check(native.lib().b2s_op_conv(0, None, bufs[0].ptr, n, H, W, C, bufs[1].ptr, Cout, KS, stride, pad,
+                                              bufs[2].ptr, dres.ptr if dres else None, dy.ptr, act, act_after))
+        return dy.download(np.float16, n * OH * OW * Cout).reshape(n, OH, OW, Cout)
+    finally:
+        for b in bufs + [dy, dres]:
+            if b is not None:
+                b.free()
+
+
+@pytest.mark.parametrize("n,H,W,C,Cout,KS,stride,pad", [
+    (2, 56, 56, 64, 64, 3, 1, 1),      # ResNet-50 layer1 conv2 (N = 64 tiles)
+    (3, 28, 28, 128, 128, 3, 1, 1),    # layer2 conv2
+    (2, 56, 56, 128, 128, 3, 2, 1),    # layer2.0 conv2: stride 2
+    (5, 14, 14, 256, 256, 3, 1, 1),    # layer3 conv2: tiles straddle image rows and images
+    (9, 7, 7, 512, 512, 3, 1, 1),      # layer4 conv2: 49-pixel images, 128-pixel tiles span 3 images
+    (2, 56, 56, 256, 512, 1, 2, 0),    # layer2.0 downsample: 1x1 stride 2
+    (1, 7, 7, 64, 64, 3, 1, 1),        # one small image: tensor < 128 KiB (descriptor workaround path)
+    (4, 2, 2, 64, 128, 3, 1, 1),       # resnet18 on 64x64 images, layer4: the filter is larger than the image
+    (2, 9, 11, 64, 72, 3, 2, 1),       # odd sizes, Cout not a multiple of the tile
+    (40, 14, 14, 256, 1024, 1, 2, 0),  # wide output: 128 x 256 tiles / CTA pairs
+])
+def test_conv_implicit_gemm_matches_torch_fp32(gpu_native, n, H, W, C, Cout, KS, stride, pad):
+    """the fp32 reference of the same op: torch conv2d on the fp16-rounded operands"""
+    import torch
+    rng = np.random.default_rng(H * 131 + C + KS)
+    x = (rng.standard_normal((n, H, W, C)) * 0.5).astype(np.float16)
+    w = (rng.standard_normal((Cout, KS, KS, C)) * (0.5 / np.sqrt(KS * KS * C))).astype(np.float16)
+    bias = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x.astype(np.float32)).permute(0, 3, 1, 2),
+                                     torch.from_numpy(w.astype(np.float32)).permute(0, 3, 1, 2),
+                                     torch.from_numpy(bias), stride=stride, padding=pad).permute(0, 2, 3, 1).numpy()
+    got = _conv(gpu_native, x, w, bias, stride, pad).astype(np.float32)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
+    # fused ResNet tail: relu(conv + bias + identity)
+    res = rng.standard_normal(ref.shape).astype(np.float16)
+    got2 = _conv(gpu_native, x, w, bias, stride, pad, residual=res, act=2, act_after=1).astype(np.float32)
+    ref2 = np.maximum(ref + res.astype(np.float32), 0)
+    np.testing.assert_allclose(got2, ref2, rtol=2e-3, atol=2e-3 * np.abs(ref2).max())
+
+
 # ---------------------------------------------------------------- LayerNorm / embedding / attention
 def _dev(native, arr):
     b = native.DeviceBuffer(max(arr.nbytes, 16))

@@ -42,7 +42,9 @@ def _run(native, pm, x, max_rows):
         model.free()
 
 
-def test_resnet18_small_images(gpu_native):
+@pytest.mark.parametrize("implicit", [True, False])
+def test_resnet18_small_images(gpu_native, implicit):
+    """implicit: KxK / strided convolutions as implicit GEMM (im2col-mode TMA); explicit: im2col kernel + GEMM"""
     import torch
     import torchvision
     from clearml_serving_b200 import formats
@@ -51,7 +53,7 @@ def test_resnet18_small_images(gpu_native):
     x = np.random.default_rng(1).standard_normal((5, 3, 64, 64)).astype(np.float32)
     with torch.no_grad():
         ref = m(torch.from_numpy(x)).numpy()
-    got = _run(gpu_native, formats.pack_resnet(m, image_hw=(64, 64)), x, 8)
+    got = _run(gpu_native, formats.pack_resnet(m, image_hw=(64, 64), implicit_conv=implicit), x, 8)
     assert got.shape == ref.shape and got.dtype == np.float32
     err = np.abs(got - ref).max() / np.abs(ref).max()
     assert err <= REL_TOL, "relative error {:.2e}".format(err)
