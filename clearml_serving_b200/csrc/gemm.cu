@@ -44,16 +44,32 @@ struct GemmSmem {
 // GELU (erf form, as torch.nn.functional.gelu): erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far
 // below the fp16 rounding of the stored activation) -- one MUFU.RCP + one MUFU.EX2 instead of erff's
 // ~25-instruction polynomial, which made the epilogue the bottleneck of the FFN-up GEMM.
+// Both special functions are the raw MUFU forms: `__frcp_rn` / `exp2f` expand to MUFU + a fix-up sequence with a
+// divergent slow-path branch per element (IEEE rounding, denormal scaling), which made this epilogue 2x the MMA
+// time of a K = 768 tile.  The argument of the reciprocal is >= 1 and ex2 underflows to 0 exactly where erf is 1.
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float gelu_erf(float x)
 {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float e = 1.0f - p * t * exp2f(-z * z * 1.4426950408889634f);  // erf(|x|/sqrt2)
-    return 0.5f * x * (1.0f + copysignf(e, x));
+    const float e = fmaf(-p * t, ex2_approx(z * z * -1.4426950408889634f), 1.0f);  // erf(|x|/sqrt2)
+    const float hx = 0.5f * x;
+    return fmaf(hx, copysignf(e, x), hx);
 }
 
 // tanh(x) = 1 - 2 / (exp(2x) + 1): branch-free (tanhf's range split costs a divergent branch per element);
@@ -247,8 +263,9 @@ __device__ __forceinline__ void epilogue_swiglu32(const GemmEpilogue &ep, int wa
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
-        const float a0 = g0 / (1.0f + __expf(-g0)) * __uint_as_float(u[2 * j]);
-        const float a1 = g1 / (1.0f + __expf(-g1)) * __uint_as_float(u[2 * j + 1]);
+        // silu(g) * u with the raw MUFU reciprocal (an IEEE `/` costs a fix-up sequence + slow-path branch per element)
+        const float a0 = g0 * rcp_approx(1.0f + __expf(-g0)) * __uint_as_float(u[2 * j]);
+        const float a1 = g1 * rcp_approx(1.0f + __expf(-g1)) * __uint_as_float(u[2 * j + 1]);
         if (ep.is_bf16) {
             __nv_bfloat162 p = __floats2bfloat162_rn(a0, a1);
             w[j] = *reinterpret_cast<uint32_t *>(&p);

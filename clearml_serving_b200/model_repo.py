@@ -522,3 +522,17 @@ class ModelRepository(object):
                 del self._packed[fp]
         self._current = seen
         return changed + removed
+
+
+_default_repo = None
+_default_repo_lock = threading.Lock()
+
+
+def default_repository():
+    """process-wide packed-model cache: engines are rebuilt after every configuration change
+    (model_request_processor.py:1026-1028), the lowering of an unchanged model file is not repeated"""
+    global _default_repo
+    with _default_repo_lock:
+        if _default_repo is None:
+            _default_repo = ModelRepository()
+        return _default_repo

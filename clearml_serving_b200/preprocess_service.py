@@ -32,7 +32,7 @@ from pathlib import Path
 
 import numpy as np
 
-from . import formats, native
+from . import formats, model_repo, native
 from .router import Replica, ReplicaSet, parse_devices
 from .scheduler import BatchPolicy, DynamicBatcher
 
@@ -152,15 +152,21 @@ class BasePreprocessRequest(object):
         if not model_id:
             return None
         resolver = BasePreprocessRequest._model_resolver
+        self._model_framework = None   # the registry's framework tag, when known (triton_helper.py:159)
         if resolver is not None:
-            return resolver(model_id)
+            r = resolver(model_id)
+            if isinstance(r, tuple):   # (local_path, framework)
+                r, self._model_framework = r[0], (r[1] if len(r) > 1 else None)
+            return r
         if os.path.exists(str(model_id)):
             return str(model_id)
         try:
             from clearml import Model  # the control plane's model registry, when deployed with it
         except ImportError:
             raise ValueError("model '{}' is not a local file and no model resolver is configured".format(model_id))
-        return Model(model_id=model_id).get_local_copy()
+        m = Model(model_id=model_id)
+        self._model_framework = getattr(m, "framework", None)
+        return m.get_local_copy()
 
     @classmethod
     def set_model_resolver(cls, resolver):
@@ -287,7 +293,8 @@ class B200EngineMixin(object):
             path = self._get_local_model_file()
             if not path:
                 raise ValueError("b200 engine: endpoint '{}' has no model (model_id / load())".format(ep.serving_url))
-            packed = formats.load_model_file(path)
+            model_repo.validate_auxiliary_cfg(aux)
+            packed, _fp = model_repo.default_repository().get(path, getattr(self, "_model_framework", None))
         self._packed_description = packed.description
         self._policy = BatchPolicy.from_auxiliary_cfg(aux)
         name = str(ep.serving_url).replace("/", "_")
@@ -311,7 +318,7 @@ class B200EngineMixin(object):
         if isinstance(obj, formats.PackedModel):
             return obj
         if isinstance(obj, (str, os.PathLike)):
-            return formats.load_model_file(str(obj))
+            return model_repo.load_model(str(obj))
         if isinstance(obj, dict) and "learner" in obj:
             return formats.pack_xgboost_json(obj)
         if hasattr(obj, "predict"):

@@ -1,0 +1,202 @@
+"""Model-repository ingestion (reference: engines/triton/triton_helper.py:91-194, :291-409):
+framework tag -> loader, file sniffing, TorchScript lowering, XGBoost JSON / UBJSON, Triton repo folders,
+auxiliary pbtxt validation, change detection.  CPU only: the packed blob is compared with the blob the direct
+packers produce (the kernels that execute the blob are covered by the -m gpu suites)."""
+import json
+
+import numpy as np
+import pytest
+
+from clearml_serving_b200 import formats, model_repo
+from tests import blob_interp
+
+
+def _mini_xgb_model():
+    """hand-written model in the XGBoost JSON schema (two stumps + one depth-2 tree)"""
+    def tree(left, right, feat, cond, dl):
+        return dict(left_children=left, right_children=right, split_indices=feat, split_conditions=cond,
+                    default_left=dl, split_type=[0] * len(left), categories=[], base_weights=[0.0] * len(left))
+    trees = [tree([1, -1, -1], [2, -1, -1], [0, 0, 0], [0.5, -1.25, 2.5], [1, 0, 0]),
+             tree([1, -1, -1], [2, -1, -1], [2, 0, 0], [-0.125, 0.75, -0.5], [0, 0, 0]),
+             tree([1, 3, -1, -1, -1], [2, 4, -1, -1, -1], [1, 0, 0, 0, 0], [0.0, 1.5, 0.0625, -3.0, 4.0], [1, 1, 0, 0, 0])]
+    return {"learner": {"objective": {"name": "reg:squarederror"},
+                        "learner_model_param": {"base_score": "5E-1", "num_feature": "3", "num_class": "0"},
+                        "gradient_booster": {"name": "gbtree", "model": {"trees": trees}}},
+            "version": [1, 7, 5]}
+
+
+def test_ubjson_round_trip_and_typed_arrays():
+    obj = {"a": [1, 2, 300, -70000], "f": [0.5, -1.25, 3.0], "s": "héllo", "n": None, "t": True, "x": False,
+           "nested": {"k": [{"q": 1.5}, [1, "two", 3.0]], "big": 2 ** 40, "neg": -5}, "empty": [], "eo": {}}
+    data = model_repo.ubjson_dumps(obj)
+    assert b"[$l#" in data and b"[$d#" in data       # homogeneous lists use the strongly typed form
+    back = model_repo.ubjson_loads(data)
+    assert back == obj
+    with pytest.raises(ValueError):
+        model_repo.ubjson_loads(data[:-3])
+
+
+def test_xgboost_ubj_and_json_pack_to_the_same_blob(tmp_path):
+    model = _mini_xgb_model()
+    pj, pu = tmp_path / "m.json", tmp_path / "m.ubj"
+    pj.write_text(json.dumps(model))
+    pu.write_bytes(model_repo.ubjson_dumps(model))
+    a = model_repo.load_model(str(pj))
+    b = model_repo.load_model(str(pu), framework="XGBoost")
+    assert a.blob == b.blob and a.kind == b.kind
+    # and the blob predicts what the schema says (fp32 sequential sum from base_score, x < cond, NaN -> default)
+    X = np.array([[0.4, -1.0, 0.0], [0.6, 2.0, -1.0], [np.nan, np.nan, np.nan]], np.float32)
+    got = blob_interp.predict(a.blob, X)
+    want = np.array([np.float32(0.5) + np.float32(-1.25) + np.float32(-0.5) + np.float32(-3.0),
+                     np.float32(0.5) + np.float32(2.5) + np.float32(0.75) + np.float32(0.0625),
+                     np.float32(0.5) + np.float32(-1.25) + np.float32(-0.5) + np.float32(-3.0)], np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_framework_tag_picks_the_loader_like_the_triton_helper():
+    f = model_repo.loader_for_framework
+    assert f("PyTorch") == "torchscript" and f("pytorch_libtorch") == "torchscript" and f("caffe2") == "torchscript"
+    assert f("XGBoost") == "xgboost" and f("ScikitLearn") == "sklearn" and f(None) is None and f("custom") is None
+    assert f("ONNX") == "onnx" and f("TensorFlow") == "tensorflow" and f("Keras") == "tensorflow" and f("TensorRT") == "tensorrt"
+
+
+@pytest.mark.parametrize("fw", ["onnx", "tensorflow", "keras", "tensorrt"])
+def test_unsupported_frameworks_fail_loudly(tmp_path, fw):
+    p = tmp_path / "model.bin"
+    p.write_bytes(b"\0" * 64)
+    with pytest.raises(ValueError, match="b200 engine"):
+        model_repo.load_model(str(p), framework=fw)
+
+
+def test_legacy_xgboost_binary_is_refused(tmp_path):
+    p = tmp_path / "xgb_model"
+    p.write_bytes(b"binf" + b"\0" * 200)
+    with pytest.raises(ValueError, match="legacy binary"):
+        model_repo.load_model(str(p))
+
+
+def test_sklearn_joblib_file(tmp_path):
+    import joblib
+    from sklearn.linear_model import LogisticRegression
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((60, 4))
+    y = (X[:, 0] + X[:, 1] > 0).astype(int) + (X[:, 2] > 1).astype(int)
+    m = LogisticRegression(max_iter=200).fit(X, y)
+    p = tmp_path / "sklearn-model.pkl"
+    joblib.dump(m, p)
+    a = model_repo.load_model(str(p), framework="ScikitLearn")
+    assert a.blob == formats.pack_sklearn(m).blob
+
+
+def test_torchscript_resnet_lowers_to_the_same_blob_as_the_eager_module(tmp_path):
+    import torch
+    import torchvision
+    torch.manual_seed(0)
+    m = torchvision.models.resnet18(weights=None, num_classes=10).eval()
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.5, 1.5)
+    p = tmp_path / "model.pt"
+    torch.jit.script(m).save(str(p))
+    got = model_repo.load_model(str(p), framework="PyTorch")
+    assert got.description["arch"] == "resnet" and got.description["num_classes"] == 10
+    assert got.blob == formats.pack_resnet(m).blob
+    # bottleneck variant through a Triton-style repository folder <name>/<version>/model.pt
+    m50 = torchvision.models.resnet50(weights=None, num_classes=4).eval()
+    d = tmp_path / "repo" / "test_model_pytorch" / "1"
+    d.mkdir(parents=True)
+    torch.jit.script(m50).save(str(d / "model.pt"))
+    (tmp_path / "repo" / "test_model_pytorch" / "config.pbtxt").write_text('backend: "pytorch"\nmax_batch_size: 8\n')
+    got50 = model_repo.load_model(str(tmp_path / "repo" / "test_model_pytorch"))
+    assert got50.blob == formats.pack_resnet(m50).blob
+
+
+def test_torchscript_bert_lowers_to_the_same_blob(tmp_path):
+    import torch
+    from transformers import BertConfig, BertForSequenceClassification
+    torch.manual_seed(0)
+    cfg = BertConfig(vocab_size=120, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                     max_position_embeddings=64, type_vocab_size=2, num_labels=3, torchscript=True)
+    m = BertForSequenceClassification(cfg).eval()
+
+    # transformers 5.x modules no longer trace under torch.jit; the loader only consumes the archive's parameters,
+    # so the archive is scripted from a module tree carrying the same parameter names (what a traced model holds)
+    class Holder(torch.nn.Module):
+        def forward(self, x):
+            return x
+
+    root = Holder()
+    for name, value in m.state_dict().items():
+        node, parts = root, name.split(".")
+        for part in parts[:-1]:
+            if not hasattr(node, part):
+                node.add_module(part, Holder())
+            node = getattr(node, part)
+        if value.dtype.is_floating_point:
+            node.register_parameter(parts[-1], torch.nn.Parameter(value.clone(), requires_grad=False))
+        else:
+            node.register_buffer(parts[-1], value.clone())
+    p = tmp_path / "model.pt"
+    torch.jit.script(root).save(str(p))
+    got = model_repo.load_model(str(p))
+    assert got.description["arch"] == "bert" and got.description["num_labels"] == 3
+    assert got.blob == formats.pack_bert(m).blob
+
+
+def test_unknown_torchscript_architecture_is_refused(tmp_path):
+    import torch
+    p = tmp_path / "model.pt"
+    torch.jit.script(torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.ReLU())).save(str(p))
+    with pytest.raises(ValueError, match="not recognised"):
+        model_repo.load_model(str(p), framework="pytorch")
+
+
+def test_highest_version_folder_wins(tmp_path):
+    model = _mini_xgb_model()
+    for v, base in ((1, "5E-1"), (3, "2.5E-1"), (2, "7.5E-1")):
+        d = tmp_path / "ep" / str(v)
+        d.mkdir(parents=True)
+        model["learner"]["learner_model_param"]["base_score"] = base
+        (d / "model.json").write_text(json.dumps(model))
+    pm = model_repo.load_model(str(tmp_path / "ep"))
+    assert blob_interp.decode(pm.blob)["base"] == 0.25
+
+
+def test_auxiliary_cfg_validation_mirrors_the_triton_rules():
+    ok = 'max_batch_size: 64\ndynamic_batching { max_queue_delay_microseconds: 5000 preferred_batch_size: [16, 32] }\n' \
+         'instance_group [ { count: 2 kind: KIND_GPU gpus: [0, 1] } ]\n# input in a comment\nparameters { key: "input" value: { string_value: "x" } }'
+    keys = model_repo.validate_auxiliary_cfg(ok)
+    assert "max_batch_size" in keys and "dynamic_batching" in keys and "instance_group" in keys and "input" not in keys
+    assert model_repo.parse_instance_group(ok) == (2, [0, 1])
+    assert model_repo.parse_instance_group({"instance_group": [{"count": 3, "gpus": [2]}]}) == (3, [2])
+    assert model_repo.parse_instance_group(None) == (None, None)
+    with pytest.raises(ValueError, match="manual"):
+        model_repo.validate_auxiliary_cfg('input [ { name: "x" data_type: TYPE_FP32 dims: [4] } ]\nmax_batch_size: 4')
+    with pytest.raises(ValueError, match="manual"):
+        model_repo.validate_auxiliary_cfg({"output.0.name": "y"})
+    with pytest.raises(ValueError, match="default_model_filename"):
+        model_repo.validate_auxiliary_cfg('default_model_filename: "m.pt"')
+    assert model_repo.validate_auxiliary_cfg(None) == []
+
+
+def test_repository_update_step_detects_changes(tmp_path):
+    model = _mini_xgb_model()
+    p = tmp_path / "a.json"
+    p.write_text(json.dumps(model))
+    repo = model_repo.ModelRepository(resolver=lambda mid: (str(tmp_path / mid), "xgboost"))
+    eps = {"ep/1": dict(engine_type="b200", serving_url="ep", model_id="a.json", version="1"),
+           "other": dict(engine_type="sklearn", serving_url="other", model_id="zzz")}
+    assert repo.update_step(eps) == ["ep/1"]
+    assert repo.update_step(eps) == []                      # nothing changed: nothing to rebuild
+    model["learner"]["learner_model_param"]["base_score"] = "1.5"
+    p.write_text(json.dumps(model))                          # new model content behind the same id
+    assert repo.update_step(eps) == ["ep/1"]
+    eps["ep/1"]["auxiliary_cfg"] = {"max_batch_size": 8}    # endpoint reconfigured
+    assert repo.update_step(eps) == ["ep/1"]
+    del eps["ep/1"]
+    assert repo.update_step(eps) == ["ep/1"] and repo._packed == {}
+    eps["bad"] = dict(engine_type="b200", serving_url="bad", model_id="a.json", auxiliary_cfg='input [ { name: "x" } ]')
+    with pytest.raises(ValueError):
+        repo.update_step(eps)
