@@ -74,6 +74,13 @@ struct ConvGeom {
     int cblocks = 1;   // Cin / 64: k-blocks per filter tap
     int OH = 1, OW = 1;
     int stride = 1, pad = 0;
+    // Stem form (s2d > 0): the 7x7 stride-2 convolution over 3 channels rewritten as a 4x4 stride-1 convolution over
+    // the 2x2 space-to-depth image z[n, Hz, Wz, 16]; k-block a = filter row a: the 4 taps x 16 channels of one output
+    // pixel are 128 contiguous bytes of z, so the A tile is a plain (overlapping-stride) tiled TMA box.  An M tile is
+    // `tile_rows` = rows_per_tile * OW output pixels (whole output rows), not 128.
+    int s2d = 0;
+    int tile_rows = 128;
+    int rows_per_tile = 1;
 };
 
 // ---- internal model interface: each model kind implements launch() on a stream -----------------

@@ -431,7 +431,11 @@ struct ConvTileOrigin { int w, h, n; };
 __device__ __forceinline__ ConvTileOrigin conv_tile_origin(const ConvGeom &cg, int m_blk)
 {
     ConvTileOrigin o{0, 0, 0};
-    if (cg.taps) {
+    if (cg.s2d) {   // whole output rows: tile = rows_per_tile rows of image n starting at row p
+        const int row = m_blk * cg.rows_per_tile;
+        o.n = row / cg.OH;
+        o.h = row - o.n * cg.OH;
+    } else if (cg.taps) {
         const int m0 = m_blk * GEMM_BM, hw = cg.OH * cg.OW;
         o.n = m0 / hw;
         const int rem = m0 - o.n * hw, p = rem / cg.OW, q = rem - p * cg.OW;
@@ -443,7 +447,9 @@ __device__ __forceinline__ ConvTileOrigin conv_tile_origin(const ConvGeom &cg, i
 __device__ __forceinline__ void load_a_tile(void *sa, const CUtensorMap *tmap_a, uint64_t *bar, const ConvGeom &cg,
                                             const ConvTileOrigin &o, int kb, int m_blk)
 {
-    if (cg.taps) {
+    if (cg.s2d) {
+        tma_load_5d(sa, tmap_a, bar, 0, 0, o.h, o.n, kb);
+    } else if (cg.taps) {
         const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
         const int r = tap / cg.KS, s_ = tap - r * cg.KS;
         tma_load_im2col_4d(sa, tmap_a, bar, cb * GEMM_BK, o.w, o.h, o.n, (uint16_t)s_, (uint16_t)r);
@@ -494,7 +500,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
-    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + G2_BN - 1) / G2_BN;
+    const int tile_rows = cg.tile_rows;   // 128 except for the space-to-depth stem (whole output rows per tile)
+    const int m_tiles = (M + tile_rows - 1) / tile_rows, n_tiles = (N + G2_BN - 1) / G2_BN;
     const int total_tiles = m_tiles * n_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -531,7 +538,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * S::STAGE_BYTES;
                     unsigned char *sb = sa + S::A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[stage], tile_rows * (GEMM_BK * 2) + S::B_BYTES);
                     load_a_tile(sa, &tmap_a, &full_bar[stage], cg, org, kb, m_blk);
                     tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, n_blk * G2_BN);
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
@@ -576,7 +583,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             tile_coords(tile, m_tiles, n_tiles, group_m, m_blk, n_blk);
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
-            const int warp_row0 = m_blk * GEMM_BM + q * 32;
+            const int warp_row0 = m_blk * tile_rows + q * 32;
+            const int M_tile = min(M, (m_blk + 1) * tile_rows);   // rows of this tile that exist (stem tiles: < 128)
             constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
@@ -594,7 +602,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                         }
-                        epilogue_swiglu32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, g, u, epi_scratch);
+                        epilogue_swiglu32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M_tile, N, g, u, epi_scratch);
                     }
                 }
             } else {
@@ -610,7 +618,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv, epi_scratch);
+                epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M_tile, N, v, bv, epi_scratch);
             }
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
@@ -884,7 +892,7 @@ static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const 
         attr_err = cudaFuncSetAttribute(gemm_tn_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     });
     if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(gemm v2)");
-    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+    const int tiles = ((M + cg.tile_rows - 1) / cg.tile_rows) * ((N + BN - 1) / BN);
     const int grid = tiles < g_num_sms() ? tiles : g_num_sms();
     // the L2 slab of a convolution is the activation tensor itself (K / taps channels per pixel), not the patch matrix
     const int group_m = gemm_group_m(M, cg.taps ? K / cg.taps : K);
@@ -1009,6 +1017,52 @@ int make_tmap_im2col_nhwc(CUtensorMap *out, const void *base, int64_t n_img, int
     if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (int64_t)n_img * H * W * C * 2 < 131072)
         reinterpret_cast<uint64_t *>(out)[1] &= ~(1ull << 21);
     return 0;
+}
+
+// Space-to-depth stem operand: z[n_img, Hz, Wz, 16] fp16.  Row (n, p, q) of k-block a is the 128 contiguous bytes
+// z[n, p + a, q .. q + 3, 0 .. 15]: a 5-D view {64 k, OW q (stride 1 pixel), OH p, n_img, 4 a} whose q / a strides
+// overlap the inner extent; box = {64, OW, rows_per_tile} -> rows_per_tile * OW rows of 128 B, 128-byte swizzle.
+int make_tmap_stem_s2d(CUtensorMap *out, const void *base, int64_t n_img, int Hz, int Wz, int OH, int OW, int rows_per_tile)
+{
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || OW + 3 > Wz || OH + 3 > Hz || OW > 256 || rows_per_tile * OW > GEMM_BM)
+        return fail(B2S_ERR_INVALID, "stem: bad space-to-depth geometry");
+    const cuuint64_t px = 16 * 2;   // bytes per z pixel
+    cuuint64_t gdim[5] = {64, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)n_img, 4};
+    cuuint64_t gstride[4] = {px, (cuuint64_t)Wz * px, (cuuint64_t)Hz * Wz * px, (cuuint64_t)Wz * px};
+    cuuint32_t box[5] = {64, (cuuint32_t)OW, (cuuint32_t)rows_per_tile, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void *>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeTiled (stem) failed with %d", (int)r);
+    return 0;
+}
+
+ConvGeom make_stem_geom(int OH, int OW)
+{
+    ConvGeom cg;
+    cg.s2d = 1;
+    cg.OH = OH;
+    cg.OW = OW;
+    int r = GEMM_BM / OW;
+    if (r < 1) r = 1;
+    while (r > 1 && OH % r != 0) --r;   // tiles never straddle two images
+    cg.rows_per_tile = r;
+    cg.tile_rows = r * OW;
+    return cg;
+}
+
+// y[n_img*OH*OW, Cout] = act(stem conv + bias): `ta` from make_tmap_stem_s2d, `tb` over w'[Cout, 256] (box height `bn`)
+int conv_stem_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, int M, int N, const GemmEpilogue &ep,
+                   const ConvGeom &cg)
+{
+    if (M <= 0 || N <= 0) return 0;
+    if (!cg.s2d || cg.tile_rows > GEMM_BM || M % cg.tile_rows != 0) return fail(B2S_ERR_INVALID, "stem: bad tile geometry");
+    if (bn == 64) return launch_gemm_persistent<64, 8>(st, ta, tb, M, N, 256, ep, cg);
+    if (bn == 128) return launch_gemm_persistent<128, 6>(st, ta, tb, M, N, 256, ep, cg);
+    return fail(B2S_ERR_INVALID, "stem: unsupported tile width %d", bn);
 }
 
 ConvGeom make_conv_geom(int H, int W, int C, int KS, int stride, int pad)

@@ -111,6 +111,17 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// 5-D tiled load (space-to-depth stem: (k, q, p, n, filter row))
+__device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+        : "memory");
+}
+
 // 4-D im2col-mode load (implicit-GEMM convolution over NHWC activations): the tensor map describes the
 // activation tensor (c, w, h, n) plus the bounding box of filter BASE positions; (c0, w, h, n) is the base pixel
 // of the first of `pixelsPerColumn` output positions (the hardware walks w, then h, then n inside the bounding

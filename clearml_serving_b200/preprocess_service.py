@@ -32,7 +32,7 @@ from pathlib import Path
 
 import numpy as np
 
-from . import formats, model_repo, native
+from . import formats, model_repo, native, wire
 from .router import Replica, ReplicaSet, parse_devices
 from .scheduler import BatchPolicy, DynamicBatcher
 
@@ -401,6 +401,26 @@ class B200EngineMixin(object):
                 a = a.astype(np.dtype(types[min(i, len(types) - 1)]), copy=False)
             res.append(a)
         return res[0] if len(res) == 1 else res
+
+    # ---- binary tensor frames (wire.py): a request body that IS a frame needs no user preprocess code, and the
+    #      reply goes back in the same framing; JSON / user-defined bodies take the reference's path untouched
+    def preprocess(self, request, state, collect_custom_statistics_fn=None):
+        if (self._preprocess is None or not hasattr(self._preprocess, "preprocess")) and wire.is_tensor_frame(request):
+            tensors = wire.decode_tensors(request)
+            state["_b200_wire"] = True
+            names = getattr(self.model_endpoint, "input_name", None)
+            n_in = len(names) if names else self._native_model.n_inputs
+            if len(tensors) != n_in:
+                raise ValueError("b200 engine: frame carries {} tensors, endpoint takes {}".format(len(tensors), n_in))
+            return tensors[0] if n_in == 1 else tensors
+        return super(B200EngineMixin, self).preprocess(request, state, collect_custom_statistics_fn)
+
+    def postprocess(self, data, state, collect_custom_statistics_fn=None):
+        if state.get("_b200_wire") and (self._preprocess is None or not hasattr(self._preprocess, "postprocess")):
+            from starlette.responses import Response
+            outs = data if isinstance(data, (list, tuple)) else [data]
+            return Response(content=wire.encode_tensors(outs), media_type=wire.MEDIA_TYPE)
+        return super(B200EngineMixin, self).postprocess(data, state, collect_custom_statistics_fn)
 
     async def process(self, data, state, collect_custom_statistics_fn=None):
         # user override wins, exactly like the Triton engine (preprocess_service.py:340-341)
