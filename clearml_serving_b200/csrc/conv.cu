@@ -42,6 +42,43 @@ nchw_to_nhwc_kernel(const void *__restrict__ in, int in_dtype, int64_t n_pix_tot
     }
 }
 
+// Stem operand (see make_tmap_stem_s2d in gemm.cu): the 7x7 stride-2 pad-3 convolution over C <= 4 channels becomes a
+// 4x4 stride-1 convolution over z[n, Hz, Wz, 16], z[n, hz, wz, (dy*2 + dx)*4 + c] = x[n, c, 2hz + dy - 3, 2wz + dx - 3]
+// (0 outside the image and for c >= C).  in: NCHW fp32 / uint8 request pixels; one thread writes one 32-byte z pixel.
+__global__ void __launch_bounds__(256)
+nchw_to_s2d_kernel(const void *__restrict__ in, int in_dtype, int64_t n_zpix_total, int C, int H, int W, int Hz, int Wz,
+                   __half *__restrict__ out)
+{
+    const int64_t zp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (n*Hz + hz)*Wz + wz
+    if (zp >= n_zpix_total) return;
+    const int wz = (int)(zp % Wz);
+    const int64_t t = zp / Wz;
+    const int hz = (int)(t % Hz);
+    const int64_t n = t / Hz;
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int ih = 2 * hz + dy - 3;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int iw = 2 * wz + dx - 3;
+            const bool inside = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float f = 0.f;
+                if (inside && c < C) {
+                    const int64_t idx = ((n * C + c) * H + ih) * (int64_t)W + iw;
+                    f = in_dtype == B2S_U8 ? (float)static_cast<const uint8_t *>(in)[idx] : static_cast<const float *>(in)[idx];
+                }
+                v[(dy * 2 + dx) * 4 + c] = __float2half_rn(f);
+            }
+        }
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(out + zp * 16);
+    o[0] = *reinterpret_cast<const uint4 *>(v);
+    o[1] = *reinterpret_cast<const uint4 *>(v + 8);
+}
+
 // out[row, (kh*KW + kw)*C + c] = in[n, oh*s - pad + kh, ow*s - pad + kw, c]  (0 outside), row = (n, oh, ow);
 // columns K..Kp-1 are zero.  One thread moves one 16-byte (8-channel) chunk.
 __global__ void __launch_bounds__(256)
@@ -142,6 +179,18 @@ int nchw_to_nhwc(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, i
     if (in_dtype != B2S_F32 && in_dtype != B2S_U8) return fail(B2S_ERR_INVALID, "nchw_to_nhwc: input must be float32 or uint8");
     const int64_t pix = n_img * H * W;
     nchw_to_nhwc_kernel<<<blocks_for(pix), 256, 0, st>>>(in, in_dtype, pix, C, H * W, Cp, static_cast<__half *>(out));
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nchw_to_s2d(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Hz, int Wz, void *out)
+{
+    if (n_img <= 0) return 0;
+    if (C < 1 || C > 4 || 2 * Hz < H + 6 || 2 * Wz < W + 6) return fail(B2S_ERR_INVALID, "stem: bad space-to-depth geometry");
+    if (in_dtype != B2S_F32 && in_dtype != B2S_U8) return fail(B2S_ERR_INVALID, "stem: input must be float32 or uint8");
+    const int64_t zpix = n_img * Hz * Wz;
+    nchw_to_s2d_kernel<<<blocks_for(zpix), 256, 0, st>>>(in, in_dtype, zpix, C, H, W, Hz, Wz, static_cast<__half *>(out));
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;

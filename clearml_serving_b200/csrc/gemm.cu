@@ -23,6 +23,7 @@
 #include <mutex>
 
 namespace b2s {
+int nchw_to_s2d(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Hz, int Wz, void *out);   // conv.cu
 
 using namespace sm100;
 
@@ -1161,4 +1162,38 @@ extern "C" B2S_API int b2s_op_conv(int device, void *cuda_stream, const void *x,
     const int bn = Cout <= 64 ? 64 : (bn256 && !pair ? 256 : 128);
     B2S_TRY(make_tmap_2d_kmajor(&tb, w, Cout, K, K, bn, 0));
     return conv_implicit_maps(static_cast<cudaStream_t>(cuda_stream), ta, tb, bn, pair, M, Cout, K, ep, cg);
+}
+
+/* Stem convolution (7x7, stride 2, pad 3, <= 4 input channels) straight from the request pixels: space-to-depth into
+ * `z_scratch`, then the 4x4 stride-1 form on the tensor cores (see make_tmap_stem_s2d).  `w2` is the filter rearranged
+ * by the packer to [Cout, 256] (k = a*64 + b*16 + (dy*2 + dx)*4 + c <- w[co, c, 2a + dy, 2b + dx], 0 where the tap or
+ * channel does not exist). */
+extern "C" B2S_API int b2s_op_conv_stem(int device, void *cuda_stream, const void *x_nchw, int in_dtype, int64_t n_img, int C,
+                                         int H, int W, const void *w2, int Cout, const float *bias, void *z_scratch, void *y,
+                                         int act)
+{
+    using namespace b2s;
+    B2S_CUDA(cudaSetDevice(device));
+    if (n_img <= 0) return 0;
+    const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1, Hz = OH + 3, Wz = OW + 3;
+    if (Cout > 128 || Cout % 8 != 0 || OW > 128) return fail(B2S_ERR_INVALID, "stem: Cout <= 128 (multiple of 8) and OW <= 128");
+    const int64_t M64 = n_img * OH * OW;
+    if (M64 > 0x7fffffff) return fail(B2S_ERR_INVALID, "stem: too many output pixels");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    B2S_TRY(nchw_to_s2d(st, x_nchw, in_dtype, n_img, C, H, W, Hz, Wz, z_scratch));
+    const ConvGeom cg = make_stem_geom(OH, OW);
+    GemmEpilogue ep;
+    ep.bias = bias;
+    ep.residual = nullptr;
+    ep.C = y;
+    ep.ldc = Cout;
+    ep.act = act;
+    ep.out_f32 = 0;
+    ep.is_bf16 = 0;
+    ep.act_after = 0;
+    CUtensorMap ta, tb;
+    B2S_TRY(make_tmap_stem_s2d(&ta, z_scratch, n_img, Hz, Wz, OH, OW, cg.rows_per_tile));
+    const int bn = Cout <= 64 ? 64 : 128;
+    B2S_TRY(make_tmap_2d_kmajor(&tb, w2, Cout, 256, 256, bn, 0));
+    return conv_stem_maps(st, ta, tb, bn, (int)M64, Cout, ep, cg);
 }

@@ -53,7 +53,12 @@ int make_tmap_im2col_nhwc(CUtensorMap *out, const void *base, int64_t n_img, int
 ConvGeom make_conv_geom(int H, int W, int C, int KS, int stride, int pad);
 int conv_implicit_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, bool pair, int M, int N, int K,
                        const GemmEpilogue &ep, const ConvGeom &cg);
+int make_tmap_stem_s2d(CUtensorMap *out, const void *base, int64_t n_img, int Hz, int Wz, int OH, int OW, int rows_per_tile);
+ConvGeom make_stem_geom(int OH, int OW);
+int conv_stem_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, int M, int N, const GemmEpilogue &ep,
+                   const ConvGeom &cg);
 // conv.cu
+int nchw_to_s2d(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Hz, int Wz, void *out);
 int nchw_to_nhwc(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Cp, void *out);
 int im2col_nhwc(cudaStream_t st, const void *in, int64_t n_img, int H, int W, int C, int KH, int KW, int stride, int pad,
                 int OH, int OW, int Kp, void *out);
@@ -64,7 +69,8 @@ namespace {
 
 enum GraphOp {
     OP_EMBED_LN = 1, OP_LINEAR = 2, OP_LAYERNORM = 3, OP_ATTENTION = 4, OP_GATHER_FIRST = 5,
-    OP_NCHW_TO_NHWC = 6, OP_IM2COL = 7, OP_MAXPOOL = 8, OP_AVGPOOL = 9, OP_CONV = 10
+    OP_NCHW_TO_NHWC = 6, OP_IM2COL = 7, OP_MAXPOOL = 8, OP_AVGPOOL = 9, OP_CONV = 10,
+    OP_STEM_S2D = 11, OP_CONV_STEM = 12
 };
 
 struct GHeader {
@@ -150,6 +156,12 @@ struct GraphModel : Model {
             if (op.opcode == OP_CONV) {   // im2col view of the NHWC input buffer, `max_rows` images
                 B2S_TRY(make_tmap_im2col_nhwc(&pl.amap[i], pl.buf[op.a[0]], max_rows, op.a[8], op.a[9], op.a[10], op.a[11],
                                               op.a[12], op.a[13]));
+                continue;
+            }
+            if (op.opcode == OP_CONV_STEM) {   // overlapping-stride view of the space-to-depth image, `max_rows` images
+                const ConvGeom cg = make_stem_geom(op.a[10], op.a[11]);
+                B2S_TRY(make_tmap_stem_s2d(&pl.amap[i], pl.buf[op.a[0]], max_rows, op.a[8], op.a[9], op.a[10], op.a[11],
+                                           cg.rows_per_tile));
                 continue;
             }
             if (op.opcode != OP_LINEAR) continue;
@@ -248,6 +260,27 @@ struct GraphModel : Model {
                     B2S_TRY(conv_implicit_maps(st, pl->amap[i], bmap[i], gemm_bn_for(op.a[6]), false, M, op.a[6], op.a[7], ep, cg));
                 break;
             }
+            case OP_CONV_STEM: {
+                // a: z_buf, W'[N,256], bias(-1), -, out_buf, act, N, K (256), Hz, Wz, OH, OW
+                const ConvGeom cg = make_stem_geom(op.a[10], op.a[11]);
+                const int M = (int)(n_rows * (int64_t)cg.OH * cg.OW);
+                GemmEpilogue ep;
+                ep.bias = tptr(op.a[2]);
+                ep.residual = nullptr;
+                ep.C = pl->buf[op.a[4]];
+                ep.ldc = op.a[6];
+                ep.act = op.a[5];
+                ep.out_f32 = 0;
+                ep.is_bf16 = 0;
+                ep.act_after = 0;
+                B2S_TRY(conv_stem_maps(st, pl->amap[i], bmap[i], gemm_bn_for(op.a[6]), M, op.a[6], ep, cg));
+                break;
+            }
+            case OP_STEM_S2D:
+                // a: in_input, z_buf, C, H, W, Hz, Wz
+                B2S_TRY(nchw_to_s2d(st, d_in[op.a[0]], h.in_dtype[op.a[0]], n_rows, op.a[2], op.a[3], op.a[4], op.a[5], op.a[6],
+                                    pl->buf[op.a[1]]));
+                break;
             case OP_LAYERNORM: {
                 // a: in32_buf, gamma, beta, out16(-1), out32(-1), H
                 const GBuffer &ib = buffers[op.a[0]];
@@ -368,6 +401,25 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
             }
             break;
         }
+        case OP_STEM_S2D:
+            ok = iok(op.a[0], false) && bok(op.a[1], false) && op.a[2] >= 1 && op.a[2] <= 4 && op.a[3] > 0 && op.a[4] > 0 &&
+                 2 * op.a[5] >= op.a[3] + 6 && 2 * op.a[6] >= op.a[4] + 6 && m->buffers[op.a[1]].dtype == B2S_F16 &&
+                 m->buffers[op.a[1]].cols == 16 && (int64_t)m->buffers[op.a[1]].rows_kind == (int64_t)op.a[5] * op.a[6] &&
+                 h.in_row_elems[op.a[0]] == (int64_t)op.a[2] * op.a[3] * op.a[4];
+            break;
+        case OP_CONV_STEM: {
+            ok = bok(op.a[0], false) && tok(op.a[1], false) && tok(op.a[2], true) && bok(op.a[4], false) && op.a[6] > 0 &&
+                 op.a[6] % 8 == 0 && op.a[6] <= 128 && op.a[7] == 256 && op.a[10] > 0 && op.a[11] > 0 && op.a[11] <= 128 &&
+                 op.a[10] + 3 <= op.a[8] && op.a[11] + 3 <= op.a[9];
+            if (ok) {
+                const GTensor &w = m->tensors[op.a[1]];
+                const GBuffer &ib = m->buffers[op.a[0]], &ob = m->buffers[op.a[4]];
+                ok = w.dtype == B2S_F16 && w.ndim == 2 && w.shape[0] == op.a[6] && w.shape[1] == 256 && ib.dtype == B2S_F16 &&
+                     ib.cols == 16 && (int64_t)ib.rows_kind == (int64_t)op.a[8] * op.a[9] && ob.dtype == B2S_F16 &&
+                     ob.cols == op.a[6] && (int64_t)ob.rows_kind == (int64_t)op.a[10] * op.a[11];
+            }
+            break;
+        }
         case OP_LAYERNORM:
             ok = bok(op.a[0], false) && tok(op.a[1], false) && tok(op.a[2], false) && bok(op.a[3], true) && bok(op.a[4], true);
             break;
@@ -411,7 +463,7 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
     int64_t flops_fixed = 0;
     for (size_t i = 0; i < m->ops.size(); ++i) {
         const GOp &op = m->ops[i];
-        if (op.opcode != OP_LINEAR && op.opcode != OP_CONV) continue;
+        if (op.opcode != OP_LINEAR && op.opcode != OP_CONV && op.opcode != OP_CONV_STEM) continue;
         int rc = make_tmap_2d_kmajor(&m->bmap[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], gemm_bn_for(op.a[6]), 0);
         if (rc == 0 && op.a[6] >= 256)
             rc = make_tmap_2d_kmajor(&m->bmap256[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], 256, 0);

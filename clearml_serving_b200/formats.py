@@ -416,6 +416,21 @@ def pack_bert(model):
 
 
 OP_NCHW_TO_NHWC, OP_IM2COL, OP_MAXPOOL, OP_AVGPOOL, OP_CONV = 6, 7, 8, 9, 10
+OP_STEM_S2D, OP_CONV_STEM = 11, 12
+
+
+def stem_s2d_weight(w):
+    """7x7 filter [Cout, C<=4, 7, 7] -> [Cout, 256]: the stride-2 convolution rewritten as a 4x4 stride-1 convolution
+    over the 2x2 space-to-depth image (csrc/conv.cu nchw_to_s2d_kernel): k = a*64 + b*16 + (dy*2 + dx)*4 + c holds
+    w[co, c, 2a + dy, 2b + dx]; the taps with 2a + dy == 7 or 2b + dx == 7 and channels >= C are zero."""
+    w = np.asarray(w, np.float64)
+    Cout, C, KH, KW = w.shape
+    if KH != 7 or KW != 7 or C > 4:
+        raise ValueError("b200 engine: stem_s2d_weight wants a [Cout, <=4, 7, 7] filter")
+    w8 = np.zeros((Cout, 4, 8, 8), np.float64)
+    w8[:, :C, :7, :7] = w
+    # [co, c, a, dy, b, dx] -> [co, a, b, dy, dx, c]
+    return w8.reshape(Cout, 4, 4, 2, 4, 2).transpose(0, 2, 4, 3, 5, 1).reshape(Cout, 256)
 
 
 def _fold_bn(conv_w, bn):
@@ -500,9 +515,28 @@ def pack_resnet(model, input_dtype="float32", image_hw=(224, 224), implicit_conv
         import os
         implicit_conv = os.environ.get("B2S_CONV_IMPLICIT", "1") != "0"
     low = _ConvNetLowering(g, implicit=implicit_conv)
-    x = g.buffer("float16", False, 8, rows_per_item=H * W)
-    g.op(OP_NCHW_TO_NHWC, [0, x, 3, H, W, 8])
-    x, H, W, C = low.conv_bn(x, H, W, 8, model.conv1, model.bn1, relu=True)
+    c1 = model.conv1
+    sOH, sOW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    stem_s2d = (implicit_conv and tuple(c1.kernel_size) == (7, 7) and tuple(c1.stride) == (2, 2) and
+                tuple(c1.padding) == (3, 3) and c1.in_channels <= 4 and c1.groups == 1 and tuple(c1.dilation) == (1, 1) and
+                c1.out_channels <= 128 and c1.out_channels % 8 == 0 and sOW <= 128)
+    if stem_s2d:
+        # the stem as a 4x4 stride-1 implicit GEMM over the 2x2 space-to-depth image (no patch matrix, K = 256)
+        Hz, Wz = sOH + 3, sOW + 3
+        z = g.buffer("float16", False, 16, rows_per_item=Hz * Wz)
+        g.op(OP_STEM_S2D, [0, z, c1.in_channels, H, W, Hz, Wz])
+        w, b = _fold_bn(c1.weight, model.bn1)
+        if c1.bias is not None:
+            b = b + c1.bias.detach().double().numpy()
+        C = c1.out_channels
+        x = low.buf(sOH * sOW, C)
+        g.op(OP_CONV_STEM, [z, g.tensor(stem_s2d_weight(w), np.float16), g.tensor(b, np.float32), -1, x, ACT_RELU, C, 256,
+                            Hz, Wz, sOH, sOW])
+        H, W = sOH, sOW
+    else:
+        x = g.buffer("float16", False, 8, rows_per_item=H * W)
+        g.op(OP_NCHW_TO_NHWC, [0, x, 3, H, W, 8])
+        x, H, W, C = low.conv_bn(x, H, W, 8, model.conv1, model.bn1, relu=True)
     OH, OW = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
     y = low.buf(OH * OW, C)
     g.op(OP_MAXPOOL, [x, y, H, W, C, OH, OW])

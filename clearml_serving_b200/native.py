@@ -101,6 +101,7 @@ PROTOTYPES = [
     ("b2s_timer_destroy", _i, [_u64]),
     ("b2s_op_gemm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i]),
     ("b2s_op_conv", _i, [_i, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i]),
+    ("b2s_op_conv_stem", _i, [_i, _vp, _vp, _i, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i]),
     ("b2s_op_layernorm", _i, [_i, _vp, _vp, _i64, _i, _vp, _vp, ctypes.c_float, _vp, _vp]),
     ("b2s_op_embed_layernorm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp,
                                     ctypes.c_float, _vp, _vp]),

@@ -201,6 +201,15 @@ B2S_API int b2s_op_conv(int device, void *cuda_stream, const void *x, int64_t n_
                         const void *w, int Cout, int KS, int stride, int pad, const float *bias,
                         const void *residual, void *y, int act, int act_after);
 
+/* y[n_img,OH,OW,Cout] = act(conv2d(x, w, stride 2, pad 3) + bias) for the 7x7 network stem, straight from the request
+ * pixels x[n_img,C,H,W] (NCHW, float32 or uint8 -- the dtypes the reference's Triton client can send,
+ * preprocess_service.py:271-282; C <= 4).  The pixels are rearranged 2x2 space-to-depth into `z_scratch`
+ * (n_img*(OH+3)*(OW+3)*32 bytes) and the convolution runs as a 4x4 stride-1 implicit GEMM; `w2` is the filter packed to
+ * [Cout,256] fp16 (clearml_serving_b200/formats.py: stem_s2d_weight).  Cout <= 128, OW <= 128. */
+B2S_API int b2s_op_conv_stem(int device, void *cuda_stream, const void *x_nchw, int in_dtype, int64_t n_img, int C,
+                             int H, int W, const void *w2, int Cout, const float *bias, void *z_scratch, void *y,
+                             int act);
+
 /* LayerNorm over the last dim of fp32 in[rows,H] (torch.nn.LayerNorm numerics): writes an fp16 copy
  * (next GEMM operand) and/or an fp32 copy (residual stream); either output may be NULL. */
 B2S_API int b2s_op_layernorm(int device, void *cuda_stream, const float *in, int64_t rows, int H,

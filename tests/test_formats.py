@@ -105,3 +105,28 @@ def test_pack_forest_rejects_bad_trees():
         formats.pack_forest(bad, "xgb")
     with pytest.raises(ValueError):
         formats.pack_forest(f, "lightgbm")
+
+
+def test_stem_space_to_depth_weight_is_the_same_convolution():
+    """formats.stem_s2d_weight + the z layout of csrc/conv.cu nchw_to_s2d_kernel, executed in numpy fp64, reproduce
+    torch's 7x7 stride-2 pad-3 convolution (the ResNet stem the engine runs as a 4x4 stride-1 implicit GEMM)"""
+    import torch
+    from clearml_serving_b200 import formats
+    rng = np.random.default_rng(5)
+    for (n, C, H, W, Cout) in [(2, 3, 20, 24, 8), (1, 3, 15, 13, 16), (1, 1, 8, 8, 8)]:
+        x = rng.standard_normal((n, C, H, W))
+        w = rng.standard_normal((Cout, C, 7, 7))
+        ref = torch.nn.functional.conv2d(torch.from_numpy(x), torch.from_numpy(w), stride=2, padding=3).numpy()
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        Hz, Wz = OH + 3, OW + 3
+        xp = np.zeros((n, 4, 2 * Hz, 2 * Wz))
+        xp[:, :C, 3:3 + H, 3:3 + W] = x
+        # z[n, hz, wz, (dy, dx, c)]
+        z = xp.reshape(n, 4, Hz, 2, Wz, 2).transpose(0, 2, 4, 3, 5, 1).reshape(n, Hz, Wz, 16)
+        w2 = formats.stem_s2d_weight(w)
+        assert w2.shape == (Cout, 256)
+        got = np.zeros((n, OH, OW, Cout))
+        for a in range(4):
+            for b in range(4):
+                got += z[:, a:a + OH, b:b + OW, :] @ w2[:, a * 64 + b * 16:a * 64 + b * 16 + 16].T
+        np.testing.assert_allclose(got.transpose(0, 3, 1, 2), ref, rtol=1e-10, atol=1e-10)

@@ -124,6 +124,44 @@ def test_conv_implicit_gemm_matches_torch_fp32(gpu_native, n, H, W, C, Cout, KS,
     np.testing.assert_allclose(got2, ref2, rtol=2e-3, atol=2e-3 * np.abs(ref2).max())
 
 
+@pytest.mark.parametrize("n,C,H,W,Cout,dtype", [
+    (2, 3, 224, 224, 64, np.float32),    # ResNet stem: 112-pixel output rows, one row per tile
+    (3, 3, 64, 64, 64, np.float32),      # 32-pixel rows, four rows per tile
+    (2, 3, 112, 96, 64, np.uint8),       # two 48-pixel rows per tile (96 of 128 rows live), uint8 pixels
+    (1, 3, 50, 38, 128, np.float32),     # odd output size (25 x 19), N = 128 tiles
+    (5, 1, 30, 30, 8, np.float32),       # one channel, 15-pixel rows (5 rows per tile), narrow output
+])
+def test_conv_stem_space_to_depth_matches_torch_fp32(gpu_native, n, C, H, W, Cout, dtype):
+    """7x7 stride-2 pad-3 stem straight from NCHW request pixels; reference: torch conv2d on the fp16-rounded operands"""
+    import torch
+    from clearml_serving_b200 import formats
+    native = gpu_native
+    rng = np.random.default_rng(H * 7 + W + Cout)
+    if dtype == np.uint8:
+        x = rng.integers(0, 256, (n, C, H, W)).astype(np.uint8)
+    else:
+        x = (rng.standard_normal((n, C, H, W)) * 0.5).astype(np.float32)
+    w = (rng.standard_normal((Cout, C, 7, 7)) * (0.5 / np.sqrt(49 * C))).astype(np.float16)
+    bias = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    x16 = x.astype(np.float16).astype(np.float32)
+    ref = torch.nn.functional.conv2d(torch.from_numpy(x16), torch.from_numpy(w.astype(np.float32)), torch.from_numpy(bias),
+                                     stride=2, padding=3).relu().permute(0, 2, 3, 1).numpy()
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    w2 = formats.stem_s2d_weight(w.astype(np.float64)).astype(np.float16)
+    dx, dw, db = _dev(native, x), _dev(native, w2), _dev(native, bias)
+    dz = native.DeviceBuffer(n * (OH + 3) * (OW + 3) * 32)
+    dy = native.DeviceBuffer(n * OH * OW * Cout * 2)
+    try:
+        native.check(native.lib().b2s_op_conv_stem(0, None, dx.ptr, 4 if dtype == np.uint8 else 0, n, C, H, W, dw.ptr, Cout,
+                                                   db.ptr, dz.ptr, dy.ptr, 2))
+        got = dy.download(np.float16, n * OH * OW * Cout).reshape(n, OH, OW, Cout).astype(np.float32)
+    finally:
+        for b in (dx, dw, db, dz, dy):
+            b.free()
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
+
+
 # ---------------------------------------------------------------- LayerNorm / embedding / attention
 def _dev(native, arr):
     b = native.DeviceBuffer(max(arr.nbytes, 16))
