@@ -63,6 +63,8 @@ struct GemmEpilogue {
     int out_f32;           // 1: C (and residual) fp32, 0: 16-bit like A/B
     int is_bf16;
     int act_after;         // 1: activation applied AFTER the residual add (ResNet), 0: before (BERT)
+    int res_prefetch = 0;  // set by the launchers: epilogue warps request the next tile's residual slab into L2
+    int tma_store = 0;     // set by the launchers: output tiles leave through TMA stores (the kernel's C tensor map is valid)
 };
 
 // Implicit-GEMM convolution geometry (gemm.cu): when `taps` > 0 the A operand of the GEMM is not a matrix in

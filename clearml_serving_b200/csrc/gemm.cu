@@ -19,10 +19,13 @@
 #include <cuda_bf16.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
 namespace b2s {
+static bool gemm_res_prefetch_enabled();
+static int prepare_tma_store(CUtensorMap *tc, GemmEpilogue &ep, int M, int N, int bn, const ConvGeom &cg);
 int nchw_to_s2d(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Hz, int Wz, void *out);   // conv.cu
 
 using namespace sm100;
@@ -84,7 +87,7 @@ __device__ __forceinline__ float tanh_fast(float x)
 // written directly that is 32 rows x 16 B per store instruction, i.e. 32 half-filled 32-byte sectors.  Staged
 // through a 2.5 KB per-warp shared-memory scratch (80-byte pitch: conflict-free 128-bit accesses) four adjacent
 // lanes emit one row's 64 contiguous bytes, so each instruction writes 8 rows x 2 full sectors.
-constexpr int EPI_SCRATCH_WORDS = 32 * 20;
+constexpr int EPI_SCRATCH_WORDS = 32 * 20;   // (documents the 80-byte pitch used below)
 __device__ __forceinline__ void warp_store_rows64(uint32_t *scratch, const uint32_t (&w)[16], unsigned char *gbase,
                                                   size_t row_pitch_bytes, int rows_valid, int lane)
 {
@@ -109,18 +112,13 @@ __device__ __forceinline__ void warp_store_rows64(uint32_t *scratch, const uint3
 // bottleneck of the persistent kernels: the tile's own output stores keep evicting the bias lines from the
 // ~30 KB of L1 left beside 197 KB of shared memory, so every chunk paid L2 latency 32 times
 // (profiles/r01_ncu_gemm_tn_persistent.txt: long-scoreboard stalls on the FADDs behind LDG.E.CONSTANT).
-// `scratch`: per-warp shared memory for the cooperative store, or nullptr for per-thread row stores.
-__device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int warp_row0, int lane, int col0, int M, int N,
-                                                 const uint32_t (&v)[32], const float *bv = nullptr,
-                                                 uint32_t *scratch = nullptr)
+//
+// epilogue_math32: everything up to the final fp32 values f[] of this lane's row (bias, activation, residual).
+__device__ __forceinline__ void epilogue_math32(const GemmEpilogue &ep, int row, bool row_ok, int col0, int ncols,
+                                                const uint32_t (&v)[32], const float *bv, float (&f)[32])
 {
-    if (col0 >= N) return;   // warp-uniform
-    const int row = warp_row0 + lane;
-    const bool row_ok = row < M;
-    const int ncols = min(32, N - col0);
     const bool full = ncols == 32;
     const float *bias = static_cast<const float *>(ep.bias);
-    float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
     if (bv) {
@@ -143,12 +141,10 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
         for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
     }
     const size_t off = (size_t)row * ep.ldc + col0;
-    const int rows_valid = min(32, max(0, M - warp_row0));
-    if (ep.out_f32) {
-        const bool vec = full && (ep.ldc & 3) == 0;
-        if (ep.residual && row_ok) {
+    if (ep.residual && row_ok) {
+        if (ep.out_f32) {
             const float *R = static_cast<const float *>(ep.residual) + off;
-            if (vec) {
+            if (full && (ep.ldc & 3) == 0) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 r4 = *reinterpret_cast<const float4 *>(R + j);
@@ -159,11 +155,72 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
                 for (int j = 0; j < 32; ++j)
                     if (j < ncols) f[j] += R[j];
             }
-        }
-        if (ep.act_after && ep.act == ACT_RELU) {
+        } else if (ep.is_bf16) {
+            const __nv_bfloat16 *R = static_cast<const __nv_bfloat16 *>(ep.residual) + off;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) f[j] += __bfloat162float(R[j]);
+        } else {
+            const __half *R = static_cast<const __half *>(ep.residual) + off;
+            if (full && (ep.ldc & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 u = *reinterpret_cast<const uint4 *>(R + j);
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 r2 = __half22float2(h[t]);
+                        f[j + 2 * t] += r2.x;
+                        f[j + 2 * t + 1] += r2.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncols) f[j] += __half2float(R[j]);
+            }
         }
+    }
+    if (ep.act_after && ep.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
+}
+
+// 32 fp32 values -> 16 words of packed fp16 / bf16 pairs
+__device__ __forceinline__ void pack16(const GemmEpilogue &ep, const float (&f)[32], uint32_t (&w)[16])
+{
+    if (ep.is_bf16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t *>(&p);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            __half2 p = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t *>(&p);
+        }
+    }
+}
+
+// `scratch`: per-warp shared memory for the cooperative store, or nullptr for per-thread row stores.
+__device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int warp_row0, int lane, int col0, int M, int N,
+                                                 const uint32_t (&v)[32], const float *bv = nullptr,
+                                                 uint32_t *scratch = nullptr)
+{
+    if (col0 >= N) return;   // warp-uniform
+    const int row = warp_row0 + lane;
+    const bool row_ok = row < M;
+    const int ncols = min(32, N - col0);
+    const bool full = ncols == 32;
+    float f[32];
+    epilogue_math32(ep, row, row_ok, col0, ncols, v, bv, f);
+    const size_t off = (size_t)row * ep.ldc + col0;
+    const int rows_valid = min(32, max(0, M - warp_row0));
+    if (ep.out_f32) {
+        const bool vec = full && (ep.ldc & 3) == 0;
         float *C = static_cast<float *>(ep.C);
         if (vec && scratch) {   // two 64-byte halves per row
             uint32_t w[16];
@@ -189,51 +246,8 @@ __device__ __forceinline__ void epilogue_store32(const GemmEpilogue &ep, int war
     }
     // 16-bit output (fp16 / bf16)
     const bool vec = full && (ep.ldc & 7) == 0;
-    if (ep.residual && row_ok) {
-        if (ep.is_bf16) {
-            const __nv_bfloat16 *R = static_cast<const __nv_bfloat16 *>(ep.residual) + off;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j < ncols) f[j] += __bfloat162float(R[j]);
-        } else {
-            const __half *R = static_cast<const __half *>(ep.residual) + off;
-            if (vec) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const uint4 u = *reinterpret_cast<const uint4 *>(R + j);
-                    const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float2 r2 = __half22float2(h[t]);
-                        f[j + 2 * t] += r2.x;
-                        f[j + 2 * t + 1] += r2.y;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < ncols) f[j] += __half2float(R[j]);
-            }
-        }
-    }
-    if (ep.act_after && ep.act == ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-    }
     uint32_t w[16];
-    if (ep.is_bf16) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t *>(&p);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            __half2 p = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t *>(&p);
-        }
-    }
+    pack16(ep, f, w);
     unsigned char *C = static_cast<unsigned char *>(ep.C);
     if (vec && scratch) {
         warp_store_rows64(scratch, w, C + ((size_t)warp_row0 * ep.ldc + col0) * 2, (size_t)ep.ldc * 2, rows_valid, lane);
@@ -407,6 +421,105 @@ __device__ __forceinline__ void broadcast32(const float4 &b, int chunk, float (&
     }
 }
 
+// One epilogue warp's share (32 rows x HALF columns) of a finished accumulator, leaving through TMA stores.
+// The per-thread row stores this replaces (even staged into 64-byte row segments, warp_store_rows64) kept the warp busy
+// with a shared-memory round trip, address arithmetic and predicates for every 32-column chunk: ncu on ResNet's
+// K = 64 expansion GEMM showed ~1800 cycles per chunk with the issue slots 29 % busy, i.e. 3.8 us of epilogue per
+// 128 x 256 tile against 0.4 us of MMA (profiles/r01_ncu_gemm_epilogue_k64.txt).  Here a lane writes its row's bytes
+// once, into a 4 KB per-warp staging tile in the tensor map's swizzled layout (conflict-free 128-bit stores), and one
+// lane hands the tile to the TMA engine: full-line writes, rows / columns outside the matrix clipped by the hardware.
+//   16-bit output, HALF >= 64: 32 rows x 128 B (two chunks per store), SWIZZLE_128B
+//   16-bit output, HALF == 32: 32 rows x  64 B, SWIZZLE_64B
+//   fp32 output:               32 rows x 128 B (one chunk per store), SWIZZLE_128B
+// `zmap`: the C map is 3-D {N, tile_rows, m_tiles} (space-to-depth stem: tiles hold fewer than 128 rows), coordinates
+// (col, row_in_tile, m_blk); otherwise 2-D {N, M}, coordinates (col, row).
+template <int HALF>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue &ep, const CUtensorMap *cmap, unsigned char *stage,
+                                                  uint32_t t_addr, uint64_t *tmem_empty, int lane, int warp_row0, int M_tile,
+                                                  int N, int col_base, bool zmap, int z_row, int z_blk, const float4 &b4)
+{
+    constexpr int NCH = HALF / 32;
+    const uint32_t st = smem_u32(stage);
+    const int row = warp_row0 + lane;
+    const bool row_ok = row < M_tile;
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t v[32];
+        float bv[32];
+        tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
+        broadcast32(b4, c, bv);
+        tmem_ld_wait();
+        if (c == NCH - 1) {   // last TMEM read of this warp: hand the accumulator back before the math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        const int col0 = col_base + c * 32;
+        if (col0 >= N) continue;   // warp-uniform
+        float f[32];
+        epilogue_math32(ep, row, row_ok, col0, min(32, N - col0), v, bv, f);
+        int store_col = -1;
+        if (ep.out_f32) {
+            if (lane == 0) bulk_wait_group_read<0>();   // the previous store has read the staging tile
+            __syncwarp();
+            const uint32_t ra = st + (uint32_t)lane * 128u;
+            const int x = lane & 7;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                sts_v4(ra + (uint32_t)((i ^ x) << 4), __float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
+                       __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3]));
+            store_col = col0;
+        } else {
+            uint32_t w[16];
+            pack16(ep, f, w);
+            if constexpr (NCH >= 2) {
+                const int sub = c & 1;
+                if (sub == 0) {
+                    if (lane == 0) bulk_wait_group_read<0>();
+                    __syncwarp();
+                }
+                const uint32_t ra = st + (uint32_t)lane * 128u;
+                const int x = lane & 7;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    sts_v4(ra + (uint32_t)(((sub * 4 + i) ^ x) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                if (sub == 1 || col0 + 32 >= N) store_col = col0 - sub * 32;
+            } else {
+                if (lane == 0) bulk_wait_group_read<0>();
+                __syncwarp();
+                const uint32_t ra = st + (uint32_t)lane * 64u;
+                const int x = (lane >> 1) & 3;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sts_v4(ra + (uint32_t)((i ^ x) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                store_col = col0;
+            }
+        }
+        if (store_col >= 0) {   // warp-uniform
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                if (zmap) tma_store_3d(cmap, stage, store_col, z_row, z_blk);
+                else tma_store_2d(cmap, stage, store_col, warp_row0);
+                bulk_commit_group();
+            }
+        }
+    }
+}
+
+// Residual rows of one warp's slab (32 rows x `ncols` columns) requested into L2 ahead of use.  The residual add of a
+// memory-bound GEMM (ResNet's 1x1 expansions with K = 64..512: the identity tensor is as large as the output and never
+// L2-resident) was latency-bound: a lane's four 16-byte loads per chunk are all a warp has in flight, ~16 KB per SM
+// against the ~100 KB that HBM latency x bandwidth needs.  Every epilogue warp therefore asks for the slab of its NEXT
+// tile while it drains the current one; the loads proper then hit L2.
+__device__ __forceinline__ void prefetch_residual_slab(const GemmEpilogue &ep, int row, int M, int col0, int ncols, int N)
+{
+    if (!ep.residual || row >= M || col0 >= N) return;
+    const int es = ep.out_f32 ? 4 : 2;
+    const unsigned char *p = static_cast<const unsigned char *>(ep.residual) + ((size_t)row * ep.ldc + col0) * es;
+    const int bytes = min(ncols, N - col0) * es;
+    for (int b = 0; b < bytes; b += 128) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p + b));
+}
+
 // Tile order of the persistent kernels.  With m fastest over ALL m-tiles a sweep of one weight panel touches
 // the whole activation matrix: for the LLM prefill (M = 16384, K = 4096: 134 MB of A) that does not fit in
 // L2 and every panel re-read A from DRAM (ncu: 9.6 GB of DRAM reads for a 0.37 GB problem,
@@ -478,8 +591,8 @@ struct G2Smem {
     static constexpr int B_BYTES = G2_BN * GEMM_BK * 2;     // 32 KB (BN 256) / 16 KB (BN 128)
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = G2_STAGES * STAGE_BYTES;
-    static constexpr int SCRATCH_OFFSET = BAR_OFFSET + 256;                       // 12 warps x 2.5 KB epilogue scratch
-    static constexpr int TOTAL = SCRATCH_OFFSET + 12 * 32 * 20 * 4 + 1024;        // + alignment slack
+    static constexpr int SCRATCH_OFFSET = BAR_OFFSET + 1024;                      // 8 epilogue warps x 4 KB staging (1024-aligned)
+    static constexpr int TOTAL = SCRATCH_OFFSET + 8 * 4096 + 1024;                // + alignment slack
 };
 
 // BN = 256 (4 stages) for wide outputs; BN = 128 (6 stages) when 128 x 256 tiles would leave the last
@@ -487,7 +600,8 @@ struct G2Smem {
 template <int G2_BN, int G2_STAGES>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                          int M, int N, int K, GemmEpilogue ep, int group_m, ConvGeom cg)
+                          const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpilogue ep, int group_m,
+                          ConvGeom cg)
 {
     using S = G2Smem<G2_BN, G2_STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -497,7 +611,9 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     uint64_t *tmem_full_bar = empty_bar + G2_STAGES;   // [2]
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;      // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
-    uint32_t *epi_scratch = reinterpret_cast<uint32_t *>(smem + S::SCRATCH_OFFSET) + (threadIdx.x >> 5) * EPI_SCRATCH_WORDS;
+    // per epilogue warp: 4 KB staging tile of the TMA-store epilogue; the row-store forms use its first 2.5 KB as scratch
+    unsigned char *epi_stage = smem + S::SCRATCH_OFFSET + (((threadIdx.x >> 5) - 4) & 7) * 4096;
+    uint32_t *epi_scratch = reinterpret_cast<uint32_t *>(epi_stage);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
@@ -508,6 +624,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmap_a);
         prefetch_tensormap(&tmap_b);
+        if (ep.tma_store) prefetch_tensormap(&tmap_c);
         for (int s = 0; s < G2_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -582,11 +699,23 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int m_blk, n_blk;
             tile_coords(tile, m_tiles, n_tiles, group_m, m_blk, n_blk);
+            constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
+            if (ep.res_prefetch) {   // residual slab of this warp's next tile (and of its first one) into L2
+                if (tile == (int)blockIdx.x)
+                    prefetch_residual_slab(ep, m_blk * tile_rows + q * 32 + lane, min(M, (m_blk + 1) * tile_rows),
+                                           n_blk * G2_BN + half * HALF, HALF, N);
+                const int nxt = tile + (int)gridDim.x;
+                if (nxt < total_tiles) {
+                    int m2, n2;
+                    tile_coords(nxt, m_tiles, n_tiles, group_m, m2, n2);
+                    prefetch_residual_slab(ep, m2 * tile_rows + q * 32 + lane, min(M, (m2 + 1) * tile_rows),
+                                           n2 * G2_BN + half * HALF, HALF, N);
+                }
+            }
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const int warp_row0 = m_blk * tile_rows + q * 32;
             const int M_tile = min(M, (m_blk + 1) * tile_rows);   // rows of this tile that exist (stem tiles: < 128)
-            constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
             const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
@@ -606,6 +735,9 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                         epilogue_swiglu32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M_tile, N, g, u, epi_scratch);
                     }
                 }
+            } else if (ep.tma_store) {
+                epilogue_tile_tma<HALF>(ep, &tmap_c, epi_stage, t_addr, &tmem_empty_bar[as], lane, warp_row0, M_tile, N,
+                                        n_blk * G2_BN + half * HALF, cg.s2d != 0, q * 32, m_blk, b4);
             } else {
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
@@ -624,6 +756,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (ep.tma_store && lane == 0) bulk_wait_group<0>();   // the staging tiles live in this CTA's shared memory
     }
 
     tc_fence_before();
@@ -646,7 +779,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 template <int G2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_half,
-                    int M, int N, int K, GemmEpilogue ep, int group_mp, ConvGeom cg)
+                    const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpilogue ep, int group_mp,
+                    ConvGeom cg)
 {
     constexpr int G2_BN = 256;
     using S = G2Smem<G2_BN, G2_STAGES>;
@@ -657,7 +791,9 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t *tmem_full_bar = empty_bar + G2_STAGES;
     uint64_t *tmem_empty_bar = tmem_full_bar + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
-    uint32_t *epi_scratch = reinterpret_cast<uint32_t *>(smem + S::SCRATCH_OFFSET) + (threadIdx.x >> 5) * EPI_SCRATCH_WORDS;
+    // per epilogue warp: 4 KB staging tile of the TMA-store epilogue; the row-store forms use its first 2.5 KB as scratch
+    unsigned char *epi_stage = smem + S::SCRATCH_OFFSET + (((threadIdx.x >> 5) - 4) & 7) * 4096;
+    uint32_t *epi_scratch = reinterpret_cast<uint32_t *>(epi_stage);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -670,6 +806,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmap_a);
         prefetch_tensormap(&tmap_b_half);
+        if (ep.tma_store) prefetch_tensormap(&tmap_c);
         for (int s = 0; s < G2_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 2);            // both CTAs of the pair release a stage
@@ -749,10 +886,19 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int mp, n_blk;
             tile_coords(pt, m_pairs, n_tiles, group_mp, mp, n_blk);
             const int m_blk = 2 * mp + (int)rank;
+            constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
+            if (ep.res_prefetch) {   // residual slab of this warp's next tile (and of its first one) into L2
+                if (pt == pair0)
+                    prefetch_residual_slab(ep, m_blk * GEMM_BM + q * 32 + lane, M, n_blk * G2_BN + half * HALF, HALF, N);
+                if (pt + pair_stride < total) {
+                    int mp2, n2;
+                    tile_coords(pt + pair_stride, m_pairs, n_tiles, group_mp, mp2, n2);
+                    prefetch_residual_slab(ep, (2 * mp2 + (int)rank) * GEMM_BM + q * 32 + lane, M, n2 * G2_BN + half * HALF, HALF, N);
+                }
+            }
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const int warp_row0 = m_blk * GEMM_BM + q * 32;
-            constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             // this warp's bias slice, fetched once per tile while the accumulator is still being produced
             const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
@@ -772,6 +918,9 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         epilogue_swiglu32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, g, u, epi_scratch);
                     }
                 }
+            } else if (ep.tma_store) {
+                epilogue_tile_tma<HALF>(ep, &tmap_c, epi_stage, t_addr, &tmem_empty_bar[as], lane, warp_row0, M, N,
+                                        n_blk * G2_BN + half * HALF, false, 0, 0, b4);
             } else {
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
@@ -790,6 +939,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (ep.tma_store && lane == 0) bulk_wait_group<0>();   // the staging tiles live in this CTA's shared memory
     }
 
     tc_fence_before();
@@ -821,6 +971,45 @@ static PFN_encodeTiled get_encode_tiled()
             fn = reinterpret_cast<PFN_encodeTiled>(p);
     });
     return fn;
+}
+
+// Output tensor map of the TMA-store epilogue (epilogue_tile_tma): box = one warp's staging tile, 32 rows x 128 B
+// (64 B for 16-bit outputs of 64-wide tiles).  Plain GEMM / convolution: 2-D {N, M}.  Space-to-depth stem (tiles of
+// tile_rows < 128 rows): 3-D {N, tile_rows, M / tile_rows}, so the rows a tile does not own are clipped.
+// Falls back to the row-store epilogue (ep.tma_store = 0) when C is not 16-byte aligned / pitched.
+static int prepare_tma_store(CUtensorMap *tc, GemmEpilogue &ep, int M, int N, int bn, const ConvGeom &cg)
+{
+    static const bool on = []() { const char *e = getenv("B2S_TMA_STORE"); return !(e && e[0] == '0'); }();
+    memset(tc, 0, sizeof(*tc));
+    ep.tma_store = 0;
+    const int es = ep.out_f32 ? 4 : 2;
+    if (!on || ep.act == ACT_SWIGLU || (reinterpret_cast<uintptr_t>(ep.C) & 15) != 0 || ((size_t)ep.ldc * es) % 16 != 0) return 0;
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
+    const int rowb = (ep.out_f32 || bn >= 128) ? 128 : 64;
+    const CUtensorMapDataType dt = ep.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                              : (ep.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    const CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const cuuint64_t pitch = (cuuint64_t)ep.ldc * es;
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r;
+    if (cg.s2d) {
+        if (M % cg.tile_rows != 0) return fail(B2S_ERR_INVALID, "stem: M is not a whole number of tiles");
+        cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)cg.tile_rows, (cuuint64_t)(M / cg.tile_rows)};
+        cuuint64_t gstride[2] = {pitch, pitch * (cuuint64_t)cg.tile_rows};
+        cuuint32_t box[3] = {(cuuint32_t)(rowb / es), 32, 1};
+        r = enc(tc, dt, 3, ep.C, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+        cuuint64_t gstride[1] = {pitch};
+        cuuint32_t box[2] = {(cuuint32_t)(rowb / es), 32};
+        r = enc(tc, dt, 2, ep.C, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(B2S_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with %d", (int)r);
+    ep.tma_store = 1;
+    return 0;
 }
 
 // 2-D K-major tensor map: global [rows, K] row-major 16-bit, box [box_rows, 64], 128-byte swizzle
@@ -897,7 +1086,11 @@ static int launch_gemm_persistent(cudaStream_t st, const CUtensorMap &ta, const 
     const int grid = tiles < g_num_sms() ? tiles : g_num_sms();
     // the L2 slab of a convolution is the activation tensor itself (K / taps channels per pixel), not the patch matrix
     const int group_m = gemm_group_m(M, cg.taps ? K / cg.taps : K);
-    gemm_tn_persistent_kernel<BN, STAGES><<<grid, G2_THREADS, S::TOTAL, st>>>(ta, tb, M, N, K, ep, group_m, cg);
+    GemmEpilogue epk = ep;
+    epk.res_prefetch = ep.residual != nullptr && gemm_res_prefetch_enabled();
+    CUtensorMap tc;
+    B2S_TRY(prepare_tma_store(&tc, epk, M, N, BN, cg));
+    gemm_tn_persistent_kernel<BN, STAGES><<<grid, G2_THREADS, S::TOTAL, st>>>(ta, tb, tc, M, N, K, epk, group_m, cg);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
@@ -918,10 +1111,20 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtens
     const int max_pairs = g_num_sms() / 2;
     const int pairs = total < max_pairs ? total : max_pairs;
     const int group_mp = gemm_group_m(M, cg.taps ? K / cg.taps : K) / 2;
-    gemm_tn_pair_kernel<4><<<2 * pairs, G2_THREADS, S::TOTAL, st>>>(ta, tb_half, M, N, K, ep, group_mp, cg);
+    GemmEpilogue epk = ep;
+    epk.res_prefetch = ep.residual != nullptr && gemm_res_prefetch_enabled();
+    CUtensorMap tc;
+    B2S_TRY(prepare_tma_store(&tc, epk, M, N, 256, cg));
+    gemm_tn_pair_kernel<4><<<2 * pairs, G2_THREADS, S::TOTAL, st>>>(ta, tb_half, tc, M, N, K, epk, group_mp, cg);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
+}
+
+static bool gemm_res_prefetch_enabled()
+{
+    static const bool on = []() { const char *e = getenv("B2S_RES_PREFETCH"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 bool gemm_pair_enabled()

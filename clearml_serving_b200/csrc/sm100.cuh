@@ -111,6 +111,31 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// ---- TMA stores (shared -> global, bulk async-group completion) ------------------------------------
+// The smem tile must have been written with generic-proxy stores followed by fence_proxy_async() and a warp / CTA
+// level sync before ONE thread issues the store; the tile may be rewritten after bulk_wait_group_read<0>().
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *m, const void *smem_src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *smem_src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // 5-D tiled load (space-to-depth stem: (k, q, p, n, filter row))
 __device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2,
                                             int c3, int c4)
