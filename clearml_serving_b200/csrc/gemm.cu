@@ -115,7 +115,8 @@ __device__ __forceinline__ void warp_store_rows64(uint32_t *scratch, const uint3
 //
 // epilogue_math32: everything up to the final fp32 values f[] of this lane's row (bias, activation, residual).
 __device__ __forceinline__ void epilogue_math32(const GemmEpilogue &ep, int row, bool row_ok, int col0, int ncols,
-                                                const uint32_t (&v)[32], const float *bv, float (&f)[32])
+                                                const uint32_t (&v)[32], const float *bv, float (&f)[32],
+                                                const uint4 *res16 = nullptr)
 {
     const bool full = ncols == 32;
     const float *bias = static_cast<const float *>(ep.bias);
@@ -141,7 +142,18 @@ __device__ __forceinline__ void epilogue_math32(const GemmEpilogue &ep, int row,
         for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
     }
     const size_t off = (size_t)row * ep.ldc + col0;
-    if (ep.residual && row_ok) {
+    if (res16) {   // this lane's 32 residual values (fp16), fetched by the caller ahead of the accumulator
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const __half2 *h = reinterpret_cast<const __half2 *>(&res16[j >> 3]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 r2 = __half22float2(h[t]);
+                f[j + 2 * t] += r2.x;
+                f[j + 2 * t + 1] += r2.y;
+            }
+        }
+    } else if (ep.residual && row_ok) {
         if (ep.out_f32) {
             const float *R = static_cast<const float *>(ep.residual) + off;
             if (full && (ep.ldc & 3) == 0) {
@@ -442,10 +454,22 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue &ep, const 
     const uint32_t st = smem_u32(stage);
     const int row = warp_row0 + lane;
     const bool row_ok = row < M_tile;
+    // fp16 residual with whole 16-byte row segments: this lane's 64 bytes of a chunk are requested BEFORE the TMEM load,
+    // so their latency (L2 / HBM) overlaps the accumulator read and the bias shuffles instead of stalling the adds
+    const bool res_early = ep.residual && !ep.out_f32 && !ep.is_bf16 && (ep.ldc & 7) == 0;
+    const __half *res_row = static_cast<const __half *>(ep.residual) + (size_t)row * ep.ldc;
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
         uint32_t v[32];
         float bv[32];
+        const int col0 = col_base + c * 32;
+        uint4 rr[4];
+        const bool rr_ok = res_early && col0 + 32 <= N;   // warp-uniform
+        if (rr_ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                rr[i] = row_ok ? __ldg(reinterpret_cast<const uint4 *>(res_row + col0) + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
         tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
         broadcast32(b4, c, bv);
         tmem_ld_wait();
@@ -454,10 +478,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue &ep, const 
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);
         }
-        const int col0 = col_base + c * 32;
         if (col0 >= N) continue;   // warp-uniform
         float f[32];
-        epilogue_math32(ep, row, row_ok, col0, min(32, N - col0), v, bv, f);
+        epilogue_math32(ep, row, row_ok, col0, min(32, N - col0), v, bv, f, rr_ok ? rr : nullptr);
         int store_col = -1;
         if (ep.out_f32) {
             if (lane == 0) bulk_wait_group_read<0>();   // the previous store has read the staging tile
