@@ -44,7 +44,9 @@ def _ref_act(x, act):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 768), (256, 768, 768), (300, 2304, 768),
                                     (1000, 3072, 768), (77, 768, 3072), (5, 2, 768), (130, 200, 72), (260, 520, 136),
-                                    (4000, 256, 64), (20000, 768, 768)])
+                                    (4000, 256, 64), (20000, 768, 768),
+                                    # narrow, deep shapes (BERT FFN-down class): many k-blocks per tile, partly filled last wave
+                                    (7424, 768, 3072), (2000, 1024, 4096), (640, 512, 8192)])
 def test_gemm_fp16_matches_fp32_reference(gpu_native, M, N, K):
     rng = np.random.default_rng(M * 7 + N)
     A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
@@ -68,6 +70,27 @@ def test_gemm_fused_epilogue(gpu_native, act):
     ref = _ref_act(A.astype(np.float32) @ B.astype(np.float32).T + bias, act) + res.astype(np.float32)
     got = _gemm(gpu_native, A, B, bias=bias, residual=res, act=act).astype(np.float32)
     np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max())
+
+
+def test_gemm_fp32_residual_stream_is_batch_invariant(gpu_native):
+    """BERT's FFN-down shape (fp32 output + fp32 residual + bias): repeated launches are bit-identical and a row's
+    result does not depend on the batch it is computed in (SURVEY.md 5.9 rule 4) -- the tile shape may change with M,
+    the order in which a row's k-blocks are summed may not"""
+    rng = np.random.default_rng(11)
+    M, N, K = 7424, 768, 3072
+    A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
+    B = (rng.standard_normal((N, K)) * 0.05).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float32)
+    res = rng.standard_normal((M, N)).astype(np.float32)
+    ref = A.astype(np.float32) @ B.astype(np.float32).T + bias + res
+    first = None
+    for _ in range(3):
+        got = _gemm(gpu_native, A, B, bias=bias, residual=res, out_f32=True)
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+        assert first is None or np.array_equal(got, first)
+        first = got
+    sub = _gemm(gpu_native, A[1000:1300], B, bias=bias, residual=res[1000:1300], out_f32=True)   # another batch composition
+    assert np.array_equal(sub, first[1000:1300])
 
 
 # ---------------------------------------------------------------- implicit-GEMM convolution
@@ -103,6 +126,7 @@ def _conv(native, x, w, bias, stride, pad, residual=None, act=0, act_after=0):
     (4, 2, 2, 64, 128, 3, 1, 1),       # resnet18 on 64x64 images, layer4: the filter is larger than the image
     (2, 9, 11, 64, 72, 3, 2, 1),       # odd sizes, Cout not a multiple of the tile
     (40, 14, 14, 256, 1024, 1, 2, 0),  # wide output: 128 x 256 tiles / CTA pairs
+    (64, 7, 7, 512, 512, 3, 1, 1),     # layer4 conv2 at batch 64: 26 pair-tiles x 72 k-blocks
 ])
 def test_conv_implicit_gemm_matches_torch_fp32(gpu_native, n, H, W, C, Cout, KS, stride, pad):
     """the fp32 reference of the same op: torch conv2d on the fp16-rounded operands"""
