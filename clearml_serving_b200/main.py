@@ -161,6 +161,14 @@ def create_app(processor: Optional[ModelRequestProcessor] = None, logger=None, i
                                              serve_type=endpoint_type)
 
     app.include_router(router)
+
+    @app.get("/metrics", response_class=PlainTextResponse)
+    async def engine_metrics():
+        # what the reference's sidecar scraped from tritonserver :8002/metrics (triton_helper.py:45-89), same line format
+        from . import metrics
+        return PlainTextResponse(metrics.render(metrics.collect(state["processor"])),
+                                 media_type="text/plain; version=0.0.4")
+
     return app
 
 

@@ -428,7 +428,16 @@ class B200EngineMixin(object):
             return await self._preprocess.process(data, state, collect_custom_statistics_fn)
         arrays, rows = self._marshal(data)
         # the deadline (self._timeout, preprocess_service.py:48-49) is enforced by the batcher on the queue age
-        outs = await self._next_batcher().submit_async(arrays, rows)
+        if collect_custom_statistics_fn is None:
+            outs = await self._next_batcher().submit_async(arrays, rows)
+        else:
+            # a sampled request (model_request_processor.py:1341-1367) also reports what the batcher did with it: the
+            # figures tritonserver kept per model behind :8002/metrics, here per request on the reference's stats channel
+            info = {}
+            outs = await self._next_batcher().submit_async(arrays, rows, info)
+            collect_custom_statistics_fn({"_b200_batch_rows": info.get("batch_rows", 0),
+                                          "_b200_queue_us": round(info.get("queue_us", 0.0), 1),
+                                          "_b200_exec_us": round(info.get("exec_us", 0.0), 1)})
         return self._unmarshal(outs)
 
     def process_sync(self, data, timeout=None):

@@ -41,10 +41,12 @@ class ReplicaSet(object):
     def snapshot_stats(self):
         per = [r.batcher.snapshot_stats() for r in self.replicas]
         tot = dict(replicas=len(per), devices=[r.device for r in self.replicas])
-        for k in ("batches", "requests", "rows", "queue_delay_us_sum"):
-            tot[k] = sum(p[k] for p in per)
+        for k in ("batches", "requests", "rows", "failed_requests", "queue_delay_us_sum", "exec_us_sum", "in_bytes", "out_bytes"):
+            tot[k] = sum(p.get(k, 0) for p in per)
+        tot["batch_rows_hist"] = [sum(col) for col in zip(*[p["batch_rows_hist"] for p in per])] if per else []
         tot["max_batch_rows"] = max(p["max_batch_rows"] for p in per)
         tot["mean_batch_rows"] = tot["rows"] / tot["batches"] if tot["batches"] else 0.0
+        tot["mean_exec_us"] = tot["exec_us_sum"] / tot["batches"] if tot["batches"] else 0.0
         tot["mean_queue_delay_us"] = tot["queue_delay_us_sum"] / tot["requests"] if tot["requests"] else 0.0
         tot["per_replica_requests"] = [p["requests"] for p in per]
         return tot

@@ -19,6 +19,7 @@ copies each request's rows out of the slot and resolves the futures -- one
 `loop.call_soon_threadsafe` per event loop per batch.
 """
 import asyncio
+import bisect
 import collections
 import concurrent.futures
 import re
@@ -96,7 +97,7 @@ def _parse_pbtxt(text):
 
 
 class _Request(object):
-    __slots__ = ("inputs", "rows", "t_enq", "loop", "afuture", "cfuture")
+    __slots__ = ("inputs", "rows", "t_enq", "loop", "afuture", "cfuture", "info")
 
     def __init__(self, inputs, rows):
         self.inputs = inputs
@@ -105,6 +106,7 @@ class _Request(object):
         self.loop = None
         self.afuture = None
         self.cfuture = None
+        self.info = None   # optional dict the caller wants filled with this request's batch figures (sampled statistics)
 
 
 def _resolve_many(pairs):
@@ -115,6 +117,9 @@ def _resolve_many(pairs):
             fut.set_exception(exc)
         else:
             fut.set_result(result)
+
+
+BATCH_ROWS_BUCKETS = (1, 2, 4, 8, 16, 32, 64, 128, 256)   # histogram upper bounds (le), + one overflow bucket
 
 
 class DynamicBatcher(object):
@@ -140,7 +145,9 @@ class DynamicBatcher(object):
         self._running = True
         self._fatal = None
         # counters (what tritonserver's :8002/metrics used to expose for the model)
-        self.stats = dict(batches=0, requests=0, rows=0, queue_delay_us_sum=0.0, max_batch_rows=0)
+        self.stats = dict(batches=0, requests=0, rows=0, failed_requests=0, queue_delay_us_sum=0.0, exec_us_sum=0.0,
+                          in_bytes=0, out_bytes=0, max_batch_rows=0,
+                          batch_rows_hist=[0] * (len(BATCH_ROWS_BUCKETS) + 1))
         self._dispatch_thread = threading.Thread(target=self._dispatch_loop, name="b2s-dispatch-" + name, daemon=True)
         self._complete_thread = threading.Thread(target=self._complete_loop, name="b2s-complete-" + name, daemon=True)
         self._dispatch_thread.start()
@@ -158,17 +165,20 @@ class DynamicBatcher(object):
             self._queued_rows += req.rows
             self._cond.notify()
 
-    def submit_async(self, inputs, rows):
-        """Called on an asyncio loop; returns an awaitable future of the list of output arrays."""
+    def submit_async(self, inputs, rows, info=None):
+        """Called on an asyncio loop; returns an awaitable future of the list of output arrays.  `info`: a dict that
+        receives this request's batch_rows / queue_us / exec_us before the future resolves."""
         req = _Request(inputs, rows)
+        req.info = info
         req.loop = asyncio.get_running_loop()
         req.afuture = req.loop.create_future()
         self._enqueue(req)
         return req.afuture
 
-    def submit(self, inputs, rows):
+    def submit(self, inputs, rows, info=None):
         """Thread-safe synchronous-style submission; returns a concurrent.futures.Future."""
         req = _Request(inputs, rows)
+        req.info = info
         req.cfuture = concurrent.futures.Future()
         self._enqueue(req)
         return req.cfuture
@@ -227,6 +237,7 @@ class DynamicBatcher(object):
             batch = self._take_batch()
             if batch is None:
                 break
+            self.stats["requests"] += len(batch)   # every request taken off the queue; failures are counted on top
             try:
                 slot = self._acquire_slot()
                 n_rows = 0
@@ -258,13 +269,19 @@ class DynamicBatcher(object):
                 ev = self.stream.submit(slot, n_rows, offsets)
                 st = self.stats
                 st["batches"] += 1
-                st["requests"] += len(batch)
                 st["rows"] += n_rows
                 st["queue_delay_us_sum"] += sum((t_disp - r.t_enq) for r in batch) * 1e6
+                st["in_bytes"] += sum(a.nbytes for r in batch for a in r.inputs)
                 if n_rows > st["max_batch_rows"]:
                     st["max_batch_rows"] = n_rows
+                st["batch_rows_hist"][bisect.bisect_left(BATCH_ROWS_BUCKETS, n_rows)] += 1
+                for r in batch:
+                    if r.info is not None:
+                        r.info["batch_rows"] = n_rows
+                        r.info["queue_us"] = (t_disp - r.t_enq) * 1e6
+                        r.info["t_dispatch"] = t_disp
                 with self._inflight_cond:
-                    self._inflight.append((ev, slot, batch))
+                    self._inflight.append((ev, slot, batch, t_disp))
                     self._inflight_cond.notify()
             except Exception as ex:  # a failed batch fails only its own requests
                 self._fail(batch, ex)
@@ -290,9 +307,14 @@ class DynamicBatcher(object):
                     if not self._running:
                         break
                     continue
-                ev, slot, batch = self._inflight.popleft()
+                ev, slot, batch, t_disp = self._inflight.popleft()
             try:
                 self.stream.wait(ev)
+                exec_us = (time.perf_counter() - t_disp) * 1e6   # collate hand-off -> results in the pinned slot
+                self.stats["exec_us_sum"] += exec_us
+                for r in batch:
+                    if r.info is not None:
+                        r.info["exec_us"] = exec_us
                 # one copy per output per batch out of the pinned slot; requests get row views of it
                 n_rows = sum(r.rows for r in batch)
                 outs = [slot.outputs[o][:n_rows].copy() for o in range(m.n_outputs)]
@@ -301,6 +323,7 @@ class DynamicBatcher(object):
                 for r in batch:
                     results.append([out[row:row + r.rows] for out in outs])
                     row += r.rows
+                self.stats["out_bytes"] += sum(o.nbytes for o in outs)
                 self.stream.release(slot)
                 with self._inflight_cond:
                     self._inflight_cond.notify_all()
@@ -332,6 +355,7 @@ class DynamicBatcher(object):
     def _fail(self, batch, ex):
         if not isinstance(ex, Exception):
             ex = ValueError(str(ex))
+        self.stats["failed_requests"] += len(batch)
         self._resolve(batch, None, ex)
 
     # ------------------------------------------------------------------ lifetime
@@ -356,6 +380,8 @@ class DynamicBatcher(object):
 
     def snapshot_stats(self):
         st = dict(self.stats)
+        st["batch_rows_hist"] = list(st["batch_rows_hist"])
+        st["mean_exec_us"] = st["exec_us_sum"] / st["batches"] if st["batches"] else 0.0
         st["mean_batch_rows"] = st["rows"] / st["batches"] if st["batches"] else 0.0
         st["mean_queue_delay_us"] = st["queue_delay_us_sum"] / st["requests"] if st["requests"] else 0.0
         return st
