@@ -209,16 +209,31 @@ class LlmEngine(object):
                 raise ValueError("generate: prompt of {} tokens + {} new exceeds max_ctx {}".format(
                     len(p), max_new_tokens, self.max_ctx))
 
-    def generate(self, prompts, max_new_tokens, use_graph=True):
-        """prompts: list of token-id sequences -> int32 array [len(prompts), max_new_tokens]"""
+    def generate(self, prompts, max_new_tokens, use_graph=True, on_progress=None, chunk=8):
+        """prompts: list of token-id sequences -> int32 array [len(prompts), max_new_tokens].
+        `on_progress(first_prompt_index, tokens[n_wave, n_done])`, when given, is called after the prefill (one token per
+        sequence) and after every `chunk` decode steps: the same kernels, the step loop just comes up for air (one
+        stream synchronisation per chunk) so that a serving front end can stream tokens while the wave runs."""
         max_new_tokens = int(max_new_tokens)
         self._check(prompts, max_new_tokens)
         out = np.empty((len(prompts), max_new_tokens), dtype=np.int32)
         for w0 in range(0, len(prompts), self.max_batch):
             wave = prompts[w0:w0 + self.max_batch]
             self.llm.prefill(wave)
-            self.llm.decode(max_new_tokens - 1, use_graph=use_graph)
+            if on_progress is None:
+                self.llm.decode(max_new_tokens - 1, use_graph=use_graph)
+            else:
+                done, chunk = 1, max(1, int(chunk))
+                on_progress(w0, self.llm.tokens(done))
+                while done < max_new_tokens:
+                    n = min(chunk, max_new_tokens - done)
+                    self.llm.decode(n, use_graph=use_graph)
+                    done += n
+                    if done < max_new_tokens:
+                        on_progress(w0, self.llm.tokens(done))
             out[w0:w0 + len(wave)] = self.llm.tokens(max_new_tokens)
+            if on_progress is not None:
+                on_progress(w0, out[w0:w0 + len(wave)])
         return out
 
     def close(self):

@@ -8,7 +8,8 @@ and async flags.  What replaces vLLM underneath:
 
   * `WaveBatcher`   -- per-endpoint request queue: collects up to `max_batch` prompts (or until
                        `max_queue_delay_microseconds` after the first one), runs ONE prefill + CUDA-graph decode
-                       wave on the engine thread, completes the callers' futures.  (Static waves; continuous
+                       wave on the engine thread, completes the callers' futures; `"stream": true` requests get
+                       their tokens every few decode steps as server-sent events.  (Static waves; continuous
                        batching is the next item of SURVEY.md section 8f.)
   * `TensorParallelLeader` / `follower_loop` -- with tensor_parallel_size 2 the serving process is rank 0; rank 1
                        is a worker process that replays every engine call (torchrun starts both,
@@ -38,21 +39,24 @@ __version__ = "0.1"
 
 
 class _Request(object):
-    __slots__ = ("prompt", "max_tokens", "future", "t_enqueue")
+    __slots__ = ("prompt", "max_tokens", "future", "t_enqueue", "on_tokens", "sent")
 
-    def __init__(self, prompt, max_tokens):
+    def __init__(self, prompt, max_tokens, on_tokens=None):
         self.prompt = prompt
         self.max_tokens = int(max_tokens)
         self.future = Future()
         self.t_enqueue = time.perf_counter()
+        self.on_tokens = on_tokens   # streaming: called on the engine thread with (new token ids, finished)
+        self.sent = 0
 
 
 class WaveBatcher(object):
     """Timeout / max-batch scheduler for generation requests (the Triton dynamic-batcher keys of
     `triton_helper.create_config_pbtxt`, triton_helper.py:291-409, applied to prompt waves)."""
 
-    def __init__(self, engine, max_batch, max_queue_delay_us=2000, name="llm"):
+    def __init__(self, engine, max_batch, max_queue_delay_us=2000, name="llm", stream_chunk=8):
         self.engine = engine
+        self.stream_chunk = int(stream_chunk)   # decode steps between two deliveries to streaming clients
         self.max_batch = int(max_batch)
         self.delay_s = max(0.0, float(max_queue_delay_us) * 1e-6)
         self._cv = threading.Condition()
@@ -62,8 +66,8 @@ class WaveBatcher(object):
         self._thread = threading.Thread(target=self._run, name="b2s-llm-" + name, daemon=True)
         self._thread.start()
 
-    def submit(self, prompt, max_tokens):
-        r = _Request(prompt, max_tokens)
+    def submit(self, prompt, max_tokens, on_tokens=None):
+        r = _Request(prompt, max_tokens, on_tokens)
         with self._cv:
             if self._closed:
                 raise RuntimeError("llm endpoint is shutting down")
@@ -94,7 +98,16 @@ class WaveBatcher(object):
             t0 = time.perf_counter()
             try:
                 n_new = max(r.max_tokens for r in wave)
-                out = self.engine.generate([r.prompt for r in wave], n_new)
+                if any(r.on_tokens is not None for r in wave):
+                    def progress(w0, toks, wave=wave):   # engine thread: hand every streaming caller its new tokens
+                        for i, r in enumerate(wave[w0:w0 + len(toks)]):
+                            upto = min(toks.shape[1], r.max_tokens)
+                            if r.on_tokens is not None and upto > r.sent:
+                                r.on_tokens([int(t) for t in toks[i, r.sent:upto]], upto == r.max_tokens)
+                                r.sent = upto
+                    out = self.engine.generate([r.prompt for r in wave], n_new, on_progress=progress, chunk=self.stream_chunk)
+                else:
+                    out = self.engine.generate([r.prompt for r in wave], n_new)
                 for i, r in enumerate(wave):
                     r.future.set_result(np.array(out[i, :r.max_tokens]))
             except Exception as ex:  # noqa -- every caller of the wave sees the engine error (mapped to 422 / restart)
@@ -130,9 +143,11 @@ class TensorParallelLeader(object):
         import torch.distributed as dist
         dist.broadcast_object_list([msg], src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
 
-    def generate(self, prompts, max_new_tokens):
-        self._announce(("generate", [np.asarray(p, np.int32) for p in prompts], int(max_new_tokens)))
-        return self.engine.generate(prompts, max_new_tokens)
+    def generate(self, prompts, max_new_tokens, on_progress=None, chunk=8):
+        # the follower chunks its decode loop the same way, so both ranks synchronise at the same steps
+        self._announce(("generate", [np.asarray(p, np.int32) for p in prompts], int(max_new_tokens),
+                        int(chunk) if on_progress is not None else 0))
+        return self.engine.generate(prompts, max_new_tokens, on_progress=on_progress, chunk=chunk)
 
     def close(self):
         self._announce(("close",))
@@ -147,7 +162,8 @@ def follower_loop(engine, group=None):
         dist.broadcast_object_list(box, src=src, group=group)
         msg = box[0]
         if msg[0] == "generate":
-            engine.generate(msg[1], msg[2])
+            chunk = msg[3] if len(msg) > 3 else 0
+            engine.generate(msg[1], msg[2], on_progress=(lambda w0, toks: None) if chunk else None, chunk=chunk or 8)
         elif msg[0] == "close":
             engine.close()
             return
@@ -273,10 +289,50 @@ class B200LlmPreprocessRequest(BasePreprocessRequest):
             raise ValueError("prompt token ids must be in [0, {})".format(self._spec.vocab_size))
         return ids.astype(np.int32)
 
-    async def _generate(self, prompts, max_tokens):
+    def _check_len(self, prompts, max_tokens):
         for p in prompts:
             if len(p) + max_tokens > self._max_ctx:
                 raise ValueError("prompt ({} tokens) + max_tokens ({}) exceeds max_model_len {}".format(len(p), max_tokens, self._max_ctx))
+
+    def _stream(self, prompts, max_tokens, make_chunk):
+        """Server-sent events for `"stream": true` (the reference hands vLLM's generator to a StreamingResponse,
+        preprocess_service.py:1219-1234 / :1262-1277): one `data: {chunk}` event per delivery of the wave's decode loop and
+        per prompt, `finish_reason` on a prompt's last one, then `data: [DONE]`.  `make_chunk(index, token_ids, text,
+        finish_reason)` builds the OpenAI chunk object; text is the newly completed suffix of the decoded output."""
+        import json
+        from starlette.responses import StreamingResponse
+        self._check_len(prompts, max_tokens)
+        loop = asyncio.get_running_loop()
+        queue = asyncio.Queue()
+        futs = []
+        for i, p in enumerate(prompts):
+            def on_tokens(toks, finished, i=i):
+                loop.call_soon_threadsafe(queue.put_nowait, (i, toks, finished, None))
+            f = self._batcher.submit(p, max_tokens, on_tokens)
+            f.add_done_callback(lambda f, i=i: f.exception() is not None and
+                                loop.call_soon_threadsafe(queue.put_nowait, (i, [], True, f.exception())))
+            futs.append(f)
+
+        async def events():
+            open_prompts, seen, texts = len(prompts), [[] for _ in prompts], ["" for _ in prompts]
+            while open_prompts:
+                i, toks, finished, err = await queue.get()
+                if err is not None:
+                    yield "data: " + json.dumps(dict(error=dict(message=str(err), type=type(err).__name__))) + "\n\n"
+                    break
+                seen[i].extend(toks)
+                text = ""
+                if self._tokenizer is not None:
+                    full = self._tokenizer.decode(seen[i])
+                    if finished or not full.endswith("\ufffd"):   # hold back an incomplete multi-token character
+                        text, texts[i] = full[len(texts[i]):], full
+                yield "data: " + json.dumps(make_chunk(i, toks, text, "length" if finished else None)) + "\n\n"
+                open_prompts -= 1 if finished else 0
+            yield "data: [DONE]\n\n"
+        return StreamingResponse(content=events(), media_type="text/event-stream")
+
+    async def _generate(self, prompts, max_tokens):
+        self._check_len(prompts, max_tokens)
         futs = [asyncio.wrap_future(self._batcher.submit(p, max_tokens)) for p in prompts]
         return await asyncio.gather(*futs)
 
@@ -290,6 +346,11 @@ class B200LlmPreprocessRequest(BasePreprocessRequest):
         max_tokens = 16 if body.get("max_tokens") is None else int(body["max_tokens"])   # OpenAI default
         if max_tokens < 1:
             raise ValueError("completions: max_tokens must be >= 1")
+        if body.get("stream"):
+            cid, created, model = "cmpl-" + uuid.uuid4().hex, int(time.time()), body.get("model") or self._model_name
+            return self._stream(prompts, max_tokens, lambda i, toks, text, fin: dict(
+                id=cid, object="text_completion", created=created, model=model,
+                choices=[dict(index=i, text=text, token_ids=toks, logprobs=None, finish_reason=fin)]))
         outs = await self._generate(prompts, max_tokens)
         choices = []
         for i, toks in enumerate(outs):
@@ -309,6 +370,17 @@ class B200LlmPreprocessRequest(BasePreprocessRequest):
             raise ValueError("chat completions need a tokenizer with a chat template (Preprocess.load() -> {'tokenizer': ...})")
         ids = self._tokenizer.apply_chat_template(body.get("messages") or [], add_generation_prompt=True, tokenize=True)
         max_tokens = int(body.get("max_tokens") or body.get("max_completion_tokens") or 16)
+        if body.get("stream"):
+            cid, created, model = "chatcmpl-" + uuid.uuid4().hex, int(time.time()), body.get("model") or self._model_name
+            first = [True]
+
+            def chunk(i, toks, text, fin):
+                delta = dict(content=text)
+                if first[0]:
+                    delta["role"], first[0] = "assistant", False
+                return dict(id=cid, object="chat.completion.chunk", created=created, model=model,
+                            choices=[dict(index=0, delta=delta, token_ids=toks, finish_reason=fin)])
+            return self._stream([self._encode(ids)], max_tokens, chunk)
         toks = [int(t) for t in (await self._generate([self._encode(ids)], max_tokens))[0]]
         msg = dict(role="assistant", content=self._tokenizer.decode(toks))
         return dict(id="chatcmpl-" + uuid.uuid4().hex, object="chat.completion", created=int(time.time()),

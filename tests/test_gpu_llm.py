@@ -210,3 +210,39 @@ def test_plugin_completions_match_direct_engine(native):
     finally:
         direct.close()
     assert got == want.tolist()
+
+
+def test_streamed_generation_is_the_same_tokens(native):
+    """"stream": true (server-sent events, llm_service._stream): the decode loop is cut into chunks of a few steps with a
+    synchronisation in between -- every delivery is a prefix of, and the deliveries add up to, the un-streamed answer"""
+    import asyncio
+    import json
+    from clearml_serving_b200 import llm_service as S
+    from clearml_serving_b200.endpoints import ModelEndpoint
+    arch = dict(vocab_size=SPEC.vocab_size, hidden_size=SPEC.hidden_size, intermediate_size=SPEC.intermediate_size,
+                num_hidden_layers=SPEC.num_hidden_layers, num_attention_heads=SPEC.num_attention_heads,
+                num_key_value_heads=SPEC.num_key_value_heads, head_dim=128, rope_theta=SPEC.rope_theta, rms_norm_eps=SPEC.rms_norm_eps)
+    ep = ModelEndpoint(engine_type="b200_llm", serving_url="tiny", auxiliary_cfg={
+        "b200.llm": {"architecture": arch, "load_format": "dummy", "seed": 5, "init_std": 0.05, "max_batch": 4, "max_model_len": 128},
+        "dynamic_batching": {"max_queue_delay_microseconds": 20000}})
+    rng = np.random.default_rng(3)
+    prompts = [rng.integers(0, SPEC.vocab_size, n).tolist() for n in (9, 40)]
+    eng = S.B200LlmPreprocessRequest(ep)
+    try:
+        async def run():
+            plain = await eng.v1_completions({"prompt": prompts, "max_tokens": 21}, {}, None)
+            resp = await eng.v1_completions({"prompt": prompts, "max_tokens": 21, "stream": True}, {}, None)
+            text = ""
+            async for ev in resp.body_iterator:
+                text += ev
+            return plain, text
+        plain, text = asyncio.run(run())
+        events = [e[len("data: "):] for e in text.split("\n\n") if e.startswith("data: ")]
+        assert events[-1] == "[DONE]"
+        chunks = [json.loads(e)["choices"][0] for e in events[:-1]]
+        for i in (0, 1):
+            mine = [c for c in chunks if c["index"] == i]
+            assert len(mine) >= 3 and mine[-1]["finish_reason"] == "length"
+            assert sum((c["token_ids"] for c in mine), []) == plain["choices"][i]["token_ids"]
+    finally:
+        eng.unload()

@@ -26,11 +26,17 @@ class FakeLlm(object):
             vocab_size = vocab
         self.spec = _Spec()
 
-    def generate(self, prompts, n):
+    def generate(self, prompts, n, on_progress=None, chunk=8):
         assert len(prompts) <= self.max_batch
         self.waves.append((len(prompts), n))
         time.sleep(self.latency_s)
-        return np.array([[(int(np.sum(p)) + j) % 1000 for j in range(n)] for p in prompts], dtype=np.int32)
+        out = np.array([[(int(np.sum(p)) + j) % 1000 for j in range(n)] for p in prompts], dtype=np.int32)
+        if on_progress is not None:   # like LlmEngine.generate: after the prefill, then every `chunk` steps, then the end
+            self.progress_calls = 0
+            for done in [1] + list(range(1 + chunk, n, chunk)) + [n]:
+                on_progress(0, out[:, :done])
+                self.progress_calls += 1
+        return out
 
     def close(self):
         self.closed = True
@@ -59,7 +65,7 @@ def test_wave_batcher_timeout_dispatches_partial_wave_and_propagates_errors():
         assert b.submit(np.array([5]), 3).result(timeout=5).tolist() == [5, 6, 7]
         assert time.perf_counter() - t0 < 1.0 and eng.waves == [(1, 3)]
 
-        def boom(prompts, n):
+        def boom(prompts, n, **kw):
             raise ValueError("CUDA out of memory. injected")
         eng.generate = boom
         with pytest.raises(ValueError, match="CUDA out of memory. "):     # the text the reference restarts on
@@ -183,5 +189,73 @@ def test_concurrent_clients_share_waves(monkeypatch):
         rs = asyncio.run(run())
         assert [r["choices"][0]["token_ids"] for r in rs] == [[i, i + 1] for i in range(8)]
         assert len(fake.waves) <= 4 and sum(n for n, _ in fake.waves) == 8
+    finally:
+        eng.unload()
+
+
+def _sse(text):
+    import json
+    events = [e[len("data: "):] for e in text.split("\n\n") if e.startswith("data: ")]
+    assert events[-1] == "[DONE]"
+    return [json.loads(e) for e in events[:-1]]
+
+
+def test_streaming_completions_over_the_openai_route(monkeypatch):
+    """"stream": true -> server-sent events (reference: StreamingResponse around the vLLM generator, ps.py:1262-1277):
+    tokens arrive in deliveries of the wave's decode loop, per prompt, and add up to the non-streamed answer"""
+    from starlette.testclient import TestClient
+    from clearml_serving_b200.main import create_app
+    eng, fake = _engine(monkeypatch, tokenizer=_Tok())
+    p = ModelRequestProcessor()
+    p._endpoints["llama"] = eng.model_endpoint
+    p._engine_processor_lookup["llama"] = eng
+    client = TestClient(create_app(p), raise_server_exceptions=False)
+    try:
+        body = {"model": "llama", "prompt": [[1, 2, 3], [10]], "max_tokens": 20}
+        whole = client.post("/serve/openai/v1/completions", json=body).json()
+        r = client.post("/serve/openai/v1/completions", json=dict(body, stream=True))
+        assert r.status_code == 200 and r.headers["content-type"].startswith("text/event-stream")
+        chunks = _sse(r.text)
+        assert all(c["object"] == "text_completion" and len(c["choices"]) == 1 for c in chunks)
+        for i in (0, 1):
+            mine = [c["choices"][0] for c in chunks if c["choices"][0]["index"] == i]
+            assert len(mine) >= 3                                           # prefill token, decode chunks, the tail
+            assert sum((m["token_ids"] for m in mine), []) == whole["choices"][i]["token_ids"]
+            assert "".join(m["text"] for m in mine) == whole["choices"][i]["text"]
+            assert [m["finish_reason"] for m in mine[:-1]] == [None] * (len(mine) - 1) and mine[-1]["finish_reason"] == "length"
+        assert len({c["id"] for c in chunks}) == 1 and fake.progress_calls >= 3
+        # chat: role on the first delta only, content adds up
+        rc = client.post("/serve/openai/v1/chat/completions", json={"model": "llama", "stream": True, "max_tokens": 12,
+                                                                    "messages": [{"role": "user", "content": "hi"}]})
+        cc = _sse(rc.text)
+        assert cc[0]["object"] == "chat.completion.chunk" and cc[0]["choices"][0]["delta"]["role"] == "assistant"
+        assert all("role" not in c["choices"][0]["delta"] for c in cc[1:])
+        plain = client.post("/serve/openai/v1/chat/completions", json={"model": "llama", "max_tokens": 12,
+                                                                       "messages": [{"role": "user", "content": "hi"}]}).json()
+        assert "".join(c["choices"][0]["delta"]["content"] for c in cc) == plain["choices"][0]["message"]["content"]
+        # a request that cannot run is refused before any event is sent (422, like the non-streamed form)
+        bad = client.post("/serve/openai/v1/completions", json={"model": "llama", "prompt": list(range(60)), "max_tokens": 10,
+                                                                "stream": True})
+        assert bad.status_code == 422
+    finally:
+        p.shutdown()
+
+
+def test_streaming_and_plain_requests_share_a_wave(monkeypatch):
+    eng, fake = _engine(monkeypatch, max_batch=4)
+    fake.latency_s = 0.02
+    got = []
+
+    async def run():
+        resp = eng._stream([np.array([5], np.int32)], 10, lambda i, toks, text, fin: dict(t=toks, fin=fin))
+        plain = asyncio.ensure_future(eng.v1_completions({"prompt": [7], "max_tokens": 4}, {}, None))
+        async for ev in resp.body_iterator:
+            got.append(ev)
+        return await plain
+    try:
+        r = asyncio.run(run())
+        assert r["choices"][0]["token_ids"] == [7, 8, 9, 10]
+        toks = sum((e["t"] for e in _sse("".join(got))), [])
+        assert toks == list(range(5, 15)) and fake.waves == [(2, 10)]
     finally:
         eng.unload()
