@@ -76,8 +76,9 @@ def test_tensor_parallel_leader_and_follower_replay_the_same_calls(tmp_path):
         class Rec(object):
             def __init__(self):
                 self.calls, self.closed = [], False
-            def generate(self, prompts, n):
-                self.calls.append(([np.asarray(p).tolist() for p in prompts], int(n)))
+            def generate(self, prompts, n, on_progress=None, chunk=8):
+                # a streamed wave must be chunked alike on both ranks (they synchronise at the same decode steps)
+                self.calls.append(([np.asarray(p).tolist() for p in prompts], int(n), int(chunk) if on_progress else 0))
                 return np.zeros((len(prompts), n), np.int32)
             def close(self):
                 self.closed = True
@@ -89,7 +90,7 @@ def test_tensor_parallel_leader_and_follower_replay_the_same_calls(tmp_path):
         if rank == 0:
             lead = S.TensorParallelLeader(eng, group)
             lead.generate([[1, 2, 3], [4]], 5)
-            lead.generate([[9] * 7], 2)
+            lead.generate([[9] * 7], 2, on_progress=lambda w0, toks: None, chunk=4)
             lead.close()
         else:
             S.follower_loop(eng, group)
@@ -107,5 +108,5 @@ def test_tensor_parallel_leader_and_follower_replay_the_same_calls(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         res.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT ")][0][7:]))
-    assert res[0]["calls"] == res[1]["calls"] == [[[[1, 2, 3], [4]], 5], [[[9] * 7], 2]]
+    assert res[0]["calls"] == res[1]["calls"] == [[[[1, 2, 3], [4]], 5, 0], [[[9] * 7], 2, 4]]
     assert res[0]["closed"] and res[1]["closed"]
