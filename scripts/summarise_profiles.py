@@ -40,7 +40,7 @@ def launches():
             pass
     total = sum(sum(v) for v in agg.values())
     with open(os.path.join(OUT, "%s_launch_list_summary.txt" % tag), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 20 --warmup 3 --no-plugin\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 20 --warmup 3 --no-plugin --no-llama\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write("%-72s %7s %12s %12s %7s\n" % ("kernel", "count", "avg_ns", "total_ns", "share"))
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -48,7 +48,7 @@ def launches():
     print("launch list:", len(rows), "launches,", len(agg), "kernels")
 
 
-def full(name, cmd="python bench.py --steps 10 --warmup 3 --no-plugin"):
+def full(name, cmd="python bench.py --steps 6 --warmup 3 --no-plugin --no-llama", out_name=None):
     rep = os.path.join(SRC, "ncu_%s.ncu-rep" % name)
     if not os.path.exists(rep):
         return None
@@ -61,7 +61,7 @@ def full(name, cmd="python bench.py --steps 10 --warmup 3 --no-plugin"):
     for i, h in enumerate(hdr):
         if h in KEYS or h == "Kernel Name":
             out[h] = dict(unit=units[i], values=[r[i] for r in rows[2:]])
-    with open(os.path.join(OUT, "%s_ncu_%s.txt" % (tag, name)), "w") as f:
+    with open(os.path.join(OUT, "%s_ncu_%s.txt" % (tag, out_name or name)), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on -k regex:%s (%s)\n" % (name, cmd))
         for k, v in out.items():
             f.write("%-80s %-14s %s\n" % (k, v["unit"], " | ".join(x[:60] for x in v["values"])))
@@ -71,8 +71,10 @@ def full(name, cmd="python bench.py --steps 10 --warmup 3 --no-plugin"):
 def main():
     os.makedirs(OUT, exist_ok=True)
     launches()
-    for name in ("forest_staged", "gemm_tn_persistent", "attention_varlen", "layernorm_kernel", "embed_layernorm"):
-        o = full(name)
+    for name in ("forest_staged", "gemm_tn_persistent", "gemm_tn_pair", "attention_varlen", "layernorm_kernel", "embed_layernorm",
+                 "nchw_to_s2d", "maxpool3x3s2"):
+        # the pair-kernel capture of the LLM prefill shapes keeps its own file (scripts/gpu_llm_ncu.sh)
+        o = full(name, out_name="gemm_tn_pair_bert_resnet" if name == "gemm_tn_pair" else None)
         print(name, "ok" if o else "missing")
         if o and name == "forest_staged":
             try:
