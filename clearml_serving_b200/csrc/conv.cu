@@ -1,16 +1,16 @@
-// conv.cu -- data-movement kernels that turn a convolutional network (ResNet class, BASELINE.json
-// configs[2]) into GEMMs on the tcgen05 kernel of gemm.cu (K6 of SURVEY.md 2.2, first form):
-//   * activations are NHWC fp16 with channels padded to a multiple of 8 (16-byte pixels), so a 1x1
-//     stride-1 convolution IS `gemm_tn` on the activation matrix [N*H*W, C] with the weight [Cout, C];
-//   * every other convolution (7x7 stem, 3x3, strided 1x1) gathers its receptive fields into a
-//     [N*OH*OW, KH*KW*C] matrix (im2col, 128-bit moves, zero padding folded in) and runs the same GEMM
-//     with BatchNorm folded into weight/bias and bias + ReLU (+ residual) fused in the epilogue;
+// conv.cu -- data-movement kernels around the convolutions of a ResNet-class network (BASELINE.json configs[2]); the
+// convolutions themselves run on the tcgen05 GEMM kernels of gemm.cu (K6 of SURVEY.md 2.2):
+//   * activations are NHWC fp16 with channels padded to a multiple of 8 (16-byte pixels), so a 1x1 stride-1
+//     convolution IS `gemm_tn` on the activation matrix [N*H*W, C] with the weight [Cout, C];
+//   * 3x3 / strided convolutions are implicit GEMMs: im2col-mode TMA gathers the A tiles from the NHWC tensor
+//     (gemm.cu: make_tmap_im2col_nhwc), BatchNorm folded into weight/bias, bias + ReLU (+ residual) in the epilogue;
+//   * the 7x7 stride-2 stem over the request pixels becomes a 4x4 stride-1 convolution over the 2x2 space-to-depth
+//     image written by nchw_to_s2d_kernel here (gemm.cu: make_tmap_stem_s2d);
+//   * im2col_nhwc_kernel materialises patch matrices for the comparison form only (pack_resnet(implicit_conv=False),
+//     convolutions the TMA forms do not cover: input channels not a multiple of 64 outside the stem);
 //   * max-pool / global average pool are plain coalesced NHWC kernels.
 // This is what tritonserver's libtorch backend does with cuDNN for the reference's pytorch endpoint
 // (clearml_serving/engines/triton/triton_helper.py:166-168,382-383; examples/pytorch).
-// The explicit im2col costs one extra write+read of the patch matrix (HBM-bound, ~50 MB per image for
-// ResNet-50); the implicit form (4-D TMA boxes feeding the UMMA mainloop directly) is the planned
-// replacement -- see DESIGN.md section 7.
 #include "common.cuh"
 
 #include <cuda_fp16.h>
