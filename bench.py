@@ -243,14 +243,18 @@ def _plugin_metrics(forest, device, seconds=2.0, lam=2000.0):
     """requests/s + latency through B200PreprocessRequest.process (the reference-facing plugin API)."""
     from clearml_serving_b200 import BasePreprocessRequest, ModelEndpoint, formats
     packed = formats.pack_forest(forest, "xgb", base=0.5)
-    ep = ModelEndpoint(engine_type="b200", serving_url="bench_xgb",
-                       auxiliary_cfg={"max_batch_size": MAX_BATCH, "dynamic_batching.max_queue_delay_microseconds": 1000,
-                                      "b200.device": device})
     cls = BasePreprocessRequest.get_engine_cls("b200")
-    eng = cls.__new__(cls)
-    BasePreprocessRequest.__init__(eng, model_endpoint=ep, task=None)
-    eng._model = packed
-    eng._b200_setup()
+
+    def make_engine(delay_us):
+        ep = ModelEndpoint(engine_type="b200", serving_url="bench_xgb",
+                           auxiliary_cfg={"max_batch_size": MAX_BATCH, "dynamic_batching.max_queue_delay_microseconds": delay_us,
+                                          "b200.device": device})
+        e = cls.__new__(cls)
+        BasePreprocessRequest.__init__(e, model_endpoint=ep, task=None)
+        e._model = packed
+        e._b200_setup()
+        return e
+    eng = make_engine(1000)
     rng = np.random.default_rng(3)
     X = rng.standard_normal((4096, 1, N_FEATURES)).astype(np.float32)
     out = {}
@@ -300,6 +304,15 @@ def _plugin_metrics(forest, device, seconds=2.0, lam=2000.0):
         st = eng.engine_stats()
         out["mean_batch_rows"] = st["mean_batch_rows"]
         out["policy"] = repr(eng._policy)
+    finally:
+        eng.unload()
+    # the same arrival process with Triton's default queue delay (0: dispatch whatever is queued as soon as a lane is
+    # free): the latency floor of the path, without the 1 ms the policy above spends waiting for batch-mates
+    eng = make_engine(0)
+    try:
+        asyncio.run(closed_loop(16))  # warm-up
+        out["poisson_no_queue_delay"] = asyncio.run(open_loop())
+        out["poisson_no_queue_delay"]["mean_batch_rows"] = eng.engine_stats()["mean_batch_rows"]
     finally:
         eng.unload()
     return out

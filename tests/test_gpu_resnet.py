@@ -86,3 +86,45 @@ def test_resnet_uint8_input(gpu_native):
     got = _run(gpu_native, formats.pack_resnet(m, input_dtype="uint8", image_hw=(64, 64)), x, 4)
     err = np.abs(got - ref).max() / np.abs(ref).max()
     assert err <= 2e-3, "relative error {:.2e} (uint8 pixels up to 255 feed fp16 activations)".format(err)
+
+
+def test_large_batch_collate_pool_matches_small_batches(gpu_native):
+    """b2s_infer_batch collates batches >= 2 MB with the worker pool, group by group, with the host->device copy of a
+    group enqueued while the next one is gathered (csrc/api.cu): a 41-request batch of 128x128 fp32 images (15.7 MB;
+    requests of 1, 2 and 3 images, so group boundaries fall inside and between requests) must give exactly the rows the
+    same images give in small single-threaded batches"""
+    import torch
+    import torchvision
+    from clearml_serving_b200 import formats
+    native = gpu_native
+    torch.manual_seed(1)
+    m = _realistic_bn(torchvision.models.resnet18(weights=None, num_classes=10))
+    pm = formats.pack_resnet(m, image_hw=(128, 128))
+    rng = np.random.default_rng(3)
+    sizes = [1 + (i % 3) for i in range(40)] + [1]    # 41 requests, 80 images
+    assert sum(sizes) == 80
+    x = rng.standard_normal((80, 3, 128, 128)).astype(np.float32)
+    model = native.Model(pm.kind, pm.blob, device=0)
+    st = native.Stream(model, 80, 0, 2)
+    try:
+        reqs, row = [], 0
+        for n in sizes:
+            reqs.append([x[row:row + n]])
+            row += n
+        for _ in range(2):                             # twice: the slot's copy bookkeeping is reset between uses
+            ev, outs, keep = st.infer_batch(reqs)
+            st.wait(ev)
+            big = np.concatenate([o[0] for o in outs])
+        assert big.shape == (80, 10)
+        small = []
+        for i in range(0, 80, 2):                      # 2 x 196 KB per batch: the single-threaded path
+            ev, outs, keep = st.infer_batch([[x[i:i + 2]]])
+            st.wait(ev)
+            small.append(outs[0][0].copy())
+        assert np.array_equal(big, np.concatenate(small))
+        with torch.no_grad():
+            ref = m(torch.from_numpy(x[:8])).numpy()
+        assert np.abs(big[:8] - ref).max() / np.abs(ref).max() <= REL_TOL
+    finally:
+        st.destroy()
+        model.free()
