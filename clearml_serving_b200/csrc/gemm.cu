@@ -25,6 +25,7 @@
 
 namespace b2s {
 static bool gemm_res_prefetch_enabled();
+static bool gemm_2sm_enabled(int K);
 static int prepare_tma_store(CUtensorMap *tc, GemmEpilogue &ep, int M, int N, int bn, const ConvGeom &cg);
 int nchw_to_s2d(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Hz, int Wz, void *out);   // conv.cu
 
@@ -448,7 +449,8 @@ __device__ __forceinline__ void broadcast32(const float4 &b, int chunk, float (&
 template <int HALF>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue &ep, const CUtensorMap *cmap, unsigned char *stage,
                                                   uint32_t t_addr, uint64_t *tmem_empty, int lane, int warp_row0, int M_tile,
-                                                  int N, int col_base, bool zmap, int z_row, int z_blk, const float4 &b4)
+                                                  int N, int col_base, bool zmap, int z_row, int z_blk, const float4 &b4,
+                                                  uint32_t tmem_empty_cluster = 0 /* 2-SM kernel: the LEADER's barrier */)
 {
     constexpr int NCH = HALF / 32;
     const uint32_t st = smem_u32(stage);
@@ -476,7 +478,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue &ep, const 
         if (c == NCH - 1) {   // last TMEM read of this warp: hand the accumulator back before the math
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
+            if (lane == 0) {
+                if (tmem_empty_cluster) mbar_arrive_cluster(tmem_empty_cluster);
+                else mbar_arrive(tmem_empty);
+            }
         }
         if (col0 >= N) continue;   // warp-uniform
         float f[32];
@@ -976,6 +981,198 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Kernel v4: the CTA pair as ONE tensor-core unit (tcgen05 cta_group::2).  In v3 each CTA of the pair still issues its
+// own 128 x 256 MMAs and reads A (16 KB) + the WHOLE weight tile (32 KB) from its shared memory per k-block: 96 B/clk of
+// operand reads next to 64 B/clk of TMA writes, on a 128 B/clk shared-memory port.  Here the leader CTA issues
+// 256 x 256 x 16 MMAs spanning both CTAs: each CTA keeps its 128 rows of A and its HALF of the weight tile (nothing is
+// multicast, 32 KB per stage, 6 stages), the hardware reads both halves in place and each CTA's tensor memory receives
+// its 128 accumulator rows.  Both CTAs' TMA loads complete bytes on the leader's full barrier; tcgen05.commit multicasts
+// "stage free" / "accumulator ready" to both CTAs; both CTAs' epilogue warps release the accumulator on the leader's barrier.
+// ---------------------------------------------------------------------------------------------
+template <int STAGES>
+struct G2smSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB: this CTA's 128 rows of A
+    static constexpr int B_BYTES = 128 * GEMM_BK * 2;       // 16 KB: this CTA's half (128 rows) of the 256-row weight tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int SCRATCH_OFFSET = BAR_OFFSET + 1024;
+    static constexpr int TOTAL = SCRATCH_OFFSET + 8 * 4096 + 1024;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_half,
+                   const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpilogue ep, int group_mp)
+{
+    constexpr int G2_BN = 256;
+    using S = G2smSmem<STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFFSET);   // used in the leader
+    uint64_t *empty_bar = full_bar + STAGES;                                   // both CTAs (commit multicast)
+    uint64_t *tmem_full_bar = empty_bar + STAGES;                              // both CTAs (commit multicast)
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;                              // leader: 16 epilogue warps of the pair
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+    unsigned char *epi_stage = smem + S::SCRATCH_OFFSET + (((threadIdx.x >> 5) - 4) & 7) * 4096;
+    uint32_t *epi_scratch = reinterpret_cast<uint32_t *>(epi_stage);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM, n_tiles = (N + G2_BN - 1) / G2_BN;
+    const int m_pairs = (m_tiles + 1) / 2;
+    const int total = m_pairs * n_tiles;            // pair-tiles
+    const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_a);
+        prefetch_tensormap(&tmap_b_half);
+        if (ep.tma_store) prefetch_tensormap(&tmap_c);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);    // the leader's producer arrives (with the byte count of BOTH CTAs' loads)
+            mbar_init(&empty_bar[s], 1);   // one multicast commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 16);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    cluster_arrive();   // peer barriers initialised / peer CTA resident before any remote arrive or paired instruction
+    cluster_wait();
+    if (warp == 2) {    // the same warp of BOTH CTAs: two accumulators of 256 columns in each CTA's tensor memory
+        tmem_alloc_2sm(tmem_slot, 2 * G2_BN);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = pair0; pt < total; pt += pair_stride) {
+                int mp, n_blk;
+                tile_coords(pt, m_pairs, n_tiles, group_mp, mp, n_blk);
+                const int m_blk = 2 * mp + (int)rank;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                    unsigned char *sb = sa + S::A_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+                    const uint32_t bar = mapa_rank(&full_bar[stage], 0);
+                    tma_load_2d_2sm(sa, &tmap_a, bar, kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d_2sm(sb, &tmap_b_half, bar, kb * GEMM_BK, n_blk * G2_BN + (int)rank * (G2_BN / 2));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc_f16 = make_idesc_f16(2 * GEMM_BM, G2_BN, 0);
+            constexpr uint32_t idesc_bf16 = make_idesc_f16(2 * GEMM_BM, G2_BN, 1);
+            const uint32_t idesc = ep.is_bf16 ? idesc_bf16 : idesc_f16;
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int pt = pair0; pt < total; pt += pair_stride) {
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * G2_BN);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    unsigned char *sa = smem + stage * S::STAGE_BYTES;
+                    unsigned char *sb = sa + S::A_BYTES;
+                    const uint64_t adesc = make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = make_sw128_kmajor_desc(sb);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16_2sm(d_tmem, desc_advance(adesc, k * 32), desc_advance(bdesc, k * 32), idesc,
+                                     (uint32_t)((kb | k) != 0));
+                    umma_commit_2sm(&empty_bar[stage], (uint16_t)0x3);   // frees the stage in BOTH CTAs
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full_bar[as], (uint16_t)0x3);      // accumulator ready, in BOTH CTAs
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int pt = pair0; pt < total; pt += pair_stride) {
+            int mp, n_blk;
+            tile_coords(pt, m_pairs, n_tiles, group_mp, mp, n_blk);
+            const int m_blk = 2 * mp + (int)rank;
+            constexpr int HALF = G2_BN / 2, NCH = HALF / 32;
+            if (ep.res_prefetch) {   // residual slab of this warp's next tile (and of its first one) into L2
+                if (pt == pair0)
+                    prefetch_residual_slab(ep, m_blk * GEMM_BM + q * 32 + lane, M, n_blk * G2_BN + half * HALF, HALF, N);
+                if (pt + pair_stride < total) {
+                    int mp2, n2;
+                    tile_coords(pt + pair_stride, m_pairs, n_tiles, group_mp, mp2, n2);
+                    prefetch_residual_slab(ep, (2 * mp2 + (int)rank) * GEMM_BM + q * 32 + lane, M, n2 * G2_BN + half * HALF, HALF, N);
+                }
+            }
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+            const int warp_row0 = m_blk * GEMM_BM + q * 32;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
+            const uint32_t release = mapa_rank(&tmem_empty_bar[as], 0);   // the leader counts all 16 warps of the pair
+            const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+            if (ep.act == ACT_SWIGLU) {   // (gate, up) chunk pairs, see epilogue_swiglu32
+#pragma unroll 1
+                for (int c = 0; c < NCH; c += 2) {
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32(t_addr + (uint32_t)(c * 32), g);
+                    tmem_ld_32x32(t_addr + (uint32_t)(c * 32 + 32), u);
+                    tmem_ld_wait();
+                    if (c == NCH - 2) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(release);
+                    }
+                    epilogue_swiglu32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, g, u, epi_scratch);
+                }
+            } else if (ep.tma_store) {
+                epilogue_tile_tma<HALF>(ep, &tmap_c, epi_stage, t_addr, &tmem_empty_bar[as], lane, warp_row0, M, N,
+                                        n_blk * G2_BN + half * HALF, false, 0, 0, b4, release);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    uint32_t v[32];
+                    float bv[32];
+                    tmem_ld_32x32(t_addr + (uint32_t)(c * 32), v);
+                    broadcast32(b4, c, bv);
+                    tmem_ld_wait();
+                    if (c == NCH - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(release);
+                    }
+                    epilogue_store32(ep, warp_row0, lane, n_blk * G2_BN + half * HALF + c * 32, M, N, v, bv, epi_scratch);
+                }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+        if (ep.tma_store && lane == 0) bulk_wait_group<0>();   // the staging tiles live in this CTA's shared memory
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_arrive();   // the leader's MMAs read this CTA's shared memory; peers arrive on each other's barriers
+    cluster_wait();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 2 * G2_BN);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side: tensor maps via the driver entry point (no link-time libcuda dependency)
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -1138,10 +1335,33 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtens
     epk.res_prefetch = ep.residual != nullptr && gemm_res_prefetch_enabled();
     CUtensorMap tc;
     B2S_TRY(prepare_tma_store(&tc, epk, M, N, 256, cg));
+    if (gemm_2sm_enabled(K) && cg.taps == 0 && !cg.s2d) {   // plain GEMM: the pair as one 256-row tensor-core unit
+        using S2 = G2smSmem<6>;
+        static std::once_flag once2;
+        static cudaError_t attr_err2 = cudaSuccess;
+        std::call_once(once2, []() {
+            attr_err2 = cudaFuncSetAttribute(gemm_tn_2sm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL);
+        });
+        if (attr_err2 != cudaSuccess) return fail_cuda(attr_err2, "cudaFuncSetAttribute(gemm 2sm)");
+        gemm_tn_2sm_kernel<6><<<2 * pairs, G2_THREADS, S2::TOTAL, st>>>(ta, tb_half, tc, M, N, K, epk, group_mp);
+        count_launch();
+        B2S_CUDA(cudaGetLastError());
+        return 0;
+    }
     gemm_tn_pair_kernel<4><<<2 * pairs, G2_THREADS, S::TOTAL, st>>>(ta, tb_half, tc, M, N, K, epk, group_mp, cg);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
+}
+
+// The 2-SM form wins where the mainloop dominates (Llama prefill, K = 4096 / 14336: 1268 -> 1367 TFLOP/s, 8192^3 1392 ->
+// 1495) and loses where the epilogue does (K = 768 with GELU, ResNet's K = 64..512 expansions: the leader's MMA stream
+// waits for the epilogue warps of BOTH CTAs, so the slower CTA paces the pair): by default it takes the deep-K GEMMs.
+// B2S_GEMM_2SM=0: never, =1: every plain GEMM (tests run the whole suite this way).
+static bool gemm_2sm_enabled(int K)
+{
+    static const int mode = []() { const char *e = getenv("B2S_GEMM_2SM"); return e ? atoi(e) : -1; }();
+    return mode < 0 ? K >= 2048 : mode != 0;
 }
 
 static bool gemm_res_prefetch_enabled()
