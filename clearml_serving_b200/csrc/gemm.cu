@@ -26,6 +26,7 @@
 namespace b2s {
 static bool gemm_res_prefetch_enabled();
 static bool gemm_2sm_enabled(int K);
+bool gemm_pair_enabled();
 static int prepare_tma_store(CUtensorMap *tc, GemmEpilogue &ep, int M, int N, int bn, const ConvGeom &cg);
 int nchw_to_s2d(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Hz, int Wz, void *out);   // conv.cu
 
@@ -1378,13 +1379,17 @@ bool gemm_pair_enabled()
 
 // 128 x 256 tiles move 1.5x fewer operand bytes per flop than 128 x 128, but on a persistent grid the
 // cost is waves x tile time: pick the shape with the smaller estimate.
-bool gemm_prefer_bn256(int M, int N)
+bool gemm_prefer_bn256(int M, int N, int K)
 {
     if (N < 256) return false;
     const int sms = g_num_sms(), mt = (M + GEMM_BM - 1) / GEMM_BM;
     const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+    // cost of a 128 x 128 tile relative to half a 128 x 256 one: 1.15 measured on the K = 768 shapes against the v3 pair
+    // kernel; against the 2-SM kernel (deep K) a 128 x 128 x 3072 tile takes 17.7 us where a CTA's 128 x 256 share of a
+    // pair-tile takes 19.9 us: 128-wide tiles are bound by shared-memory operand reads (8 KB per 64-cycle MMA)
+    const double f128 = (K > 0 && gemm_pair_enabled() && gemm_2sm_enabled(K)) ? 1.78 : 1.15;
     const double e256 = (double)((t256 + sms - 1) / sms) * 2.0;
-    const double e128 = (double)((t128 + sms - 1) / sms) * 1.15;
+    const double e128 = (double)((t128 + sms - 1) / sms) * f128;
     return e256 <= e128;
 }
 
@@ -1546,7 +1551,7 @@ int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t 
     if (ep.act == ACT_SWIGLU && (N % 64 != 0 || N < 128 || ep.out_f32 || ep.bias || ep.residual || (ep.ldc & 7)))
         return fail(B2S_ERR_INVALID, "gemm: SwiGLU epilogue needs N %% 64 == 0, N >= 128, 16-bit output, no bias / residual");
     CUtensorMap ta, tb;
-    const int bn = N <= 64 ? 64 : (gemm_prefer_bn256(M, N) ? 256 : 128);
+    const int bn = N <= 64 ? 64 : (gemm_prefer_bn256(M, N, K) ? 256 : 128);
     B2S_TRY(make_tmap_2d_kmajor(&ta, A, M, K, lda, GEMM_BM, ep.is_bf16));
     if (bn == 256 && gemm_pair_enabled()) {
         B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, 128, ep.is_bf16));
@@ -1603,7 +1608,7 @@ extern "C" B2S_API int b2s_op_conv(int device, void *cuda_stream, const void *x,
     ep.act_after = act_after;
     CUtensorMap ta, tb;
     B2S_TRY(make_tmap_im2col_nhwc(&ta, x, n_img, H, W, C, KS, stride, pad));
-    const bool bn256 = gemm_prefer_bn256(M, Cout);
+    const bool bn256 = gemm_prefer_bn256(M, Cout, 0);
     const bool pair = bn256 && gemm_pair_enabled();
     const int bn = Cout <= 64 ? 64 : (bn256 && !pair ? 256 : 128);
     B2S_TRY(make_tmap_2d_kmajor(&tb, w, Cout, K, K, bn, 0));

@@ -37,7 +37,7 @@ int make_tmap_2d_kmajor(CUtensorMap *out, const void *base, int64_t rows, int64_
 int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, int M, int N, int K,
                  const GemmEpilogue &ep);
 int gemm_bn_for(int N);
-bool gemm_prefer_bn256(int M, int N);
+bool gemm_prefer_bn256(int M, int N, int K);
 bool gemm_pair_enabled();
 int gemm_tn_maps_pair(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb_half, int M, int N, int K,
                       const GemmEpilogue &ep);
@@ -230,9 +230,10 @@ struct GraphModel : Model {
                 ep.out_f32 = op.a[8];
                 ep.is_bf16 = 0;
                 ep.act_after = op.a[9];
-                if (gemm_prefer_bn256(M, op.a[6]) && gemm_pair_enabled())
+                const bool wide = gemm_prefer_bn256(M, op.a[6], op.a[7]);
+                if (wide && gemm_pair_enabled())
                     B2S_TRY(gemm_tn_maps_pair(st, pl->amap[i], bmap[i], M, op.a[6], op.a[7], ep));   // bmap: box 128 = half tile
-                else if (gemm_prefer_bn256(M, op.a[6]))
+                else if (wide)
                     B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap256[i], 256, M, op.a[6], op.a[7], ep));
                 else
                     B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap[i], gemm_bn_for(op.a[6]), M, op.a[6], op.a[7], ep));
@@ -251,7 +252,7 @@ struct GraphModel : Model {
                 ep.out_f32 = 0;
                 ep.is_bf16 = 0;
                 ep.act_after = op.a[14];
-                const bool bn256 = gemm_prefer_bn256(M, op.a[6]);
+                const bool bn256 = gemm_prefer_bn256(M, op.a[6], 0);   // convolutions stay on the v3 pair kernel
                 if (bn256 && gemm_pair_enabled())
                     B2S_TRY(conv_implicit_maps(st, pl->amap[i], bmap[i], 128, true, M, op.a[6], op.a[7], ep, cg));
                 else if (bn256)
