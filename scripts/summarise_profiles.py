@@ -71,8 +71,8 @@ def full(name, cmd="python bench.py --steps 6 --warmup 3 --no-plugin --no-llama"
 def main():
     os.makedirs(OUT, exist_ok=True)
     launches()
-    for name in ("forest_staged", "gemm_tn_persistent", "gemm_tn_pair", "attention_varlen", "layernorm_kernel", "embed_layernorm",
-                 "nchw_to_s2d", "maxpool3x3s2"):
+    for name in ("forest_staged", "gemm_tn_persistent", "gemm_tn_pair", "gemm_tn_2sm", "attention_varlen", "layernorm_kernel",
+                 "embed_layernorm", "nchw_to_s2d", "maxpool3x3s2"):
         # the pair-kernel capture of the LLM prefill shapes keeps its own file (scripts/gpu_llm_ncu.sh)
         o = full(name, out_name="gemm_tn_pair_bert_resnet" if name == "gemm_tn_pair" else None)
         print(name, "ok" if o else "missing")
@@ -94,7 +94,7 @@ def main():
 def llm():
     """captures made by scripts/gpu_llm_ncu.sh"""
     cmd = "python scripts/llm_bench.py --layers 2 --waves 1 --gen 4 --no-graph: Llama-3-8B shapes, TP 1, batch 32, prompt 512"
-    for name in ("skinny_gemm", "llm_attn_decode", "llm_attn_prefill", "llm_reduce_rms", "gemm_tn_pair"):
+    for name in ("skinny_gemm", "llm_attn_decode", "llm_attn_prefill", "llm_reduce_rms", "gemm_tn_pair", "gemm_tn_2sm_llm"):
         print(name, "ok" if full(name, cmd) else "missing")
 
 
