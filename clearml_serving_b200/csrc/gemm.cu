@@ -723,8 +723,9 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         }
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;
-        int as = 0;
+        int as = 0, bias_n = -1;
         uint32_t aphase = 0;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);   // this warp's bias slice (128 columns), fetched when the weight panel changes
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int m_blk, n_blk;
             tile_coords(tile, m_tiles, n_tiles, group_m, m_blk, n_blk);
@@ -746,8 +747,10 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
             const int warp_row0 = m_blk * tile_rows + q * 32;
             const int M_tile = min(M, (m_blk + 1) * tile_rows);   // rows of this tile that exist (stem tiles: < 128)
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
-            // this warp's bias slice, fetched once per tile while the accumulator is still being produced
-            const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+            if (n_blk != bias_n) {   // consecutive tiles of a CTA mostly share the weight panel: keep its bias slice
+                b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+                bias_n = n_blk;
+            }
             if (ep.act == ACT_SWIGLU) {   // (gate, up) chunk pairs, see epilogue_swiglu32
                 if constexpr (NCH >= 2) {
 #pragma unroll 1
@@ -909,8 +912,9 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;
-        int as = 0;
+        int as = 0, bias_n = -1;
         uint32_t aphase = 0;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);   // this warp's bias slice (128 columns), fetched when the weight panel changes
         for (int pt = pair0; pt < total; pt += pair_stride) {
             int mp, n_blk;
             tile_coords(pt, m_pairs, n_tiles, group_mp, mp, n_blk);
@@ -929,8 +933,10 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tc_fence_after();
             const int warp_row0 = m_blk * GEMM_BM + q * 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
-            // this warp's bias slice, fetched once per tile while the accumulator is still being produced
-            const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+            if (n_blk != bias_n) {   // consecutive tiles of a CTA mostly share the weight panel: keep its bias slice
+                b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+                bias_n = n_blk;
+            }
             if (ep.act == ACT_SWIGLU) {   // (gate, up) chunk pairs, see epilogue_swiglu32
                 if constexpr (NCH >= 2) {
 #pragma unroll 1
@@ -1103,8 +1109,9 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;
-        int as = 0;
+        int as = 0, bias_n = -1;
         uint32_t aphase = 0;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);   // this warp's bias slice (128 columns), fetched when the weight panel changes
         for (int pt = pair0; pt < total; pt += pair_stride) {
             int mp, n_blk;
             tile_coords(pt, m_pairs, n_tiles, group_mp, mp, n_blk);
@@ -1124,7 +1131,10 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const int warp_row0 = m_blk * GEMM_BM + q * 32;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G2_BN + half * HALF);
             const uint32_t release = mapa_rank(&tmem_empty_bar[as], 0);   // the leader counts all 16 warps of the pair
-            const float4 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+            if (n_blk != bias_n) {   // consecutive tiles of a CTA mostly share the weight panel: keep its bias slice
+                b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
+                bias_n = n_blk;
+            }
             if (ep.act == ACT_SWIGLU) {   // (gate, up) chunk pairs, see epilogue_swiglu32
 #pragma unroll 1
                 for (int c = 0; c < NCH; c += 2) {
