@@ -25,7 +25,7 @@
 
 namespace b2s {
 static bool gemm_res_prefetch_enabled();
-static bool gemm_2sm_enabled(int K);
+static bool gemm_2sm_enabled(int K, bool light_epilogue);
 bool gemm_pair_enabled();
 static int prepare_tma_store(CUtensorMap *tc, GemmEpilogue &ep, int M, int N, int bn, const ConvGeom &cg);
 int nchw_to_s2d(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Hz, int Wz, void *out);   // conv.cu
@@ -1346,7 +1346,7 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtens
     epk.res_prefetch = ep.residual != nullptr && gemm_res_prefetch_enabled();
     CUtensorMap tc;
     B2S_TRY(prepare_tma_store(&tc, epk, M, N, 256, cg));
-    if (gemm_2sm_enabled(K) && cg.taps == 0 && !cg.s2d) {   // plain GEMM: the pair as one 256-row tensor-core unit
+    if (gemm_2sm_enabled(K, ep.act == ACT_NONE && !ep.residual && !ep.out_f32) && cg.taps == 0 && !cg.s2d) {   // plain GEMM: the pair as one 256-row tensor-core unit
         using S2 = G2smSmem<6>;
         static std::once_flag once2;
         static cudaError_t attr_err2 = cudaSuccess;
@@ -1369,10 +1369,11 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtens
 // 1495) and loses where the epilogue does (K = 768 with GELU, ResNet's K = 64..512 expansions: the leader's MMA stream
 // waits for the epilogue warps of BOTH CTAs, so the slower CTA paces the pair): by default it takes the deep-K GEMMs.
 // B2S_GEMM_2SM=0: never, =1: every plain GEMM (tests run the whole suite this way).
-static bool gemm_2sm_enabled(int K)
+static bool gemm_2sm_enabled(int K, bool light_epilogue = false)
 {
     static const int mode = []() { const char *e = getenv("B2S_GEMM_2SM"); return e ? atoi(e) : -1; }();
-    return mode < 0 ? K >= 2048 : mode != 0;
+    if (mode >= 0) return mode != 0;
+    return K >= 2048 || (K >= 768 && light_epilogue);   // light: 16-bit output, no activation, no residual (BERT's QKV projection)
 }
 
 static bool gemm_res_prefetch_enabled()
@@ -1397,7 +1398,7 @@ bool gemm_prefer_bn256(int M, int N, int K)
     // cost of a 128 x 128 tile relative to half a 128 x 256 one: 1.15 measured on the K = 768 shapes against the v3 pair
     // kernel; against the 2-SM kernel (deep K) a 128 x 128 x 3072 tile takes 17.7 us where a CTA's 128 x 256 share of a
     // pair-tile takes 19.9 us: 128-wide tiles are bound by shared-memory operand reads (8 KB per 64-cycle MMA)
-    const double f128 = (K > 0 && gemm_pair_enabled() && gemm_2sm_enabled(K)) ? 1.78 : 1.15;
+    const double f128 = (K > 0 && gemm_pair_enabled() && gemm_2sm_enabled(K, false)) ? 1.78 : 1.15;
     const double e256 = (double)((t256 + sms - 1) / sms) * 2.0;
     const double e128 = (double)((t128 + sms - 1) / sms) * f128;
     return e256 <= e128;
