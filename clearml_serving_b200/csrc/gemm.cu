@@ -26,6 +26,7 @@
 namespace b2s {
 static bool gemm_res_prefetch_enabled();
 static bool gemm_2sm_enabled(int K, bool light_epilogue);
+bool gemm_prefer_bn192(int M, int N, int K, int out_f32, int act);
 bool gemm_pair_enabled();
 static int prepare_tma_store(CUtensorMap *tc, GemmEpilogue &ep, int M, int N, int bn, const ConvGeom &cg);
 int nchw_to_s2d(cudaStream_t st, const void *in, int in_dtype, int64_t n_img, int C, int H, int W, int Hz, int Wz, void *out);   // conv.cu
@@ -996,23 +997,27 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // its 128 accumulator rows.  Both CTAs' TMA loads complete bytes on the leader's full barrier; tcgen05.commit multicasts
 // "stage free" / "accumulator ready" to both CTAs; both CTAs' epilogue warps release the accumulator on the leader's barrier.
 // ---------------------------------------------------------------------------------------------
-template <int STAGES>
+template <int STAGES, int BN2 = 256>
 struct G2smSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB: this CTA's 128 rows of A
-    static constexpr int B_BYTES = 128 * GEMM_BK * 2;       // 16 KB: this CTA's half (128 rows) of the 256-row weight tile
+    static constexpr int B_BYTES = (BN2 / 2) * GEMM_BK * 2;   // 16 / 12 KB: this CTA's half of the 256- / 192-row weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int SCRATCH_OFFSET = BAR_OFFSET + 1024;
     static constexpr int TOTAL = SCRATCH_OFFSET + 8 * 4096 + 1024;
 };
 
-template <int STAGES>
+// BN2 = 192: pair-tiles of 256 x 192 for outputs whose width is a multiple of 192 but fills the last wave of 256-wide tiles
+// badly (BERT hidden size 768: 3 x 256 -> 87 pair-tiles on 74 pairs, 4 x 192 -> 116 tiles of 3/4 the length); fp32 outputs
+// only (three 32-column chunks per epilogue warp: the 16-bit TMA-store path pairs chunks).
+template <int STAGES, int BN2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b_half,
                    const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpilogue ep, int group_mp)
 {
-    constexpr int G2_BN = 256;
-    using S = G2smSmem<STAGES>;
+    constexpr int G2_BN = BN2;
+    constexpr int TMEM_COLS = 2 * BN2 <= 256 ? 256 : 512;   // power of two >= two accumulators
+    using S = G2smSmem<STAGES, BN2>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFFSET);   // used in the leader
@@ -1050,7 +1055,7 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     cluster_arrive();   // peer barriers initialised / peer CTA resident before any remote arrive or paired instruction
     cluster_wait();
     if (warp == 2) {    // the same warp of BOTH CTAs: two accumulators of 256 columns in each CTA's tensor memory
-        tmem_alloc_2sm(tmem_slot, 2 * G2_BN);
+        tmem_alloc_2sm(tmem_slot, TMEM_COLS);
         tmem_relinquish_2sm();
     }
     tc_fence_before();
@@ -1135,14 +1140,14 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 b4 = load_bias128(static_cast<const float *>(ep.bias), n_blk * G2_BN + half * HALF, lane, N);
                 bias_n = n_blk;
             }
-            if (ep.act == ACT_SWIGLU) {   // (gate, up) chunk pairs, see epilogue_swiglu32
+            if (NCH % 2 == 0 && ep.act == ACT_SWIGLU) {   // (gate, up) chunk pairs, see epilogue_swiglu32
 #pragma unroll 1
-                for (int c = 0; c < NCH; c += 2) {
+                for (int c = 0; c + 1 < NCH; c += 2) {
                     uint32_t g[32], u[32];
                     tmem_ld_32x32(t_addr + (uint32_t)(c * 32), g);
                     tmem_ld_32x32(t_addr + (uint32_t)(c * 32 + 32), u);
                     tmem_ld_wait();
-                    if (c == NCH - 2) {
+                    if (c + 2 >= NCH) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(release);
@@ -1179,7 +1184,7 @@ gemm_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     cluster_wait();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc_2sm(tmem_base, 2 * G2_BN);
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     }
 }
 
@@ -1347,14 +1352,14 @@ static int launch_gemm_pair(cudaStream_t st, const CUtensorMap &ta, const CUtens
     CUtensorMap tc;
     B2S_TRY(prepare_tma_store(&tc, epk, M, N, 256, cg));
     if (gemm_2sm_enabled(K, ep.act == ACT_NONE && !ep.residual && !ep.out_f32) && cg.taps == 0 && !cg.s2d) {   // plain GEMM: the pair as one 256-row tensor-core unit
-        using S2 = G2smSmem<6>;
+        using S2 = G2smSmem<6, 256>;
         static std::once_flag once2;
         static cudaError_t attr_err2 = cudaSuccess;
         std::call_once(once2, []() {
-            attr_err2 = cudaFuncSetAttribute(gemm_tn_2sm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL);
+            attr_err2 = cudaFuncSetAttribute(gemm_tn_2sm_kernel<6, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL);
         });
         if (attr_err2 != cudaSuccess) return fail_cuda(attr_err2, "cudaFuncSetAttribute(gemm 2sm)");
-        gemm_tn_2sm_kernel<6><<<2 * pairs, G2_THREADS, S2::TOTAL, st>>>(ta, tb_half, tc, M, N, K, epk, group_mp);
+        gemm_tn_2sm_kernel<6, 256><<<2 * pairs, G2_THREADS, S2::TOTAL, st>>>(ta, tb_half, tc, M, N, K, epk, group_mp);
         count_launch();
         B2S_CUDA(cudaGetLastError());
         return 0;
@@ -1406,6 +1411,46 @@ bool gemm_prefer_bn256(int M, int N, int K)
 
 // narrow tile width for an N-column weight (box height of its "small" tensor map)
 int gemm_bn_for(int N) { return N <= 64 ? 64 : 128; }
+
+// 256 x 192 pair-tiles on the 2-SM kernel: `tb_half96` is the weight map with box height 96.  fp32 outputs only.
+int gemm_tn_maps_2sm192(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb_half96, int M, int N, int K,
+                        const GemmEpilogue &ep)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    if (!ep.out_f32 || ep.act == ACT_SWIGLU || N % 192 != 0) return fail(B2S_ERR_INVALID, "gemm: 192-wide tiles need an fp32 output whose width is a multiple of 192");
+    using S2 = G2smSmem<6, 192>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, []() {
+        attr_err = cudaFuncSetAttribute(gemm_tn_2sm_kernel<6, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::TOTAL);
+    });
+    if (attr_err != cudaSuccess) return fail_cuda(attr_err, "cudaFuncSetAttribute(gemm 2sm 192)");
+    const int m_pairs = (((M + GEMM_BM - 1) / GEMM_BM) + 1) / 2;
+    const int total = m_pairs * (N / 192);
+    const int max_pairs = g_num_sms() / 2;
+    const int pairs = total < max_pairs ? total : max_pairs;
+    const int group_mp = gemm_group_m(M, K) / 2;
+    GemmEpilogue epk = ep;
+    epk.res_prefetch = ep.residual != nullptr && gemm_res_prefetch_enabled();
+    CUtensorMap tc;
+    B2S_TRY(prepare_tma_store(&tc, epk, M, N, 192, ConvGeom()));
+    gemm_tn_2sm_kernel<6, 192><<<2 * pairs, G2_THREADS, S2::TOTAL, st>>>(ta, tb_half96, tc, M, N, K, epk, group_mp);
+    count_launch();
+    B2S_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// 192-wide 2-SM tiles pay when the output is fp32, its width a multiple of 192, the GEMM deep enough for the 2-SM kernel,
+// and 256-wide tiles would leave the last wave mostly idle (cost in units of half a 256-wide tile, as gemm_prefer_bn256)
+bool gemm_prefer_bn192(int M, int N, int K, int out_f32, int act)
+{
+    static const bool on = []() { const char *e = getenv("B2S_GEMM_192"); return !(e && e[0] == '0'); }();
+    if (!on || !out_f32 || act == ACT_SWIGLU || N < 192 || N % 192 != 0 || !gemm_pair_enabled() || !gemm_2sm_enabled(K, false)) return false;
+    const int pairs = g_num_sms() / 2, mp = (((M + GEMM_BM - 1) / GEMM_BM) + 1) / 2;
+    const int t192 = mp * (N / 192), t256 = mp * ((N + 255) / 256);
+    const double e192 = (double)((t192 + pairs - 1) / pairs) * 1.5, e256 = (double)((t256 + pairs - 1) / pairs) * 2.0;
+    return e192 < e256;
+}
 
 // GEMM with caller-provided tensor maps (graph executor: maps are cached per stream / per model).
 // `tb` must have been built with box height `bn` (64, 128 or 256).
@@ -1564,6 +1609,10 @@ int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t 
     CUtensorMap ta, tb;
     const int bn = N <= 64 ? 64 : (gemm_prefer_bn256(M, N, K) ? 256 : 128);
     B2S_TRY(make_tmap_2d_kmajor(&ta, A, M, K, lda, GEMM_BM, ep.is_bf16));
+    if (gemm_prefer_bn192(M, N, K, ep.out_f32, ep.act)) {
+        B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, 96, ep.is_bf16));
+        return gemm_tn_maps_2sm192(st, ta, tb, M, N, K, ep);
+    }
     if (bn == 256 && gemm_pair_enabled()) {
         B2S_TRY(make_tmap_2d_kmajor(&tb, B, N, K, ldb, 128, ep.is_bf16));
         return gemm_tn_maps_pair(st, ta, tb, M, N, K, ep);

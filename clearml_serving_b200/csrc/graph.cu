@@ -39,6 +39,9 @@ int gemm_tn_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, 
 int gemm_bn_for(int N);
 bool gemm_prefer_bn256(int M, int N, int K);
 bool gemm_pair_enabled();
+bool gemm_prefer_bn192(int M, int N, int K, int out_f32, int act);
+int gemm_tn_maps_2sm192(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb_half96, int M, int N, int K,
+                        const GemmEpilogue &ep);
 int gemm_tn_maps_pair(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb_half, int M, int N, int K,
                       const GemmEpilogue &ep);
 int layernorm(cudaStream_t st, const float *in, int64_t rows, int H, const float *gamma, const float *beta, float eps,
@@ -111,6 +114,7 @@ struct GraphModel : Model {
     std::vector<GOp> ops;
     std::vector<CUtensorMap> bmap;     // weight tensor maps (narrow tiles: box 64 / 128), one per op
     std::vector<CUtensorMap> bmap256;  // weight tensor maps for 128 x 256 tiles (N >= 256)
+    std::vector<CUtensorMap> bmap96;   // box 96 = half of a 192-wide 2-SM tile (fp32 outputs whose width is a multiple of 192)
     unsigned char *d_data = nullptr;
     std::mutex mu;
     std::map<void *, Plan> plans;   // keyed by the stream's scratch base
@@ -231,7 +235,9 @@ struct GraphModel : Model {
                 ep.is_bf16 = 0;
                 ep.act_after = op.a[9];
                 const bool wide = gemm_prefer_bn256(M, op.a[6], op.a[7]);
-                if (wide && gemm_pair_enabled())
+                if (op.a[6] % 192 == 0 && gemm_prefer_bn192(M, op.a[6], op.a[7], op.a[8], op.a[5]))
+                    B2S_TRY(gemm_tn_maps_2sm192(st, pl->amap[i], bmap96[i], M, op.a[6], op.a[7], ep));
+                else if (wide && gemm_pair_enabled())
                     B2S_TRY(gemm_tn_maps_pair(st, pl->amap[i], bmap[i], M, op.a[6], op.a[7], ep));   // bmap: box 128 = half tile
                 else if (wide)
                     B2S_TRY(gemm_tn_maps(st, pl->amap[i], bmap256[i], 256, M, op.a[6], op.a[7], ep));
@@ -461,6 +467,7 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
     // weight tensor maps
     m->bmap.resize(m->ops.size());
     m->bmap256.resize(m->ops.size());
+    m->bmap96.resize(m->ops.size());
     int64_t flops_fixed = 0;
     for (size_t i = 0; i < m->ops.size(); ++i) {
         const GOp &op = m->ops[i];
@@ -468,6 +475,8 @@ int graph_model_create(int device, const void *blob, size_t bytes, Model **out)
         int rc = make_tmap_2d_kmajor(&m->bmap[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], gemm_bn_for(op.a[6]), 0);
         if (rc == 0 && op.a[6] >= 256)
             rc = make_tmap_2d_kmajor(&m->bmap256[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], 256, 0);
+        if (rc == 0 && op.opcode == OP_LINEAR && op.a[8] && op.a[6] % 192 == 0)
+            rc = make_tmap_2d_kmajor(&m->bmap96[i], m->tptr(op.a[1]), op.a[6], op.a[7], op.a[7], 96, 0);
         if (rc != 0) return bail(rc);
         flops_fixed += 2LL * op.a[6] * op.a[7];
     }

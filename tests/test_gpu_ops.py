@@ -49,7 +49,9 @@ def _ref_act(x, act):
                                     (7424, 768, 3072), (2000, 1024, 4096), (640, 512, 8192),
                                     # 2-SM (cta_group::2) kernel: odd number of 128-row tiles (the last pair's second CTA is all
                                     # padding), last 256-column tile partial
-                                    (4990, 1000, 2048)])
+                                    (4990, 1000, 2048),
+                                    # 256 x 192 pair-tiles (fp32 output, width a multiple of 192)
+                                    (4990, 960, 2048)])
 def test_gemm_fp16_matches_fp32_reference(gpu_native, M, N, K):
     rng = np.random.default_rng(M * 7 + N)
     A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
