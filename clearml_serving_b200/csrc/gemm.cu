@@ -90,7 +90,6 @@ __device__ __forceinline__ float tanh_fast(float x)
 // written directly that is 32 rows x 16 B per store instruction, i.e. 32 half-filled 32-byte sectors.  Staged
 // through a 2.5 KB per-warp shared-memory scratch (80-byte pitch: conflict-free 128-bit accesses) four adjacent
 // lanes emit one row's 64 contiguous bytes, so each instruction writes 8 rows x 2 full sectors.
-constexpr int EPI_SCRATCH_WORDS = 32 * 20;   // (documents the 80-byte pitch used below)
 __device__ __forceinline__ void warp_store_rows64(uint32_t *scratch, const uint32_t (&w)[16], unsigned char *gbase,
                                                   size_t row_pitch_bytes, int rows_valid, int lane)
 {
