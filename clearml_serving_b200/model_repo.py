@@ -16,7 +16,11 @@ Supported containers
     `XGBoostPreprocessRequest` loads at preprocess_service.py:475-476;
   * joblib / pickle sklearn estimators (`SKLearnPreprocessRequest`, preprocess_service.py:456-457);
   * a Triton model-repository folder `<name>/<version>/model.*` (the layout triton_helper.py:124-186 writes).
-Refused loudly (no silent fallback): ONNX / TensorFlow / TensorRT containers, XGBoost's legacy binary format.
+  * ONNX files of residual convolutional networks (torchvision ResNet family as `torch.onnx.export` writes them:
+    Conv with the BatchNorm already folded, Relu, MaxPool, Add, GlobalAveragePool, Flatten, Gemm), read without the
+    `onnx` package (onnx_reader.py) -- the file the reference places as model.onnx for Triton's ONNX-Runtime backend
+    (triton_helper.py:169-171).
+Refused loudly (no silent fallback): other ONNX graphs, TensorFlow / TensorRT containers, XGBoost's legacy binary format.
 """
 import hashlib
 import os
@@ -39,7 +43,6 @@ _FRAMEWORK_RULES = (
     (("tensorrt",), "tensorrt"),
 )
 _UNSUPPORTED = {
-    "onnx": "ONNX graphs are not lowered by the b200 engine (export the torch module as TorchScript instead)",
     "tensorflow": "TensorFlow / Keras models are not supported by the b200 engine",
     "tensorrt": "TensorRT plans are device-specific binaries the b200 engine cannot read",
 }
@@ -299,6 +302,168 @@ def lower_torchscript(path):
 
 
 # ------------------------------------------------------------------------------------------------
+# ONNX: residual convolutional networks.  The graph is walked in file (= topological) order and matched against the
+# torchvision block structure -- stem Conv 7x7/2 (+Relu) + MaxPool 3x3/2, then blocks `Conv Relu Conv [Relu Conv]
+# [downsample Conv] Add Relu`, then GlobalAveragePool, Flatten, Gemm -- and rebuilt as the eager module formats.pack_resnet
+# lowers (the exporter has folded every BatchNorm into its convolution: the rebuilt BatchNorms are identities carrying
+# the convolution bias), so an ONNX file and the TorchScript / eager form of the same network give the same op list.
+# ------------------------------------------------------------------------------------------------
+def _onnx_conv_spec(g, node):
+    a = node.attrs
+    w = g.initializers.get(node.inputs[1]) if len(node.inputs) > 1 else None
+    if w is None or w.ndim != 4:
+        raise ValueError("b200 engine: ONNX Conv '{}' without a constant 4-D weight".format(node.name or node.outputs[0]))
+    b = g.initializers.get(node.inputs[2]) if len(node.inputs) > 2 else None
+    ks = list(a.get("kernel_shape", w.shape[2:]))
+    st = list(a.get("strides", [1, 1]))
+    pads = list(a.get("pads", [0, 0, 0, 0]))
+    if a.get("group", 1) != 1 or any(d != 1 for d in a.get("dilations", [1, 1])) or ks[0] != ks[1] or st[0] != st[1] or \
+            len(set(pads)) != 1 or a.get("auto_pad", b"NOTSET") not in (b"NOTSET", "NOTSET"):
+        raise ValueError("b200 engine: ONNX Conv '{}': grouped / dilated / asymmetric convolutions are not supported".format(
+            node.name or node.outputs[0]))
+    return dict(w=np.array(w, np.float32), b=None if b is None else np.array(b, np.float32), k=int(ks[0]),
+                stride=int(st[0]), pad=int(pads[0]))
+
+
+def lower_onnx(data):
+    """bytes / path of an ONNX file -> formats.PackedModel (torchvision-style ResNet: Bottleneck or BasicBlock stages)"""
+    import torch
+    import torchvision
+    from torchvision.models.resnet import BasicBlock, Bottleneck
+    from . import onnx_reader
+    try:
+        g = onnx_reader.load(data)
+    except onnx_reader.OnnxError as ex:
+        raise ValueError("b200 engine: {}".format(ex))
+    if len(g.inputs) != 1 or len(g.outputs) != 1:
+        raise ValueError("b200 engine: ONNX graphs with {} inputs / {} outputs are not supported".format(len(g.inputs), len(g.outputs)))
+    in_name, in_dtype, in_shape = g.inputs[0]
+    if in_dtype not in (np.float32, np.uint8) or not in_shape or len(in_shape) != 4 or in_shape[1] not in (1, 3, 4):
+        raise ValueError("b200 engine: ONNX input must be NCHW float32 / uint8 images, got {} {}".format(in_dtype, in_shape))
+    consumers = {}
+    for n in g.nodes:
+        for t in n.inputs:
+            consumers.setdefault(t, []).append(n)
+    producer = {t: n for n in g.nodes for t in n.outputs}
+
+    def only(t, op=None):
+        c = consumers.get(t, [])
+        if len(c) != 1 or (op and c[0].op_type != op):
+            raise ValueError("b200 engine: ONNX graph is not a residual conv net (tensor '{}' feeds {})".format(
+                t, [x.op_type for x in c]))
+        return c[0]
+
+    unsupported = sorted({n.op_type for n in g.nodes} - {"Conv", "Relu", "MaxPool", "Add", "GlobalAveragePool", "Flatten", "Gemm"})
+    if unsupported:
+        raise ValueError("b200 engine: ONNX operators {} are not lowered (supported graphs: residual convolutional networks; "
+                         "export transformer encoders as TorchScript)".format(unsupported))
+    # ---- stem
+    n = only(in_name, "Conv")
+    stem = _onnx_conv_spec(g, n)
+    n = only(n.outputs[0], "Relu")
+    n = only(n.outputs[0], "MaxPool")
+    a = n.attrs
+    if list(a.get("kernel_shape", [])) != [3, 3] or list(a.get("strides", [])) != [2, 2] or list(a.get("pads", [])) != [1, 1, 1, 1] or a.get("ceil_mode", 0):
+        raise ValueError("b200 engine: ONNX MaxPool must be 3x3 stride 2 pad 1")
+    x = n.outputs[0]
+    # ---- residual blocks
+    blocks = []
+    while True:
+        users = consumers.get(x, [])
+        if len(users) == 1 and users[0].op_type == "GlobalAveragePool":
+            break
+        convs = [u for u in users if u.op_type == "Conv"]
+        adds = [u for u in users if u.op_type == "Add"]
+        if not convs or len(convs) + len(adds) != len(users) or len(convs) > 2 or len(adds) > 1 or len(convs) + len(adds) != 2:
+            raise ValueError("b200 engine: ONNX graph is not a residual conv net (block input '{}' feeds {})".format(
+                x, [u.op_type for u in users]))
+        main = [_onnx_conv_spec(g, convs[0])]   # file order: the main path's first convolution precedes the downsample one
+        t = convs[0].outputs[0]
+        while True:
+            nx = only(t)
+            if nx.op_type == "Relu":
+                nx2 = only(nx.outputs[0], "Conv")
+                main.append(_onnx_conv_spec(g, nx2))
+                t = nx2.outputs[0]
+            elif nx.op_type == "Add":
+                add = nx
+                break
+            else:
+                raise ValueError("b200 engine: ONNX graph is not a residual conv net ('{}' after a convolution)".format(nx.op_type))
+        other = [i for i in add.inputs if i != t]
+        if len(other) != 1:
+            raise ValueError("b200 engine: ONNX Add with unexpected operands")
+        down = None
+        if other[0] != x:
+            dn = producer.get(other[0])
+            if dn is None or dn.op_type != "Conv" or dn.inputs[0] != x or len(convs) != 2 or dn is not convs[1]:
+                raise ValueError("b200 engine: ONNX residual branch is neither the block input nor one convolution of it")
+            down = _onnx_conv_spec(g, dn)
+        elif len(convs) != 1:
+            raise ValueError("b200 engine: ONNX block input feeds two convolutions but the identity is not a convolution")
+        blocks.append(dict(main=main, down=down))
+        x = only(add.outputs[0], "Relu").outputs[0]
+        if len(blocks) > 512:
+            raise ValueError("b200 engine: ONNX graph too deep")
+    n = only(x, "GlobalAveragePool")
+    n = only(n.outputs[0], "Flatten")
+    n = only(n.outputs[0], "Gemm")
+    a = n.attrs
+    fw, fb = g.initializers.get(n.inputs[1]), g.initializers.get(n.inputs[2]) if len(n.inputs) > 2 else None
+    if fw is None or a.get("alpha", 1.0) != 1.0 or a.get("beta", 1.0) != 1.0 or a.get("transA", 0):
+        raise ValueError("b200 engine: ONNX Gemm must be a plain fully connected layer with constant weights")
+    fw = np.array(fw, np.float32) if a.get("transB", 0) else np.array(fw, np.float32).T
+    if n.outputs[0] != g.outputs[0][0] or not blocks:
+        raise ValueError("b200 engine: ONNX graph does not end in the classifier")
+    # ---- rebuild the torchvision module
+    n_main = {len(b["main"]) for b in blocks}
+    if n_main not in ({2}, {3}):
+        raise ValueError("b200 engine: ONNX residual blocks must all have 2 (BasicBlock) or 3 (Bottleneck) convolutions")
+    block = Bottleneck if n_main == {3} else BasicBlock
+    layers, cur = [], 0
+    for i, b in enumerate(blocks):
+        if b["down"] is not None and i > 0:
+            layers.append(cur)
+            cur = 0
+        cur += 1
+    layers.append(cur)
+    if len(layers) != 4:
+        raise ValueError("b200 engine: ONNX conv net has {} stages; torchvision-style ResNets have 4".format(len(layers)))
+    kwargs = {}
+    width = int(blocks[0]["main"][0]["w"].shape[0])
+    if block is Bottleneck and width != 64:
+        kwargs["width_per_group"] = width
+    m = torchvision.models.resnet.ResNet(block, layers, num_classes=int(fw.shape[0]), **kwargs)
+
+    def put(conv, bn, spec, what):
+        if tuple(conv.weight.shape) != tuple(spec["w"].shape) or conv.stride[0] != spec["stride"] or conv.padding[0] != spec["pad"]:
+            raise ValueError("b200 engine: ONNX {} {} stride {} pad {} does not match torchvision's {} stride {} pad {}".format(
+                what, spec["w"].shape, spec["stride"], spec["pad"], tuple(conv.weight.shape), conv.stride[0], conv.padding[0]))
+        with torch.no_grad():
+            conv.weight.copy_(torch.from_numpy(spec["w"]))
+            bn.weight.fill_(1.0)
+            bn.running_mean.zero_()
+            bn.running_var.fill_(1.0)
+            bn.bias.copy_(torch.from_numpy(spec["b"]) if spec["b"] is not None else torch.zeros_like(bn.bias))
+        bn.eps = 0.0   # identity: y = x + bias, exactly
+    put(m.conv1, m.bn1, stem, "stem")
+    mods = [blk for layer in (m.layer1, m.layer2, m.layer3, m.layer4) for blk in layer]
+    for i, (blk, b) in enumerate(zip(mods, blocks)):
+        names = ("conv1", "conv2", "conv3")[:len(b["main"])]
+        for nm, spec in zip(names, b["main"]):
+            put(getattr(blk, nm), getattr(blk, nm.replace("conv", "bn")), spec, "block {} {}".format(i, nm))
+        if (blk.downsample is None) != (b["down"] is None):
+            raise ValueError("b200 engine: ONNX block {} downsample branch does not match torchvision's layout".format(i))
+        if b["down"] is not None:
+            put(blk.downsample[0], blk.downsample[1], b["down"], "block {} downsample".format(i))
+    with torch.no_grad():
+        m.fc.weight.copy_(torch.from_numpy(np.ascontiguousarray(fw)))
+        m.fc.bias.copy_(torch.from_numpy(np.array(fb, np.float32)) if fb is not None else torch.zeros_like(m.fc.bias))
+    hw = (int(in_shape[2]), int(in_shape[3])) if in_shape[2] and in_shape[3] else (224, 224)
+    return formats.pack_resnet(m.eval(), input_dtype="uint8" if in_dtype == np.uint8 else "float32", image_hw=hw)
+
+
+# ------------------------------------------------------------------------------------------------
 def _sniff(path):
     with open(path, "rb") as f:
         head = f.read(64)
@@ -313,8 +478,8 @@ def _sniff(path):
         return "xgboost-json" if nxt in (b'"', b" ", b"\n", b"\r", b"\t", b"}") else "xgboost-ubj"
     if head[:1] == b"\x80" or head[:2] == b"\x78\x9c" or head[:3] == b"ZF\x01":   # pickle / zlib-joblib
         return "sklearn"
-    if head[:1] == b"\x08" and b"onnx" in head.lower():
-        return "onnx"
+    if head[:1] == b"\x08" and (path.endswith(".onnx") or b"onnx" in head.lower() or b"pytorch" in head.lower()):
+        return "onnx"   # ModelProto: field 1 (ir_version) first, then producer_name
     return "unknown"
 
 
@@ -323,7 +488,7 @@ def _find_in_repo_folder(path):
     cands = []
     for root, _dirs, files in os.walk(path):
         for fn in files:
-            if fn.startswith("model.") or fn.endswith((".pt", ".json", ".ubj", ".pkl", ".joblib")):
+            if fn.startswith("model.") or fn.endswith((".pt", ".onnx", ".json", ".ubj", ".pkl", ".joblib")):
                 cands.append(os.path.join(root, fn))
     if not cands:
         return None
@@ -354,8 +519,8 @@ def load_model(path, framework=None):
     if kind == "xgboost-legacy":
         raise ValueError("b200 engine: XGBoost legacy binary models are not supported; re-save with "
                          "Booster.save_model('model.json') or 'model.ubj'")
-    if kind == "onnx":
-        raise ValueError("b200 engine: {}".format(_UNSUPPORTED["onnx"]))
+    if loader == "onnx" or (loader is None and kind == "onnx"):
+        return lower_onnx(path)
     if loader == "torchscript" or (loader is None and kind == "torchscript"):
         return lower_torchscript(path)
     if kind == "xgboost-ubj" and loader in (None, "xgboost"):

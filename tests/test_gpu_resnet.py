@@ -128,3 +128,27 @@ def test_large_batch_collate_pool_matches_small_batches(gpu_native):
     finally:
         st.destroy()
         model.free()
+
+
+def test_onnx_file_serves_like_the_eager_module(gpu_native, tmp_path):
+    """model.onnx (what the reference hands to Triton's ONNX-Runtime backend, triton_helper.py:169-171) read by
+    onnx_reader.py and lowered by model_repo.lower_onnx: logits within 1e-3 of torch-CPU-fp32 of the exported network"""
+    import torch
+    import torchvision
+    from clearml_serving_b200 import model_repo
+    from tests.test_model_repo import _export_onnx
+    torch.manual_seed(2)
+    m = _realistic_bn(torchvision.models.resnet18(weights=None, num_classes=12))
+    try:
+        proto = _export_onnx(m, torch.zeros(1, 3, 64, 64))
+    except Exception as ex:
+        pytest.skip("torch's ONNX serialiser is not reachable here: {}".format(ex))
+    p = tmp_path / "model.onnx"
+    p.write_bytes(proto)
+    pm = model_repo.load_model(str(p), framework="onnx")
+    x = np.random.default_rng(4).standard_normal((6, 3, 64, 64)).astype(np.float32)
+    with torch.no_grad():
+        ref = m(torch.from_numpy(x)).numpy()
+    got = _run(gpu_native, pm, x, 8)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert got.shape == ref.shape and err <= REL_TOL, "relative error {:.2e}".format(err)

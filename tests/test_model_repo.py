@@ -200,3 +200,88 @@ def test_repository_update_step_detects_changes(tmp_path):
     eps["bad"] = dict(engine_type="b200", serving_url="bad", model_id="a.json", auxiliary_cfg='input [ { name: "x" } ]')
     with pytest.raises(ValueError):
         repo.update_step(eps)
+
+
+# ---------------------------------------------------------------- ONNX (model.onnx of the Triton repository, triton_helper.py:169-171)
+def _export_onnx(model, example, names=("INPUT__0", "OUTPUT__0"), opset=13):
+    """torch's own ONNX serialiser (the TorchScript exporter's C++ path): what `torch.onnx.export` writes, without the
+    `onnx` python package its wrapper imports for post-processing"""
+    import torch
+    import torch._C._onnx as _C_onnx
+    from torch.onnx import utils as U
+    dyn = {names[0]: {0: "batch"}, names[1]: {0: "batch"}}
+    with torch.no_grad():
+        graph, params, _ = U._model_to_graph(model, (example,), input_names=[names[0]], output_names=[names[1]], dynamic_axes=dyn)
+    proto = graph._export_onnx(params, opset, dyn, False, _C_onnx.OperatorExportTypes.ONNX, True, True, {}, True, "", {})[0]
+    return proto
+
+
+def _graph_tables(blob):
+    """(ops, buffers, tensors as float arrays) of a B2SG blob (layout: csrc/graph.cu header comment)"""
+    import struct
+    magic, version, n_t, n_b, n_o = struct.unpack_from("<4sIIII", blob, 0)
+    assert magic == b"B2SG"
+    off = 96
+    tensors = [struct.unpack_from("<II4qQQ", blob, off + 56 * i) for i in range(n_t)]
+    off += 56 * n_t
+    buffers = [struct.unpack_from("<IIq", blob, off + 16 * i) for i in range(n_b)]
+    off += 16 * n_b
+    ops = [struct.unpack_from("<I15i4f", blob, off + 80 * i) for i in range(n_o)]
+    off += 80 * n_o
+    data0 = (off + 255) // 256 * 256
+    arrs = []
+    for dt, nd, s0, s1, s2, s3, o, nb in tensors:
+        np_dt = {8: np.float16, 0: np.float32}[dt]
+        arrs.append(np.frombuffer(blob, np_dt, count=nb // np.dtype(np_dt).itemsize, offset=data0 + o).astype(np.float64))
+    return ops, buffers, [t[:6] for t in tensors], arrs
+
+
+@pytest.mark.parametrize("arch,classes,hw", [("resnet18", 10, 64), ("resnet50", 7, 96)])
+def test_onnx_resnet_lowers_to_the_op_list_of_the_eager_module(tmp_path, arch, classes, hw):
+    """the exporter folds every BatchNorm into its convolution (in fp32), so the ONNX route cannot be byte-identical to
+    the eager packer (which folds in fp64) -- but it must give the same ops on the same buffers, and weights that agree
+    to an fp16 ulp"""
+    import torch
+    import torchvision
+    torch.manual_seed(0)
+    m = getattr(torchvision.models, arch)(weights=None, num_classes=classes).eval()
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.75, 1.25)
+                mod.bias.normal_(0, 0.1)
+    try:
+        proto = _export_onnx(m, torch.zeros(1, 3, hw, hw))
+    except Exception as ex:  # the private serialiser moved: nothing to test against
+        pytest.skip("torch's ONNX serialiser is not reachable here: {}".format(ex))
+    d = tmp_path / "repo" / "test_model_onnx" / "1"
+    d.mkdir(parents=True)
+    (d / "model.onnx").write_bytes(proto)
+    got = model_repo.load_model(str(tmp_path / "repo" / "test_model_onnx"), framework="ONNX")
+    want = formats.pack_resnet(m, image_hw=(hw, hw))
+    assert got.description["num_classes"] == classes and got.description["image_hw"] == [hw, hw]
+    assert model_repo.load_model(str(d / "model.onnx")).blob == got.blob      # sniffed without the framework tag
+    g_ops, g_buf, g_t, g_arr = _graph_tables(got.blob)
+    w_ops, w_buf, w_t, w_arr = _graph_tables(want.blob)
+    assert g_ops == w_ops and g_buf == w_buf and g_t == w_t
+    for a, b in zip(g_arr, w_arr):
+        np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-4)               # fp16 weights: one ulp of folding precision
+
+
+def test_onnx_graphs_outside_the_supported_family_are_refused(tmp_path):
+    import torch
+    m = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.Sigmoid(), torch.nn.AdaptiveAvgPool2d(1),
+                            torch.nn.Flatten(), torch.nn.Linear(8, 2)).eval()
+    try:
+        proto = _export_onnx(m, torch.zeros(1, 3, 16, 16))
+    except Exception as ex:
+        pytest.skip("torch's ONNX serialiser is not reachable here: {}".format(ex))
+    p = tmp_path / "m.onnx"
+    p.write_bytes(proto)
+    with pytest.raises(ValueError, match="Sigmoid"):
+        model_repo.load_model(str(p))
+    p.write_bytes(proto[:len(proto) // 2])
+    with pytest.raises(ValueError, match="onnx"):
+        model_repo.load_model(str(p), framework="onnx")
