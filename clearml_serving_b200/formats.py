@@ -186,6 +186,96 @@ def pack_xgboost_json(model):
     return pack_forest(forest, "xgb", base=base_score)
 
 
+# --------------------------------------------------------------------------------------------
+# LightGBM text models (`Booster.save_model("model.txt")`, what `LightGBMPreprocessRequest` loads with
+# `lgbm.Booster(model_file=...)`, clearml_serving/serving/preprocess_service.py:486-501; lightgbm 3.3.x,
+# requirements.txt:17).  lightgbm is not installable here and the reference has no golden vectors for it: the semantics are
+# restated from the library's published model format and predictor (Tree::Predict: numerical decision `fval <= threshold`
+# on double; child index >= 0 = internal node, < 0 = leaf ~index; decision_type bit 1 = default left, bits 2-3 = missing
+# type {0 none: NaN reads as 0.0, 1 zero, 2 NaN: missing goes to the default side}; the raw score is the sum of
+# `leaf_value` over trees in order, in double; `average_output` (boosting=rf) divides by the number of trees).
+# PARITY UNPINNED like the xgboost row of DESIGN.md section 3.
+# --------------------------------------------------------------------------------------------
+_LGB_IDENTITY = ("regression", "regression_l1", "huber", "fair", "quantile", "mape", "custom", "none")
+
+
+def parse_lightgbm_text(model):
+    """LightGBM model text (or a path to it) -> (source form for pack_forest, divisor)"""
+    if isinstance(model, (bytes, bytearray)):
+        model = model.decode("utf-8")
+    if "\n" not in model:
+        with open(model, "rt") as f:
+            model = f.read()
+    head, _, rest = model.partition("Tree=")
+    hdr = dict(ln.split("=", 1) for ln in head.splitlines() if "=" in ln)
+    if not head.lstrip().startswith("tree") or "max_feature_idx" not in hdr:
+        raise ValueError("b200 engine: not a LightGBM text model (save it with Booster.save_model('model.txt'))")
+    objective = hdr.get("objective", "regression").split()[0]
+    if objective not in _LGB_IDENTITY:
+        raise ValueError("b200 engine: LightGBM objective '{}' is not supported yet (identity-link objectives only: {})".format(
+            objective, ", ".join(_LGB_IDENTITY)))
+    if int(hdr.get("num_class", "1")) != 1 or int(hdr.get("num_tree_per_iteration", "1")) != 1:
+        raise ValueError("b200 engine: multi-class LightGBM models are not supported yet")
+    n_features = int(hdr["max_feature_idx"]) + 1
+    average = "average_output" in head.split()
+    off, left, right, feat, thr, dl, val = [0], [], [], [], [], [], []
+    body = ("Tree=" + rest).split("end of trees")[0]
+    for block in body.split("Tree=")[1:]:
+        kv = dict(ln.split("=", 1) for ln in block.splitlines() if "=" in ln)
+        n_leaves = int(kv["num_leaves"])
+        if int(kv.get("num_cat", "0")) != 0:
+            raise ValueError("b200 engine: categorical splits are not supported")
+        if int(kv.get("is_linear", "0")) != 0:
+            raise ValueError("b200 engine: LightGBM linear trees are not supported")
+        leaf_value = np.array(kv["leaf_value"].split(), dtype=np.float64)
+        n_int = n_leaves - 1
+        if leaf_value.size != n_leaves:
+            raise ValueError("b200 engine: LightGBM tree with {} leaf values for {} leaves".format(leaf_value.size, n_leaves))
+        if n_int == 0:   # a stump that never split: one leaf
+            left.append(np.array([-1], np.int32)); right.append(np.array([-1], np.int32)); feat.append(np.zeros(1, np.int32))
+            thr.append(np.zeros(1)); dl.append(np.zeros(1, np.uint8)); val.append(leaf_value[:1])
+            off.append(off[-1] + 1)
+            continue
+        sf = np.array(kv["split_feature"].split(), dtype=np.int64)
+        th = np.array(kv["threshold"].split(), dtype=np.float64)
+        dt = np.array(kv["decision_type"].split(), dtype=np.int64)
+        lc = np.array(kv["left_child"].split(), dtype=np.int64)
+        rc = np.array(kv["right_child"].split(), dtype=np.int64)
+        if not (sf.size == th.size == dt.size == lc.size == rc.size == n_int):
+            raise ValueError("b200 engine: LightGBM tree arrays disagree on the number of internal nodes")
+        if np.any(dt & 1):
+            raise ValueError("b200 engine: categorical splits are not supported")
+        missing = (dt >> 2) & 3
+        if np.any(missing == 1):
+            raise ValueError("b200 engine: LightGBM zero_as_missing splits are not supported")
+        if sf.max() >= n_features or sf.min() < 0:
+            raise ValueError("b200 engine: LightGBM split feature out of range")
+        # missing type 2 (NaN): the stored default side; type 0 (none): NaN reads as 0.0, so its side is known now
+        default_left = np.where(missing == 2, (dt >> 1) & 1, (0.0 <= th).astype(np.int64))
+        child = lambda c: np.where(c >= 0, c, n_int + (~c))   # noqa: E731 -- leaves are appended after the internal nodes
+        n = n_int + n_leaves
+        l_all, r_all = np.full(n, -1, np.int32), np.full(n, -1, np.int32)
+        l_all[:n_int], r_all[:n_int] = child(lc), child(rc)
+        if l_all[:n_int].max() >= n or r_all[:n_int].max() >= n or l_all[:n_int].min() < 0 or r_all[:n_int].min() < 0:
+            raise ValueError("b200 engine: LightGBM child index out of range")
+        f_all, t_all, d_all, v_all = np.zeros(n, np.int32), np.zeros(n), np.zeros(n, np.uint8), np.zeros(n)
+        f_all[:n_int], t_all[:n_int], d_all[:n_int] = sf, th, default_left
+        v_all[n_int:] = leaf_value
+        left.append(l_all); right.append(r_all); feat.append(f_all); thr.append(t_all); dl.append(d_all); val.append(v_all)
+        off.append(off[-1] + n)
+    if len(off) == 1:
+        raise ValueError("b200 engine: LightGBM model without trees")
+    forest = dict(tree_offset=np.asarray(off, np.int32), left=np.concatenate(left), right=np.concatenate(right),
+                  feat=np.concatenate(feat), thr=np.concatenate(thr), default_left=np.concatenate(dl),
+                  value=np.concatenate(val), n_features=n_features)
+    return forest, float(len(off) - 1) if average else 1.0
+
+
+def pack_lightgbm_text(model):
+    forest, divisor = parse_lightgbm_text(model)
+    return pack_forest(forest, "skl", base=0.0, scale=1.0, divisor=divisor)
+
+
 def _forest_from_sklearn_trees(estimators, n_features):
     off, left, right, feat, thr, dl, val = [0], [], [], [], [], [], []
     for e in estimators:

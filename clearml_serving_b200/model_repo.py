@@ -14,6 +14,7 @@ Supported containers
   * transformers `save_pretrained` folders;
   * XGBoost models saved as JSON or UBJSON (`Booster.save_model("m.json" | "m.ubj")`), the formats
     `XGBoostPreprocessRequest` loads at preprocess_service.py:475-476;
+  * LightGBM text models (`Booster.save_model("m.txt")`, `LightGBMPreprocessRequest`, preprocess_service.py:486-501);
   * joblib / pickle sklearn estimators (`SKLearnPreprocessRequest`, preprocess_service.py:456-457);
   * a Triton model-repository folder `<name>/<version>/model.*` (the layout triton_helper.py:124-186 writes).
   * ONNX files of residual convolutional networks (torchvision ResNet family as `torch.onnx.export` writes them:
@@ -37,6 +38,7 @@ from . import formats
 _FRAMEWORK_RULES = (
     (("pytorch", "torch", "caffe"), "torchscript"),
     (("xgboost",), "xgboost"),
+    (("lightgbm",), "lightgbm"),
     (("scikit", "sklearn", "joblib"), "sklearn"),
     (("onnx",), "onnx"),
     (("tensorflow", "keras"), "tensorflow"),
@@ -472,6 +474,8 @@ def _sniff(path):
     if head[:4] == b"binf" or head[:4] == b"bs64":
         return "xgboost-legacy"
     s = head.lstrip()
+    if s[:5] == b"tree\n" or s[:6] == b"tree\r\n":
+        return "lightgbm"   # Booster.save_model text: "tree", "version=v3", ...
     if s[:1] == b"{":
         # JSON text continues with whitespace / a quote; UBJSON with a length marker (U/i/I/l/L), '$' or '#'
         nxt = s[1:2]
@@ -488,7 +492,7 @@ def _find_in_repo_folder(path):
     cands = []
     for root, _dirs, files in os.walk(path):
         for fn in files:
-            if fn.startswith("model.") or fn.endswith((".pt", ".onnx", ".json", ".ubj", ".pkl", ".joblib")):
+            if fn.startswith("model.") or fn.endswith((".pt", ".onnx", ".json", ".ubj", ".txt", ".pkl", ".joblib")):
                 cands.append(os.path.join(root, fn))
     if not cands:
         return None
@@ -530,6 +534,8 @@ def load_model(path, framework=None):
         return formats.pack_xgboost_json(path)
     if loader == "xgboost":
         raise ValueError("b200 engine: '{}' is neither an XGBoost JSON nor a UBJSON model".format(path))
+    if loader == "lightgbm" or (loader is None and kind == "lightgbm"):
+        return formats.pack_lightgbm_text(path)
     if kind in ("sklearn", "unknown") or loader == "sklearn":
         import joblib   # the reference's sklearn engine loads with joblib too (preprocess_service.py:456)
         try:

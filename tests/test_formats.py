@@ -130,3 +130,132 @@ def test_stem_space_to_depth_weight_is_the_same_convolution():
             for b in range(4):
                 got += z[:, a:a + OH, b:b + OW, :] @ w2[:, a * 64 + b * 16:a * 64 + b * 16 + 16].T
         np.testing.assert_allclose(got.transpose(0, 3, 1, 2), ref, rtol=1e-10, atol=1e-10)
+
+
+# ---------------------------------------------------------------- LightGBM text models (reference engine "lightgbm", ps.py:486-501)
+_LGB_MODEL = """tree
+version=v3
+num_class=1
+num_tree_per_iteration=1
+label_index=0
+max_feature_idx=3
+objective=regression
+feature_names=a b c d
+feature_infos=[-3:3] [-3:3] [-3:3] [-3:3]
+tree_sizes=400 300 120
+
+Tree=0
+num_leaves=4
+num_cat=0
+split_feature=0 2 1
+split_gain=10 5 3
+threshold=0.5 -0.25 1.0000000180025095e-35
+decision_type=2 10 8
+left_child=1 -1 -3
+right_child=2 -2 -4
+leaf_value=0.125 -0.25 0.5 0.0625
+leaf_weight=1 1 1 1
+leaf_count=1 1 1 1
+internal_value=0 0 0
+internal_weight=0 0 0
+internal_count=4 2 2
+is_linear=0
+shrinkage=1
+
+
+Tree=1
+num_leaves=3
+num_cat=0
+split_feature=3 0
+split_gain=4 2
+threshold=1.5 -1.75
+decision_type=0 0
+left_child=1 -1
+right_child=-2 -3
+leaf_value=0.03125 -0.015625 0.75
+leaf_weight=1 1 1
+leaf_count=1 1 1
+internal_value=0 0
+internal_weight=0 0
+internal_count=3 2
+is_linear=0
+shrinkage=0.1
+
+
+Tree=2
+num_leaves=1
+num_cat=0
+leaf_value=0.001953125
+is_linear=0
+shrinkage=0.1
+
+
+end of trees
+
+feature_importances:
+a=2
+"""
+
+
+def _lgb_reference_predict(text, X, average=False):
+    """the published predictor, straight from the text: fval <= threshold in double, child >= 0 internal / < 0 leaf ~child,
+    decision_type bit 1 default-left, bits 2-3 missing type (0: NaN reads as 0.0, 2: NaN takes the default side)"""
+    trees = []
+    for block in text.split("end of trees")[0].split("Tree=")[1:]:
+        kv = dict(ln.split("=", 1) for ln in block.splitlines() if "=" in ln)
+        trees.append({k: np.array(v.split(), dtype=np.float64) for k, v in kv.items()
+                      if k in ("split_feature", "threshold", "decision_type", "left_child", "right_child", "leaf_value")})
+    out = np.zeros(len(X), np.float64)
+    for i, row in enumerate(X):
+        acc = 0.0
+        for t in trees:
+            if "split_feature" not in t:
+                acc += t["leaf_value"][0]
+                continue
+            node = 0
+            while node >= 0:
+                f, thr, dt = int(t["split_feature"][node]), t["threshold"][node], int(t["decision_type"][node])
+                x = float(row[f])
+                missing = (dt >> 2) & 3
+                if np.isnan(x) and missing == 2:
+                    left = bool(dt & 2)
+                else:
+                    left = (0.0 if np.isnan(x) else x) <= thr
+                node = int(t["left_child"][node] if left else t["right_child"][node])
+            acc += t["leaf_value"][~node]
+        out[i] = acc / (len(trees) if average else 1)
+    return out
+
+
+def test_lightgbm_text_model_packs_to_the_published_semantics(tmp_path):
+    from clearml_serving_b200 import formats, model_repo
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((200, 4)).astype(np.float32)
+    X[rng.random(X.shape) < 0.15] = np.nan                     # both missing types are exercised
+    X[:4] = [[0.5, 0, 0, 0], [np.float32(0.5000001), 1e-35, -0.25, 1.5], [0.5, 0, np.nextafter(np.float32(-0.25), np.float32(0)), 1.5],
+             [np.nan, np.nan, np.nan, np.nan]]               # rows sitting exactly on thresholds
+    p = tmp_path / "model.txt"
+    p.write_text(_LGB_MODEL)
+    pm = model_repo.load_model(str(p), framework="LightGBM")
+    assert model_repo.load_model(str(p)).blob == pm.blob         # sniffed without the tag
+    got = blob_interp.predict(pm.blob, X)
+    want = _lgb_reference_predict(_LGB_MODEL, X)
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    # boosting=rf models average the trees
+    rf = _LGB_MODEL.replace("objective=regression\n", "objective=regression\naverage_output\n")
+    got_rf = blob_interp.predict(formats.pack_lightgbm_text(rf).blob, X)
+    assert np.array_equal(got_rf, _lgb_reference_predict(rf, X, average=True))
+
+
+@pytest.mark.parametrize("edit,msg", [
+    (lambda t: t.replace("objective=regression", "objective=binary sigmoid:1"), "objective"),
+    (lambda t: t.replace("num_class=1", "num_class=3"), "multi-class"),
+    (lambda t: t.replace("decision_type=2 10 8", "decision_type=3 10 8"), "categorical"),
+    (lambda t: t.replace("decision_type=2 10 8", "decision_type=6 10 8"), "zero_as_missing"),
+    (lambda t: t.replace("split_feature=3 0", "split_feature=9 0"), "out of range"),
+    (lambda t: t.replace("tree\nversion", "forest\nversion"), "not a LightGBM"),
+])
+def test_lightgbm_models_outside_the_supported_set_are_refused(edit, msg):
+    from clearml_serving_b200 import formats
+    with pytest.raises(ValueError, match=msg):
+        formats.pack_lightgbm_text(edit(_LGB_MODEL))
