@@ -2,7 +2,8 @@
 
     import clearml_serving_b200.integration as b2s
     b2s.register_with_reference()            # adds engine_type "b200"
-    b2s.register_with_reference("triton")    # or shadow the Triton engine name
+    b2s.register_with_reference("triton")    # or shadow an existing engine name -- "triton", "xgboost", "lightgbm",
+                                             # "sklearn": endpoints registered for it are then served by the b200 engine
 
 After this, `clearml-serving model add --engine b200 ...` validates (endpoints.py:5-8 consults the
 registry) and ModelRequestProcessor.process_request builds the engine lazily on the first request

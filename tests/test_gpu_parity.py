@@ -244,3 +244,25 @@ def test_two_endpoints_two_streams_concurrently(gpu_native, cfg2, golden_dir):
                 assert np.array_equal(outs[0][0], g["y"][k * 64:(k + 1) * 64])
     finally:
         s1.destroy(); s2.destroy(); model2.free()
+
+
+def test_lightgbm_text_model_bit_exact(gpu_native):
+    """LightGBM text model (the reference's `lightgbm` engine, preprocess_service.py:486-501) on the fp64 forest kernel:
+    bit-identical to the restatement of the published predictor (tests/test_formats.py), NaN rows of both missing types
+    and rows sitting on thresholds included, plain and `average_output`"""
+    from tests.test_formats import _LGB_MODEL, _lgb_reference_predict
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((300, 4)).astype(np.float32)
+    X[rng.random(X.shape) < 0.15] = np.nan
+    X[:3] = [[0.5, 0, 0, 0], [np.float32(0.5000001), 1e-35, -0.25, 1.5], [np.nan, np.nan, np.nan, np.nan]]
+    for text, avg in ((_LGB_MODEL, False), (_LGB_MODEL.replace("objective=regression\n", "objective=regression\naverage_output\n"), True)):
+        pm = formats.pack_lightgbm_text(text)
+        model = gpu_native.Model(pm.kind, pm.blob, device=0)
+        stream = gpu_native.Stream(model, 512, 0, 2)
+        try:
+            got = np.concatenate(_run_batch(gpu_native, model, stream, [X[:1], X[1:65], X[65:]]))
+            want = _lgb_reference_predict(text, X, average=avg)
+            assert got.dtype == np.float64 and np.array_equal(got, want)
+        finally:
+            stream.destroy()
+            model.free()
