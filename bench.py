@@ -326,6 +326,122 @@ def _plugin_metrics(forest, device, seconds=2.0, lam=2000.0):
     return out
 
 
+def rest_load(app, path, bodies, headers, seconds=2.0, concurrency=64, check=None):
+    """Level L1 of SURVEY.md 8(d): the FastAPI app behind uvicorn on 127.0.0.1, an aiohttp closed-loop client in the same
+    process (no `ab` / `wrk` in the image).  `bodies`: request payloads (bytes) cycled by the workers.  Returns requests/s,
+    p50 / p99 latency and the count of non-200 replies; `check(reply bytes, body index)` may assert on every reply."""
+    import socket
+    import threading
+
+    import aiohttp
+    import uvicorn
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    server = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=port, log_level="error", access_log=False))
+    th = threading.Thread(target=server.run, name="b2s-rest-bench", daemon=True)
+    th.start()
+    t_wait = time.time() + 10.0
+    while not server.started and time.time() < t_wait:
+        time.sleep(0.01)
+    if not server.started:
+        raise RuntimeError("uvicorn did not start")
+    url = "http://127.0.0.1:{}{}".format(port, path)
+    lat, bad, wrong = [], [0], [0]
+
+    async def run():
+        async with aiohttp.ClientSession(connector=aiohttp.TCPConnector(limit=concurrency),
+                                         timeout=aiohttp.ClientTimeout(total=20)) as session:
+            async def one(i):
+                t = time.perf_counter()
+                async with session.post(url, data=bodies[i % len(bodies)], headers=headers) as r:
+                    payload = await r.read()
+                    if r.status != 200:
+                        bad[0] += 1
+                    elif check is not None:
+                        try:
+                            ok = check(payload, i % len(bodies))
+                        except Exception:  # noqa
+                            ok = False
+                        if ok is False:
+                            wrong[0] += 1
+                lat.append(time.perf_counter() - t)
+            for i in range(min(concurrency, 32)):   # warm-up: connections, first batches
+                await one(i)
+            lat.clear()
+            bad[0] = wrong[0] = 0
+            stop = time.perf_counter() + seconds
+
+            async def worker(w):
+                i = w
+                while time.perf_counter() < stop:
+                    await one(i)
+                    i += concurrency
+            t0 = time.perf_counter()
+            await asyncio.gather(*[worker(w) for w in range(concurrency)])
+            return time.perf_counter() - t0
+    try:
+        elapsed = asyncio.run(run())
+    finally:
+        server.should_exit = True
+        th.join(timeout=10)
+    a = np.asarray(lat) * 1e6
+    return dict(req_s=len(lat) / elapsed, p50_us=float(np.percentile(a, 50)), p99_us=float(np.percentile(a, 99)),
+                completed=len(lat), failed=bad[0], mismatched=wrong[0], concurrency=concurrency, server="uvicorn (1 worker) + aiohttp client, same process")
+
+
+def _rest_metrics(forest, device, seconds=2.0):
+    """REST-level requests/s of the configs[1] endpoint: JSON bodies through a user Preprocess class (the reference's route,
+    examples/xgboost) and binary tensor frames (clearml_serving_b200/wire.py), both against the real engine."""
+    from clearml_serving_b200 import BasePreprocessRequest, ModelEndpoint, formats, wire
+    from clearml_serving_b200.main import create_app
+    from clearml_serving_b200.model_request_processor import ModelRequestProcessor
+    from oracle import oracle as orc   # the checker of the replies
+    packed = formats.pack_forest(forest, "xgb", base=0.5)
+    cls = BasePreprocessRequest.get_engine_cls("b200")
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((512, N_FEATURES)).astype(np.float32)
+    want = orc.forest_predict_xgb(forest, X, 0.5)
+
+    class _User(object):   # examples/xgboost/preprocess.py, inline
+        def preprocess(self, body, state, collect_custom_statistics_fn=None):
+            return np.array([[body.get("x{}".format(i)) for i in range(N_FEATURES)]], dtype=np.float32)
+
+        def postprocess(self, data, state, collect_custom_statistics_fn=None):
+            return dict(y=data.tolist())
+    out = {}
+    for name in ("json", "frames"):
+        p = ModelRequestProcessor()
+        ep = ModelEndpoint(engine_type="b200", serving_url="bench_xgb",
+                           auxiliary_cfg={"max_batch_size": MAX_BATCH, "dynamic_batching.max_queue_delay_microseconds": 1000,
+                                          "b200.device": device})
+        eng = cls.__new__(cls)
+        BasePreprocessRequest.__init__(eng, model_endpoint=ep, task=None)
+        eng._model = packed
+        eng._b200_setup()
+        p._endpoints["bench_xgb"] = ep
+        p._engine_processor_lookup["bench_xgb"] = eng
+        try:
+            if name == "json":
+                eng._preprocess = _User()
+                bodies = [json.dumps({"x{}".format(j): float(X[i, j]) for j in range(N_FEATURES)}).encode() for i in range(len(X))]
+                headers = {"Content-Type": "application/json"}
+
+                def check(payload, i):
+                    return bool(np.float32(json.loads(payload)["y"][0]) == want[i])
+            else:
+                bodies = [wire.encode_tensors([X[i:i + 1]]) for i in range(len(X))]
+                headers = {"Content-Type": wire.MEDIA_TYPE}
+
+                def check(payload, i):
+                    return bool(wire.decode_tensors(payload)[0][0] == want[i])
+            out[name] = rest_load(create_app(p), "/serve/bench_xgb", bodies, headers, seconds=seconds, check=check)
+        finally:
+            p.shutdown()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # second workload (BASELINE.json configs[3]): BERT-base fp16, mixed S in {16,64,128,256}, max_batch=64
 # ------------------------------------------------------------------------------------------------
@@ -713,6 +829,11 @@ def run_b200(args):
                 plugin["closed_loop_req_s_all_ranks"] = _sum_over_ranks(dist, local, plugin["closed_loop_req_s"])
         except Exception as ex:  # noqa
             plugin = dict(error=str(ex))
+        if local == 0 and isinstance(plugin, dict) and "error" not in plugin:
+            try:   # REST level: front-end bound by construction, reported beside the engine-level figures
+                plugin["rest"] = _rest_metrics(forest, device)
+            except Exception as ex:  # noqa
+                plugin["rest"] = dict(error="{}: {}".format(type(ex).__name__, ex))
 
     bert = None
     if args.bert and rank == 0:
