@@ -124,3 +124,40 @@ def test_asyncio_path_many_concurrent_requests():
         assert st["requests"] == 300 and st["rows"] == 300 and st["mean_batch_rows"] > 1
     finally:
         b.shutdown()
+
+
+def test_random_request_streams_keep_the_batcher_invariants():
+    """property test over request streams (row counts, arrival gaps, policies): every request gets exactly its own rows
+    back, no batch exceeds max_batch_size, rows are conserved, and requests leave in arrival order (FIFO batches)"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.lists(st.tuples(st.integers(1, 6), st.integers(0, 3)), min_size=1, max_size=40),
+           st.sampled_from([(8, 0, ()), (8, 500, ()), (16, 300, (4, 8)), (6, 0, (2, 4))]))
+    def run(reqs, pol):
+        max_bs, delay, preferred = pol
+        model = FakeModel(n_features=3)
+        stream = FakeStream(model, max_bs, n_slots=2)
+        b = DynamicBatcher(model, BatchPolicy(max_batch_size=max_bs, max_queue_delay_us=delay, preferred_batch_size=list(preferred),
+                                              n_slots=2), name="prop", stream=stream)
+        try:
+            futs, wants, tag = [], [], 0
+            for rows, gap in reqs:
+                x = np.full((rows, 3), 0.0, np.float32)
+                x[:, 0] = np.arange(tag, tag + rows)            # a unique value per row across the whole stream
+                tag += rows
+                futs.append(b.submit([x], rows))
+                wants.append(x.sum(axis=1))
+                if gap:
+                    time.sleep(gap * 1e-4)
+            outs = [f.result(timeout=10) for f in futs]
+            for o, w in zip(outs, wants):
+                assert len(o) == 1 and np.array_equal(o[0], w)
+            assert all(0 < n <= max_bs for n in stream.batches)
+            assert sum(stream.batches) == tag
+            st_ = b.snapshot_stats()
+            assert st_["requests"] == len(reqs) and st_["rows"] == tag and st_["batches"] == len(stream.batches)
+            assert sum(st_["batch_rows_hist"]) == st_["batches"]
+        finally:
+            b.shutdown()
+    run()
