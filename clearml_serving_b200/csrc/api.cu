@@ -840,6 +840,81 @@ int b2s_slot_submit(b2s_model_t model, b2s_stream_t stream, int32_t slot, int64_
     return 0;
 }
 
+int b2s_slot_collate(b2s_model_t model, b2s_stream_t stream, int32_t slot, int32_t n_req,
+                     const void *const *in_ptrs, const int64_t *req_rows, const int64_t *req_row_len,
+                     b2s_event_t *out_done)
+{
+    Model *m = get_model(model);
+    Stream *s = get_stream(stream);
+    if (!m || !s || s->model != m || !out_done) return fail(B2S_ERR_INVALID, "b2s_slot_collate: bad handle");
+    if (slot < 0 || slot >= (int)s->slots.size()) return fail(B2S_ERR_INVALID, "b2s_slot_collate: bad slot");
+    if (n_req <= 0 || !in_ptrs || !req_rows) return fail(B2S_ERR_INVALID, "b2s_slot_collate: null or empty request list");
+    const b2s_model_info &info = m->info;
+    bool ragged = false;
+    for (int i = 0; i < info.n_inputs; ++i) ragged = ragged || info.in_row_elems[i] < 0;
+    if (ragged && !req_row_len) return fail(B2S_ERR_INVALID, "b2s_slot_collate: variable-length model needs req_row_len");
+    Slot &sl = s->slots[slot];
+    {
+        std::lock_guard<std::mutex> l(s->mu);
+        if (sl.state != SLOT_ACQUIRED) return fail(B2S_ERR_INVALID, "b2s_slot_collate: slot %d is not acquired", slot);
+    }
+    int64_t total_rows = 0, total_elems = 0;
+    for (int r = 0; r < n_req; ++r) {
+        if (req_rows[r] < 0) return fail(B2S_ERR_INVALID, "b2s_slot_collate: request %d has negative rows", r);
+        total_rows += req_rows[r];
+        if (ragged) {
+            if (req_row_len[r] <= 0 || req_row_len[r] > s->max_row_elems)
+                return fail(B2S_ERR_INVALID, "b2s_slot_collate: request %d: sequence length %lld outside (0, %lld]", r,
+                            (long long)req_row_len[r], (long long)s->max_row_elems);
+            total_elems += req_rows[r] * req_row_len[r];
+        }
+        for (int i = 0; i < info.n_inputs; ++i)
+            if (!in_ptrs[(size_t)r * info.n_inputs + i] && req_rows[r] > 0)
+                return fail(B2S_ERR_INVALID, "b2s_slot_collate: request %d input %d: null data", r, i);
+    }
+    if (total_rows > s->max_rows)
+        return fail(B2S_ERR_INVALID, "b2s_slot_collate: %lld rows exceed the stream's max_rows %lld", (long long)total_rows,
+                    (long long)s->max_rows);
+    if (ragged && total_elems > s->max_rows * s->max_row_elems)
+        return fail(B2S_ERR_INVALID, "b2s_slot_collate: %lld tokens exceed the stream's capacity %lld", (long long)total_elems,
+                    (long long)(s->max_rows * s->max_row_elems));
+    size_t fixed_bytes = 0;
+    if (!ragged)
+        for (int i = 0; i < info.n_inputs; ++i) fixed_bytes += (size_t)total_rows * s->in_row_bytes[i];
+    const bool pooled = !ragged && fixed_bytes >= kParallelGatherMin;
+    std::vector<CopyJob> jobs;
+    int64_t row = 0, elem = 0;
+    if (ragged) sl.h_row_offsets[0] = 0;
+    for (int r = 0; r < n_req; ++r) {
+        const int64_t rows = req_rows[r];
+        for (int i = 0; i < info.n_inputs; ++i) {
+            const unsigned char *src = static_cast<const unsigned char *>(in_ptrs[(size_t)r * info.n_inputs + i]);
+            if (info.in_row_elems[i] < 0) {
+                const size_t es = dtype_size(info.in_dtype[i]);
+                memcpy(sl.h_in[i] + (size_t)elem * es, src, (size_t)(rows * req_row_len[r]) * es);
+            } else {
+                unsigned char *dst = sl.h_in[i] + (size_t)row * s->in_row_bytes[i];
+                const size_t nb = (size_t)rows * s->in_row_bytes[i];
+                if (pooled) jobs.push_back(CopyJob{dst, src, nb});
+                else memcpy(dst, src, nb);
+            }
+        }
+        if (ragged) {
+            for (int64_t k = 0; k < rows; ++k) sl.h_row_offsets[row + k + 1] = elem + (k + 1) * req_row_len[r];
+            elem += rows * req_row_len[r];
+        }
+        row += rows;
+    }
+    if (pooled) GatherPool::get().run(jobs);
+    sl.scatter = false;
+    const int rc = submit_slot(m, s, slot, total_rows, ragged ? sl.h_row_offsets : nullptr);
+    std::lock_guard<std::mutex> l(s->mu);
+    if (rc != 0) return rc;
+    sl.state = SLOT_INFLIGHT;
+    *out_done = make_event(stream, slot, sl.gen);
+    return 0;
+}
+
 int b2s_slot_release(b2s_stream_t stream, int32_t slot)
 {
     Stream *s = get_stream(stream);

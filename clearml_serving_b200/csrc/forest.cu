@@ -495,6 +495,194 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
 #undef B2S_STAMP
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Kernel D (serving batches, default): "wide" clusters over COMPACT tree slices.
+// What bounded kernel C (profiles/r01_forest_staged_phase_timing.txt, r01_ncu_forest_staged.txt):
+//   (1) 8-byte leaf slots: 1.37x the algorithmic DRAM bytes and 130 KB per CTA to stage;
+//   (2) every leaf value of a 16-row tile funnelled into ONE SM through distributed shared memory, whose
+//       ingest rate is ~20 B/clk (57 KB -> ~2900 cycles of the 4400-cycle traverse+publish phase);
+//   (3) a per-source-rank barrier round trip (~230 cycles x 8) inside the ordered sum.
+// Here
+//   * the model is re-packed at load time into one COMPACT image per cluster rank: internal nodes 8 B
+//     {f32 threshold | feat, default_left, left ref, right ref}, leaves 4 B (fp32 mode) / 8 B (fp64 mode, the
+//     pre-scaled double itself: no leaf64[] indirection) -- exactly the algorithmic bytes of SURVEY.md 8(d);
+//   * a cluster of up to 16 CTAs (non-portable size) shares a tile of R rows: rank r stages trees
+//     [r*TPC, (r+1)*TPC) (48.6 KB for 64 depth-6 trees) with cp.async.bulk and traverses them for all R rows out
+//     of shared memory, one (tree, row) pair per thread;
+//   * ALL-TO-ALL publish: row `i` of the tile is OWNED by rank i / rows_per_rank; a warp holds 32 consecutive trees
+//     of one row, so it sends one coalesced 128-byte st.shared::cluster to the owner: every SM ingests only
+//     rows_per_rank * T values (4 KB at R = 16, C = 16) instead of one SM ingesting R * T;
+//   * ONE cluster barrier, then each rank runs the bit-exactness-mandated sequential chain of ITS rows out of local
+//     shared memory (128-bit loads one block ahead of the dependent adds).
+// grid = C * ceil(rows / R) CTAs, cluster (C,1,1), 1 CTA per SM.  Forests the compact encoding or a single image
+// per rank cannot hold fall back to kernels C / B.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWideMaxC = 16;
+struct WideParams {
+    const unsigned char *images;          // all rank images back to back (16-byte aligned each)
+    uint32_t image_off[kWideMaxC + 1];    // byte offset of rank r's image, [C] = end
+    int n_trees, n_features, feat_bits, child_bits, tpc, max_depth;
+    double base, divisor;
+};
+
+template <bool F64>
+__global__ void __launch_bounds__(1024, 1)
+forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict__ X, int64_t n_rows, void *__restrict__ out, int R, int rpr,
+                   int image_cap, int bulk_piece, long long *__restrict__ dbg)
+{
+#define B2S_STAMP(k)                                                                    \
+    do {                                                                                \
+        if (dbg && blockIdx.x < 8 && threadIdx.x == 0) dbg[blockIdx.x * 8 + (k)] = clock64(); \
+    } while (0)
+    using acc_t = typename std::conditional<F64, double, float>::type;
+    constexpr int VEC = 16 / (int)sizeof(acc_t);
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int F = p.n_features, T = p.n_trees, TPC = p.tpc;
+    const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
+    const int64_t r0 = (int64_t)(blockIdx.x / C) * R;
+    const int rows_here = (int)min((int64_t)R, n_rows - r0);
+    const int LD = (int)C * TPC + VEC;     // leaf-matrix row pitch (+16 B: 128-bit row reads of different rows hit different banks)
+    const int XP = F | 1;                  // x tile pitch
+    acc_t *leafbuf = reinterpret_cast<acc_t *>(smem + image_cap);                               // [rpr][LD], rows this rank owns
+    float *xs = reinterpret_cast<float *>(smem + image_cap + (size_t)rpr * LD * sizeof(acc_t));  // [R][XP]
+    uint64_t *load_bar = reinterpret_cast<uint64_t *>(
+        (reinterpret_cast<uintptr_t>(xs + (size_t)R * XP) + 15) & ~(uintptr_t)15);
+
+    B2S_STAMP(0);
+    const uint32_t img_lo = p.image_off[rank], img_bytes = p.image_off[rank + 1] - img_lo;
+    if (threadIdx.x == 0) {
+        mbar_init_cta(load_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    // split-phase cluster barrier #1: arrive now, wait right before the first remote store
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    if (warp == 0 && img_bytes > 0) {
+        if (lane == 0) mbar_expect_tx_cta(load_bar, img_bytes);
+        __syncwarp();
+        const unsigned char *src = p.images + img_lo;
+        for (uint32_t o = (uint32_t)lane * (uint32_t)bulk_piece; o < img_bytes; o += 32u * (uint32_t)bulk_piece)
+            bulk_g2s(smem + o, src + o, min((uint32_t)bulk_piece, img_bytes - o), load_bar);
+    }
+    {   // x tile, overlapped with the bulk copy
+        const float *src = X + r0 * F;
+        const int n = rows_here * F;
+        for (int i = threadIdx.x; i < R * F; i += blockDim.x) {
+            const int r = i / F, f = i - r * F;
+            xs[r * XP + f] = (i < n) ? __ldg(src + i) : 0.0f;
+        }
+    }
+    __syncthreads();
+    if (img_bytes > 0) {
+        uint32_t spins = 0;
+        while (!mbar_try_wait_cta(load_bar, 0u)) {
+            if (++spins > B2S_SPIN_LIMIT) __trap();
+        }
+    }
+    B2S_STAMP(1);
+
+    // ---- traverse out of shared memory: task q = (row, block of 32 trees), lane = tree inside the block
+    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(smem);   // {inode byte offset, leaf byte offset, trees here, -}
+    const int n_my = img_bytes > 0 ? (int)hdr[2] : 0;
+    const uint2 *tdesc = reinterpret_cast<const uint2 *>(smem + 16);
+    const uint2 *inodes = reinterpret_cast<const uint2 *>(smem + (img_bytes > 0 ? hdr[0] : 0u));
+    const acc_t *leaves = reinterpret_cast<const acc_t *>(smem + (img_bytes > 0 ? hdr[1] : 0u));
+    const int fb = p.feat_bits, cb = p.child_bits;
+    const uint32_t fmask = (1u << fb) - 1u, cmask = (1u << cb) - 1u, leafbit = 1u << (cb - 1);
+    const uint32_t leaf_local = (uint32_t)__cvta_generic_to_shared(leafbuf);
+    const int n_tb = (n_my + 31) >> 5;
+    const int n_tasks = n_tb * R;
+    bool waited = false;
+    for (int q = warp; q < n_tasks; q += n_warps) {
+        const int row = q % R, tb = q / R;
+        const int tl = tb * 32 + lane;
+        acc_t v = (acc_t)0;
+        if (tl < n_my) {
+            const uint2 d = tdesc[tl];
+            const float *xr = xs + row * XP;
+            uint2 nd = inodes[d.x];
+            for (int it = 0; it <= p.max_depth; ++it) {
+                const float x = xr[nd.y & fmask];
+                const float thr = __uint_as_float(nd.x);
+                const bool dl = (nd.y >> fb) & 1u;
+                const bool go_left = (x != x) ? dl : (x < thr);
+                const uint32_t ref = (go_left ? (nd.y >> (fb + 1)) : (nd.y >> (fb + 1 + cb))) & cmask;
+                if (ref & leafbit) {
+                    v = leaves[d.y + (ref & (leafbit - 1u))];
+                    break;
+                }
+                nd = inodes[d.x + ref];
+            }
+        }
+        __syncwarp();
+        if (!waited) {   // peers have started (their shared memory exists) before the first remote store
+            asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+            waited = true;
+        }
+        if (tl < n_my) {
+            const int owner = row / rpr, lr = row - owner * rpr;
+            const uint32_t remote = [&]() {
+                uint32_t ra;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(leaf_local), "r"((uint32_t)owner));
+                return ra;
+            }();
+            st_cluster(remote + (uint32_t)(((size_t)lr * LD + (size_t)rank * TPC + tl) * sizeof(acc_t)), v);
+        }
+    }
+    if (!waited) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    B2S_STAMP(2);
+    // every leaf value of the tile has landed in its owner's shared memory
+    cluster_sync_all();
+    B2S_STAMP(3);
+
+    // ---- ordered sum: lane i of warp 0 adds the column of row rank*rpr + i in tree order
+    if (warp == 0 && lane < rpr) {
+        const int row = (int)rank * rpr + lane;
+        if (row < rows_here) {
+            acc_t acc = F64 ? (acc_t)p.base : (acc_t)(float)p.base;
+            const acc_t *bp = leafbuf + (size_t)lane * LD;
+            typedef typename std::conditional<F64, double2, float4>::type vec_t;
+            constexpr int BLK = 4;                    // vectors per block (16 fp32 / 8 fp64 values): 64 cycles of dependent adds cover the 29-cycle LDS
+            const vec_t *vp = reinterpret_cast<const vec_t *>(bp);
+            const int n_blk = T / (VEC * BLK);
+            vec_t cur[BLK], nxt[BLK];
+            if (n_blk > 0) {
+#pragma unroll
+                for (int k = 0; k < BLK; ++k) cur[k] = vp[k];
+            }
+            for (int blk = 0; blk < n_blk; ++blk) {
+                if (blk + 1 < n_blk) {                // the next block's loads issue among this block's dependent adds
+#pragma unroll
+                    for (int k = 0; k < BLK; ++k) nxt[k] = vp[(blk + 1) * BLK + k];
+                }
+#pragma unroll
+                for (int k = 0; k < BLK; ++k) {
+                    if (F64) {
+                        const double2 d2 = *reinterpret_cast<const double2 *>(&cur[k]);
+                        acc = acc + (acc_t)d2.x;
+                        acc = acc + (acc_t)d2.y;
+                    } else {
+                        const float4 f4 = *reinterpret_cast<const float4 *>(&cur[k]);
+                        acc = acc + (acc_t)f4.x;
+                        acc = acc + (acc_t)f4.y;
+                        acc = acc + (acc_t)f4.z;
+                        acc = acc + (acc_t)f4.w;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < BLK; ++k) cur[k] = nxt[k];
+            }
+            for (int t = n_blk * VEC * BLK; t < T; ++t) acc = acc + bp[t];
+            if (F64) reinterpret_cast<double *>(out)[r0 + row] = (double)acc / p.divisor;
+            else reinterpret_cast<float *>(out)[r0 + row] = (float)acc;
+        }
+        B2S_STAMP(4);
+    }
+#undef B2S_STAMP
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernel A: one row per thread, all trees in order (large batches; no scratch).
 // ---------------------------------------------------------------------------------------------
@@ -568,6 +756,12 @@ struct ForestModel : Model {
     bool f64 = false;
     int max_smem_optin = 0;
     long long *dbg_stamps = nullptr;  // device buffer [8 CTAs][8 phases], only with B2S_FOREST_TIMING=1
+    // wide-cluster kernel over compact per-rank images (default serving path)
+    bool wide_ok = false;
+    WideParams wp{};
+    void *d_images = nullptr;
+    int wide_C = 1, wide_cap = 0;
+    size_t wide_fixed_smem = 0;   // image + barrier; the leaf matrix and the x tile depend on the row tile
     // staged (shared-memory resident) fast path
     bool staged_ok = false;
     SliceTable slices{};
@@ -577,6 +771,7 @@ struct ForestModel : Model {
     ~ForestModel() override
     {
         if (d_blob) { cudaSetDevice(device); cudaFree(d_blob); }
+        if (d_images) { cudaSetDevice(device); cudaFree(d_images); }
         if (dbg_stamps) cudaFree(dbg_stamps);
     }
 
@@ -625,6 +820,185 @@ struct ForestModel : Model {
         return 0;
     }
 
+
+    // row tile of the wide kernel for a batch: 16 rows per cluster at serving sizes, 32 for big batches
+    int wide_rows_per_tile(int64_t n_rows) const { return n_rows > 1024 ? 32 : 16; }
+    size_t wide_smem(int R) const
+    {
+        const size_t esz = f64 ? 8 : 4, vec = 16 / esz;
+        const int rpr = (R + wide_C - 1) / wide_C;
+        return (size_t)wide_cap + (size_t)rpr * ((size_t)wide_C * wp.tpc + vec) * esz + (size_t)R * (size_t)(p.n_features | 1) * 4 + 64;
+    }
+
+    template <bool F64>
+    int launch_wide(cudaStream_t st, const float *X, int64_t n_rows, void *out)
+    {
+        const int R = wide_rows_per_tile(n_rows);
+        const int rpr = (R + wide_C - 1) / wide_C;
+        const unsigned tiles = (unsigned)((n_rows + R - 1) / R);
+        int threads = ((wp.tpc + 31) / 32) * R * 32;     // one (tree, row) pair per thread when it fits
+        if (threads > 1024) threads = 1024;
+        if (threads < 64) threads = 64;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(tiles * wide_C, 1, 1);
+        cfg.blockDim = dim3(threads, 1, 1);
+        cfg.dynamicSmemBytes = wide_smem(R);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = wide_C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        static const int bulk_piece = []() {
+            const char *e = getenv("B2S_FOREST_BULK_PIECE");
+            int v = e ? atoi(e) : 4096;
+            return (v >= 1024 && v % 16 == 0) ? v : 4096;
+        }();
+        B2S_CUDA(cudaLaunchKernelEx(&cfg, forest_wide_kernel<F64>, wp, X, n_rows, out, R, rpr, wide_cap, bulk_piece, dbg_stamps));
+        return 0;
+    }
+
+    // Re-pack the v1 node array into one compact image per cluster rank (see kernel D) and upload them.
+    int build_wide(const uint32_t *toff, const uint64_t *nodes, const double *leaf64, const ForestBlobHeader &h, int max_depth)
+    {
+        const char *off = getenv("B2S_FOREST_WIDE");
+        if (off && off[0] == '0') return 0;
+        const int fb = (int)h.feat_bits;
+        const uint32_t T = h.n_trees;
+        // per-tree internal / leaf counts -> index width of the child references
+        uint32_t max_cnt = 1;
+        for (uint32_t t = 0; t < T; ++t) {
+            uint32_t ni = 0, nl = 0;
+            for (uint32_t i = toff[t]; i < toff[t + 1]; ++i) (((uint32_t)(nodes[i] >> 32) >> (fb + 1)) ? ni : nl) += 1;
+            if (ni > max_cnt) max_cnt = ni;
+            if (nl > max_cnt) max_cnt = nl;
+        }
+        int idx_bits = 1;
+        while ((1u << idx_bits) < max_cnt) ++idx_bits;
+        const int cb = idx_bits + 1;                       // + leaf flag
+        if (fb + 1 + 2 * cb > 32) return 0;                // trees too large for the compact node: kernels C / B serve the model
+        // cluster size: the largest the device schedules for this kernel, no larger than the forest can use
+        int c_max = 8;
+        {
+            const char *e = getenv("B2S_FOREST_WIDE_C");
+            int want = e ? atoi(e) : 16;
+            if (want > 8) {
+                cudaError_t ce = f64 ? cudaFuncSetAttribute(forest_wide_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)
+                                     : cudaFuncSetAttribute(forest_wide_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (ce == cudaSuccess) c_max = 16; else cudaGetLastError();
+            } else if (want >= 1) {
+                c_max = want;
+            }
+        }
+        int C = 1;
+        while (C < c_max && C * 32 < (int)T) C *= 2;
+        for (;; C /= 2) {
+            const int tpc = (int)round_up(((int64_t)T + C - 1) / C, 32);
+            // images
+            std::vector<std::vector<unsigned char>> img(C);
+            size_t cap = 0;
+            const size_t lsz = f64 ? 8 : 4;
+            for (int r = 0; r < C; ++r) {
+                const uint32_t t_lo = (uint32_t)r * (uint32_t)tpc;
+                if (t_lo >= T) continue;                   // empty rank: no image, no bytes
+                const uint32_t t_hi = t_lo + (uint32_t)tpc < T ? t_lo + (uint32_t)tpc : T;
+                std::vector<uint32_t> tdesc;
+                std::vector<uint64_t> inodes;
+                std::vector<unsigned char> leaves;
+                for (uint32_t t = t_lo; t < t_hi; ++t) {
+                    const uint32_t s = toff[t], n = toff[t + 1] - s;
+                    // local index of every node inside the internal / leaf arrays of its tree
+                    std::vector<uint32_t> loc(n);
+                    uint32_t ni = 0, nl = 0;
+                    for (uint32_t i = 0; i < n; ++i) loc[i] = ((uint32_t)(nodes[s + i] >> 32) >> (fb + 1)) ? ni++ : nl++;
+                    tdesc.push_back((uint32_t)inodes.size());
+                    tdesc.push_back((uint32_t)(leaves.size() / lsz));
+                    auto ref_of = [&](uint32_t i) -> uint32_t {
+                        const bool internal = ((uint32_t)(nodes[s + i] >> 32) >> (fb + 1)) != 0;
+                        return internal ? loc[i] : (loc[i] | (1u << (cb - 1)));
+                    };
+                    if (ni == 0) {   // a tree that is a single leaf: one dummy split whose both sides are leaf 0
+                        inodes.push_back(((uint64_t)((1u << (cb - 1)) << (fb + 1) | (1u << (cb - 1)) << (fb + 1 + cb))) << 32);
+                    }
+                    for (uint32_t i = 0; i < n; ++i) {
+                        const uint32_t val = (uint32_t)(nodes[s + i] & 0xffffffffu), meta = (uint32_t)(nodes[s + i] >> 32);
+                        const uint32_t left = meta >> (fb + 1);
+                        if (left) {
+                            const uint32_t m2 = (meta & ((1u << (fb + 1)) - 1u)) | ref_of(left) << (fb + 1) | ref_of(left + 1) << (fb + 1 + cb);
+                            inodes.push_back((uint64_t)val | ((uint64_t)m2 << 32));
+                        } else if (f64) {
+                            const double dv = leaf64[val];
+                            const unsigned char *b = reinterpret_cast<const unsigned char *>(&dv);
+                            leaves.insert(leaves.end(), b, b + 8);
+                        } else {
+                            const unsigned char *b = reinterpret_cast<const unsigned char *>(&val);
+                            leaves.insert(leaves.end(), b, b + 4);
+                        }
+                    }
+                }
+                const uint32_t n_here = t_hi - t_lo;
+                const size_t off_tdesc = 16, off_in = off_tdesc + (size_t)tpc * 8, off_leaf = off_in + inodes.size() * 8;
+                const size_t total = (size_t)round_up((int64_t)(off_leaf + leaves.size()), 16);
+                std::vector<unsigned char> &im = img[r];
+                im.assign(total, 0);
+                const uint32_t hdr[4] = {(uint32_t)off_in, (uint32_t)off_leaf, n_here, 0u};
+                memcpy(im.data(), hdr, 16);
+                memcpy(im.data() + off_tdesc, tdesc.data(), tdesc.size() * 4);
+                memcpy(im.data() + off_in, inodes.data(), inodes.size() * 8);
+                if (!leaves.empty()) memcpy(im.data() + off_leaf, leaves.data(), leaves.size());
+                if (total > cap) cap = total;
+            }
+            wide_C = C;
+            wide_cap = (int)round_up((int64_t)cap, 128);
+            wp.tpc = tpc;
+            const bool fits = wide_smem(32) <= (size_t)max_smem_optin;
+            bool schedulable = fits;
+            if (fits) {   // can the device co-schedule a cluster of C CTAs with this much shared memory?
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(C, 1, 1);
+                cfg.blockDim = dim3(1024, 1, 1);
+                cfg.dynamicSmemBytes = wide_smem(32);
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = C;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                int n_clusters = 0;
+                cudaError_t ce = f64 ? cudaOccupancyMaxActiveClusters(&n_clusters, forest_wide_kernel<true>, &cfg)
+                                     : cudaOccupancyMaxActiveClusters(&n_clusters, forest_wide_kernel<false>, &cfg);
+                if (ce != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
+                schedulable = n_clusters >= 1;
+            }
+            if (schedulable) {
+                size_t total = 0;
+                for (int r = 0; r < C; ++r) { wp.image_off[r] = (uint32_t)total; total += img[r].size(); }
+                for (int r = C; r <= kWideMaxC; ++r) wp.image_off[r] = (uint32_t)total;
+                B2S_CUDA(cudaMalloc(&d_images, total + 256));
+                B2S_CUDA(cudaMemset(d_images, 0, total + 256));
+                for (int r = 0; r < C; ++r)
+                    if (!img[r].empty())
+                        B2S_CUDA(cudaMemcpy(static_cast<unsigned char *>(d_images) + wp.image_off[r], img[r].data(), img[r].size(), cudaMemcpyHostToDevice));
+                wp.images = static_cast<const unsigned char *>(d_images);
+                wp.n_trees = (int)T;
+                wp.n_features = (int)h.n_features;
+                wp.feat_bits = fb;
+                wp.child_bits = cb;
+                wp.max_depth = max_depth;
+                wp.base = h.base;
+                wp.divisor = h.divisor;
+                wide_ok = true;
+                return 0;
+            }
+            if (C == 1) return 0;   // not even a single CTA can hold the forest: kernels C / B / A serve the model
+            // halving C doubles the image: only worth retrying when the cluster could not be scheduled
+            if (!fits) return 0;
+        }
+    }
+
     template <bool F64, int U>
     int launch_staged(cudaStream_t st, const float *X, int64_t n_rows, void *out)
     {
@@ -658,7 +1032,10 @@ struct ForestModel : Model {
         const float *X = static_cast<const float *>(d_in[0]);
         void *out = d_out[0];
         const int F = p.n_features;
-        if (n_rows <= kClusterMaxRows && staged_ok) {
+        if (n_rows <= kClusterMaxRows && wide_ok) {
+            if (f64) B2S_TRY((launch_wide<true>(st, X, n_rows, out)));
+            else B2S_TRY((launch_wide<false>(st, X, n_rows, out)));
+        } else if (n_rows <= kClusterMaxRows && staged_ok) {
             if (f64) B2S_TRY((launch_staged<true, kStU64>(st, X, n_rows, out)));
             else B2S_TRY((launch_staged<false, kStU32>(st, X, n_rows, out)));
         } else if (n_rows <= kClusterMaxRows) {
@@ -775,6 +1152,12 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
     cudaFuncSetAttribute(forest_rows_kernel<false, kRowsBlock, kRowsU>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     cudaFuncSetAttribute(forest_rows_kernel<true, kRowsBlock, kRowsU>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     m->max_smem_optin = want;
+    cudaFuncSetAttribute(forest_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    cudaFuncSetAttribute(forest_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    {
+        const int wrc = m->build_wide(toff, nodes, reinterpret_cast<const double *>(base + sizeof(h) + off_bytes + node_bytes), h, max_depth);
+        if (wrc != 0) { delete m; return wrc; }
+    }
     cudaFuncSetAttribute(forest_staged_kernel<false, kStWarps, kStU32>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     cudaFuncSetAttribute(forest_staged_kernel<true, kStWarps, kStU64>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     {   // can every CTA keep its slice of the forest in shared memory?

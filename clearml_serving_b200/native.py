@@ -84,6 +84,7 @@ PROTOTYPES = [
     ("b2s_infer_batch", _i, [_u64, _u64, _i32, _P(Tensor), _P(Tensor), _P(_u64)]),
     ("b2s_slot_acquire", _i, [_u64, _P(_i32), _P(_vp), _P(_vp)]),
     ("b2s_slot_submit", _i, [_u64, _u64, _i32, _i64, _vp, _P(_u64)]),
+    ("b2s_slot_collate", _i, [_u64, _u64, _i32, _i32, _vp, _vp, _vp, _P(_u64)]),
     ("b2s_slot_release", _i, [_u64, _i32]),
     ("b2s_event_wait", _i, [_u64]),
     ("b2s_event_query", _i, [_u64]),
@@ -330,6 +331,22 @@ class Stream(object):
             ro = row_offsets.ctypes.data
         check(lib().b2s_slot_submit(self.model.handle, self.handle, slot.index, int(n_rows), ro, ctypes.byref(ev)))
         return ev.value
+
+    def collate_submit(self, slot, requests):
+        """Collate `requests` (objects with .ptrs = host addresses of their inputs, .rows, .row_len) into `slot` INSIDE
+        the library (b2s_slot_collate: memcpy without the GIL, worker pool for large batches) and submit the batch.
+        Returns (event, n_rows)."""
+        n = len(requests)
+        ni = self.model.n_inputs
+        ptrs = np.fromiter((p for r in requests for p in r.ptrs), dtype=np.uint64, count=n * ni)
+        rows = np.fromiter((r.rows for r in requests), dtype=np.int64, count=n)
+        lens = None
+        if any(e < 0 for e in self.model.in_row_elems):
+            lens = np.fromiter((r.row_len for r in requests), dtype=np.int64, count=n)
+        ev = ctypes.c_uint64(0)
+        check(lib().b2s_slot_collate(self.model.handle, self.handle, slot.index, n, ptrs.ctypes.data, rows.ctypes.data,
+                                     lens.ctypes.data if lens is not None else None, ctypes.byref(ev)))
+        return ev.value, int(rows.sum())
 
     def release(self, slot):
         check(lib().b2s_slot_release(self.handle, slot.index))

@@ -337,7 +337,28 @@ class B200EngineMixin(object):
         return reps.pick().batcher if reps is not None else self._batcher
 
     # ---- request marshalling: the rules of preprocess_service.py:385-406 --------------------------
+    def _io_plan(self):
+        """Per-engine constants of the marshalling rules, computed once: (single fixed-width input without an io spec ->
+        its dtype and row width, else None; number of visible outputs; declared output dtypes or None)."""
+        ep = self.model_endpoint
+        m = self._native_model
+        fast = None
+        if not (getattr(ep, "input_name", None) and getattr(ep, "input_type", None)) and m.n_inputs == 1 \
+                and m.in_row_elems[0] > 0:
+            fast = (m.in_dtypes[0], m.in_row_elems[0])
+        n_visible = len(getattr(ep, "output_name", None) or []) or (1 if m.info.kind != native.MODEL_GRAPH else m.n_outputs)
+        n_visible = min(n_visible, m.n_outputs)
+        types = getattr(ep, "output_type", None)
+        out_types = [np.dtype(types[min(i, len(types) - 1)]) for i in range(n_visible)] if types else None
+        self._b200_plan = (fast, n_visible, out_types)
+        return self._b200_plan
+
     def _marshal(self, data):
+        plan = getattr(self, "_b200_plan", None) or self._io_plan()
+        fast = plan[0]
+        if fast is not None and type(data) is np.ndarray and data.ndim == 2 and data.dtype == fast[0] \
+                and data.shape[1] == fast[1] and data.flags.c_contiguous:
+            return [data], data.shape[0]    # the common serving case: one [rows, features] array of the model's dtype
         ep = self.model_endpoint
         m = self._native_model
         names = getattr(ep, "input_name", None)
@@ -389,18 +410,12 @@ class B200EngineMixin(object):
         """np.frombuffer + np.resize semantics of preprocess_service.py:430-446: arrays own their
         memory, dtype from the endpoint's output_type (clamped to the last declared), single output
         returned bare."""
-        ep = self.model_endpoint
-        m = self._native_model
-        n_visible = len(getattr(ep, "output_name", None) or []) or (1 if m.info.kind != native.MODEL_GRAPH else m.n_outputs)
-        n_visible = min(n_visible, m.n_outputs)
-        types = getattr(ep, "output_type", None)
-        res = []
-        for i in range(n_visible):
-            a = outs[i]
-            if types:
-                a = a.astype(np.dtype(types[min(i, len(types) - 1)]), copy=False)
-            res.append(a)
-        return res[0] if len(res) == 1 else res
+        _fast, n_visible, out_types = getattr(self, "_b200_plan", None) or self._io_plan()
+        if n_visible == 1:
+            return outs[0] if out_types is None else outs[0].astype(out_types[0], copy=False)
+        if out_types is None:
+            return list(outs[:n_visible])
+        return [outs[i].astype(out_types[i], copy=False) for i in range(n_visible)]
 
     # ---- binary tensor frames (wire.py): a request body that IS a frame needs no user preprocess code, and the
     #      reply goes back in the same framing; JSON / user-defined bodies take the reference's path untouched

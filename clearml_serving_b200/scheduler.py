@@ -13,10 +13,11 @@ implements those semantics in front of libb200serve:
     what is there.  D = 0 (default) dispatches immediately.
   * responses are per request (the batch output is split on dim 0).
 
-Threads: `dispatch` forms batches and collates the requests' rows straight into a pinned staging
-slot (numpy views over the library's arena), `complete` blocks in b2s_event_wait (GIL released),
-copies each request's rows out of the slot and resolves the futures -- one
-`loop.call_soon_threadsafe` per event loop per batch.
+Threads: `dispatch` forms batches and hands the requests' host pointers to the library, which collates
+their rows into a pinned staging slot and submits the batch (b2s_slot_collate: one C call per batch, GIL
+released); `complete` blocks in b2s_event_wait (GIL released), takes one copy per output out of the slot,
+gives every request row views of it and resolves the futures -- one `loop.call_soon_threadsafe` per event
+loop per batch.
 """
 import asyncio
 import bisect
@@ -97,11 +98,13 @@ def _parse_pbtxt(text):
 
 
 class _Request(object):
-    __slots__ = ("inputs", "rows", "t_enq", "loop", "afuture", "cfuture", "info")
+    __slots__ = ("inputs", "rows", "row_len", "ptrs", "t_enq", "loop", "afuture", "cfuture", "info")
 
     def __init__(self, inputs, rows):
-        self.inputs = inputs
+        self.inputs = inputs          # C-contiguous arrays [rows, row_elems], kept alive until the batch is collated
         self.rows = rows
+        self.row_len = inputs[0].shape[1] if inputs and inputs[0].ndim > 1 else 0
+        self.ptrs = [a.__array_interface__["data"][0] for a in inputs]
         self.t_enq = time.perf_counter()
         self.loop = None
         self.afuture = None
@@ -224,49 +227,42 @@ class DynamicBatcher(object):
             if expired:
                 self._fail(expired, ValueError("b200 engine: request timed out after {}s in the queue".format(
                     self.request_timeout_s)))
-            if not batch and self._queue:  # head does not fit a preferred size: take it alone
+            while not batch and self._queue:  # head does not fit a preferred size: take it alone
                 r = self._queue.popleft()
+                if self.request_timeout_s is not None and time.perf_counter() - r.t_enq > self.request_timeout_s:
+                    self._queued_rows -= r.rows
+                    self._fail([r], ValueError("b200 engine: request timed out after {}s in the queue".format(
+                        self.request_timeout_s)))
+                    continue
                 rows += r.rows
                 batch.append(r)
             self._queued_rows -= rows
             return batch
 
     def _dispatch_loop(self):
-        m = self.model
         while True:
             batch = self._take_batch()
             if batch is None:
                 break
+            if not batch:      # every popped request had expired in the queue
+                continue
             self.stats["requests"] += len(batch)   # every request taken off the queue; failures are counted on top
+            slot = None
             try:
                 slot = self._acquire_slot()
-                n_rows = 0
-                offsets = None
-                if self.ragged:
-                    # collate variable-length rows back to back (packed tokens) + cu_seqlens
-                    lens = []
-                    for r in batch:
-                        a = r.inputs[0]
-                        lens.extend([a.shape[1]] * a.shape[0])
-                    offsets = np.zeros(len(lens) + 1, dtype=np.int64)
-                    np.cumsum(lens, out=offsets[1:])
-                    n_rows, n_tok = len(lens), int(offsets[-1])
-                    for i in range(m.n_inputs):
-                        parts = [r.inputs[i].reshape(-1) for r in batch]
-                        if len(parts) == 1:
-                            slot.inputs[i][:n_tok] = parts[0]
-                        else:
-                            np.concatenate(parts, out=slot.inputs[i][:n_tok])
-                else:
-                    for i in range(m.n_inputs):
-                        parts = [r.inputs[i] for r in batch]
-                        n_rows = sum(p.shape[0] for p in parts)
-                        if len(parts) == 1:
-                            slot.inputs[i][:n_rows] = parts[0]
-                        else:
-                            np.concatenate(parts, axis=0, out=slot.inputs[i][:n_rows])
                 t_disp = time.perf_counter()
-                ev = self.stream.submit(slot, n_rows, offsets)
+                if self.request_timeout_s is not None:   # the wait for a free slot counts against the deadline too
+                    late = [r for r in batch if t_disp - r.t_enq > self.request_timeout_s]
+                    if late:
+                        batch = [r for r in batch if t_disp - r.t_enq <= self.request_timeout_s]
+                        self._fail(late, ValueError("b200 engine: request timed out after {}s in the queue".format(
+                            self.request_timeout_s)))
+                        if not batch:
+                            self.stream.release(slot)
+                            continue
+                # the collate (rows back to back in request order, cu_seqlens for variable-length models) happens inside
+                # the library, without the GIL
+                ev, n_rows = self.stream.collate_submit(slot, batch)
                 st = self.stats
                 st["batches"] += 1
                 st["rows"] += n_rows
@@ -276,6 +272,7 @@ class DynamicBatcher(object):
                     st["max_batch_rows"] = n_rows
                 st["batch_rows_hist"][bisect.bisect_left(BATCH_ROWS_BUCKETS, n_rows)] += 1
                 for r in batch:
+                    r.inputs = None    # the rows now live in the slot
                     if r.info is not None:
                         r.info["batch_rows"] = n_rows
                         r.info["queue_us"] = (t_disp - r.t_enq) * 1e6
@@ -283,7 +280,14 @@ class DynamicBatcher(object):
                 with self._inflight_cond:
                     self._inflight.append((ev, slot, batch, t_disp))
                     self._inflight_cond.notify()
-            except Exception as ex:  # a failed batch fails only its own requests
+            except Exception as ex:  # a failed batch fails only its own requests -- and gives its slot back
+                if slot is not None:
+                    try:
+                        self.stream.release(slot)
+                    except Exception:  # noqa
+                        pass
+                    with self._inflight_cond:
+                        self._inflight_cond.notify_all()
                 self._fail(batch, ex)
 
     def _acquire_slot(self):

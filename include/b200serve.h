@@ -150,6 +150,17 @@ B2S_API int b2s_slot_acquire(b2s_stream_t stream, int32_t *out_slot, void **in_p
                      void **out_ptr /*[n_outputs]*/);
 B2S_API int b2s_slot_submit(b2s_model_t model, b2s_stream_t stream, int32_t slot, int64_t n_rows,
                     const int64_t *row_offsets, b2s_event_t *out_done);
+/* Collate INSIDE the library (no GIL, worker pool for large batches) into an acquired slot and submit it:
+ * in_ptrs[req * n_inputs + i] = host pointer of request `req`'s input i (C-contiguous, the model's dtype),
+ * req_rows[req] = that request's own batch rows, req_row_len[req] = elements per row of its variable-length inputs
+ * (NULL for fixed-width models).  Rows are packed back to back in request order; for variable-length models the
+ * slot's row-offset table (cu_seqlens) is written too.  The outputs are read from the slot's out_ptr after
+ * b2s_event_wait, then b2s_slot_release.  This is what the Python dynamic batcher calls per batch: it replaces
+ * the per-request np.array(...).flatten() -> protobuf of preprocess_service.py:393-406 and tritonserver's batch
+ * gather. */
+B2S_API int b2s_slot_collate(b2s_model_t model, b2s_stream_t stream, int32_t slot, int32_t n_req,
+                             const void *const *in_ptrs, const int64_t *req_rows, const int64_t *req_row_len,
+                             b2s_event_t *out_done);
 B2S_API int b2s_slot_release(b2s_stream_t stream, int32_t slot);
 
 /* Completion: wait (blocking, no GIL needed) / poll.  b2s_event_wait performs the scatter of

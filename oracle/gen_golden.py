@@ -9,6 +9,9 @@ Fixtures
                        ModelRequestProcessor.process_request -> SKLearnPreprocessRequest.process
                        (model_request_processor.py:253-304,1309-1369; preprocess_service.py:459-464)
   sk_gbr.npz sk_rf.npz tree ensembles through the same reference engine class (fp64 outputs)
+  sk_gbr_cfg2.npz      the same engine class at the BASELINE.json configs[1] SHAPE: GradientBoostingRegressor with
+                       1000 stages x depth 6 on 32 features (the headline workload's tree count / depth / width,
+                       produced by the reference itself), incl. rows on thresholds +-1 ulp
   triton_marshal.json  the reference's TritonPreprocessRequest.process (preprocess_service.py:313-446)
                        run unmodified against an in-process fake tritonserver: wire-level dtypes /
                        shapes and decoded outputs for the marshalling edge cases
@@ -139,6 +142,35 @@ def gen_trees(ref):
           "max|d|", float(np.abs(chk - y).max()))
 
 
+def gen_trees_cfg2(ref):
+    """BASELINE.json configs[1] shape through the REAL reference engine class
+    (SKLearnPreprocessRequest.process, preprocess_service.py:459-464): 1000 trees x depth 6 x 32 features."""
+    from sklearn.ensemble import GradientBoostingRegressor
+    rng = np.random.default_rng(11)
+    F = 32
+    Xtr = rng.standard_normal((3000, F))
+    ytr = (Xtr[:, 0] * 2 + np.sin(Xtr[:, 1] * 3) + Xtr[:, 2] * Xtr[:, 3] + np.abs(Xtr[:, 4:12]).sum(1) * 0.3
+           + 0.5 * rng.standard_normal(3000))
+    gbr = GradientBoostingRegressor(n_estimators=1000, max_depth=6, learning_rate=0.05, subsample=0.5,
+                                    random_state=0).fit(Xtr, ytr)
+    forest = orc.forest_from_sklearn([e[0] for e in gbr.estimators_], F)
+    X = _tree_inputs(forest, F, rng, n=320)
+    ep = ref.endpoints.ModelEndpoint(engine_type="sklearn", serving_url="trees_cfg2")
+    eng = rh.make_engine(ref, ref.ps.SKLearnPreprocessRequest, ep, model=gbr)
+    y = np.asarray(eng.process(X, {}, None), dtype=np.float64)
+    # one request at a time as the serving path sees them (batch = 1): must be the same bits
+    y1 = np.concatenate([np.asarray(eng.process(X[i:i + 1], {}, None), dtype=np.float64) for i in range(64)])
+    assert np.array_equal(y1, y[:64])
+    init = float(gbr.init_.constant_.ravel()[0])
+    compact = dict(forest)
+    compact["feat"] = forest["feat"].astype(np.int16)
+    np.savez_compressed(os.path.join(GOLD, "sk_gbr_cfg2.npz"), X=X, y=y, init=init, scale=float(gbr.learning_rate),
+                        divisor=1.0, **compact)
+    chk = orc.forest_predict_f64(forest, X, init, float(gbr.learning_rate), 1.0)
+    print("sk_gbr_cfg2: trees", len(forest["tree_offset"]) - 1, "nodes", len(forest["left"]),
+          "oracle bit-identical to reference:", bool(np.array_equal(chk, y)), "max|d|", float(np.abs(chk - y).max()))
+
+
 def gen_triton_marshal(ref):
     """Each case: endpoint io spec + python `data` -> what went on the wire + what came back."""
     cases = []
@@ -254,6 +286,7 @@ def main():
     ref = rh.load_reference()
     lr = gen_lr(ref)
     gen_trees(ref)
+    gen_trees_cfg2(ref)
     gen_triton_marshal(ref)
     gen_rest(ref, lr)
 

@@ -41,6 +41,7 @@ class FakeStream(object):
         self.fail_on = fail_on
         self.pending = {}
         self.n = 0
+        self.max_row_elems = 0
 
     def acquire(self):
         from clearml_serving_b200 import native
@@ -52,10 +53,18 @@ class FakeStream(object):
     def submit(self, slot, n_rows, row_offsets=None):
         self.n += 1
         self.batches.append(int(n_rows))
-        if self.fail_on is not None and self.n == self.fail_on:
+        if self.fail_on is not None and (self.n in self.fail_on if isinstance(self.fail_on, (set, list, tuple)) else self.n == self.fail_on):
             raise ValueError("injected submit failure")
         self.pending[self.n] = (slot, n_rows, time.perf_counter())
         return self.n
+
+    def collate_submit(self, slot, requests):
+        """host-side stand-in for b2s_slot_collate: rows back to back in request order"""
+        n_rows = 0
+        for r in requests:
+            slot.inputs[0][n_rows:n_rows + r.rows] = r.inputs[0]
+            n_rows += r.rows
+        return self.submit(slot, n_rows), n_rows
 
     def wait(self, ev):
         slot, n_rows, t0 = self.pending.pop(ev)

@@ -68,6 +68,27 @@ def test_cfg2_ragged_batch_sizes_with_nan(gpu_native, cfg2, n_rows):
         st.destroy()
 
 
+@pytest.mark.parametrize("env", [{"B2S_FOREST_WIDE": "0"}, {"B2S_FOREST_WIDE": "0", "B2S_FOREST_NO_STAGED": "1"},
+                                 {"B2S_FOREST_WIDE_C": "8"}, {"B2S_FOREST_WIDE_C": "4"}])
+def test_cfg2_other_kernel_forms_same_bits(gpu_native, monkeypatch, env):
+    """the fallback kernels (staged slices / plain cluster: forests the compact images cannot hold) and the wide
+    kernel at smaller cluster sizes (2 / 4 rows per owner rank) produce the same bits as the default form"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    forest = orc.synth_xgb_forest(n_trees=1000, depth=6, n_features=32, seed=0)
+    pm = formats.pack_forest(forest, "xgb", base=0.5)
+    model = gpu_native.Model(pm.kind, pm.blob, device=0)     # the switches are read at model load
+    rng = np.random.default_rng(21)
+    st = gpu_native.Stream(model, 1500, 0, 2)
+    try:
+        for n in (1, 17, 64, 300, 1500):
+            X = rng.standard_normal((n, 32)).astype(np.float32)
+            X[rng.random(X.shape) < 0.01] = np.nan
+            assert np.array_equal(_run_batch(gpu_native, model, st, [X])[0], orc.forest_predict_xgb(forest, X, 0.5))
+    finally:
+        st.destroy(); model.free()
+
+
 def test_cfg2_large_batch_rows_kernel_and_device_path(gpu_native, cfg2):
     """> 4096 rows takes the one-row-per-thread kernel; also exercises b2s_infer_device."""
     forest, model = cfg2
@@ -132,6 +153,25 @@ def test_sklearn_goldens_bit_exact(gpu_native, golden_dir, name):
         X = g["X"]
         got = np.concatenate(_run_batch(gpu_native, model, st, [X[:100], X[100:101], X[101:]]))
         assert got.dtype == np.float64 and np.array_equal(got, g["y"])
+    finally:
+        st.destroy(); model.free()
+
+
+def test_cfg2_shape_golden_bit_exact(gpu_native, golden_dir):
+    """BASELINE.json configs[1] SHAPE (1000 trees x depth 6 x 32 features), outputs of the reference's own
+    SKLearnPreprocessRequest.process: the GPU fp64 forest must reproduce every bit, as one batch, as single-row
+    requests collated by the C ABI (max_batch 64, the serving shape) and on rows sitting on thresholds +-1 ulp."""
+    g = _load(golden_dir, "sk_gbr_cfg2.npz")
+    pm = formats.pack_forest(g, "skl", base=float(g["init"]), scale=float(g["scale"]), divisor=float(g["divisor"]))
+    model = gpu_native.Model(pm.kind, pm.blob, device=0)
+    st = gpu_native.Stream(model, 320, 0, 2)
+    try:
+        X = g["X"]
+        got = _run_batch(gpu_native, model, st, [X])[0]
+        assert got.dtype == np.float64 and np.array_equal(got, g["y"])
+        for s in range(0, 320, 64):
+            got = np.concatenate(_run_batch(gpu_native, model, st, [X[i:i + 1] for i in range(s, s + 64)]))
+            assert np.array_equal(got, g["y"][s:s + 64])
     finally:
         st.destroy(); model.free()
 

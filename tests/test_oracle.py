@@ -12,12 +12,34 @@ def _load(golden_dir, name):
     return dict(np.load(os.path.join(golden_dir, name)))
 
 
-@pytest.mark.parametrize("name", ["sk_gbr.npz", "sk_rf.npz"])
+@pytest.mark.parametrize("name", ["sk_gbr.npz", "sk_rf.npz", "sk_gbr_cfg2.npz"])
 def test_forest_f64_bit_identical_to_reference(golden_dir, name):
     g = _load(golden_dir, name)
     y = orc.forest_predict_f64(g, g["X"], float(g["init"]), float(g["scale"]), float(g["divisor"]))
     assert y.dtype == np.float64
     assert np.array_equal(y, g["y"]), "oracle differs from the reference's SKLearnPreprocessRequest.process"
+
+
+def test_cfg2_shape_golden_is_the_baseline_shape(golden_dir):
+    """tests/golden/sk_gbr_cfg2.npz pins the oracle at the BASELINE.json configs[1] SHAPE with outputs of the
+    reference's own engine class: 1000 trees, depth 6, 32 features, rows on thresholds +-1 ulp included."""
+    g = _load(golden_dir, "sk_gbr_cfg2.npz")
+    off = g["tree_offset"]
+    assert len(off) - 1 == 1000 and int(g["n_features"]) == 32
+    depth = 0
+    for t in range(0, 1000, 97):
+        s, e = int(off[t]), int(off[t + 1])
+        d = np.zeros(e - s, np.int32)
+        for i in range(e - s):
+            if g["left"][s + i] >= 0:
+                d[g["left"][s + i]] = d[g["right"][s + i]] = d[i] + 1
+        depth = max(depth, int(d.max()))
+    assert depth == 6
+    # rows 0..2 of every triple sit on / just above / just below a split threshold of the model
+    internal = np.nonzero(g["left"] >= 0)[0]
+    thr32 = set(np.float32(g["thr"][internal]).tolist())
+    on = sum(1 for j in range(0, 288, 3) if any(np.float32(v) in thr32 for v in g["X"][j]))
+    assert on >= 90
 
 
 def test_forest_f64_multithreaded_same_bits(golden_dir):

@@ -161,3 +161,42 @@ def test_random_request_streams_keep_the_batcher_invariants():
         finally:
             b.shutdown()
     run()
+
+
+def test_failed_batches_give_their_staging_slot_back():
+    """regression: a submit / collate failure used to leave the slot ACQUIRED; after n_slots failures the
+    dispatcher spun in _acquire_slot forever and every later request of the endpoint hung"""
+    b, s = _mk(BatchPolicy(max_batch_size=4, n_slots=2), fail_on={1, 2, 3})
+    try:
+        for _ in range(3):
+            f = b.submit([np.ones((1, 3), np.float32)], 1)
+            with pytest.raises(ValueError, match="injected"):
+                f.result(timeout=5)
+        assert sorted(s.free) == [0, 1]
+        ok = b.submit([np.ones((2, 3), np.float32)], 2)
+        assert np.array_equal(ok.result(timeout=5)[0], [3.0, 3.0])
+        assert b.snapshot_stats()["failed_requests"] == 3
+    finally:
+        b.shutdown()
+
+
+def test_expired_requests_do_not_form_an_empty_batch():
+    """every queued request older than request_timeout_s: all of them fail with the timeout error, nothing is
+    dispatched, and the endpoint keeps serving (the head-alone path honours the deadline too)"""
+    model = FakeModel(n_features=3)
+    stream = FakeStream(model, 4, n_slots=1, latency_s=0.15)
+    b = DynamicBatcher(model, BatchPolicy(max_batch_size=4, n_slots=1, preferred_batch_size=[4]), name="exp", stream=stream,
+                       request_timeout_s=0.05)
+    try:
+        first = b.submit([np.ones((4, 3), np.float32)], 4)          # occupies the only slot for 150 ms
+        time.sleep(0.01)
+        late = [b.submit([np.ones((3, 3), np.float32)], 3) for _ in range(3)]   # 3 rows: each goes "head alone"
+        assert first.result(timeout=5)[0].shape == (4,)
+        for f in late:
+            with pytest.raises(ValueError, match="timed out"):
+                f.result(timeout=5)
+        fresh = b.submit([np.ones((1, 3), np.float32)], 1)
+        assert fresh.result(timeout=5)[0][0] == 3
+        assert all(n > 0 for n in stream.batches)
+    finally:
+        b.shutdown()
