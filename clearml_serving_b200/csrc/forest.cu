@@ -39,8 +39,9 @@ struct ForestBlobHeader {
     uint32_t n_trees, n_features, n_nodes, feat_bits;
     uint32_t acc_mode;  // 0: fp32 sequential (xgboost), 1: fp64 sequential (sklearn)
     uint32_t n_leaf64;
-    uint32_t reserved0, reserved1;
-    double base;     // base_score / init
+    uint32_t link;   // 0 identity, 1 xgboost's fp32 logistic transform of the margin (binary:logistic / reg:logistic)
+    uint32_t reserved1;
+    double base;     // base margin / init
     double divisor;  // 1.0 unless random-forest averaging
 };
 static_assert(sizeof(ForestBlobHeader) == 56, "blob header layout");
@@ -51,7 +52,19 @@ struct ForestParams {
     const double *leaf64;
     int n_trees, n_features, feat_bits, max_depth;
     double base, divisor;
+    int link;
 };
+
+// xgboost's Sigmoid (src/common/math.h): 1 / (expf(min(-x, 88.7f)) + 1 + 1e-16f), fp32.  expf here is CUDA's
+// (<= 2 ulp), the CPU library's is libm's: the MARGIN is bit-exact, the probability is within a few ulp.
+__device__ __forceinline__ float forest_link_f32(float margin, int link)
+{
+    if (link == 1) {
+        const float x = fminf(-margin, 88.7f);
+        return __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(expf(x), 1.0f), 1e-16f));
+    }
+    return margin;
+}
 
 __device__ __forceinline__ uint2 ld_node(const uint2 *p) { return __ldg(p); }
 
@@ -214,7 +227,7 @@ forest_cluster_kernel(ForestParams p, const float *__restrict__ X, int64_t n_row
     }
     if (rank == 0 && warp == 0 && row_ok) {
         if (F64) reinterpret_cast<double *>(out)[r0 + lane] = (double)acc / p.divisor;
-        else reinterpret_cast<float *>(out)[r0 + lane] = (float)acc;
+        else reinterpret_cast<float *>(out)[r0 + lane] = forest_link_f32((float)acc, p.link);
     }
 #undef B2S_STAMP
 }
@@ -490,83 +503,108 @@ forest_staged_kernel(ForestParams p, SliceTable st, const float *__restrict__ X,
     }
     if (rank == 0 && warp == 0 && half == 0 && row16 < rows_here) {
         if (F64) reinterpret_cast<double *>(out)[r0 + row16] = (double)acc / p.divisor;
-        else reinterpret_cast<float *>(out)[r0 + row16] = (float)acc;
+        else reinterpret_cast<float *>(out)[r0 + row16] = forest_link_f32((float)acc, p.link);
     }
 #undef B2S_STAMP
 }
 
 
 // ---------------------------------------------------------------------------------------------
-// Kernel D (serving batches, default): "wide" clusters over COMPACT tree slices.
+// Kernel D (serving batches, default): "wide" clusters over COMPACT, lane-interleaved tree blocks.
 // What bounded kernel C (profiles/r01_forest_staged_phase_timing.txt, r01_ncu_forest_staged.txt):
 //   (1) 8-byte leaf slots: 1.37x the algorithmic DRAM bytes and 130 KB per CTA to stage;
 //   (2) every leaf value of a 16-row tile funnelled into ONE SM through distributed shared memory, whose
 //       ingest rate is ~20 B/clk (57 KB -> ~2900 cycles of the 4400-cycle traverse+publish phase);
-//   (3) a per-source-rank barrier round trip (~230 cycles x 8) inside the ordered sum.
+//   (3) a per-source-rank barrier round trip (~230 cycles x 8) inside the ordered sum;
+//   (4) random 8-byte node reads out of shared memory: ~4-way bank conflicts on every level.
 // Here
-//   * the model is re-packed at load time into one COMPACT image per cluster rank: internal nodes 8 B
-//     {f32 threshold | feat, default_left, left ref, right ref}, leaves 4 B (fp32 mode) / 8 B (fp64 mode, the
-//     pre-scaled double itself: no leaf64[] indirection) -- exactly the algorithmic bytes of SURVEY.md 8(d);
+//   * the model is re-packed at load time into one image per cluster rank, made of BLOCKS of 32 consecutive trees:
+//     internal nodes 8 B {f32 threshold | feat, default_left, left ref, right ref}, leaves 4 B (fp32 mode) / 8 B
+//     (fp64 mode, the pre-scaled double itself: no leaf64[] indirection) -- the algorithmic bytes of SURVEY.md 8(d) for
+//     complete trees; inside a block, node j of tree t sits at [j][t] (lane-interleaved, trees padded to the block's
+//     largest): a warp walks 32 trees, lane = tree, so every level's node read hits 32 distinct banks whatever
+//     path each lane took;
 //   * a cluster of up to 16 CTAs (non-portable size) shares a tile of R rows: rank r stages trees
-//     [r*TPC, (r+1)*TPC) (48.6 KB for 64 depth-6 trees) with cp.async.bulk and traverses them for all R rows out
-//     of shared memory, one (tree, row) pair per thread;
+//     [r*TPC, (r+1)*TPC) (48.6 KB for 64 depth-6 trees) with cp.async.bulk, one mbarrier per block, so the warps
+//     of block 0 start walking while block 1 is still in flight; one (tree, row) pair per thread;
 //   * ALL-TO-ALL publish: row `i` of the tile is OWNED by rank i / rows_per_rank; a warp holds 32 consecutive trees
-//     of one row, so it sends one coalesced 128-byte st.shared::cluster to the owner: every SM ingests only
-//     rows_per_rank * T values (4 KB at R = 16, C = 16) instead of one SM ingesting R * T;
-//   * ONE cluster barrier, then each rank runs the bit-exactness-mandated sequential chain of ITS rows out of local
-//     shared memory (128-bit loads one block ahead of the dependent adds).
+//     of one row, so it sends one coalesced 128-byte st.shared::cluster to the owner and arrives (release.cluster) on
+//     the owner's mbarrier: every SM ingests only rows_per_rank * T values (4 KB at R = 16, C = 16), and nobody
+//     waits for more than its own rows -- no cluster-wide barrier after start-up;
+//   * each rank then runs the bit-exactness-mandated sequential chain of ITS rows out of local shared memory
+//     (128-bit loads one block ahead of the dependent adds, 64 adds per branch).
 // grid = C * ceil(rows / R) CTAs, cluster (C,1,1), 1 CTA per SM.  Forests the compact encoding or a single image
 // per rank cannot hold fall back to kernels C / B.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWideMaxC = 16;
+constexpr int kWideMaxBlocks = 8;         // 32-tree blocks per rank image (TPC <= 256)
 struct WideParams {
     const unsigned char *images;          // all rank images back to back (16-byte aligned each)
     uint32_t image_off[kWideMaxC + 1];    // byte offset of rank r's image, [C] = end
-    int n_trees, n_features, feat_bits, child_bits, tpc, max_depth;
+    int n_trees, n_features, feat_bits, child_bits, tpc, max_depth, link;
+    int total_blocks;                     // 32-tree blocks of the whole forest
+    int null_mode;                        // developer aid (B2S_FOREST_WIDE_NULL=1): every thread returns at once -> launch floor
+    uint32_t sentinel;                    // fp32 bit pattern no leaf of the model carries (fp64: high and low word)
     double base, divisor;
+    uint32_t blk_end[kWideMaxC][kWideMaxBlocks];   // byte offset of the end of block b inside rank r's image
 };
+// rank image: [hdr 16 B: trees here | blocks here | - | -][block table: kWideMaxBlocks x {u32 inode byte offset, u32 leaf
+// byte offset, u32 end byte offset, u32 -}][block 0: inodes [ni0][32] uint2, leaves [nl0][32]][block 1 ...]
+constexpr int kWideHdrBytes = 16 + kWideMaxBlocks * 16;
 
 template <bool F64>
 __global__ void __launch_bounds__(1024, 1)
-forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict__ X, int64_t n_rows, void *__restrict__ out, int R, int rpr,
-                   int image_cap, int bulk_piece, long long *__restrict__ dbg)
+forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict__ X, int64_t n_rows, void *__restrict__ out, int R_log2,
+                   int rpr_log2, int image_cap, int bulk_piece, long long *__restrict__ dbg)
 {
 #define B2S_STAMP(k)                                                                    \
     do {                                                                                \
         if (dbg && blockIdx.x < 8 && threadIdx.x == 0) dbg[blockIdx.x * 8 + (k)] = clock64(); \
     } while (0)
+    if (p.null_mode) return;
     using acc_t = typename std::conditional<F64, double, float>::type;
+    using bits_t = typename std::conditional<F64, unsigned long long, uint32_t>::type;
     constexpr int VEC = 16 / (int)sizeof(acc_t);
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int F = p.n_features, T = p.n_trees, TPC = p.tpc;
+    const int R = 1 << R_log2, rpr = 1 << rpr_log2;
     const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
-    const int64_t r0 = (int64_t)(blockIdx.x / C) * R;
+    const int64_t r0 = (int64_t)(blockIdx.x / C) << R_log2;
     const int rows_here = (int)min((int64_t)R, n_rows - r0);
     const int LD = (int)C * TPC + VEC;     // leaf-matrix row pitch (+16 B: 128-bit row reads of different rows hit different banks)
     const int XP = F | 1;                  // x tile pitch
     acc_t *leafbuf = reinterpret_cast<acc_t *>(smem + image_cap);                               // [rpr][LD], rows this rank owns
     float *xs = reinterpret_cast<float *>(smem + image_cap + (size_t)rpr * LD * sizeof(acc_t));  // [R][XP]
-    uint64_t *load_bar = reinterpret_cast<uint64_t *>(
-        (reinterpret_cast<uintptr_t>(xs + (size_t)R * XP) + 15) & ~(uintptr_t)15);
+    uint64_t *load_bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(xs + (size_t)R * XP) + 15) & ~(uintptr_t)15);  // [kWideMaxBlocks]
 
     B2S_STAMP(0);
     const uint32_t img_lo = p.image_off[rank], img_bytes = p.image_off[rank + 1] - img_lo;
+    const int n_my = max(0, min(T - (int)rank * TPC, TPC));
+    const int n_tb = (n_my + 31) >> 5;     // 32-tree blocks of this rank
+    const bits_t sentinel = F64 ? (((unsigned long long)p.sentinel << 32) | p.sentinel) : (bits_t)p.sentinel;
     if (threadIdx.x == 0) {
-        mbar_init_cta(load_bar, 1);
+        for (int b = 0; b < n_tb; ++b) mbar_init_cta(&load_bar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-    // split-phase cluster barrier #1: arrive now, wait right before the first remote store
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-    if (warp == 0 && img_bytes > 0) {
-        if (lane == 0) mbar_expect_tx_cta(load_bar, img_bytes);
-        __syncwarp();
+        // one bulk copy per piece, all issued by this thread: block b's bytes are [end of block b-1, end of block b)
         const unsigned char *src = p.images + img_lo;
-        for (uint32_t o = (uint32_t)lane * (uint32_t)bulk_piece; o < img_bytes; o += 32u * (uint32_t)bulk_piece)
-            bulk_g2s(smem + o, src + o, min((uint32_t)bulk_piece, img_bytes - o), load_bar);
+        uint32_t lo = 0;
+        for (int b = 0; b < n_tb; ++b) {
+            const uint32_t hi = p.blk_end[rank][b];
+            mbar_expect_tx_cta(&load_bar[b], hi - lo);
+            for (uint32_t o = lo; o < hi; o += (uint32_t)bulk_piece)
+                bulk_g2s(smem + o, src + o, min((uint32_t)bulk_piece, hi - o), &load_bar[b]);
+            lo = hi;
+        }
     }
-    {   // x tile, overlapped with the bulk copy
+    {   // the rows this rank owns start as "nothing has landed": every slot carries the sentinel pattern
+        bits_t *lb = reinterpret_cast<bits_t *>(leafbuf);
+        for (int i = threadIdx.x; i < rpr * LD; i += blockDim.x) lb[i] = sentinel;
+    }
+    // split-phase cluster barrier: arrive (sentinels written: release) now, wait right before the first remote store
+    __syncwarp();   // .aligned: lane 0 of warp 0 is back from its bulk-copy loop
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    {   // x tile, overlapped with the bulk copies
         const float *src = X + r0 * F;
         const int n = rows_here * F;
         for (int i = threadIdx.x; i < R * F; i += blockDim.x) {
@@ -575,72 +613,102 @@ forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict
         }
     }
     __syncthreads();
-    if (img_bytes > 0) {
-        uint32_t spins = 0;
-        while (!mbar_try_wait_cta(load_bar, 0u)) {
-            if (++spins > B2S_SPIN_LIMIT) __trap();
-        }
-    }
-    B2S_STAMP(1);
 
-    // ---- traverse out of shared memory: task q = (row, block of 32 trees), lane = tree inside the block
-    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(smem);   // {inode byte offset, leaf byte offset, trees here, -}
-    const int n_my = img_bytes > 0 ? (int)hdr[2] : 0;
-    const uint2 *tdesc = reinterpret_cast<const uint2 *>(smem + 16);
-    const uint2 *inodes = reinterpret_cast<const uint2 *>(smem + (img_bytes > 0 ? hdr[0] : 0u));
-    const acc_t *leaves = reinterpret_cast<const acc_t *>(smem + (img_bytes > 0 ? hdr[1] : 0u));
+    // ---- traverse out of shared memory: task q = (block of 32 trees, row), lane = tree inside the block
     const int fb = p.feat_bits, cb = p.child_bits;
     const uint32_t fmask = (1u << fb) - 1u, cmask = (1u << cb) - 1u, leafbit = 1u << (cb - 1);
     const uint32_t leaf_local = (uint32_t)__cvta_generic_to_shared(leafbuf);
-    const int n_tb = (n_my + 31) >> 5;
-    const int n_tasks = n_tb * R;
+    const int n_tasks = n_tb << R_log2;
     bool waited = false;
+    int tb_ready = -1;
     for (int q = warp; q < n_tasks; q += n_warps) {
-        const int row = q % R, tb = q / R;
+        const int row = q & (R - 1), tb = q >> R_log2;
         const int tl = tb * 32 + lane;
+        if (tb != tb_ready) {
+            uint32_t spins = 0;
+            if (tb_ready < 0 && tb > 0) {     // the block table rides with block 0
+                while (!mbar_try_wait_cta(&load_bar[0], 0u)) {
+                    if (++spins > B2S_SPIN_LIMIT) __trap();
+                }
+            }
+            while (!mbar_try_wait_cta(&load_bar[tb], 0u)) {
+                if (++spins > B2S_SPIN_LIMIT) __trap();
+            }
+            tb_ready = tb;
+            if (q == 0) B2S_STAMP(1);
+        }
         acc_t v = (acc_t)0;
         if (tl < n_my) {
-            const uint2 d = tdesc[tl];
+            const uint32_t *tab = reinterpret_cast<const uint32_t *>(smem + 16) + tb * 4;
+            const uint2 *inodes = reinterpret_cast<const uint2 *>(smem + tab[0]) + lane;
+            const acc_t *leaves = reinterpret_cast<const acc_t *>(smem + tab[1]) + lane;
             const float *xr = xs + row * XP;
-            uint2 nd = inodes[d.x];
+            uint2 nd = inodes[0];
             for (int it = 0; it <= p.max_depth; ++it) {
                 const float x = xr[nd.y & fmask];
                 const float thr = __uint_as_float(nd.x);
                 const bool dl = (nd.y >> fb) & 1u;
                 const bool go_left = (x != x) ? dl : (x < thr);
-                const uint32_t ref = (go_left ? (nd.y >> (fb + 1)) : (nd.y >> (fb + 1 + cb))) & cmask;
+                const uint32_t ref = (nd.y >> (go_left ? fb + 1 : fb + 1 + cb)) & cmask;
                 if (ref & leafbit) {
-                    v = leaves[d.y + (ref & (leafbit - 1u))];
+                    v = leaves[(ref & (leafbit - 1u)) * 32u];
                     break;
                 }
-                nd = inodes[d.x + ref];
+                nd = inodes[ref * 32u];
             }
         }
         __syncwarp();
-        if (!waited) {   // peers have started (their shared memory exists) before the first remote store
+        if (!waited) {   // peers have started and filled their leaf matrices with sentinels before the first remote store
+            if (q == 0) B2S_STAMP(5);
             asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
             waited = true;
+            if (q == 0) B2S_STAMP(6);
         }
-        if (tl < n_my) {
-            const int owner = row / rpr, lr = row - owner * rpr;
-            const uint32_t remote = [&]() {
-                uint32_t ra;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(leaf_local), "r"((uint32_t)owner));
-                return ra;
-            }();
-            st_cluster(remote + (uint32_t)(((size_t)lr * LD + (size_t)rank * TPC + tl) * sizeof(acc_t)), v);
-        }
+        const int owner = row >> rpr_log2, lr = row & (rpr - 1);
+        uint32_t remote_leaf;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote_leaf) : "r"(leaf_local), "r"((uint32_t)owner));
+        if (tl < n_my)
+            st_cluster(remote_leaf + (uint32_t)(((size_t)lr * LD + (size_t)rank * TPC + tl) * sizeof(acc_t)), v);
     }
     if (!waited) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     B2S_STAMP(2);
-    // every leaf value of the tile has landed in its owner's shared memory
-    cluster_sync_all();
-    B2S_STAMP(3);
 
-    // ---- ordered sum: lane i of warp 0 adds the column of row rank*rpr + i in tree order
-    if (warp == 0 && lane < rpr) {
-        const int row = (int)rank * rpr + lane;
-        if (row < rows_here) {
+    // ---- ordered sum: lane i of warp 0 adds the column of row rank*rpr + i in tree order.  A value IS its own
+    // arrival flag: a slot still holding the sentinel has not landed yet (the leaf values of a model never carry that
+    // bit pattern: checked when the images are built).  The whole warp scans the rows this rank owns with 128-bit
+    // volatile loads until nothing is missing -- normally one pass of ~100 cycles -- instead of a release + mbarrier
+    // round trip per publishing warp (~1400 cycles measured between the last remote store and the first add).
+    if (warp == 0) {
+        {
+            const uint32_t base_addr = (uint32_t)__cvta_generic_to_shared(leafbuf);
+            const int vec_per_row = (T + VEC - 1) / VEC;           // the pad slots of the last vector are skipped below
+            uint32_t spins = 0;
+            for (;;) {
+                bool ok = true;
+                for (int r = 0; r < rpr; ++r) {
+                    for (int i = lane; i < vec_per_row; i += 32) {
+                        const uint32_t a = base_addr + (uint32_t)(((size_t)r * LD) * sizeof(acc_t)) + (uint32_t)i * 16u;
+                        uint32_t w0, w1, w2, w3;
+                        asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a) : "memory");
+                        const int t0 = i * VEC;
+                        if (F64) {
+                            ok = ok && !(w0 == p.sentinel && w1 == p.sentinel);
+                            if (t0 + 1 < T) ok = ok && !(w2 == p.sentinel && w3 == p.sentinel);
+                        } else {
+                            ok = ok && w0 != p.sentinel;
+                            if (t0 + 1 < T) ok = ok && w1 != p.sentinel;
+                            if (t0 + 2 < T) ok = ok && w2 != p.sentinel;
+                            if (t0 + 3 < T) ok = ok && w3 != p.sentinel;
+                        }
+                    }
+                }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > (B2S_SPIN_LIMIT >> 6)) __trap();
+            }
+        }
+        B2S_STAMP(3);
+        const int row = ((int)rank << rpr_log2) + lane;
+        if (lane < rpr && row < rows_here) {
             acc_t acc = F64 ? (acc_t)p.base : (acc_t)(float)p.base;
             const acc_t *bp = leafbuf + (size_t)lane * LD;
             typedef typename std::conditional<F64, double2, float4>::type vec_t;
@@ -652,6 +720,7 @@ forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict
 #pragma unroll
                 for (int k = 0; k < BLK; ++k) cur[k] = vp[k];
             }
+#pragma unroll 4
             for (int blk = 0; blk < n_blk; ++blk) {
                 if (blk + 1 < n_blk) {                // the next block's loads issue among this block's dependent adds
 #pragma unroll
@@ -676,7 +745,7 @@ forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict
             }
             for (int t = n_blk * VEC * BLK; t < T; ++t) acc = acc + bp[t];
             if (F64) reinterpret_cast<double *>(out)[r0 + row] = (double)acc / p.divisor;
-            else reinterpret_cast<float *>(out)[r0 + row] = (float)acc;
+            else reinterpret_cast<float *>(out)[r0 + row] = forest_link_f32((float)acc, p.link);
         }
         B2S_STAMP(4);
     }
@@ -732,7 +801,7 @@ forest_rows_kernel(ForestParams p, const float *__restrict__ X, int64_t n_rows,
     }
     if (row_ok) {
         if (F64) reinterpret_cast<double *>(out)[r0 + threadIdx.x] = (double)acc / p.divisor;
-        else reinterpret_cast<float *>(out)[r0 + threadIdx.x] = (float)acc;
+        else reinterpret_cast<float *>(out)[r0 + threadIdx.x] = forest_link_f32((float)acc, p.link);
     }
 }
 
@@ -827,17 +896,19 @@ struct ForestModel : Model {
     {
         const size_t esz = f64 ? 8 : 4, vec = 16 / esz;
         const int rpr = (R + wide_C - 1) / wide_C;
-        return (size_t)wide_cap + (size_t)rpr * ((size_t)wide_C * wp.tpc + vec) * esz + (size_t)R * (size_t)(p.n_features | 1) * 4 + 64;
+        return (size_t)wide_cap + (size_t)rpr * ((size_t)wide_C * wp.tpc + vec) * esz + (size_t)R * (size_t)(p.n_features | 1) * 4 + 32 + kWideMaxBlocks * 8;
     }
 
     template <bool F64>
     int launch_wide(cudaStream_t st, const float *X, int64_t n_rows, void *out)
     {
         const int R = wide_rows_per_tile(n_rows);
-        const int rpr = (R + wide_C - 1) / wide_C;
+        const int rpr = (R + wide_C - 1) / wide_C;          // R in {16, 32}, C a power of two: rpr is one too
         const unsigned tiles = (unsigned)((n_rows + R - 1) / R);
         int threads = ((wp.tpc + 31) / 32) * R * 32;     // one (tree, row) pair per thread when it fits
         if (threads > 1024) threads = 1024;
+        static const int thread_cap = []() { const char *e = getenv("B2S_FOREST_WIDE_THREADS"); return e ? atoi(e) : 1024; }();
+        if (thread_cap >= 64 && threads > thread_cap) threads = thread_cap;
         if (threads < 64) threads = 64;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(tiles * wide_C, 1, 1);
@@ -853,10 +924,13 @@ struct ForestModel : Model {
         cfg.numAttrs = 1;
         static const int bulk_piece = []() {
             const char *e = getenv("B2S_FOREST_BULK_PIECE");
-            int v = e ? atoi(e) : 4096;
-            return (v >= 1024 && v % 16 == 0) ? v : 4096;
+            int v = e ? atoi(e) : 8192;
+            return (v >= 1024 && v % 16 == 0) ? v : 8192;
         }();
-        B2S_CUDA(cudaLaunchKernelEx(&cfg, forest_wide_kernel<F64>, wp, X, n_rows, out, R, rpr, wide_cap, bulk_piece, dbg_stamps));
+        int R_log2 = 0, rpr_log2 = 0;
+        while ((1 << R_log2) < R) ++R_log2;
+        while ((1 << rpr_log2) < rpr) ++rpr_log2;
+        B2S_CUDA(cudaLaunchKernelEx(&cfg, forest_wide_kernel<F64>, wp, X, n_rows, out, R_log2, rpr_log2, wide_cap, bulk_piece, dbg_stamps));
         return 0;
     }
 
@@ -896,59 +970,96 @@ struct ForestModel : Model {
         while (C < c_max && C * 32 < (int)T) C *= 2;
         for (;; C /= 2) {
             const int tpc = (int)round_up(((int64_t)T + C - 1) / C, 32);
-            // images
+            // images: per rank, blocks of 32 trees, node j of tree t at [j][t]
             std::vector<std::vector<unsigned char>> img(C);
             size_t cap = 0;
             const size_t lsz = f64 ? 8 : 4;
-            for (int r = 0; r < C; ++r) {
+            int total_blocks = 0;
+            bool too_many_blocks = tpc / 32 > kWideMaxBlocks;
+            for (int r = 0; r < C && !too_many_blocks; ++r) {
                 const uint32_t t_lo = (uint32_t)r * (uint32_t)tpc;
                 if (t_lo >= T) continue;                   // empty rank: no image, no bytes
                 const uint32_t t_hi = t_lo + (uint32_t)tpc < T ? t_lo + (uint32_t)tpc : T;
-                std::vector<uint32_t> tdesc;
-                std::vector<uint64_t> inodes;
-                std::vector<unsigned char> leaves;
-                for (uint32_t t = t_lo; t < t_hi; ++t) {
-                    const uint32_t s = toff[t], n = toff[t + 1] - s;
-                    // local index of every node inside the internal / leaf arrays of its tree
-                    std::vector<uint32_t> loc(n);
-                    uint32_t ni = 0, nl = 0;
-                    for (uint32_t i = 0; i < n; ++i) loc[i] = ((uint32_t)(nodes[s + i] >> 32) >> (fb + 1)) ? ni++ : nl++;
-                    tdesc.push_back((uint32_t)inodes.size());
-                    tdesc.push_back((uint32_t)(leaves.size() / lsz));
-                    auto ref_of = [&](uint32_t i) -> uint32_t {
-                        const bool internal = ((uint32_t)(nodes[s + i] >> 32) >> (fb + 1)) != 0;
-                        return internal ? loc[i] : (loc[i] | (1u << (cb - 1)));
-                    };
-                    if (ni == 0) {   // a tree that is a single leaf: one dummy split whose both sides are leaf 0
-                        inodes.push_back(((uint64_t)((1u << (cb - 1)) << (fb + 1) | (1u << (cb - 1)) << (fb + 1 + cb))) << 32);
+                const int n_blocks = (int)((t_hi - t_lo + 31) / 32);
+                total_blocks += n_blocks;
+                std::vector<unsigned char> &im = img[r];
+                im.assign(kWideHdrBytes, 0);
+                uint32_t hdr[4] = {t_hi - t_lo, (uint32_t)n_blocks, 0u, 0u};
+                memcpy(im.data(), hdr, 16);
+                for (int bk = 0; bk < n_blocks; ++bk) {
+                    const uint32_t b_lo = t_lo + (uint32_t)bk * 32u, b_hi = b_lo + 32u < t_hi ? b_lo + 32u : t_hi;
+                    // per tree: compact internal / leaf arrays
+                    std::vector<std::vector<uint64_t>> tin(32);
+                    std::vector<std::vector<unsigned char>> tlf(32);
+                    size_t ni_max = 1, nl_max = 1;
+                    for (uint32_t t = b_lo; t < b_hi; ++t) {
+                        const uint32_t s = toff[t], n = toff[t + 1] - s;
+                        std::vector<uint32_t> loc(n);
+                        uint32_t ni = 0, nl = 0;
+                        for (uint32_t i = 0; i < n; ++i) loc[i] = ((uint32_t)(nodes[s + i] >> 32) >> (fb + 1)) ? ni++ : nl++;
+                        auto ref_of = [&](uint32_t i) -> uint32_t {
+                            const bool internal = ((uint32_t)(nodes[s + i] >> 32) >> (fb + 1)) != 0;
+                            return internal ? loc[i] : (loc[i] | (1u << (cb - 1)));
+                        };
+                        std::vector<uint64_t> &in = tin[t - b_lo];
+                        std::vector<unsigned char> &lf = tlf[t - b_lo];
+                        if (ni == 0)   // a tree that is a single leaf: one dummy split whose both sides are leaf 0
+                            in.push_back(((uint64_t)((1u << (cb - 1)) << (fb + 1) | (1u << (cb - 1)) << (fb + 1 + cb))) << 32);
+                        for (uint32_t i = 0; i < n; ++i) {
+                            const uint32_t val = (uint32_t)(nodes[s + i] & 0xffffffffu), meta = (uint32_t)(nodes[s + i] >> 32);
+                            const uint32_t left = meta >> (fb + 1);
+                            if (left) {
+                                const uint32_t m2 = (meta & ((1u << (fb + 1)) - 1u)) | ref_of(left) << (fb + 1) | ref_of(left + 1) << (fb + 1 + cb);
+                                in.push_back((uint64_t)val | ((uint64_t)m2 << 32));
+                            } else if (f64) {
+                                const double dv = leaf64[val];
+                                const unsigned char *bb = reinterpret_cast<const unsigned char *>(&dv);
+                                lf.insert(lf.end(), bb, bb + 8);
+                            } else {
+                                const unsigned char *bb = reinterpret_cast<const unsigned char *>(&val);
+                                lf.insert(lf.end(), bb, bb + 4);
+                            }
+                        }
+                        if (in.size() > ni_max) ni_max = in.size();
+                        if (lf.size() / lsz > nl_max) nl_max = lf.size() / lsz;
                     }
-                    for (uint32_t i = 0; i < n; ++i) {
-                        const uint32_t val = (uint32_t)(nodes[s + i] & 0xffffffffu), meta = (uint32_t)(nodes[s + i] >> 32);
-                        const uint32_t left = meta >> (fb + 1);
-                        if (left) {
-                            const uint32_t m2 = (meta & ((1u << (fb + 1)) - 1u)) | ref_of(left) << (fb + 1) | ref_of(left + 1) << (fb + 1 + cb);
-                            inodes.push_back((uint64_t)val | ((uint64_t)m2 << 32));
-                        } else if (f64) {
-                            const double dv = leaf64[val];
-                            const unsigned char *b = reinterpret_cast<const unsigned char *>(&dv);
-                            leaves.insert(leaves.end(), b, b + 8);
-                        } else {
-                            const unsigned char *b = reinterpret_cast<const unsigned char *>(&val);
-                            leaves.insert(leaves.end(), b, b + 4);
+                    const size_t off_in = (size_t)round_up((int64_t)im.size(), 16);
+                    const size_t off_lf = off_in + ni_max * 32 * 8;
+                    const size_t end = (size_t)round_up((int64_t)(off_lf + nl_max * 32 * lsz), 16);
+                    im.resize(end, 0);
+                    for (uint32_t t = 0; t < b_hi - b_lo; ++t) {
+                        for (size_t j = 0; j < tin[t].size(); ++j) memcpy(im.data() + off_in + (j * 32 + t) * 8, &tin[t][j], 8);
+                        for (size_t j = 0; j < tlf[t].size() / lsz; ++j) memcpy(im.data() + off_lf + (j * 32 + t) * lsz, tlf[t].data() + j * lsz, lsz);
+                    }
+                    const uint32_t ent[4] = {(uint32_t)off_in, (uint32_t)off_lf, (uint32_t)end, 0u};
+                    memcpy(im.data() + 16 + (size_t)bk * 16, ent, 16);
+                    wp.blk_end[r][bk] = (uint32_t)end;
+                }
+                if (im.size() > cap) cap = im.size();
+            }
+            if (too_many_blocks) return 0;   // more than kWideMaxBlocks blocks per rank: kernels C / B serve the model
+            wp.total_blocks = total_blocks;
+            {   // a bit pattern (a quiet NaN with a payload) that no leaf of THIS model carries marks "not landed yet"
+                uint32_t sent = 0x7fc5a5a5u;
+                for (int tries = 0; tries < 64; ++tries, sent += 0x1003u) {
+                    bool clash = false;
+                    for (uint32_t i = 0; i < h.n_nodes && !clash; ++i) {
+                        const uint32_t val = (uint32_t)(nodes[i] & 0xffffffffu), meta = (uint32_t)(nodes[i] >> 32);
+                        if (meta >> (fb + 1)) continue;
+                        if (!f64) clash = val == sent;
+                        else {
+                            unsigned long long bits;
+                            memcpy(&bits, &leaf64[val], 8);
+                            clash = bits == (((unsigned long long)sent << 32) | sent);
                         }
                     }
+                    if (!clash) break;
                 }
-                const uint32_t n_here = t_hi - t_lo;
-                const size_t off_tdesc = 16, off_in = off_tdesc + (size_t)tpc * 8, off_leaf = off_in + inodes.size() * 8;
-                const size_t total = (size_t)round_up((int64_t)(off_leaf + leaves.size()), 16);
-                std::vector<unsigned char> &im = img[r];
-                im.assign(total, 0);
-                const uint32_t hdr[4] = {(uint32_t)off_in, (uint32_t)off_leaf, n_here, 0u};
-                memcpy(im.data(), hdr, 16);
-                memcpy(im.data() + off_tdesc, tdesc.data(), tdesc.size() * 4);
-                memcpy(im.data() + off_in, inodes.data(), inodes.size() * 8);
-                if (!leaves.empty()) memcpy(im.data() + off_leaf, leaves.data(), leaves.size());
-                if (total > cap) cap = total;
+                wp.sentinel = sent;
+            }
+            {
+                const char *nm = getenv("B2S_FOREST_WIDE_NULL");
+                wp.null_mode = (nm && nm[0] == '1') ? 1 : 0;
             }
             wide_C = C;
             wide_cap = (int)round_up((int64_t)cap, 128);
@@ -988,6 +1099,7 @@ struct ForestModel : Model {
                 wp.feat_bits = fb;
                 wp.child_bits = cb;
                 wp.max_depth = max_depth;
+                wp.link = (int)h.link;
                 wp.base = h.base;
                 wp.divisor = h.divisor;
                 wide_ok = true;
@@ -1070,6 +1182,7 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
     if (h.n_trees == 0 || h.n_nodes == 0 || h.n_features == 0 || h.feat_bits == 0 || h.feat_bits > 24)
         return fail(B2S_ERR_INVALID, "forest blob: empty model or bad feat_bits");
     if (h.acc_mode > 1) return fail(B2S_ERR_INVALID, "forest blob: bad acc_mode");
+    if (h.link > 1 || (h.link != 0 && h.acc_mode != 0)) return fail(B2S_ERR_INVALID, "forest blob: bad link");
     const size_t off_bytes = (size_t)round_up((int64_t)(h.n_trees + 1) * 4, 8);
     const size_t node_bytes = (size_t)h.n_nodes * 8;
     const size_t leaf_bytes = (size_t)h.n_leaf64 * 8;
@@ -1137,6 +1250,7 @@ int forest_model_create(int device, const void *blob, size_t bytes, Model **out)
     m->p.max_depth = max_depth;
     m->p.base = h.base;
     m->p.divisor = h.divisor;
+    m->p.link = (int)h.link;
 
     const char *dbg_env = getenv("B2S_FOREST_TIMING");
     if (dbg_env && dbg_env[0] == '1') {

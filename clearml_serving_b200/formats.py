@@ -12,8 +12,13 @@ import numpy as np
 
 from . import native
 
-_IDENTITY_OBJECTIVES = ("reg:squarederror", "reg:linear", "reg:absoluteerror",
-                        "reg:pseudohubererror", "binary:logitraw")
+_IDENTITY_OBJECTIVES = ("reg:squarederror", "reg:linear", "reg:absoluteerror", "reg:pseudohubererror")
+# objectives whose base_score is a PROBABILITY: the booster adds logit(base_score) to the margin
+# (xgboost LogisticRegression::ProbToMargin; LogisticRaw inherits it) ...
+_LOGIT_BASE_OBJECTIVES = ("binary:logitraw", "binary:logistic", "reg:logistic")
+# ... and those whose prediction is sigmoid(margin) (PredTransform)
+_SIGMOID_OBJECTIVES = ("binary:logistic", "reg:logistic")
+LINK_IDENTITY, LINK_SIGMOID = 0, 1
 
 
 class PackedModel(object):
@@ -40,11 +45,14 @@ def _skl_threshold_to_f32_strict(thr64):
     return np.nextafter(t, np.float32(np.inf)).astype(np.float32)
 
 
-def pack_forest(forest, mode, base=0.0, scale=1.0, divisor=1.0):
+def pack_forest(forest, mode, base=0.0, scale=1.0, divisor=1.0, link=LINK_IDENTITY):
     """forest: source form (dict of arrays: tree_offset,left,right,feat,thr,default_left,value,
     n_features; children local to each tree, left<0 => leaf).
     mode 'xgb': fp32 sequential sum, split `x < float32(thr)`.
-    mode 'skl': fp64 sequential sum of scale*value, split `x <= thr64`, result / divisor."""
+    mode 'skl': fp64 sequential sum of scale*value, split `x <= thr64`, result / divisor.
+    link: LINK_SIGMOID applies xgboost's fp32 logistic transform to the margin on the device ('xgb' mode only)."""
+    if link not in (LINK_IDENTITY, LINK_SIGMOID) or (link != LINK_IDENTITY and mode != "xgb"):
+        raise ValueError("pack_forest: bad link")
     if mode not in ("xgb", "skl"):
         raise ValueError("pack_forest: mode must be 'xgb' or 'skl'")
     off = np.asarray(forest["tree_offset"], dtype=np.int64)
@@ -124,15 +132,44 @@ def pack_forest(forest, mode, base=0.0, scale=1.0, divisor=1.0):
     leaf64 = np.asarray(leaf64, dtype="<f8")
     base_v = float(base) if f64 else float(np.float32(base))
     header = struct.pack("<4sIIIIIIIIIdd", b"B2SF", 1, n_trees, n_features, int(nodes.size), feat_bits,
-                         1 if f64 else 0, int(leaf64.size), 0, 0, base_v, float(divisor))
+                         1 if f64 else 0, int(leaf64.size), int(link), 0, base_v, float(divisor))
     blob = header + toff_bytes + nodes.tobytes() + leaf64.tobytes()
     desc = dict(kind="forest", mode=mode, n_trees=n_trees, n_features=n_features, n_nodes=int(nodes.size),
-                input_dtype="float32", output_dtype="float64" if f64 else "float32")
+                input_dtype="float32", output_dtype="float64" if f64 else "float32", link=int(link))
     return PackedModel(native.MODEL_FOREST, blob, desc)
 
 
+def _xgb_base_score(text):
+    """learner_model_param.base_score: "5E-1", or the vector form "[5E-1]" newer releases write"""
+    t = str(text).strip()
+    if t.startswith("["):
+        vals = [v for v in t.strip("[]").split(",") if v.strip()]
+        if len(vals) != 1:
+            raise ValueError("b200 engine: multi-target base_score {} is not supported".format(text))
+        t = vals[0]
+    return np.float32(float(t))
+
+
+def _xgb_objective_plan(objective, base_score, base_is_margin=False):
+    """objective name + stored base_score -> (base margin as fp32, link).  PARITY UNPINNED (xgboost not installable)."""
+    if objective in _IDENTITY_OBJECTIVES:
+        return np.float32(base_score), LINK_IDENTITY
+    if objective in _LOGIT_BASE_OBJECTIVES:
+        bs = np.float32(base_score)
+        if base_is_margin:      # files written by xgboost < 1.0 store the margin itself
+            margin = bs
+        else:
+            if not (0.0 < float(bs) < 1.0):
+                raise ValueError("b200 engine: base_score {} must be in (0, 1) for objective '{}'".format(float(bs), objective))
+            with np.errstate(all="ignore"):
+                margin = np.float32(-np.log(np.float32(np.float32(1.0) / bs - np.float32(1.0))))   # -logf(1/bs - 1), fp32
+        return np.float32(margin), LINK_SIGMOID if objective in _SIGMOID_OBJECTIVES else LINK_IDENTITY
+    raise ValueError("b200 engine: XGBoost objective '{}' is not supported yet (supported: {})".format(
+        objective, ", ".join(_IDENTITY_OBJECTIVES + _LOGIT_BASE_OBJECTIVES)))
+
+
 def parse_xgboost_json(model):
-    """XGBoost JSON model schema (learner.gradient_booster.model.trees[*]) -> (source form, base_score).
+    """XGBoost JSON model schema (learner.gradient_booster.model.trees[*]) -> (source form, base margin, link).
     Accepts a dict, a JSON string/bytes, or a path."""
     if isinstance(model, (bytes, bytearray)):
         model = json.loads(model.decode("utf-8"))
@@ -150,16 +187,13 @@ def parse_xgboost_json(model):
                 model = json.load(f)
     learner = model["learner"]
     objective = learner.get("objective", {}).get("name", "reg:squarederror")
-    if objective not in _IDENTITY_OBJECTIVES:
-        raise ValueError("b200 engine: XGBoost objective '{}' is not supported yet (identity-link "
-                         "objectives only: {})".format(objective, ", ".join(_IDENTITY_OBJECTIVES)))
     lmp = learner["learner_model_param"]
+    base_margin, link = _xgb_objective_plan(objective, _xgb_base_score(lmp.get("base_score", "0.5")))
     if int(lmp.get("num_class", "0") or 0) > 1 or int(lmp.get("num_target", "1") or 1) > 1:
         raise ValueError("b200 engine: multi-class / multi-target XGBoost models are not supported yet")
     gb = learner["gradient_booster"]
     if gb.get("name", "gbtree") not in ("gbtree",):
         raise ValueError("b200 engine: booster '{}' is not supported (gbtree only)".format(gb.get("name")))
-    base_score = np.float32(float(lmp.get("base_score", "0.5")))
     n_features = int(lmp["num_feature"])
     trees = gb["model"]["trees"]
     off, left, right, feat, thr, dl, val = [0], [], [], [], [], [], []
@@ -178,12 +212,118 @@ def parse_xgboost_json(model):
     forest = dict(tree_offset=np.asarray(off, np.int32), left=np.concatenate(left),
                   right=np.concatenate(right), feat=np.concatenate(feat), thr=np.concatenate(thr),
                   default_left=np.concatenate(dl), value=np.concatenate(val), n_features=n_features)
-    return forest, float(base_score)
+    return forest, float(base_margin), link
 
 
 def pack_xgboost_json(model):
-    forest, base_score = parse_xgboost_json(model)
-    return pack_forest(forest, "xgb", base=base_score)
+    forest, base_margin, link = parse_xgboost_json(model)
+    return pack_forest(forest, "xgb", base=base_margin, link=link)
+
+
+# --------------------------------------------------------------------------------------------
+# XGBoost legacy binary models: what `Booster.save_model("xgb_model")` (no .json / .ubj extension) writes -- the
+# reference's own example does exactly that (examples/xgboost/train_model.py:28) and its engine loads the file
+# with Booster.load_model (preprocess_service.py:475-476).  Layout restated from xgboost 1.7 (src/learner.cc
+# LearnerModelParamLegacy / LearnerIO::LoadModel, src/gbm/gbtree_model.h GBTreeModelParam, include/xgboost/tree_model.h
+# TreeParam / RegTree::Node / RTreeNodeStat; little endian):
+#   ["binf"]                                        optional 4-byte tag of pre-1.0 writers
+#   LearnerModelParamLegacy  136 B                  f32 base_score | u32 num_feature | i32 num_class |
+#                                                   i32 contain_extra_attrs | i32 contain_eval_metrics |
+#                                                   u32 major_version | u32 minor_version | u32 num_target | reserved
+#   u64 len + bytes          objective name         ("reg:squarederror")
+#   u64 len + bytes          booster name           ("gbtree")
+#   GBTreeModelParam         160 B                  i32 num_trees | i32 num_parallel_tree | i32 | i32 pad |
+#                                                   i64 num_pbuffer | i32 num_output_group | i32 size_leaf_vector | reserved
+#   per tree: TreeParam 148 B (i32 num_roots | i32 num_nodes | i32 num_deleted | i32 max_depth | i32 num_feature |
+#             i32 size_leaf_vector | reserved), num_nodes x Node 20 B (i32 parent | i32 cleft | i32 cright |
+#             u32 sindex (bit 31 = default left) | f32 leaf value / split condition), num_nodes x RTreeNodeStat 16 B
+#   num_trees x i32 tree_info; then optional attributes / metric names (ignored here)
+# xgboost is not installable here and the reference ships no model file: PARITY UNPINNED (tests/test_formats.py
+# round-trips a writer of the same published layout).
+# --------------------------------------------------------------------------------------------
+def looks_like_xgboost_legacy_binary(head):
+    """`head`: the first >= 160 bytes of a file"""
+    o = 4 if head[:4] == b"binf" else 0
+    if len(head) < o + 136 + 8 + 4:
+        return False
+    n = struct.unpack_from("<Q", head, o + 136)[0]
+    name = head[o + 144:o + 144 + min(n, 32)]
+    return 3 <= n <= 64 and b":" in name and all(32 <= c < 127 for c in name)
+
+
+def parse_xgboost_legacy_binary(data):
+    """bytes of a legacy binary model -> (source form, base margin, link)"""
+    data = bytes(data)
+    o = 4 if data[:4] == b"binf" else 0
+    if data[:4] == b"bs64":
+        raise ValueError("b200 engine: base64 XGBoost models (xgboost < 0.6) are not supported")
+
+    def need(n):
+        if o + n > len(data):
+            raise ValueError("b200 engine: truncated XGBoost binary model")
+    need(136)
+    base_score, num_feature, num_class, has_attrs, has_metrics, major, _minor, num_target = struct.unpack_from("<fIiiiIII", data, o)
+    o += 136
+
+    def read_str():
+        nonlocal o
+        need(8)
+        n = struct.unpack_from("<Q", data, o)[0]
+        o += 8
+        if n > 256:
+            raise ValueError("b200 engine: not an XGBoost binary model (implausible string length)")
+        need(n)
+        sv = data[o:o + n].decode("ascii", "replace")
+        o += n
+        return sv
+    objective = read_str()
+    booster = read_str()
+    if booster != "gbtree":
+        raise ValueError("b200 engine: booster '{}' is not supported (gbtree only)".format(booster))
+    if num_class > 1 or num_target > 1:
+        raise ValueError("b200 engine: multi-class / multi-target XGBoost models are not supported yet")
+    need(160)
+    num_trees, _npt, _nf, _pad, num_pbuffer, _nog, size_leaf_vector = struct.unpack_from("<iiiiqii", data, o)
+    o += 160
+    if num_trees <= 0 or size_leaf_vector not in (0, 1):
+        raise ValueError("b200 engine: XGBoost binary model with {} trees / leaf vectors of {}".format(num_trees, size_leaf_vector))
+    off, left, right, feat, thr, dl, val = [0], [], [], [], [], [], []
+    node_t = np.dtype([("parent", "<i4"), ("cleft", "<i4"), ("cright", "<i4"), ("sindex", "<u4"), ("info", "<f4")])
+    for _t in range(num_trees):
+        need(148)
+        _roots, num_nodes, _deleted, _depth, _tnf, _slv = struct.unpack_from("<iiiiii", data, o)
+        o += 148
+        if num_nodes <= 0:
+            raise ValueError("b200 engine: XGBoost binary model: tree without nodes")
+        need(num_nodes * 36)
+        nodes = np.frombuffer(data, dtype=node_t, count=num_nodes, offset=o)
+        o += num_nodes * 36          # nodes (20 B each) + statistics (16 B each)
+        l = nodes["cleft"].astype(np.int32)
+        left.append(l)
+        right.append(np.where(l < 0, -1, nodes["cright"]).astype(np.int32))
+        feat.append(np.where(l < 0, 0, nodes["sindex"] & np.uint32(0x7FFFFFFF)).astype(np.int32))
+        dl.append(((nodes["sindex"] >> np.uint32(31)) & np.uint32(1)).astype(np.uint8))
+        cond = nodes["info"].astype(np.float64)
+        thr.append(cond)
+        val.append(cond)
+        off.append(off[-1] + num_nodes)
+    need(num_trees * 4)
+    o += num_trees * 4               # tree_info (output group of every tree: all 0 for single-output models)
+    forest = dict(tree_offset=np.asarray(off, np.int32), left=np.concatenate(left), right=np.concatenate(right),
+                  feat=np.concatenate(feat), thr=np.concatenate(thr), default_left=np.concatenate(dl),
+                  value=np.concatenate(val), n_features=int(num_feature))
+    if forest["feat"].size and int(forest["feat"].max()) >= int(num_feature):
+        raise ValueError("b200 engine: XGBoost binary model: split feature out of range")
+    base_margin, link = _xgb_objective_plan(objective, base_score, base_is_margin=major < 1)
+    return forest, float(base_margin), link
+
+
+def pack_xgboost_legacy_binary(data):
+    if isinstance(data, str):
+        with open(data, "rb") as f:
+            data = f.read()
+    forest, base_margin, link = parse_xgboost_legacy_binary(data)
+    return pack_forest(forest, "xgb", base=base_margin, link=link)
 
 
 # --------------------------------------------------------------------------------------------

@@ -80,6 +80,12 @@ def create_app(processor: Optional[ModelRequestProcessor] = None, logger=None, i
             cfg = os.environ.get("B2S_ENDPOINTS")
             if cfg:
                 p.load_endpoints_file(cfg)
+            # model hot reload (the reference polls every CLEARML_SERVING_POLL_FREQ minutes, serving/main.py:55-57;
+            # its Triton sidecar every --repository-poll-secs): 0 disables
+            poll_min = float(os.environ.get("B2S_POLL_FREQ_MIN", os.environ.get("CLEARML_SERVING_POLL_FREQ", "1.0")) or 0)
+            if poll_min > 0:
+                p.sync_models()
+                p.start_sync_daemon(poll_min * 60.0, endpoints_file=cfg)
             state["processor"] = p
         yield
         if state["processor"] is not None:

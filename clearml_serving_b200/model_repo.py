@@ -468,10 +468,10 @@ def lower_onnx(data):
 # ------------------------------------------------------------------------------------------------
 def _sniff(path):
     with open(path, "rb") as f:
-        head = f.read(64)
+        head = f.read(256)
     if head[:2] == b"PK":
         return "torchscript" if zipfile.is_zipfile(path) else "unknown"
-    if head[:4] == b"binf" or head[:4] == b"bs64":
+    if head[:4] == b"bs64" or formats.looks_like_xgboost_legacy_binary(head):
         return "xgboost-legacy"
     s = head.lstrip()
     if s[:5] == b"tree\n" or s[:6] == b"tree\r\n":
@@ -520,9 +520,8 @@ def load_model(path, framework=None):
             raise ValueError("b200 engine: no model file under '{}'".format(path))
         return load_model(inner, framework)
     kind = _sniff(path)
-    if kind == "xgboost-legacy":
-        raise ValueError("b200 engine: XGBoost legacy binary models are not supported; re-save with "
-                         "Booster.save_model('model.json') or 'model.ubj'")
+    if kind == "xgboost-legacy" and loader in (None, "xgboost"):
+        return formats.pack_xgboost_legacy_binary(path)   # what examples/xgboost/train_model.py:28 writes
     if loader == "onnx" or (loader is None and kind == "onnx"):
         return lower_onnx(path)
     if loader == "torchscript" or (loader is None and kind == "torchscript"):
@@ -652,9 +651,13 @@ class ModelRepository(object):
         return h.hexdigest()
 
     def resolve(self, model_id):
-        if self._resolver is None:
+        resolver = self._resolver
+        if resolver is None:   # the engines' own resolver (a model registry lookup installed by the host application)
+            from .preprocess_service import BasePreprocessRequest
+            resolver = BasePreprocessRequest._model_resolver
+        if resolver is None:
             return model_id, None
-        r = self._resolver(model_id)
+        r = resolver(model_id)
         return r if isinstance(r, tuple) else (r, None)
 
     def get(self, path, framework=None):

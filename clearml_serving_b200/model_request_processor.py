@@ -15,6 +15,7 @@ the same swap protocol (:700-720) so that in-flight requests never see a half-up
 """
 import asyncio
 import gc
+import os
 import itertools
 import json
 import threading
@@ -114,7 +115,11 @@ class ModelRequestProcessor(object):
             endpoint = ModelEndpoint(**endpoint)
         self._validate_model(endpoint)
         url = self._normalize_endpoint_url(endpoint.serving_url)
-        self._swap(lambda: self._endpoints.__setitem__(url, endpoint))
+
+        def mutate():   # the canary table is rebuilt with every swap: a new version under a prefix is routed to at once
+            self._endpoints[url] = endpoint
+            self._update_canary_lookup()
+        self._swap(mutate)
         if preload:
             self._get_engine(url, endpoint)
         return url
@@ -123,7 +128,10 @@ class ModelRequestProcessor(object):
         url = self._normalize_endpoint_url(endpoint_url, version)
         if url not in self._endpoints:
             return False
-        self._swap(lambda: self._endpoints.pop(url, None))
+        def mutate():   # ... and a removed endpoint loses its share of the canary traffic
+            self._endpoints.pop(url, None)
+            self._update_canary_lookup()
+        self._swap(mutate)
         return True
 
     def add_canary_endpoint(self, canary):
@@ -267,6 +275,77 @@ class ModelRequestProcessor(object):
                 pass
         return reply
 
+    # ------------------------------------------------------------------ model hot reload
+    def sync_models(self, repository=None):
+        """One pass of the reference's periodic model sync, in process: `TritonHelper.model_service_update_step`
+        (engines/triton/triton_helper.py:91-194, driven every `update_frequency_sec` by maintenance_daemon :226-289)
+        re-fetches every endpoint's model and tritonserver (`--model-control-mode=poll`) reloads what changed.  Here
+        the packed-model cache re-reads the model files; an endpoint whose model CONTENT or description changed gets
+        its engine dropped with no request in flight -- only that endpoint's (the reference drops every engine on a
+        configuration change, model_request_processor.py:1026-1028) -- and the next request rebuilds it on the GPU.
+        Returns the list of reloaded urls."""
+        from . import model_repo
+        repo = repository or model_repo.default_repository()
+        eps = dict(self._endpoints)
+        eps.update(self._model_monitoring_endpoints)
+        first = not getattr(self, "_models_synced", False)
+        changed = repo.update_step(eps)
+        self._models_synced = True
+        stale_urls = [u for u in changed if u in self._engine_processor_lookup]
+        if first or not stale_urls:
+            return [] if first else stale_urls
+        stale = []
+        with self._update_lock_guard:
+            self._update_lock_flag = True
+            try:
+                while self._request_processing_state.value() != 0:
+                    sleep(0.001)
+                for u in stale_urls:
+                    eng = self._engine_processor_lookup.pop(u, None)
+                    if eng is not None:
+                        stale.append(eng)
+            finally:
+                self._update_lock_flag = False
+        for eng in stale:
+            unload = getattr(eng, "unload", None)
+            if callable(unload):
+                try:
+                    unload()
+                except Exception:  # noqa
+                    pass
+        del stale
+        gc.collect()
+        return stale_urls
+
+    def start_sync_daemon(self, poll_frequency_sec=60.0, endpoints_file=None):
+        """Background thread: every `poll_frequency_sec` (the reference's `--repository-poll-secs` /
+        CLEARML_SERVING_POLL_FREQ) re-read `endpoints_file` when it changed and run sync_models()."""
+        if getattr(self, "_sync_thread", None) is not None:
+            return self._sync_thread
+        self._sync_stop = threading.Event()
+        state = dict(mtime=os.path.getmtime(endpoints_file) if endpoints_file and os.path.exists(endpoints_file) else None)
+
+        def run():
+            while not self._sync_stop.wait(poll_frequency_sec):
+                try:
+                    if endpoints_file and os.path.exists(endpoints_file):
+                        mt = os.path.getmtime(endpoints_file)
+                        if mt != state["mtime"]:
+                            state["mtime"] = mt
+                            self.load_endpoints_file(endpoints_file)
+                    self.sync_models()
+                except Exception as ex:  # noqa -- keep serving with what is loaded (the reference prints and carries on)
+                    print("Warning: model sync failed: {}: {}".format(type(ex).__name__, ex))
+        self._sync_thread = threading.Thread(target=run, name="b2s-model-sync", daemon=True)
+        self._sync_thread.start()
+        return self._sync_thread
+
+    def stop_sync_daemon(self):
+        t, self._sync_thread = getattr(self, "_sync_thread", None), None
+        if t is not None:
+            self._sync_stop.set()
+            t.join(timeout=5)
+
     # ------------------------------------------------------------------ misc
     def set_stats_sink(self, sink, default_frequency=1.0):
         self._stats_sink = sink
@@ -282,4 +361,5 @@ class ModelRequestProcessor(object):
         pass
 
     def shutdown(self):
+        self.stop_sync_daemon()
         self._swap(lambda: None)

@@ -207,6 +207,25 @@ void oracle_compiled_predict_xgb(const oracle_compiled *c, const float *X, int64
     }
 }
 
+/* xgboost's logistic link and its inverse, as the CPU library computes them in fp32
+ * (src/common/math.h Sigmoid: 1 / (expf(min(-x, 88.7f)) + 1 + 1e-16f); src/objective/regression_loss.h
+ * LogisticRegression::ProbToMargin: -logf(1/base_score - 1)).  Third-party (xgboost >=1.7.5,<1.8,
+ * clearml_serving/serving/requirements.txt:16), restated: PARITY UNPINNED like the rest of the xgboost mode. */
+void oracle_xgb_sigmoid(float *y, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        float x = -y[i];
+        if (x > 88.7f) x = 88.7f;
+        const float denom = expf(x) + 1.0f + 1e-16f;
+        y[i] = 1.0f / denom;
+    }
+}
+
+float oracle_xgb_prob_to_margin(float base_score)
+{
+    return -logf(1.0f / base_score - 1.0f);
+}
+
 int oracle_max_threads(void)
 {
 #ifdef _OPENMP

@@ -118,6 +118,20 @@ def forest_predict_xgb(forest, X, base_score, n_threads=1):
     return out
 
 
+def xgb_sigmoid(margin):
+    """binary:logistic / reg:logistic link as the xgboost CPU library computes it (fp32 expf)."""
+    y = np.ascontiguousarray(margin, dtype=np.float32).copy()
+    lib().oracle_xgb_sigmoid(ctypes.c_void_p(y.ctypes.data), ctypes.c_int64(y.size))
+    return y
+
+
+def xgb_prob_to_margin(base_score):
+    f = lib().oracle_xgb_prob_to_margin
+    f.restype = ctypes.c_float
+    f.argtypes = [ctypes.c_float]
+    return float(f(ctypes.c_float(float(np.float32(base_score)))))
+
+
 def forest_predict_f64(forest, X, init, scale, divisor, n_threads=1):
     """sklearn tree-ensemble semantics (fp64 sequential). Returns float64[n]."""
     X = np.ascontiguousarray(X, dtype=np.float32)

@@ -19,12 +19,25 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("B2S_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def _find_reference():
+    """/root/reference in the build container; on the GPU box the pip --target install of it under baseline/_ref
+    (git-ignored, travels with the repo snapshot: `python -m pip install --no-index --no-build-isolation --no-deps
+    --target baseline/_ref /root/reference`, also run by __graft_entry__.build() when the source tree is present)"""
+    for c in (os.environ.get("B2S_REFERENCE_ROOT"), "/root/reference",
+              os.path.join(os.path.dirname(_HERE), "baseline", "_ref")):
+        if c and os.path.isdir(os.path.join(c, "clearml_serving", "serving")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
+
+
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "clearml_serving"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "clearml_serving", "serving"))
 
 
 class _Logger(object):

@@ -8,7 +8,7 @@ import numpy as np
 
 
 def decode(blob):
-    (magic, version, n_trees, n_features, n_nodes, feat_bits, acc_mode, n_leaf64, _r0, _r1, base,
+    (magic, version, n_trees, n_features, n_nodes, feat_bits, acc_mode, n_leaf64, link, _r1, base,
      divisor) = struct.unpack_from("<4sIIIIIIIIIdd", blob, 0)
     assert magic == b"B2SF" and version == 1
     o = 56
@@ -18,7 +18,7 @@ def decode(blob):
     o += n_nodes * 8
     leaf64 = np.frombuffer(blob, dtype="<f8", count=n_leaf64, offset=o)
     assert o + n_leaf64 * 8 == len(blob)
-    return dict(n_trees=n_trees, n_features=n_features, feat_bits=feat_bits, acc_mode=acc_mode,
+    return dict(n_trees=n_trees, n_features=n_features, feat_bits=feat_bits, acc_mode=acc_mode, link=link,
                 base=base, divisor=divisor, toff=toff, val=(nodes & np.uint64(0xffffffff)).astype(np.uint32),
                 meta=(nodes >> np.uint64(32)).astype(np.uint32), leaf64=leaf64)
 
@@ -49,4 +49,7 @@ def predict(blob, X):
             else:
                 acc = np.float32(acc + val_f32[b + nid])
         out[i] = (acc / np.float64(d["divisor"])) if f64 else acc
+    if d["link"] == 1:   # xgboost's fp32 logistic transform (the kernel's forest_link_f32)
+        from oracle import oracle as orc
+        out = orc.xgb_sigmoid(out)
     return out

@@ -6,6 +6,7 @@ import gzip
 import json
 import os
 import textwrap
+import time
 
 import numpy as np
 import pytest
@@ -291,3 +292,67 @@ def test_round_robin_over_replicas():
         assert st["replicas"] == 4 and st["per_replica_requests"] == [10, 10, 10, 10]
     finally:
         eng.unload()
+
+
+def test_model_hot_reload_drops_only_the_changed_endpoint(tmp_path):
+    """sync_models(): the in-process counterpart of the Triton sidecar's model poll (triton_helper.py:91-194,226-289)
+    + the engine drop of model_request_processor.py:1026-1028, per endpoint"""
+    import joblib
+    from sklearn.linear_model import LogisticRegression
+    from clearml_serving_b200 import ModelEndpoint
+    from clearml_serving_b200.model_repo import ModelRepository
+    from clearml_serving_b200.model_request_processor import ModelRequestProcessor
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((80, 4))
+    paths = []
+    for k in range(2):
+        p = tmp_path / "m{}.pkl".format(k)
+        joblib.dump(LogisticRegression(max_iter=200).fit(X, (X[:, k] > 0).astype(int)), p)
+        paths.append(str(p))
+    proc = ModelRequestProcessor()
+    for k, p in enumerate(paths):
+        proc.add_endpoint(ModelEndpoint(engine_type="b200", serving_url="ep{}".format(k), model_id=p))
+
+    class _Eng(object):
+        unloaded = 0
+
+        def unload(self):
+            self.unloaded += 1
+    engines = {"ep0": _Eng(), "ep1": _Eng()}
+    proc._engine_processor_lookup.update(engines)
+    repo = ModelRepository()
+    assert proc.sync_models(repo) == []            # first pass: packs both, nothing to drop
+    assert proc.sync_models(repo) == []            # unchanged files
+    joblib.dump(LogisticRegression(max_iter=200).fit(X, (X[:, 2] > 0).astype(int)), paths[1])   # new model content
+    assert proc.sync_models(repo) == ["ep1"]
+    assert engines["ep1"].unloaded == 1 and engines["ep0"].unloaded == 0
+    assert "ep1" not in proc._engine_processor_lookup and proc._engine_processor_lookup["ep0"] is engines["ep0"]
+    # the daemon form: picks the change up by itself
+    proc._engine_processor_lookup["ep1"] = engines["ep1"]
+    proc.sync_models()                              # default repository: first pass
+    proc.start_sync_daemon(poll_frequency_sec=0.05)
+    joblib.dump(LogisticRegression(max_iter=200).fit(X, (X[:, 3] > 0).astype(int)), paths[1])
+    deadline = time.time() + 5
+    while "ep1" in proc._engine_processor_lookup and time.time() < deadline:
+        time.sleep(0.02)
+    proc.stop_sync_daemon()
+    assert "ep1" not in proc._engine_processor_lookup and engines["ep1"].unloaded == 2
+    proc._engine_processor_lookup.clear()
+
+
+def test_canary_table_follows_endpoint_changes():
+    """add_endpoint / remove_endpoint rebuild the canary route table (the reference rebuilds it on every
+    configuration reload, model_request_processor.py:772-814)"""
+    from clearml_serving_b200 import ModelEndpoint
+    from clearml_serving_b200.model_request_processor import ModelRequestProcessor
+    proc = ModelRequestProcessor()
+    proc.add_canary_endpoint(dict(endpoint="pub", weights=[0.7, 0.3], load_endpoint_prefix="m/"))
+    assert "pub" not in proc._canary_route                      # canary first, targets later
+    proc.add_endpoint(ModelEndpoint(engine_type="custom", serving_url="m/1", version="1"))
+    assert proc._canary_route["pub"]["endpoints"] == ["m/1"]
+    proc.add_endpoint(ModelEndpoint(engine_type="custom", serving_url="m/2", version="2"))
+    assert proc._canary_route["pub"]["endpoints"] == ["m/2", "m/1"] and proc._canary_route["pub"]["weights"] == [0.7, 0.3]
+    proc.remove_endpoint("m/2")
+    assert proc._canary_route["pub"]["endpoints"] == ["m/1"] and proc._canary_route["pub"]["weights"] == [1.0]
+    proc.remove_endpoint("m/1")
+    assert "pub" not in proc._canary_route

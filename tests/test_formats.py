@@ -49,10 +49,99 @@ def test_xgboost_json_roundtrip(tmp_path):
     assert pm.description["n_trees"] == 11 and pm.description["mode"] == "xgb"
 
 
+def xgb_legacy_binary_from_forest(forest, base_score=0.5, objective="reg:squarederror", binf=False, major=1, minor=7,
+                                  attrs=True):
+    """TEST-SIDE writer of XGBoost's legacy binary layout (xgboost 1.7 src/learner.cc, gbtree_model.h, tree_model.h;
+    see the comment above formats.parse_xgboost_legacy_binary): what `Booster.save_model("xgb_model")` emits."""
+    off = forest["tree_offset"]
+    n_trees = len(off) - 1
+    out = [b"binf"] if binf else []
+    out.append(struct.pack("<fIiiiIII", base_score, int(forest["n_features"]), 0, 1 if attrs else 0, 0, major, minor, 1) + b"\0" * (136 - 32))
+    for name in (objective, "gbtree"):
+        out.append(struct.pack("<Q", len(name)) + name.encode())
+    out.append(struct.pack("<iiiiqii", n_trees, 1, int(forest["n_features"]), 0, 0, 1, 0) + b"\0" * 128)
+    for t in range(n_trees):
+        s, e = int(off[t]), int(off[t + 1])
+        n = e - s
+        out.append(struct.pack("<iiiiii", 1, n, 0, 6, int(forest["n_features"]), 0) + b"\0" * 124)
+        parent = np.full(n, -1, np.int32)
+        for i in range(n):
+            if forest["left"][s + i] >= 0:
+                parent[forest["left"][s + i]] = i
+                parent[forest["right"][s + i]] = i | (1 << 31) if False else i
+        nodes = bytearray()
+        for i in range(n):
+            leaf = forest["left"][s + i] < 0
+            sindex = 0 if leaf else (int(forest["feat"][s + i]) | (int(forest["default_left"][s + i]) << 31))
+            info = forest["value"][s + i] if leaf else forest["thr"][s + i]
+            nodes += struct.pack("<iiiIf", int(parent[i]), int(forest["left"][s + i]) if not leaf else -1,
+                                 int(forest["right"][s + i]) if not leaf else 0, sindex, float(np.float32(info)))
+        out.append(bytes(nodes))
+        out.append(b"".join(struct.pack("<fffi", 0.0, 1.0, 0.0, 0) for _ in range(n)))
+    out.append(struct.pack("<" + "i" * n_trees, *([0] * n_trees)))
+    if attrs:   # vector<pair<string,string>>: the reader ignores everything after tree_info
+        out.append(struct.pack("<Q", 1) + struct.pack("<Q", 14) + b"best_iteration" + struct.pack("<Q", 2) + b"99")
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("binf", [False, True])
+def test_xgboost_legacy_binary_model(tmp_path, binf):
+    """examples/xgboost/train_model.py:28 saves `xgb_model` (no extension) = the legacy binary container."""
+    from clearml_serving_b200 import model_repo
+    f = orc.synth_xgb_forest(n_trees=13, depth=5, n_features=9, seed=4, ragged=True)
+    raw = xgb_legacy_binary_from_forest(f, base_score=0.5, binf=binf)
+    forest, base, link = formats.parse_xgboost_legacy_binary(raw)
+    assert base == 0.5 and link == formats.LINK_IDENTITY and forest["n_features"] == 9
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((50, 9)).astype(np.float32)
+    X[rng.random(X.shape) < 0.05] = np.nan
+    want = orc.forest_predict_xgb(f, X, 0.5)
+    assert np.array_equal(orc.forest_predict_xgb(forest, X, base), want)
+    p = tmp_path / "xgb_model"
+    p.write_bytes(raw)
+    pm = model_repo.load_model(str(p))                      # sniffed, no extension, no framework tag
+    assert np.array_equal(blob_interp.predict(pm.blob, X), want)
+    assert model_repo.load_model(str(p), framework="XGBoost").blob == pm.blob
+    with pytest.raises(ValueError, match="truncated"):
+        formats.parse_xgboost_legacy_binary(raw[:len(raw) // 2])
+
+
+def test_xgboost_logistic_objectives_and_base_score_forms():
+    """binary:logitraw adds logit(base_score) (it used to add base_score itself); binary:logistic /
+    reg:logistic additionally map the margin through xgboost's fp32 sigmoid; base_score may come as "[5E-1]"."""
+    f = orc.synth_xgb_forest(n_trees=9, depth=3, n_features=5, seed=6)
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((30, 5)).astype(np.float32)
+    for bs_text, bs in (("2.5E-1", 0.25), ("[7.5E-1]", 0.75), ("5E-1", 0.5)):
+        margin0 = orc.xgb_prob_to_margin(bs)
+        assert margin0 == pytest.approx(np.log(bs / (1 - bs)), abs=1e-6)
+        doc = orc.xgb_json_from_forest(f, base_score=bs, objective="binary:logitraw")
+        doc["learner"]["learner_model_param"]["base_score"] = bs_text
+        forest, base, link = formats.parse_xgboost_json(doc)
+        assert np.float32(base) == np.float32(margin0) and link == formats.LINK_IDENTITY
+        want_margin = orc.forest_predict_xgb(f, X, margin0)
+        assert np.array_equal(blob_interp.predict(formats.pack_xgboost_json(doc).blob, X), want_margin)
+        for obj in ("binary:logistic", "reg:logistic"):
+            doc["learner"]["objective"]["name"] = obj
+            pm = formats.pack_xgboost_json(doc)
+            assert pm.description["link"] == formats.LINK_SIGMOID
+            got = blob_interp.predict(pm.blob, X)
+            assert np.array_equal(got, orc.xgb_sigmoid(want_margin)) and np.all((got > 0) & (got < 1))
+    raw = xgb_legacy_binary_from_forest(f, base_score=0.25, objective="binary:logistic")
+    _forest, base, link = formats.parse_xgboost_legacy_binary(raw)
+    assert np.float32(base) == np.float32(orc.xgb_prob_to_margin(0.25)) and link == formats.LINK_SIGMOID
+    # a pre-1.0 writer stored the margin itself
+    raw = xgb_legacy_binary_from_forest(f, base_score=-1.0986123, objective="binary:logistic", binf=True, major=0, minor=0)
+    assert formats.parse_xgboost_legacy_binary(raw)[1] == pytest.approx(-1.0986123)
+
+
 def test_xgboost_json_rejects_unsupported():
     f = orc.synth_xgb_forest(n_trees=2, depth=2, n_features=3, seed=0)
-    doc = orc.xgb_json_from_forest(f, objective="binary:logistic")
+    doc = orc.xgb_json_from_forest(f, objective="multi:softprob")
     with pytest.raises(ValueError, match="objective"):
+        formats.pack_xgboost_json(doc)
+    doc = orc.xgb_json_from_forest(f, objective="binary:logistic", base_score=1.5)
+    with pytest.raises(ValueError, match="base_score"):
         formats.pack_xgboost_json(doc)
     doc = orc.xgb_json_from_forest(f)
     doc["learner"]["learner_model_param"]["num_class"] = "3"

@@ -68,11 +68,16 @@ def test_unsupported_frameworks_fail_loudly(tmp_path, fw):
         model_repo.load_model(str(p), framework=fw)
 
 
-def test_legacy_xgboost_binary_is_refused(tmp_path):
-    p = tmp_path / "xgb_model"
-    p.write_bytes(b"binf" + b"\0" * 200)
-    with pytest.raises(ValueError, match="legacy binary"):
+def test_malformed_legacy_xgboost_binary_fails_loudly(tmp_path):
+    import struct
+    p = tmp_path / "xgb_model"    # a plausible header (objective string at offset 136) followed by nothing
+    p.write_bytes(b"\0" * 136 + struct.pack("<Q", 16) + b"reg:squarederror" + struct.pack("<Q", 6) + b"gbtree" + b"\0" * 40)
+    with pytest.raises(ValueError, match="truncated|XGBoost binary"):
         model_repo.load_model(str(p))
+    q = tmp_path / "old_model"
+    q.write_bytes(b"bs64" + b"A" * 300)
+    with pytest.raises(ValueError, match="base64|b200 engine"):
+        model_repo.load_model(str(q))
 
 
 def test_sklearn_joblib_file(tmp_path):
