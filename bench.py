@@ -769,6 +769,77 @@ def _resnet_workload(native, device, steps, warmup, cpu_seconds, dist=None, loca
     return res
 
 
+def _llama_serving_leg(eng, spec, batch, prompt_len, gen, seconds=8.0):
+    """The OpenAI-route scheduler on the same engine: CONTINUOUS BATCHING over the paged KV cache (llm_service.
+    ContinuousBatcher: requests join the running batch at the next iteration, leave when done).  Closed loop at `batch`
+    clients (saturation) and an open-loop Poisson stream at 60 % of it: requests/s, time to first token, inter-token
+    latency, end-to-end latency.  Same workload shape as the waves above (prompt 512, 128 new tokens, greedy)."""
+    import threading
+    from clearml_serving_b200 import llm_service as S
+    b = S.ContinuousBatcher(eng, max_batch=batch, max_ctx=eng.max_ctx, chunk=4)
+    rng = np.random.default_rng(7)
+    prompts = [rng.integers(0, spec.vocab_size, prompt_len).astype(np.int32) for _ in range(64)]
+
+    def one(i, rec):
+        t0 = time.perf_counter()
+        stamps = []
+
+        def on_tokens(toks, finished):
+            stamps.append((time.perf_counter(), len(toks)))
+        f = b.submit(prompts[i % len(prompts)], gen, on_tokens)
+        f.result(timeout=120)
+        t1 = time.perf_counter()
+        itl = []
+        for (ta, _na), (tb, nb) in zip(stamps[:-1], stamps[1:]):
+            itl.extend([(tb - ta) / nb] * nb)
+        rec.append(dict(ttft=stamps[0][0] - t0, e2e=t1 - t0, itl=itl))
+
+    def summarise(rec, wall):
+        tt = np.array([r["ttft"] for r in rec]) * 1e3
+        ee = np.array([r["e2e"] for r in rec]) * 1e3
+        it = np.array([x for r in rec for x in r["itl"]]) * 1e3
+        return dict(completed=len(rec), requests_per_s=len(rec) / wall, gen_tokens_per_s=len(rec) * gen / wall,
+                    ttft_ms=dict(mean=float(tt.mean()), p50=float(np.percentile(tt, 50)), p99=float(np.percentile(tt, 99))),
+                    itl_ms=dict(mean=float(it.mean()), p50=float(np.percentile(it, 50)), p99=float(np.percentile(it, 99))),
+                    e2e_ms=dict(p50=float(np.percentile(ee, 50)), p99=float(np.percentile(ee, 99))))
+    try:
+        # closed loop: `batch` clients, each sends its next request when the previous one is done
+        rec, stop = [], time.perf_counter() + seconds
+        def client(k):
+            i = k
+            while time.perf_counter() < stop:
+                one(i, rec)
+                i += batch
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=client, args=(k,)) for k in range(batch)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        closed = summarise(rec, time.perf_counter() - t0)
+        # open loop: Poisson arrivals at 60 % of the closed-loop rate
+        lam = 0.6 * closed["requests_per_s"]
+        rec2, th2 = [], []
+        gaps = np.random.default_rng(2).exponential(1.0 / lam, int(lam * seconds))
+        t0 = time.perf_counter()
+        t_next = t0
+        for i, g in enumerate(gaps):
+            t_next += g
+            dt = t_next - time.perf_counter()
+            if dt > 0:
+                time.sleep(dt)
+            t = threading.Thread(target=one, args=(i, rec2))
+            t.start()
+            th2.append(t)
+        [t.join() for t in th2]
+        poisson = summarise(rec2, time.perf_counter() - t0)
+        poisson["offered_requests_per_s"] = lam
+        st = dict(b.stats)
+        return dict(scheduler="continuous batching, paged KV (64-token pages), decode chunk 4", closed_loop=closed, poisson=poisson,
+                    iterations=st["iterations"], joined_running=st["joined_running"], max_rows=st["max_rows"], pages_peak=st["pages_peak"],
+                    kv_pages=b.n_pages)
+    finally:
+        b.close()
+
+
 def _llama_workload(native, rank, world, local, dist, waves=3):
     """BASELINE.json configs[4]: Llama-3-8B bf16 random-init, prompt 512, 128 new tokens, max_batch 32, greedy.
     One GPU: TP 1.  N >= 2 (torchrun): ranks (2i, 2i+1) form tensor-parallel pairs exchanging partial sums through
@@ -831,6 +902,12 @@ def _llama_workload(native, rank, world, local, dist, waves=3):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         if int(t[0]) != digest or int(-t[1]) != digest:
             raise SystemExit("bench: the two ranks of the tensor-parallel pair disagree on the generated tokens")
+    serving = None
+    if tp == 1 and world == 1:
+        try:
+            serving = _llama_serving_leg(eng, spec, batch, prompt_len, gen)
+        except Exception as ex:  # noqa
+            serving = dict(error="{}: {}".format(type(ex).__name__, ex))
     pre = _max_over_ranks(dist, local, float(np.median([r[0] for r in res[1:]])))
     dec = _max_over_ranks(dist, local, float(np.median([r[1] for r in res[1:]])))
     e2e_s = _max_over_ranks(dist, local, min(e2e))
@@ -861,7 +938,7 @@ def _llama_workload(native, rank, world, local, dist, waves=3):
                       decode=dict(bound="hbm", achieved=(wbytes + kv_bytes) / (step_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
                                   frac=(wbytes + kv_bytes) / (step_ms * 1e-3) / 1e9 / hbm_peak,
                                   algorithmic_bytes_per_step=int(wbytes + kv_bytes))),
-        tp2_vs_tp1_check=tp_check, tokens_checked="device-timed wave == LlmEngine.generate" + (" == peer rank" if tp == 2 else ""),
+        serving=serving, tp2_vs_tp1_check=tp_check, tokens_checked="device-timed wave == LlmEngine.generate" + (" == peer rank" if tp == 2 else ""),
         cpu_baseline=None, cpu_baseline_note="the reference has no CPU path for this endpoint (it wraps vLLM)",
         waves_ms=[[round(x, 2) for x in r] for r in res])
 

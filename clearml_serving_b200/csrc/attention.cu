@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace b2s {
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // active with 22 % of the warp slots occupied: the kernel is bound by latency at low occupancy, not by the HMMA rate.
 __global__ void __launch_bounds__(128, 5)
 attention_varlen_kernel(const __half *__restrict__ qkv, const int64_t *__restrict__ cu_seqlens,
-                        const int32_t *__restrict__ key_mask, __half *__restrict__ out, int heads, float scale_log2e)
+                        const int32_t *__restrict__ key_mask, __half *__restrict__ out, int heads, float scale_log2e, int skip_upto)
 {
     __shared__ __align__(16) __half Ks2[2][ATT_BK * ATT_LD];   // double-buffered key / value blocks
     __shared__ __align__(16) __half Vs2[2][ATT_BK * ATT_LD];
@@ -84,7 +85,7 @@ attention_varlen_kernel(const __half *__restrict__ qkv, const int64_t *__restric
     const int64_t s0 = __ldg(cu_seqlens + b);
     const int S = (int)(__ldg(cu_seqlens + b + 1) - s0);
     const int q0 = qt * ATT_BQ;
-    if (q0 >= S) return;
+    if (q0 >= S || S <= skip_upto) return;     // sequences of <= skip_upto tokens belong to the tcgen05 form (attention_tc.cu)
     const int H = heads * ATT_D;
     const int64_t ld = 3 * (int64_t)H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -220,15 +221,28 @@ attention_varlen_kernel(const __half *__restrict__ qkv, const int64_t *__restric
     }
 }
 
+int attention_varlen_tc(cudaStream_t st, const void *qkv, const int64_t *cu_seqlens, const int32_t *key_mask, void *out, int n_seq,
+                        int max_seqlen, int64_t total_tokens, int heads);
+
+// total_tokens: rows of the packed qkv matrix (cu_seqlens[n_seq]), < 0 when the caller does not know it on the host
 int attention_varlen(cudaStream_t st, const void *qkv, const int64_t *cu_seqlens, const int32_t *key_mask, void *out,
-                     int n_seq, int max_seqlen, int heads, int head_dim)
+                     int n_seq, int max_seqlen, int heads, int head_dim, int64_t total_tokens)
 {
     if (n_seq <= 0 || max_seqlen <= 0) return 0;
     if (head_dim != ATT_D) return fail(B2S_ERR_INVALID, "attention: head_dim %d not supported (64 only)", head_dim);
+    // tcgen05 form (attention_tc.cu) whenever a sequence's scores fit tensor memory; B2S_ATTN_TC=0 selects the mma.sync form
+    static const bool tc_on = []() { const char *e = getenv("B2S_ATTN_TC"); return !(e && e[0] == '0'); }();
+    // WHICH form a sequence takes depends on its own length only -- never on its batch-mates (SURVEY.md 5.9 rule 4)
+    int skip_upto = 0;
+    if (tc_on && total_tokens > 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) {
+        B2S_TRY(attention_varlen_tc(st, qkv, cu_seqlens, key_mask, out, n_seq, max_seqlen, total_tokens, heads));
+        if (max_seqlen <= 384) return 0;
+        skip_upto = 384;
+    }
     dim3 grid((max_seqlen + ATT_BQ - 1) / ATT_BQ, heads, n_seq);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
     attention_varlen_kernel<<<grid, 128, 0, st>>>(static_cast<const __half *>(qkv), cu_seqlens, key_mask,
-                                                  static_cast<__half *>(out), heads, scale_log2e);
+                                                  static_cast<__half *>(out), heads, scale_log2e, skip_upto);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
@@ -238,10 +252,15 @@ int attention_varlen(cudaStream_t st, const void *qkv, const int64_t *cu_seqlens
 
 extern "C" B2S_API int b2s_op_attention(int device, void *cuda_stream, const void *qkv, const int64_t *cu_seqlens,
                                          const int32_t *key_mask, void *out, int n_seq, int max_seqlen, int heads,
-                                         int head_dim)
+                                         int head_dim, int64_t total_tokens)
 {
     using namespace b2s;
     B2S_CUDA(cudaSetDevice(device));
+    int64_t total = total_tokens;     // the tensor map of the tcgen05 form needs the row count on the host
+    if (total <= 0 && n_seq > 0 && cu_seqlens) {
+        B2S_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+        B2S_CUDA(cudaMemcpy(&total, cu_seqlens + n_seq, 8, cudaMemcpyDeviceToHost));
+    }
     return attention_varlen(static_cast<cudaStream_t>(cuda_stream), qkv, cu_seqlens, key_mask, out, n_seq, max_seqlen,
-                            heads, head_dim);
+                            heads, head_dim, total);
 }

@@ -565,7 +565,7 @@ forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict
     using acc_t = typename std::conditional<F64, double, float>::type;
     using bits_t = typename std::conditional<F64, unsigned long long, uint32_t>::type;
     constexpr int VEC = 16 / (int)sizeof(acc_t);
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int F = p.n_features, T = p.n_trees, TPC = p.tpc;
     const int R = 1 << R_log2, rpr = 1 << rpr_log2;
@@ -583,7 +583,25 @@ forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict
     const int n_my = max(0, min(T - (int)rank * TPC, TPC));
     const int n_tb = (n_my + 31) >> 5;     // 32-tree blocks of this rank
     const bits_t sentinel = F64 ? (((unsigned long long)p.sentinel << 32) | p.sentinel) : (bits_t)p.sentinel;
-    if (threadIdx.x == 0) {
+    const bool use_bulk = bulk_piece > 0;
+    if (!use_bulk) {
+        // plain cooperative copy: every thread keeps up to four 16-byte loads in flight (one L2 / DRAM round trip for the
+        // whole 49 KB image; the bulk-copy engine showed ~2500 cycles of fixed latency for a copy this small)
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.images + img_lo);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        const int n16 = (int)(img_bytes >> 4), stride = (int)blockDim.x;
+        for (int i = threadIdx.x; i < n16; i += 4 * stride) {
+            uint4 v0 = __ldg(src + i), v1, v2, v3;
+            const bool h1 = i + stride < n16, h2 = i + 2 * stride < n16, h3 = i + 3 * stride < n16;
+            if (h1) v1 = __ldg(src + i + stride);
+            if (h2) v2 = __ldg(src + i + 2 * stride);
+            if (h3) v3 = __ldg(src + i + 3 * stride);
+            dst[i] = v0;
+            if (h1) dst[i + stride] = v1;
+            if (h2) dst[i + 2 * stride] = v2;
+            if (h3) dst[i + 3 * stride] = v3;
+        }
+    } else if (threadIdx.x == 0) {
         for (int b = 0; b < n_tb; ++b) mbar_init_cta(&load_bar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         // one bulk copy per piece, all issued by this thread: block b's bytes are [end of block b-1, end of block b)
@@ -624,7 +642,7 @@ forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict
     for (int q = warp; q < n_tasks; q += n_warps) {
         const int row = q & (R - 1), tb = q >> R_log2;
         const int tl = tb * 32 + lane;
-        if (tb != tb_ready) {
+        if (use_bulk && tb != tb_ready) {
             uint32_t spins = 0;
             if (tb_ready < 0 && tb > 0) {     // the block table rides with block 0
                 while (!mbar_try_wait_cta(&load_bar[0], 0u)) {
@@ -635,8 +653,8 @@ forest_wide_kernel(const __grid_constant__ WideParams p, const float *__restrict
                 if (++spins > B2S_SPIN_LIMIT) __trap();
             }
             tb_ready = tb;
-            if (q == 0) B2S_STAMP(1);
         }
+        if (q == 0) B2S_STAMP(1);
         acc_t v = (acc_t)0;
         if (tl < n_my) {
             const uint32_t *tab = reinterpret_cast<const uint32_t *>(smem + 16) + tb * 4;
@@ -891,7 +909,12 @@ struct ForestModel : Model {
 
 
     // row tile of the wide kernel for a batch: 16 rows per cluster at serving sizes, 32 for big batches
-    int wide_rows_per_tile(int64_t n_rows) const { return n_rows > 1024 ? 32 : 16; }
+    int wide_rows_per_tile(int64_t n_rows) const
+    {
+        static const int forced = []() { const char *e = getenv("B2S_FOREST_WIDE_R"); const int v = e ? atoi(e) : 0; return (v == 16 || v == 32) ? v : 0; }();
+        if (forced) return forced;
+        return n_rows > 1024 ? 32 : 16;
+    }
     size_t wide_smem(int R) const
     {
         const size_t esz = f64 ? 8 : 4, vec = 16 / esz;
@@ -924,8 +947,8 @@ struct ForestModel : Model {
         cfg.numAttrs = 1;
         static const int bulk_piece = []() {
             const char *e = getenv("B2S_FOREST_BULK_PIECE");
-            int v = e ? atoi(e) : 8192;
-            return (v >= 1024 && v % 16 == 0) ? v : 8192;
+            int v = e ? atoi(e) : 0;      // 0: plain cooperative loads (default); >= 1024: cp.async.bulk pieces of that size
+            return (v >= 1024 && v % 16 == 0) ? v : 0;
         }();
         int R_log2 = 0, rpr_log2 = 0;
         while ((1 << R_log2) < R) ++R_log2;

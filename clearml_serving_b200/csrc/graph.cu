@@ -51,7 +51,7 @@ int embed_layernorm(cudaStream_t st, const int32_t *ids, const int32_t *types, c
                     int n_types, const float *gamma, const float *beta, float eps, void *out16, float *out32);
 int gather_first(cudaStream_t st, const void *in, const int64_t *cu_seqlens, int n_seq, int H, void *out);
 int attention_varlen(cudaStream_t st, const void *qkv, const int64_t *cu_seqlens, const int32_t *key_mask, void *out,
-                     int n_seq, int max_seqlen, int heads, int head_dim);
+                     int n_seq, int max_seqlen, int heads, int head_dim, int64_t total_tokens);
 int make_tmap_im2col_nhwc(CUtensorMap *out, const void *base, int64_t n_img, int H, int W, int C, int KS, int stride, int pad);
 ConvGeom make_conv_geom(int H, int W, int C, int KS, int stride, int pad);
 int conv_implicit_maps(cudaStream_t st, const CUtensorMap &ta, const CUtensorMap &tb, int bn, bool pair, int M, int N, int K,
@@ -302,7 +302,7 @@ struct GraphModel : Model {
                 // a: qkv_buf, mask_input(-1), out_buf, heads, head_dim
                 B2S_TRY(attention_varlen(st, pl->buf[op.a[0]], d_row_offsets,
                                          op.a[1] >= 0 ? static_cast<const int32_t *>(d_in[op.a[1]]) : nullptr, pl->buf[op.a[2]],
-                                         (int)n_rows, max_seqlen, op.a[3], op.a[4]));
+                                         (int)n_rows, max_seqlen, op.a[3], op.a[4], n_tokens));
                 break;
             }
             case OP_GATHER_FIRST: {

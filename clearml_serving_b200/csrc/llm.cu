@@ -20,7 +20,7 @@
 // is only rewritten after the peer has signalled the NEXT exchange point, i.e. finished reading it.
 //
 // Layouts: weights bf16 [out, in] as nn.Linear stores them; residual stream fp32 [T, H]; KV cache per layer
-// K, V = [slot][kv_head][max_ctx][128] bf16; decode accumulators fp32 [32, N].
+// K, V = PAGED: [page][kv_head][64][128] bf16 + a page table [slot][pages_per_seq] (llm_attention.cu); decode accumulators fp32 [32, N].
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -41,11 +41,11 @@ int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t 
 int skinny_make_maps(CUtensorMap *tw, CUtensorMap *tx, const void *W, int64_t n_out, int64_t K, const void *X, int64_t x_rows);
 int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows);
 int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *kc, const void *vc, const int32_t *cu_seqlens,
-                     const int32_t *slots, void *out, int ld_out, int n_seq, int max_seqlen, int hq_r, int kvh_r,
-                     int max_ctx, float scale);
+                     const int32_t *slots, const int32_t *page_table, int pages_per_seq, void *out, int ld_out, int n_seq,
+                     int max_seqlen, int hq_r, int kvh_r, float scale);
 int llm_attn_decode(cudaStream_t st, float *ws_qkv, void *kc, void *vc, const int32_t *ctx_len, const int32_t *slots,
-                    const float *rope_cos, const float *rope_sin, void *out, int ld_out, int n_seq, int hq_r, int kvh_r,
-                    int max_ctx, float scale);
+                    const int32_t *page_table, int pages_per_seq, const float *rope_cos, const float *rope_sin, void *out,
+                    int ld_out, int n_seq, int hq_r, int kvh_r, int max_ctx, float scale);
 
 constexpr int LLM_MAXB = 32;          // decode batch (rows of the skinny GEMM)
 constexpr int LLM_HD = 128;           // head dim
@@ -281,8 +281,8 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
 __global__ void __launch_bounds__(256)
 llm_rope_cache_prefill_kernel(__nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ kc, __nv_bfloat16 *__restrict__ vc,
                               const int32_t *__restrict__ tok_seq, const int32_t *__restrict__ tok_pos,
-                              const int32_t *__restrict__ slots, const float *__restrict__ rope_cos,
-                              const float *__restrict__ rope_sin, int hq_r, int kvh_r, int max_ctx)
+                              const int32_t *__restrict__ slots, const int32_t *__restrict__ page_table, int pages_per_seq,
+                              const float *__restrict__ rope_cos, const float *__restrict__ rope_sin, int hq_r, int kvh_r, int max_ctx)
 {
     const int t = blockIdx.x;
     const int QKV = (hq_r + 2 * kvh_r) * LLM_HD;
@@ -290,6 +290,9 @@ llm_rope_cache_prefill_kernel(__nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__
     int pos = __ldg(tok_pos + t);
     pos = pos < max_ctx ? pos : max_ctx - 1;
     const int slot = __ldg(slots + seq);
+    // paged cache: token `pos` of this slot lives in page page_table[slot][pos / 64], row pos % 64
+    const int64_t page = __ldg(page_table + (int64_t)slot * pages_per_seq + (pos >> 6));
+    const int prow = pos & 63;
     const float *cs = rope_cos + (int64_t)pos * 64, *sn = rope_sin + (int64_t)pos * 64;
     __nv_bfloat16 *srcb = qkv + (int64_t)t * QKV;
     const int n_rot = (hq_r + kvh_r) * 64;   // q heads first, then k heads: contiguous in the QKV row
@@ -303,7 +306,7 @@ llm_rope_cache_prefill_kernel(__nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__
             srcb[c0] = o1;
             srcb[c0 + 64] = o2;
         } else {
-            __nv_bfloat16 *dst = kc + (((int64_t)slot * kvh_r + (head - hq_r)) * max_ctx + pos) * LLM_HD;
+            __nv_bfloat16 *dst = kc + ((page * kvh_r + (head - hq_r)) * 64 + prow) * LLM_HD;
             dst[i] = o1;
             dst[i + 64] = o2;
         }
@@ -311,7 +314,7 @@ llm_rope_cache_prefill_kernel(__nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__
     const int v0 = (hq_r + kvh_r) * LLM_HD;
     for (int idx = threadIdx.x; idx < kvh_r * LLM_HD; idx += 256) {
         const int kh = idx >> 7, d = idx & 127;
-        vc[(((int64_t)slot * kvh_r + kh) * max_ctx + pos) * LLM_HD + d] = srcb[v0 + idx];
+        vc[((page * kvh_r + kh) * 64 + prow) * LLM_HD + d] = srcb[v0 + idx];
     }
 }
 
@@ -466,6 +469,9 @@ struct Llm {
     float *final_norm = nullptr, *rope_cos = nullptr, *rope_sin = nullptr;
     __nv_bfloat16 *kcache = nullptr, *vcache = nullptr;
     int64_t kv_layer_stride = 0;
+    int n_pages = 0, pages_per_seq = 0;     // paged KV: pool size, page-table row length (ceil(max_ctx / 64))
+    int32_t *d_page_table = nullptr;        // [LLM_MAXB][pages_per_seq]
+    std::vector<int32_t> h_page_table;
     // activations
     float *h = nullptr;
     __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr, *xlast = nullptr;
@@ -527,6 +533,7 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     if (c->hidden % 64 || c->hidden > 8192) return fail(B2S_ERR_INVALID, "llm: hidden must be a multiple of 64, <= 8192");
     if (c->max_batch < 1 || c->max_batch > LLM_MAXB) return fail(B2S_ERR_INVALID, "llm: max_batch must be 1..32");
     if (c->max_ctx < 16 || c->max_tokens < c->max_batch) return fail(B2S_ERR_INVALID, "llm: bad max_ctx / max_tokens");
+    if (c->kv_pages < 0) return fail(B2S_ERR_INVALID, "llm: bad kv_pages");
     B2S_CUDA(cudaSetDevice(device));
     Llm *m = new Llm();
     m->cfg = *c;
@@ -558,9 +565,24 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
         LA(y.ln1, H);
         LA(y.ln2, H);
     }
-    m->kv_layer_stride = (int64_t)c->max_batch * m->kvh_r * c->max_ctx * LLM_HD;
+    m->pages_per_seq = (c->max_ctx + 63) / 64;
+    m->n_pages = c->kv_pages > 0 ? c->kv_pages : c->max_batch * m->pages_per_seq;
+    m->kv_layer_stride = (int64_t)m->n_pages * m->kvh_r * 64 * LLM_HD;
     LA(m->kcache, m->kv_layer_stride * L);
     LA(m->vcache, m->kv_layer_stride * L);
+    LA(m->d_page_table, (int64_t)LLM_MAXB * m->pages_per_seq);
+    // default table: slot s owns pages [s * pages_per_seq, (s + 1) * pages_per_seq) while the pool is large enough (the
+    // fixed-slot behaviour of b2s_llm_prefill); a host that manages pages itself overwrites rows with b2s_llm_set_pages
+    m->h_page_table.assign((size_t)LLM_MAXB * m->pages_per_seq, 0);
+    for (int sl = 0; sl < LLM_MAXB; ++sl)
+        for (int pg = 0; pg < m->pages_per_seq; ++pg) {
+            const int64_t id = (int64_t)sl * m->pages_per_seq + pg;
+            m->h_page_table[(size_t)id] = id < m->n_pages ? (int32_t)id : 0;
+        }
+    if (cudaMemcpy(m->d_page_table, m->h_page_table.data(), m->h_page_table.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete m;
+        return fail(B2S_ERR_CUDA, "llm: page table upload failed");
+    }
     const int64_t Tp = T > LLM_MAXB ? T : LLM_MAXB;
     LA(m->h, Tp * H);
     LA(m->xn, Tp * H);
@@ -694,7 +716,7 @@ static int llm_gemm_bf16(cudaStream_t st, const void *A, int64_t lda, const void
     return gemm_tn(st, A, lda, W, K, M, N, K, ep);
 }
 
-static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens, const int32_t *offsets)
+static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens, const int32_t *offsets, const int32_t *slots = nullptr)
 {
     B2S_CUDA(cudaSetDevice(m->device));
     if (n_seq < 1 || n_seq > m->cfg.max_batch) return fail(B2S_ERR_INVALID, "llm prefill: n_seq %d outside 1..%d", n_seq, m->cfg.max_batch);
@@ -716,7 +738,14 @@ static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens
             s_pos[offsets[b] + i] = i;
         }
         s_cu[b] = offsets[b];
-        s_slots[b] = b;
+        s_slots[b] = slots ? slots[b] : b;
+        if (s_slots[b] < 0 || s_slots[b] >= m->cfg.max_batch) return fail(B2S_ERR_INVALID, "llm prefill: KV slot %d outside 0..%d", s_slots[b], m->cfg.max_batch - 1);
+        for (int a = 0; a < b; ++a)
+            if (s_slots[a] == s_slots[b]) return fail(B2S_ERR_INVALID, "llm prefill: KV slot %d given twice", s_slots[b]);
+        for (int pg = 0; pg <= (len - 1) / 64; ++pg) {   // every page the prompt touches must be a valid pool page
+            const int32_t id = m->h_page_table[(size_t)s_slots[b] * m->pages_per_seq + pg];
+            if (id < 0 || id >= m->n_pages) return fail(B2S_ERR_INVALID, "llm prefill: slot %d has no page for position %d", s_slots[b], pg * 64);
+        }
         s_ctx[b] = len;
         s_opos[b] = 0;
     }
@@ -741,11 +770,11 @@ static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens
         LlmLayer &y = m->layers[l];
         __nv_bfloat16 *kc = m->kcache + m->kv_layer_stride * l, *vc = m->vcache + m->kv_layer_stride * l;
         B2S_TRY(llm_gemm_bf16(st, m->xn, H, y.wqkv, Ti, m->qkv_n, H, m->qkv));
-        llm_rope_cache_prefill_kernel<<<Ti, 256, 0, st>>>(m->qkv, kc, vc, m->d_tok_seq, m->d_tok_pos, m->d_slots, m->rope_cos,
-                                                          m->rope_sin, m->hq_r, m->kvh_r, m->cfg.max_ctx);
+        llm_rope_cache_prefill_kernel<<<Ti, 256, 0, st>>>(m->qkv, kc, vc, m->d_tok_seq, m->d_tok_pos, m->d_slots, m->d_page_table,
+                                                          m->pages_per_seq, m->rope_cos, m->rope_sin, m->hq_r, m->kvh_r, m->cfg.max_ctx);
         count_launch();
-        B2S_TRY(llm_attn_prefill(st, m->qkv, m->qkv_n, kc, vc, m->d_cu, m->d_slots, m->attn, m->hq_r * LLM_HD, n_seq, max_len,
-                                 m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
+        B2S_TRY(llm_attn_prefill(st, m->qkv, m->qkv_n, kc, vc, m->d_cu, m->d_slots, m->d_page_table, m->pages_per_seq, m->attn,
+                                 m->hq_r * LLM_HD, n_seq, max_len, m->hq_r, m->kvh_r, scale));
         for (int half = 0; half < 2; ++half, ++k) {
             void *mine = m->comm + m->off_ppre[k & 1];
             const void *peer = m->peer_comm ? m->peer_comm + m->off_ppre[k & 1] : nullptr;
@@ -835,8 +864,8 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
         __nv_bfloat16 *kc = m->kcache + m->kv_layer_stride * l, *vc = m->vcache + m->kv_layer_stride * l;
         if (!(skip & 8)) B2S_TRY(skinny_gemm_maps(st, y.m_qkv_w, m->m_x_xn, m->ws_qkv, m->qkv_n, H, n_seq));
         LLM_MARK(2);
-        if (!(skip & 1)) B2S_TRY(llm_attn_decode(st, m->ws_qkv, kc, vc, m->d_ctx_len, m->d_slots, m->rope_cos, m->rope_sin, m->attn, m->hq_r * LLM_HD,
-                                n_seq, m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
+        if (!(skip & 1)) B2S_TRY(llm_attn_decode(st, m->ws_qkv, kc, vc, m->d_ctx_len, m->d_slots, m->d_page_table, m->pages_per_seq, m->rope_cos,
+                                m->rope_sin, m->attn, m->hq_r * LLM_HD, n_seq, m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
         LLM_MARK(4);
         nl += 2;
         for (int half = 0; half < 2; ++half, ++k) {
@@ -1018,6 +1047,72 @@ B2S_API int b2s_llm_prefill(b2s_llm *llm, int n_seq, const int32_t *tokens, cons
     if (!m || !tokens || !offsets) return fail(B2S_ERR_INVALID, "null argument");
     if (m->cfg.tp_size == 2 && !m->peer_comm) return fail(B2S_ERR_INVALID, "llm: tensor-parallel peer not attached");
     return llm_prefill(m, m->stream, n_seq, tokens, offsets);
+}
+
+B2S_API int b2s_llm_prefill_slots(b2s_llm *llm, int n_seq, const int32_t *tokens, const int32_t *offsets, const int32_t *slots)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || !tokens || !offsets || !slots) return fail(B2S_ERR_INVALID, "null argument");
+    if (m->cfg.tp_size == 2 && !m->peer_comm) return fail(B2S_ERR_INVALID, "llm: tensor-parallel peer not attached");
+    return llm_prefill(m, m->stream, n_seq, tokens, offsets, slots);
+}
+
+B2S_API int b2s_llm_kv_info(b2s_llm *llm, int32_t *n_pages, int32_t *page_tokens, int32_t *pages_per_seq)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m) return fail(B2S_ERR_INVALID, "null argument");
+    if (n_pages) *n_pages = m->n_pages;
+    if (page_tokens) *page_tokens = 64;
+    if (pages_per_seq) *pages_per_seq = m->pages_per_seq;
+    return 0;
+}
+
+B2S_API int b2s_llm_set_pages(b2s_llm *llm, int slot, int first, int n, const int32_t *pages)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || (n > 0 && !pages)) return fail(B2S_ERR_INVALID, "null argument");
+    if (slot < 0 || slot >= m->cfg.max_batch || first < 0 || n < 0 || first + n > m->pages_per_seq)
+        return fail(B2S_ERR_INVALID, "llm set_pages: slot %d / logical pages [%d, %d) out of range", slot, first, first + n);
+    for (int i = 0; i < n; ++i)
+        if (pages[i] < 0 || pages[i] >= m->n_pages) return fail(B2S_ERR_INVALID, "llm set_pages: page %d outside the pool of %d", pages[i], m->n_pages);
+    if (n == 0) return 0;
+    B2S_CUDA(cudaSetDevice(m->device));
+    int32_t *row = m->h_page_table.data() + (size_t)slot * m->pages_per_seq + first;
+    memcpy(row, pages, (size_t)n * 4);
+    // ordered on the model's stream behind the steps already enqueued (pageable source: staged before the call returns)
+    B2S_CUDA(cudaMemcpyAsync(m->d_page_table + (size_t)slot * m->pages_per_seq + first, row, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    return 0;
+}
+
+B2S_API int b2s_llm_set_rows(b2s_llm *llm, int n_rows, const int32_t *slots, const int32_t *ctx_len, const int32_t *next_tok)
+{
+    using namespace b2s;
+    Llm *m = reinterpret_cast<Llm *>(llm);
+    if (!m || !slots || !ctx_len || !next_tok) return fail(B2S_ERR_INVALID, "null argument");
+    if (n_rows < 1 || n_rows > m->cfg.max_batch) return fail(B2S_ERR_INVALID, "llm set_rows: %d rows outside 1..%d", n_rows, m->cfg.max_batch);
+    int32_t h_slots[LLM_MAXB] = {0}, h_ctx[LLM_MAXB] = {0}, h_tok[LLM_MAXB] = {0}, h_pos[LLM_MAXB] = {0};
+    for (int b = 0; b < n_rows; ++b) {
+        if (slots[b] < 0 || slots[b] >= m->cfg.max_batch) return fail(B2S_ERR_INVALID, "llm set_rows: KV slot %d out of range", slots[b]);
+        for (int a = 0; a < b; ++a)
+            if (slots[a] == slots[b]) return fail(B2S_ERR_INVALID, "llm set_rows: KV slot %d given twice", slots[b]);
+        if (ctx_len[b] < 1 || ctx_len[b] >= m->cfg.max_ctx) return fail(B2S_ERR_INVALID, "llm set_rows: context length %d outside 1..%d", ctx_len[b], m->cfg.max_ctx - 1);
+        const int32_t id = m->h_page_table[(size_t)slots[b] * m->pages_per_seq + ctx_len[b] / 64];
+        if (id < 0 || id >= m->n_pages) return fail(B2S_ERR_INVALID, "llm set_rows: slot %d has no page for position %d", slots[b], ctx_len[b]);
+        h_slots[b] = slots[b];
+        h_ctx[b] = ctx_len[b];
+        h_tok[b] = next_tok[b];
+    }
+    B2S_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    B2S_CUDA(cudaMemcpyAsync(m->d_slots, h_slots, LLM_MAXB * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_ctx_len, h_ctx, LLM_MAXB * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_next_tok, h_tok, LLM_MAXB * 4, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemcpyAsync(m->d_out_pos, h_pos, LLM_MAXB * 4, cudaMemcpyHostToDevice, st));
+    m->n_seq = n_rows;
+    return 0;
 }
 
 B2S_API int b2s_llm_decode(b2s_llm *llm, int n_steps, int use_graph)

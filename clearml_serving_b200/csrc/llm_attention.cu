@@ -2,8 +2,10 @@
 // (BASELINE.json configs[4]; the reference delegates it to vLLM's paged attention,
 // clearml_serving/serving/preprocess_service.py:1097-1348).  head_dim = 128, bf16 in, fp32 softmax/accumulate.
 //
-// KV cache layout (one layer): K and V each [slot][kv_head][max_ctx][128] bf16 -- one (sequence, kv head) is a
-// contiguous [ctx, 128] matrix, so both kernels stream it with full 256-byte rows.
+// KV cache layout (one layer): PAGED.  K and V each [page][kv_head][64][128] bf16; a sequence (KV slot) owns the pages its
+// row of the page table names: token `pos` of slot `s` lives in page page_table[s * pages_per_seq + pos / 64] at row
+// pos % 64.  A page is exactly one 64-key block of these kernels, so a block of one (sequence, kv head) is still one
+// contiguous [64, 128] matrix streamed with full 256-byte rows -- the indirection costs one 4-byte load per block.
 //
 //  * prefill: one CTA = (64-query tile, q head, sequence), 4 warps x 16 query rows; K/V blocks of 64 keys are
 //    double-buffered through shared memory with cp.async; S = QK^T and O += PV on mma.sync m16n8k16 (bf16) with
@@ -72,8 +74,8 @@ constexpr int LA_PREFILL_SMEM = (LA_BQ + 4 * LA_BK) * LA_LD * 2;   // Q + 2 x (K
 __global__ void __launch_bounds__(128)
 llm_attn_prefill_kernel(const __nv_bfloat16 *__restrict__ qkv, int ld_qkv, const __nv_bfloat16 *__restrict__ kc,
                         const __nv_bfloat16 *__restrict__ vc, const int32_t *__restrict__ cu_seqlens,
-                        const int32_t *__restrict__ slots, __nv_bfloat16 *__restrict__ out, int ld_out, int group,
-                        int kvh_r, int max_ctx, float scale_log2e)
+                        const int32_t *__restrict__ slots, const int32_t *__restrict__ page_table, int pages_per_seq,
+                        __nv_bfloat16 *__restrict__ out, int ld_out, int group, int kvh_r, float scale_log2e)
 {
     extern __shared__ __align__(16) unsigned char la_smem[];
     __nv_bfloat16 *Qs = reinterpret_cast<__nv_bfloat16 *>(la_smem);
@@ -89,15 +91,15 @@ llm_attn_prefill_kernel(const __nv_bfloat16 *__restrict__ qkv, int ld_qkv, const
     const int slot = __ldg(slots + b), kvh = h / group;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const __nv_bfloat16 *Kg = kc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D;
-    const __nv_bfloat16 *Vg = vc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D;
+    const int32_t *pages = page_table + (int64_t)slot * pages_per_seq;
     const int k_end = min(S, q0 + LA_BQ);                // keys [0, k_end) can be visible to this tile
 
     la_load_tile_async(Qs, qkv + (int64_t)(s0 + q0) * ld_qkv + h * LA_D, ld_qkv, min(LA_BQ, S - q0), tid);
     auto issue_block = [&](int k0, int buf) {
         const int kv_valid = min(LA_BK, k_end - k0);
-        la_load_tile_async(Ks2 + buf * LA_BK * LA_LD, Kg + (int64_t)k0 * LA_D, LA_D, kv_valid, tid);
-        la_load_tile_async(Vs2 + buf * LA_BK * LA_LD, Vg + (int64_t)k0 * LA_D, LA_D, kv_valid, tid);
+        const int64_t blk = ((int64_t)__ldg(pages + (k0 >> 6)) * kvh_r + kvh) * (LA_BK * LA_D);   // one page = one key block
+        la_load_tile_async(Ks2 + buf * LA_BK * LA_LD, kc + blk, LA_D, kv_valid, tid);
+        la_load_tile_async(Vs2 + buf * LA_BK * LA_LD, vc + blk, LA_D, kv_valid, tid);
         la_commit();
     };
     issue_block(0, 0);   // group 0 = Q + first K/V block
@@ -206,8 +208,8 @@ llm_attn_prefill_kernel(const __nv_bfloat16 *__restrict__ qkv, int ld_qkv, const
 }
 
 int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *kc, const void *vc, const int32_t *cu_seqlens,
-                     const int32_t *slots, void *out, int ld_out, int n_seq, int max_seqlen, int hq_r, int kvh_r,
-                     int max_ctx, float scale)
+                     const int32_t *slots, const int32_t *page_table, int pages_per_seq, void *out, int ld_out, int n_seq,
+                     int max_seqlen, int hq_r, int kvh_r, float scale)
 {
     if (n_seq <= 0 || max_seqlen <= 0) return 0;
     static std::once_flag once;
@@ -219,8 +221,8 @@ int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *k
     dim3 grid((max_seqlen + LA_BQ - 1) / LA_BQ, hq_r, n_seq);
     llm_attn_prefill_kernel<<<grid, 128, LA_PREFILL_SMEM, st>>>(
         static_cast<const __nv_bfloat16 *>(qkv), ld_qkv, static_cast<const __nv_bfloat16 *>(kc),
-        static_cast<const __nv_bfloat16 *>(vc), cu_seqlens, slots, static_cast<__nv_bfloat16 *>(out), ld_out, hq_r / kvh_r,
-        kvh_r, max_ctx, scale * 1.4426950408889634f);
+        static_cast<const __nv_bfloat16 *>(vc), cu_seqlens, slots, page_table, pages_per_seq, static_cast<__nv_bfloat16 *>(out),
+        ld_out, hq_r / kvh_r, kvh_r, scale * 1.4426950408889634f);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
@@ -240,6 +242,7 @@ constexpr int LDM_SMEM = (16 * LA_LD + LDM_STAGES * 2 * LDM_TILE) * 2;       // 
 __global__ void __launch_bounds__(128)
 llm_attn_decode_kernel(float *__restrict__ ws_qkv, __nv_bfloat16 *__restrict__ kc, __nv_bfloat16 *__restrict__ vc,
                        const int32_t *__restrict__ ctx_len, const int32_t *__restrict__ slots,
+                       const int32_t *__restrict__ page_table, int pages_per_seq,
                        const float *__restrict__ rope_cos, const float *__restrict__ rope_sin,
                        __nv_bfloat16 *__restrict__ out, int ld_out, int hq_r, int kvh_r, int max_ctx, float scale_log2e)
 {
@@ -258,16 +261,19 @@ llm_attn_decode_kernel(float *__restrict__ ws_qkv, __nv_bfloat16 *__restrict__ k
     pos = pos < max_ctx ? pos : max_ctx - 1;
     const int n_ctx = pos + 1;
     const int slot = __ldg(slots + b);
-    __nv_bfloat16 *Kg = kc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D;
-    __nv_bfloat16 *Vg = vc + ((int64_t)slot * kvh_r + kvh) * max_ctx * LA_D;
+    const int32_t *pages = page_table + (int64_t)slot * pages_per_seq;
+    // the row appended by this step: page of `pos`, row pos % 64
+    const int64_t app = (((int64_t)__ldg(pages + (pos >> 6)) * kvh_r + kvh) * LA_BK + (pos & 63)) * LA_D;
+    __nv_bfloat16 *Kapp = kc + app, *Vapp = vc + app;
 
     const int n_blocks = (n_ctx + LA_BK - 1) / LA_BK;
     auto issue_block = [&](int blk) {
         if (blk < n_blocks) {
             const int k0 = blk * LA_BK;
             __nv_bfloat16 *dst = ring + (blk % LDM_STAGES) * 2 * LDM_TILE;
-            la_load_tile_async(dst, Kg + (int64_t)k0 * LA_D, LA_D, min(LA_BK, n_ctx - k0), tid);
-            la_load_tile_async(dst + LDM_TILE, Vg + (int64_t)k0 * LA_D, LA_D, min(LA_BK, n_ctx - k0), tid);
+            const int64_t off = ((int64_t)__ldg(pages + blk) * kvh_r + kvh) * (LA_BK * LA_D);   // one page = one key block
+            la_load_tile_async(dst, kc + off, LA_D, min(LA_BK, n_ctx - k0), tid);
+            la_load_tile_async(dst + LDM_TILE, vc + off, LA_D, min(LA_BK, n_ctx - k0), tid);
         }
         la_commit();   // (possibly empty) group: keeps the wait_group arithmetic uniform
     };
@@ -299,16 +305,16 @@ llm_attn_decode_kernel(float *__restrict__ ws_qkv, __nv_bfloat16 *__restrict__ k
         src[tid] = 0.f;
         src[tid + 64] = 0.f;
         const float c = __ldg(rope_cos + (int64_t)pos * 64 + tid), sv = __ldg(rope_sin + (int64_t)pos * 64 + tid);
-        Kg[(int64_t)pos * LA_D + tid] = __float2bfloat16_rn(x1 * c - x2 * sv);
-        Kg[(int64_t)pos * LA_D + tid + 64] = __float2bfloat16_rn(x2 * c + x1 * sv);
+        Kapp[tid] = __float2bfloat16_rn(x1 * c - x2 * sv);
+        Kapp[tid + 64] = __float2bfloat16_rn(x2 * c + x1 * sv);
     } else {
         const int i = tid - 64;
         float *src = row + (hq_r + kvh_r + kvh) * LA_D;
         const float x1 = src[i], x2 = src[i + 64];
         src[i] = 0.f;
         src[i + 64] = 0.f;
-        Vg[(int64_t)pos * LA_D + i] = __float2bfloat16_rn(x1);
-        Vg[(int64_t)pos * LA_D + i + 64] = __float2bfloat16_rn(x2);
+        Vapp[i] = __float2bfloat16_rn(x1);
+        Vapp[i + 64] = __float2bfloat16_rn(x2);
     }
     __syncthreads();   // Qs complete; the appended K/V row is ordered before this CTA's tile loads
 
@@ -423,8 +429,8 @@ llm_attn_decode_kernel(float *__restrict__ ws_qkv, __nv_bfloat16 *__restrict__ k
 
 // decode attention fused with RoPE + KV append: reads (and clears) the fp32 QKV accumulator [32, (hq+2hkv)*128]
 int llm_attn_decode(cudaStream_t st, float *ws_qkv, void *kc, void *vc, const int32_t *ctx_len, const int32_t *slots,
-                    const float *rope_cos, const float *rope_sin, void *out, int ld_out, int n_seq, int hq_r, int kvh_r,
-                    int max_ctx, float scale)
+                    const int32_t *page_table, int pages_per_seq, const float *rope_cos, const float *rope_sin, void *out,
+                    int ld_out, int n_seq, int hq_r, int kvh_r, int max_ctx, float scale)
 {
     if (n_seq <= 0) return 0;
     const int G = hq_r / kvh_r;
@@ -446,8 +452,8 @@ int llm_attn_decode(cudaStream_t st, float *ws_qkv, void *kc, void *vc, const in
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     B2S_CUDA(cudaLaunchKernelEx(&cfg, llm_attn_decode_kernel, ws_qkv, static_cast<__nv_bfloat16 *>(kc), static_cast<__nv_bfloat16 *>(vc),
-                                ctx_len, slots, rope_cos, rope_sin, static_cast<__nv_bfloat16 *>(out), ld_out, hq_r, kvh_r, max_ctx,
-                                scale * 1.4426950408889634f));
+                                ctx_len, slots, page_table, pages_per_seq, rope_cos, rope_sin, static_cast<__nv_bfloat16 *>(out), ld_out,
+                                hq_r, kvh_r, max_ctx, scale * 1.4426950408889634f));
     count_launch();
     return 0;
 }

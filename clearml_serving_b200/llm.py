@@ -182,15 +182,17 @@ class LlmEngine(object):
     """Greedy generation in waves of up to `max_batch` prompts (BASELINE.json configs[4] workload shape:
     prompt 512, 128 new tokens, 32 sequences).  `tp_group`: a 2-rank torch.distributed group, or None (TP=1)."""
 
-    def __init__(self, spec, device=0, max_batch=32, max_ctx=1024, max_tokens=None, tp_size=1, tp_rank=0, tp_group=None):
+    def __init__(self, spec, device=0, max_batch=32, max_ctx=1024, max_tokens=None, tp_size=1, tp_rank=0, tp_group=None,
+                 kv_pages=0):
         self.spec = spec
         self.max_batch, self.max_ctx = int(max_batch), int(max_ctx)
+        self.max_prefill_tokens = int(max_tokens) if max_tokens else self.max_batch * self.max_ctx
         self.tp_size, self.tp_rank, self.tp_group = int(tp_size), int(tp_rank), tp_group
         self.llm = native.Llm(device=device, vocab=spec.vocab_size, hidden=spec.hidden_size, inter=spec.intermediate_size,
                               n_layers=spec.num_hidden_layers, n_heads=spec.num_attention_heads,
                               n_kv_heads=spec.num_key_value_heads, head_dim=spec.head_dim, max_batch=max_batch,
                               max_ctx=max_ctx, max_tokens=max_tokens, tp_size=tp_size, tp_rank=tp_rank,
-                              rope_theta=spec.rope_theta, rms_eps=spec.rms_norm_eps)
+                              rope_theta=spec.rope_theta, rms_eps=spec.rms_norm_eps, kv_pages=kv_pages)
         if self.tp_size == 2:
             attach_tensor_parallel(self.llm, tp_group)
 
@@ -235,6 +237,30 @@ class LlmEngine(object):
             if on_progress is not None:
                 on_progress(w0, out[w0:w0 + len(wave)])
         return out
+
+    # ---- continuous batching: one scheduler iteration (clearml_serving_b200/llm_service.ContinuousBatcher)
+    def kv_info(self):
+        return self.llm.kv_info()
+
+    def step(self, page_updates=(), prefill=None, decode=None, use_graph=True):
+        """One iteration of the host scheduler over the paged KV cache:
+          page_updates  [(slot, first logical page, [pool pages])...]  page-table rows to extend first
+          prefill       (prompts, slots): new sequences into free KV slots -> their first sampled tokens int32[n]
+          decode        (slots, ctx_len, last_tok, n_steps): advance these sequences n_steps -> tokens int32[rows, n_steps]
+        Sequences in slots not named keep their cache untouched."""
+        for slot, first, pages in page_updates:
+            self.llm.set_pages(slot, first, pages)
+        first_tokens = new_tokens = None
+        if prefill is not None:
+            prompts, slots = prefill
+            self.llm.prefill_slots(prompts, slots)
+            first_tokens = self.llm.tokens(1)[:, 0].copy()
+        if decode is not None:
+            slots, ctx_len, last_tok, n_steps = decode
+            self.llm.set_rows(slots, ctx_len, last_tok)
+            self.llm.decode(int(n_steps), use_graph=use_graph)
+            new_tokens = self.llm.tokens(int(n_steps))
+        return first_tokens, new_tokens
 
     def close(self):
         self.llm.free()

@@ -49,7 +49,7 @@ class LlmConfig(ctypes.Structure):
                 ("n_layers", ctypes.c_int32), ("n_heads", ctypes.c_int32), ("n_kv_heads", ctypes.c_int32),
                 ("head_dim", ctypes.c_int32), ("max_batch", ctypes.c_int32), ("max_ctx", ctypes.c_int32),
                 ("max_tokens", ctypes.c_int32), ("tp_size", ctypes.c_int32), ("tp_rank", ctypes.c_int32),
-                ("rope_theta", ctypes.c_float), ("rms_eps", ctypes.c_float)]
+                ("rope_theta", ctypes.c_float), ("rms_eps", ctypes.c_float), ("kv_pages", ctypes.c_int32)]
 
 
 class B2SError(ValueError):
@@ -106,7 +106,7 @@ PROTOTYPES = [
     ("b2s_op_layernorm", _i, [_i, _vp, _vp, _i64, _i, _vp, _vp, ctypes.c_float, _vp, _vp]),
     ("b2s_op_embed_layernorm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp,
                                     ctypes.c_float, _vp, _vp]),
-    ("b2s_op_attention", _i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    ("b2s_op_attention", _i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64]),
     ("b2s_llm_create", _i, [_i, _P(LlmConfig), _P(_vp)]),
     ("b2s_llm_free", _i, [_vp]),
     ("b2s_llm_init_random", _i, [_vp, _u64, ctypes.c_float]),
@@ -114,6 +114,10 @@ PROTOTYPES = [
     ("b2s_llm_comm_export", _i, [_vp, _vp, _P(_u64)]),
     ("b2s_llm_comm_attach", _i, [_vp, _vp]),
     ("b2s_llm_prefill", _i, [_vp, _i, _vp, _vp]),
+    ("b2s_llm_kv_info", _i, [_vp, _P(_i32), _P(_i32), _P(_i32)]),
+    ("b2s_llm_set_pages", _i, [_vp, _i, _i, _i, _vp]),
+    ("b2s_llm_prefill_slots", _i, [_vp, _i, _vp, _vp, _vp]),
+    ("b2s_llm_set_rows", _i, [_vp, _i, _vp, _vp, _vp]),
     ("b2s_llm_decode", _i, [_vp, _i, _i]),
     ("b2s_llm_get_tokens", _i, [_vp, _vp, _i]),
     ("b2s_llm_keep_logits", _i, [_vp, _i]),
@@ -145,7 +149,7 @@ def lib():
                     fn = getattr(l, name)
                     fn.restype = restype
                     fn.argtypes = argtypes
-                if l.b2s_abi_version() != 1:
+                if l.b2s_abi_version() != 2:
                     raise RuntimeError("libb200serve.so ABI version mismatch")
                 _lib = l
     return _lib
@@ -446,13 +450,14 @@ class Llm(object):
     """Decoder-only LLM executor (b2s_llm_* of include/b200serve.h).  One instance = one tensor-parallel rank."""
 
     def __init__(self, device=0, vocab=0, hidden=0, inter=0, n_layers=0, n_heads=0, n_kv_heads=0, head_dim=128,
-                 max_batch=32, max_ctx=1024, max_tokens=None, tp_size=1, tp_rank=0, rope_theta=500000.0, rms_eps=1e-5):
+                 max_batch=32, max_ctx=1024, max_tokens=None, tp_size=1, tp_rank=0, rope_theta=500000.0, rms_eps=1e-5,
+                 kv_pages=0):
         ensure_init(device)
         self.device = int(device)
         if max_tokens is None:
             max_tokens = max_batch * max_ctx
         self.cfg = LlmConfig(vocab, hidden, inter, n_layers, n_heads, n_kv_heads, head_dim, max_batch, max_ctx,
-                             int(max_tokens), tp_size, tp_rank, rope_theta, rms_eps)
+                             int(max_tokens), tp_size, tp_rank, rope_theta, rms_eps, int(kv_pages))
         h = ctypes.c_void_p(0)
         check(lib().b2s_llm_create(self.device, ctypes.byref(self.cfg), ctypes.byref(h)))
         self.handle = h
@@ -501,6 +506,31 @@ class Llm(object):
         toks = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32).reshape(-1) for p in prompts]))
         check(lib().b2s_llm_prefill(self.handle, len(prompts), toks.ctypes.data, offs.ctypes.data))
         self.n_seq = len(prompts)
+
+    # ---- continuous batching over the paged KV cache (the host scheduler owns slots and pages)
+    def kv_info(self):
+        """-> (pages in the pool, tokens per page, page-table entries per slot)"""
+        a, b, c = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        check(lib().b2s_llm_kv_info(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def set_pages(self, slot, first, pages):
+        pg = np.ascontiguousarray(pages, dtype=np.int32)
+        check(lib().b2s_llm_set_pages(self.handle, int(slot), int(first), int(pg.size), pg.ctypes.data))
+
+    def prefill_slots(self, prompts, slots):
+        """like prefill(), sequence i into KV slot slots[i]; other slots keep their sequences"""
+        offs = np.zeros(len(prompts) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(p) for p in prompts])
+        toks = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32).reshape(-1) for p in prompts]))
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        check(lib().b2s_llm_prefill_slots(self.handle, len(prompts), toks.ctypes.data, offs.ctypes.data, sl.ctypes.data))
+        self.n_seq = len(prompts)
+
+    def set_rows(self, slots, ctx_len, next_tok):
+        sl, cl, nt = (np.ascontiguousarray(a, dtype=np.int32) for a in (slots, ctx_len, next_tok))
+        check(lib().b2s_llm_set_rows(self.handle, int(sl.size), sl.ctypes.data, cl.ctypes.data, nt.ctypes.data))
+        self.n_seq = int(sl.size)
 
     def decode(self, n_steps, use_graph=True):
         check(lib().b2s_llm_decode(self.handle, int(n_steps), int(use_graph)))   # 0 eager, 1 CUDA graph, 2 eager + per-kernel timing

@@ -37,7 +37,7 @@ extern "C" {
 #define B2S_API
 #endif
 
-#define B2S_ABI_VERSION 1
+#define B2S_ABI_VERSION 2
 
 typedef enum b2s_status {
     B2S_OK = 0,
@@ -234,10 +234,12 @@ B2S_API int b2s_op_embed_layernorm(int device, void *cuda_stream, const int32_t 
                                    float *out32);
 
 /* Variable-length non-causal self-attention over packed tokens: qkv fp16 [T, 3*heads*64] (Q|K|V),
- * out fp16 [T, heads*64]; key_mask int32[T] (0 = masked key) or NULL.  Flash-style online softmax. */
+ * out fp16 [T, heads*64]; key_mask int32[T] (0 = masked key) or NULL.  Sequences of <= 384 tokens run on tcgen05
+ * (S and O accumulators in tensor memory, K / V by TMA, thread-per-row exact softmax); longer ones on the
+ * mma.sync flash form.  total_tokens = T = cu_seqlens[n_seq] (<= 0: read back from the device, which synchronises). */
 B2S_API int b2s_op_attention(int device, void *cuda_stream, const void *qkv, const int64_t *cu_seqlens,
                              const int32_t *key_mask, void *out, int n_seq, int max_seqlen, int heads,
-                             int head_dim);
+                             int head_dim, int64_t total_tokens);
 
 /* ---- decoder-only LLM endpoint (BASELINE.json configs[4]) -------------------------------------------
  * Replaces the vLLM engine the reference wraps in `VllmPreprocessRequest`
@@ -256,6 +258,8 @@ typedef struct b2s_llm_config {
     int32_t max_tokens;  /* prompt tokens of one prefill wave (workspace size) */
     int32_t tp_size, tp_rank; /* 1 or 2 */
     float rope_theta, rms_eps;
+    int32_t kv_pages;    /* pages (64 tokens x all kv heads of this rank, every layer) of the paged KV pool;
+                            0 = max_batch * ceil(max_ctx / 64), i.e. every slot can reach max_ctx */
 } b2s_llm_config;
 
 B2S_API int b2s_llm_create(int device, const b2s_llm_config *cfg, b2s_llm **out);
@@ -274,6 +278,21 @@ B2S_API int b2s_llm_comm_attach(b2s_llm *llm, const unsigned char *peer_handle64
 /* prompt wave: tokens[offsets[n_seq]] int32 (host), offsets[n_seq + 1]; sequence b takes KV slot b; samples
  * the first generated token of every sequence */
 B2S_API int b2s_llm_prefill(b2s_llm *llm, int n_seq, const int32_t *tokens, const int32_t *offsets);
+/* ---- continuous batching over the PAGED KV cache (what vLLM's scheduler + block manager do behind the reference's
+ * engine, preprocess_service.py:1097-1348).  The cache is a pool of pages of 64 tokens; a sequence occupies a KV slot
+ * (< max_batch) whose page-table row names its pages.  The HOST scheduler (clearml_serving_b200/llm_service.py) owns
+ * slot / page allocation: it admits new prompts into free slots while other sequences are mid-generation
+ * (b2s_llm_prefill_slots), then declares which sequences the next decode steps advance (b2s_llm_set_rows: any subset,
+ * any order, state carried by the host: context length and the last sampled token), runs 1..k steps (b2s_llm_decode)
+ * and reads the new tokens (b2s_llm_get_tokens: row r = r-th sequence given to set_rows / prefill_slots). */
+B2S_API int b2s_llm_kv_info(b2s_llm *llm, int32_t *n_pages, int32_t *page_tokens, int32_t *pages_per_seq);
+/* page-table row of `slot`: logical pages [first, first + n) -> pool pages `pages[i]`; ordered on the model's stream */
+B2S_API int b2s_llm_set_pages(b2s_llm *llm, int slot, int first, int n, const int32_t *pages);
+/* like b2s_llm_prefill, sequence b into KV slot slots[b] (distinct); sequences in other slots are untouched */
+B2S_API int b2s_llm_prefill_slots(b2s_llm *llm, int n_seq, const int32_t *tokens, const int32_t *offsets, const int32_t *slots);
+/* the rows of the next decode steps: row r = the sequence in KV slot slots[r] with ctx_len[r] cached tokens whose
+ * last sampled token is next_tok[r]; the rows' generated-token buffers restart at position 0 */
+B2S_API int b2s_llm_set_rows(b2s_llm *llm, int n_rows, const int32_t *slots, const int32_t *ctx_len, const int32_t *next_tok);
 /* n_steps greedy decode steps for the current wave (use_graph: replay one captured CUDA graph per step) */
 B2S_API int b2s_llm_decode(b2s_llm *llm, int n_steps, int use_graph);
 /* out[n_seq][n] int32 (host): the first n generated tokens of each sequence; synchronises */

@@ -18,7 +18,7 @@ for name, lens in (("mix", rng.choice([16, 64, 128, 256], 64)), ("all256", np.fu
     qkv = (torch.randn(T, 3 * 768, device="cuda") * 0.5).half()
     out = torch.empty(T, 768, device="cuda", dtype=torch.half)
     def fn():
-        native.check(lib.b2s_op_attention(0, None, qkv.data_ptr(), cu.data_ptr(), None, out.data_ptr(), len(lens), int(lens.max()), 12, 64))
+        native.check(lib.b2s_op_attention(0, None, qkv.data_ptr(), cu.data_ptr(), None, out.data_ptr(), len(lens), int(lens.max()), 12, 64, T))
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

@@ -23,7 +23,7 @@ def test_library_builds_and_exports_every_header_symbol():
         assert hasattr(lib, n), "libb200serve.so does not export {}".format(n)
     bound = sorted(p[0] for p in native.PROTOTYPES)
     assert bound == names, "native.PROTOTYPES and include/b200serve.h disagree"
-    assert lib.b2s_abi_version() == 1
+    assert lib.b2s_abi_version() == 2
 
 
 def test_sass_is_sm100a():

@@ -200,7 +200,8 @@ def test_plugin_completions_match_direct_engine(native):
         async def run():
             return await asyncio.gather(*[eng.v1_completions({"model": "tiny", "prompt": p, "max_tokens": 5}, {}, None) for p in prompts])
         got = [r["choices"][0]["token_ids"] for r in asyncio.run(run())]
-        assert eng.engine_stats()["waves"] == 1 and eng.engine_stats()["requests"] == 3      # one wave for the three clients
+        st = eng.engine_stats()
+        assert st["requests"] == 3 and st["prefill_batches"] <= 3 and st["max_rows"] <= 3       # continuous scheduler (default)
     finally:
         eng.unload()
     direct = L.LlmEngine(SPEC, device=0, max_batch=4, max_ctx=128)
@@ -246,3 +247,48 @@ def test_streamed_generation_is_the_same_tokens(native):
             assert sum((c["token_ids"] for c in mine), []) == plain["choices"][i]["token_ids"]
     finally:
         eng.unload()
+
+
+def test_continuous_batching_over_paged_kv_matches_static_waves(native):
+    """SURVEY.md 8 f1 on the device: sequences join a RUNNING batch (prefill into a free KV slot while the others keep
+    their cache), leave it as they finish, and their KV pages come lazily from a small shared pool in an order that
+    is NOT the identity -- every request still gets exactly the tokens the static-wave engine produces for it alone."""
+    import time
+    from clearml_serving_b200 import llm_service as S
+    rng = np.random.default_rng(17)
+    reqs = [(rng.integers(0, SPEC.vocab_size, int(n)), int(g)) for n, g in
+            ((5, 9), (70, 30), (64, 1), (63, 65), (130, 12), (9, 40), (33, 33), (128, 64), (1, 20), (100, 7), (17, 50), (65, 3))]
+    ref = L.LlmEngine(SPEC, device=0, max_batch=4, max_ctx=256)
+    try:
+        ref.init_random(seed=5, std=0.05)
+        want = [ref.generate([p], g)[0] for p, g in reqs]            # one at a time, identity page table
+    finally:
+        ref.close()
+    # 10 pages of 64 tokens for 4 slots (the identity layout would need 16): admission is bounded by the pool
+    eng = L.LlmEngine(SPEC, device=0, max_batch=4, max_ctx=256, kv_pages=10)
+    try:
+        eng.init_random(seed=5, std=0.05)
+        assert eng.kv_info() == (10, 64, 4)
+        b = S.ContinuousBatcher(eng, max_batch=4, max_ctx=256, chunk=3)
+        b._free_pages = [3, 9, 0, 7, 5, 1, 8, 2, 6, 4]               # hand pages out in a scrambled order
+        try:
+            futs = []
+            for i, (p, g) in enumerate(reqs):              # 12 requests, 4 KV slots, 10 pages: the later ones are admitted
+                futs.append(b.submit(p, g))                # while earlier ones are still generating
+            got = [f.result(timeout=120) for f in futs]
+            for i, (w, r) in enumerate(zip(want, got)):
+                assert np.array_equal(np.asarray(r), w), "request {}: {} != {}".format(i, np.asarray(r)[:8], w[:8])
+            st = b.stats
+            assert st["joined_running"] > 0 and st["max_rows"] <= 4 and st["pages_peak"] <= 10
+            assert sorted(b._free_pages) == list(range(10)) and sorted(b._free_slots) == [0, 1, 2, 3]
+        finally:
+            b.close()
+        # the slot-addressed calls refuse what would corrupt the cache
+        with pytest.raises(native.B2SError):
+            eng.llm.prefill_slots([[1, 2, 3], [4, 5]], [1, 1])          # the same KV slot twice
+        with pytest.raises(native.B2SError):
+            eng.llm.set_pages(0, 0, [10])                                # page outside the pool
+        with pytest.raises(native.B2SError):
+            eng.llm.set_rows([0], [300], [1])                            # context beyond max_ctx
+    finally:
+        eng.close()

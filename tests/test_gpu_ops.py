@@ -251,7 +251,8 @@ def test_embedding_layernorm_matches_torch(gpu_native):
             b.free()
 
 
-@pytest.mark.parametrize("lens,masked", [([16], False), ([64, 1, 256, 100, 33], False), ([128, 77], True), ([300, 512], False)])
+@pytest.mark.parametrize("lens,masked", [([16], False), ([64, 1, 256, 100, 33], False), ([128, 77], True), ([300, 512], False),
+                                         ([384, 129, 5], True), ([257, 256, 383], False), ([1, 2, 127, 128], True)])
 def test_attention_varlen_matches_torch(gpu_native, lens, masked):
     """per-sequence softmax(QK^T/8 + mask)V against torch fp32 on the fp16-rounded inputs; a request's
     output must not depend on its batch-mates (each sequence is also run alone and compared bit-wise)."""
@@ -279,7 +280,7 @@ def test_attention_varlen_matches_torch(gpu_native, lens, masked):
     dout = gpu_native.DeviceBuffer(T * H * 2)
     try:
         gpu_native.check(gpu_native.lib().b2s_op_attention(0, None, dq.ptr, dcu.ptr, dm.ptr if masked else None, dout.ptr,
-                                                           len(lens), max(lens), heads, d))
+                                                           len(lens), max(lens), heads, d, T))
         got = dout.download(np.float16, T * H).reshape(T, H)
         # fp16 P and fp16 output rounding: ~1e-3 relative to the value range of V
         np.testing.assert_allclose(got.astype(np.float32), ref, rtol=0, atol=4e-3 * np.abs(ref).max())
@@ -291,7 +292,7 @@ def test_attention_varlen_matches_torch(gpu_native, lens, masked):
             m1 = _dev(gpu_native, np.ascontiguousarray(mask[s:s + n]))
             o1 = gpu_native.DeviceBuffer(n * H * 2)
             gpu_native.check(gpu_native.lib().b2s_op_attention(0, None, one.ptr, cu1.ptr, m1.ptr if masked else None, o1.ptr,
-                                                               1, n, heads, d))
+                                                               1, n, heads, d, 0))   # 0: T read back from the device
             assert np.array_equal(o1.download(np.float16, n * H).reshape(n, H), got[s:s + n])
             for b in (one, cu1, m1, o1):
                 b.free()
