@@ -6,8 +6,13 @@
 //
 // PERSISTENT kernel, one CTA per SM, 10 warps, walking the work items (sequence, head, 128-query tile) round-robin:
 //   warp 8 (one lane)  TMA producer: Q tile + every key / value block of the sequence (<= 3 blocks of 128 keys; box
-//                      128 tokens x 64 halfs of the packed [T, 3H] qkv matrix, 128-byte swizzle) into a 2-stage ring.
-//   warp 9 (one lane)  MMA issuer:  S = Q K^T     tcgen05.mma 128 x N x 16 (N = keys of the block rounded up to 16),
+//                      128 tokens x 64 halfs of the packed [T, 3H] qkv matrix, 128-byte swizzle) into TWO rings: Q + K
+//                      (2 entries, released as soon as the score MMAs have read them, so the operands of item n+2 are
+//                      on chip before a score buffer frees up) and V (3 entries, released after the P V MMAs).
+//   warps 9-12 (one lane each)  MMA issuers, a PAIR per score buffer (issuing a tcgen05.mma costs ~125 cycles of
+//                      register -> uniform-register traffic, more than these small MMAs run): S blocks alternate between
+//                      the pair; P V is split by key range into TWO output accumulators (added in the epilogue).
+//                      S = Q K^T     tcgen05.mma 128 x N x 16 (N = keys of the block rounded up to 16),
 //                                                 accumulators in TENSOR MEMORY, 128 columns per key block;
 //                                   O = P V       tcgen05.mma 128 x 64 x 16 with A = P read FROM TENSOR MEMORY (written
 //                                                 there by the softmax threads: the score matrix never touches shared
@@ -31,6 +36,7 @@
 #include <cuda_fp16.h>
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace b2s {
 
@@ -44,8 +50,8 @@ constexpr int AT_BN = 128;                  // keys per block
 constexpr int AT_D = 64;                    // head dim
 constexpr int AT_MAX_KB = 3;                // <= 384 keys: S fits tensor memory
 constexpr int AT_TILE = AT_BM * AT_D * 2;   // 16 KB: one [128 x 64] fp16 tile
-constexpr int AT_STAGES = 2;
-constexpr int AT_THREADS = 320;              // 2 softmax warpgroups (warps 0-3, 4-7) + TMA producer (8) + MMA issuer (9)
+constexpr int AT_QK_STAGES = 2;
+constexpr int AT_THREADS = 416;              // 2 softmax warpgroups (warps 0-3, 4-7) + TMA producer (8) + 2 x 2 MMA issuers (9-12)
 
 // instruction descriptor, kind::f16, fp32 accumulate, fp16 operands; A K-major; B K-major (b_mn = 0) or MN-major (1)
 __device__ __forceinline__ uint32_t at_idesc(int m, int n, int b_mn)
@@ -106,18 +112,17 @@ struct AtItem { int b, h, q0, S; int64_t s0; };
 struct AtWalker {
     const int64_t *cu;
     int n_seq, heads, max_qt;
-    int64_t next, total;
-    int stride;
+    uint32_t next, total, stride;                         // n_seq * heads * max_qt < 2^31 (checked by the launcher)
     __device__ AtWalker(const int64_t *cu_, int n_seq_, int heads_, int max_qt_)
-        : cu(cu_), n_seq(n_seq_), heads(heads_), max_qt(max_qt_), next(blockIdx.x), total((int64_t)n_seq_ * heads_ * max_qt_), stride(gridDim.x) {}
+        : cu(cu_), n_seq(n_seq_), heads(heads_), max_qt(max_qt_), next(blockIdx.x), total((uint32_t)(n_seq_ * heads_ * max_qt_)), stride(gridDim.x) {}
     __device__ bool pop(AtItem &it)
     {
         while (next < total) {
-            const int64_t i = next;
+            const uint32_t i = next;
             next += stride;
-            const int qt = (int)(i % max_qt);
-            const int64_t r = i / max_qt;
-            const int h = (int)(r % heads), b = (int)(r / heads);
+            const int qt = (int)(i % (uint32_t)max_qt);
+            const uint32_t r = i / (uint32_t)max_qt;
+            const int h = (int)(r % (uint32_t)heads), b = (int)(r / (uint32_t)heads);
             const int64_t s0 = __ldg(cu + b);
             const int S = (int)(__ldg(cu + b + 1) - s0);
             if (S > AT_MAX_KB * AT_BN || qt * AT_BM >= S) continue;
@@ -132,27 +137,44 @@ template <int NSB>   // score buffers in tensor memory: 2 when a sequence has <=
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int64_t *__restrict__ cu_seqlens,
                     const int32_t *__restrict__ key_mask, __half *__restrict__ out, int n_seq, int heads, int max_qt, int nkb_max,
-                    float scale_log2e)
+                    float scale_log2e, long long *__restrict__ dbg)
 {
+    // developer aid (B2S_ATTN_TIMING=1): SM-clock stamps of CTA 0's first 16 items, [item][16]
+#define AT_STAMP(n, k)                                                                  \
+    do {                                                                                \
+        if (dbg && blockIdx.x == 0 && (n) < 16) dbg[(n) * 16 + (k)] = clock64();        \
+    } while (0)
     extern __shared__ unsigned char at_smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = heads * AT_D;
-    const int stage_bytes = (1 + 2 * nkb_max) * AT_TILE;         // Q | K blocks | V blocks
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + AT_STAGES * stage_bytes);
+    const int qk_bytes = (1 + nkb_max) * AT_TILE;                // one Q + K entry
+    const int v_bytes = nkb_max * AT_TILE;                       // one V entry
+    const int NV = nkb_max <= 2 ? 3 : 2;                         // V ring depth (shared memory budget)
+    unsigned char *v_ring = smem + AT_QK_STAGES * qk_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(v_ring + NV * v_bytes);
     uint64_t *bar_full = bars, *bar_empty = bars + 2, *bar_s = bars + 4, *bar_p = bars + 6, *bar_o = bars + 8, *bar_sfree = bars + 10;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
+    uint64_t *bar_vfull = bars + 12, *bar_vempty = bars + 15;    // [3] each
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 18);
     uint32_t *kbits = tmem_slot + 2;                             // [2 groups][2][12]: validity word of every 32-key chunk (masked path)
-    const int sbuf_cols = nkb_max * AT_BN;                       // tensor-memory columns of one score buffer
+    // tensor-memory columns of one score buffer: scores [0, nkb*128) (P overwrites the front), the two output accumulators
+    // behind them: NSB == 2: 256 columns, O_b at [128,192) and O_a at [192,256) (block 1's scores are dead by then);
+    // NSB == 1: scores in [0,384), O_a at [384,448), O_b at [448,512)
+    const int sbuf_cols = NSB == 2 ? 256 : 512;
+    const uint32_t oa_off = NSB == 2 ? 192u : 384u, ob_off = NSB == 2 ? 128u : 448u;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_full[i], 1);
-            mbar_init(&bar_empty[i], 1);
-            mbar_init(&bar_s[i], 1);
+            mbar_init(&bar_empty[i], 2);       // both issuers of the pair commit
+            mbar_init(&bar_s[i], 2);
             mbar_init(&bar_p[i], 128);
-            mbar_init(&bar_o[i], 1);
+            mbar_init(&bar_o[i], 2);
             mbar_init(&bar_sfree[i], 128);
+        }
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&bar_vfull[i], 1);
+            mbar_init(&bar_vempty[i], 2);
         }
         fence_barrier_init();
         prefetch_tensormap(&tm_qkv);
@@ -172,73 +194,91 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int64_t *_
             AtWalker w(cu_seqlens, n_seq, heads, max_qt);
             AtItem it;
             for (uint32_t n = 0; w.pop(it); ++n) {
-                const int st = n & 1;
+                const int st = n & 1, sv = (int)(n % (uint32_t)NV);
                 const int nkb = (it.S + AT_BN - 1) / AT_BN;
-                mbar_wait(&bar_empty[st], ((n >> 1) & 1) ^ 1);          // the MMAs that read this stage have retired
-                unsigned char *Qs = smem + st * stage_bytes, *Ks = Qs + AT_TILE, *Vs = Ks + nkb_max * AT_TILE;
-                mbar_arrive_expect_tx(&bar_full[st], (uint32_t)((1 + 2 * nkb) * AT_TILE));
+                AT_STAMP(n, 0);
+                mbar_wait(&bar_empty[st], ((n >> 1) & 1) ^ 1);          // the score MMAs that read this Q / K entry have retired
+                AT_STAMP(n, 1);
+                unsigned char *Qs = smem + st * qk_bytes, *Ks = Qs + AT_TILE;
+                mbar_arrive_expect_tx(&bar_full[st], (uint32_t)((1 + nkb) * AT_TILE));
                 tma_load_2d(Qs, &tm_qkv, &bar_full[st], it.h * AT_D, (int)(it.s0 + it.q0));
-                for (int kb = 0; kb < nkb; ++kb) {
+                for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(Ks + kb * AT_TILE, &tm_qkv, &bar_full[st], H + it.h * AT_D, (int)(it.s0 + kb * AT_BN));
-                    tma_load_2d(Vs + kb * AT_TILE, &tm_qkv, &bar_full[st], 2 * H + it.h * AT_D, (int)(it.s0 + kb * AT_BN));
-                }
+                mbar_wait(&bar_vempty[sv], ((n / (uint32_t)NV) & 1) ^ 1);  // the P V MMAs that read this V entry have retired
+                unsigned char *Vs = v_ring + sv * v_bytes;
+                mbar_arrive_expect_tx(&bar_vfull[sv], (uint32_t)(nkb * AT_TILE));
+                for (int kb = 0; kb < nkb; ++kb)
+                    tma_load_2d(Vs + kb * AT_TILE, &tm_qkv, &bar_vfull[sv], 2 * H + it.h * AT_D, (int)(it.s0 + kb * AT_BN));
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
-        // =========================================================================== MMA issuer
-        if (lane == 0) {
+    } else if (warp >= 9) {
+        // =========================================================================== MMA issuers: pair (9,10) -> buffer 0, (11,12) -> buffer 1
+        const int pair = (warp - 9) >> 1, role = (warp - 9) & 1;         // role 0: even key blocks / first half of the key range
+        if (lane == 0 && (NSB == 2 || pair == 0)) {
             AtWalker w(cu_seqlens, n_seq, heads, max_qt);
-            AtItem cur, nxt;
-            bool have = w.pop(cur);
-            auto issue_s = [&](const AtItem &it, uint32_t n) {
-                const int st = n & 1, sb = (NSB == 2) ? (int)(n & 1) : 0;
+            uint32_t n_pop = 0;
+            auto pop_own = [&](AtItem &o, uint32_t &n_o) -> bool {       // next item of THIS pair's buffer (n counts every item)
+                while (w.pop(o)) {
+                    const uint32_t n_cur = n_pop++;
+                    if (NSB == 2 && (int)(n_cur & 1u) != pair) continue;
+                    n_o = n_cur;
+                    return true;
+                }
+                return false;
+            };
+            AtItem it, nxt;
+            uint32_t n = 0, n_nxt = 0;
+            bool have = pop_own(it, n);
+            if (have) mbar_wait(&bar_full[n & 1], (n >> 1) & 1);
+            while (have) {
+                const int st = n & 1, sv = (int)(n % (uint32_t)NV), sb = (NSB == 2) ? pair : 0;
                 const uint32_t use = (NSB == 2) ? (n >> 1) : n;
-                mbar_wait(&bar_full[st], (n >> 1) & 1);
-                mbar_wait(&bar_sfree[sb], (use & 1) ^ 1);                // softmax threads are done with this score buffer
-                tc_fence_after();
-                unsigned char *Qs = smem + st * stage_bytes, *Ks = Qs + AT_TILE;
-                const uint64_t qd = make_sw128_kmajor_desc(Qs);
                 const int nkb = (it.S + AT_BN - 1) / AT_BN;
-                for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t sbase = tmem_base + (uint32_t)(sb * sbuf_cols);
+                // ---- S = Q K^T: this issuer takes the key blocks kb == role (mod 2); Q / K are on chip already
+                if (role == 0) AT_STAMP(n, 3);
+                mbar_wait(&bar_sfree[sb], (use & 1) ^ 1);                // softmax threads are done with this score buffer
+                if (role == 0) AT_STAMP(n, 4);
+                tc_fence_after();
+                unsigned char *Qs = smem + st * qk_bytes, *Ks = Qs + AT_TILE;
+                const uint64_t qd = make_sw128_kmajor_desc(Qs);
+                for (int kb = role; kb < nkb; kb += 2) {
                     const int keys = min(AT_BN, it.S - kb * AT_BN);
                     const uint32_t idesc = at_idesc(AT_BM, (keys + 15) & ~15, 0);
                     const uint64_t kd = make_sw128_kmajor_desc(Ks + kb * AT_TILE);
 #pragma unroll
                     for (int k = 0; k < AT_D / 16; ++k)
-                        umma_f16(tmem_base + (uint32_t)(sb * sbuf_cols + kb * AT_BN), desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc,
-                                 k > 0 ? 1u : 0u);
+                        umma_f16(sbase + (uint32_t)(kb * AT_BN), desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc, k > 0 ? 1u : 0u);
                 }
-                umma_commit(&bar_s[sb]);
-            };
-            auto issue_pv = [&](const AtItem &it, uint32_t n) {
-                const int st = n & 1, sb = (NSB == 2) ? (int)(n & 1) : 0;
-                const uint32_t use = (NSB == 2) ? (n >> 1) : n;
+                umma_commit(&bar_s[sb]);                                 // (an issuer without blocks still arrives)
+                umma_commit(&bar_empty[st]);                             // Q / K entry free once these MMAs retire
+                if (role == 0) AT_STAMP(n, 5);
+                // ---- while the softmax group works: find the next item of this buffer and wait for its Q / K and this item's V
+                const bool more = pop_own(nxt, n_nxt);
+                if (more) mbar_wait(&bar_full[n_nxt & 1], (n_nxt >> 1) & 1);
+                mbar_wait(&bar_vfull[sv], (n / (uint32_t)NV) & 1);
+                // ---- O_role = P[:, range] V[range]: role 0 the first half of the 16-key steps, role 1 the rest
+                if (role == 0) AT_STAMP(n, 6);
                 mbar_wait(&bar_p[sb], use & 1);                          // P of this item sits in tensor memory
+                if (role == 0) AT_STAMP(n, 7);
                 tc_fence_after();
-                unsigned char *Vs = smem + st * stage_bytes + (1 + nkb_max) * AT_TILE;
-                const int nkb = (it.S + AT_BN - 1) / AT_BN;
-                const uint32_t sbase = tmem_base + (uint32_t)(sb * sbuf_cols);
-                const uint32_t o_col = sbase + (uint32_t)(nkb * AT_BN - AT_D);      // dead upper score columns
-                const uint32_t idesc = at_idesc(AT_BM, AT_D, 1);
+                unsigned char *Vs = v_ring + sv * v_bytes;
+                const uint32_t idesc_o = at_idesc(AT_BM, AT_D, 1);
                 const int ksteps = (it.S + 15) >> 4;                     // 16 keys per MMA; P is 0 beyond the sequence
-                for (int k = 0; k < ksteps; ++k) {
+                const int half = (ksteps + 1) >> 1;
+                const int k_lo = role == 0 ? 0 : half, k_hi = role == 0 ? half : ksteps;
+                const uint32_t o_col = sbase + (role == 0 ? oa_off : ob_off);
+                for (int k = k_lo; k < k_hi; ++k) {
                     const uint64_t vd = at_desc_mnmajor(Vs + (k >> 3) * AT_TILE);
-                    at_umma_ts(o_col, sbase + (uint32_t)(k * 8), desc_advance(vd, (k & 7) * 2048), idesc, k > 0 ? 1u : 0u);
+                    at_umma_ts(o_col, sbase + (uint32_t)(k * 8), desc_advance(vd, (k & 7) * 2048), idesc_o, k > k_lo ? 1u : 0u);
                 }
                 umma_commit(&bar_o[sb]);
-                umma_commit(&bar_empty[st]);                             // ... and the stage may be refilled
-            };
-            uint32_t n = 0;
-            if (have) issue_s(cur, 0);
-            while (have) {
-                const bool more = w.pop(nxt);
-                if (NSB == 2 && more) issue_s(nxt, n + 1);               // overlap: next item's scores before this item's P
-                issue_pv(cur, n);
-                if (NSB == 1 && more) issue_s(nxt, n + 1);
-                cur = nxt;
+                umma_commit(&bar_vempty[sv]);                            // ... and the V entry may be refilled
+                if (role == 0) AT_STAMP(n, 8);
+                it = nxt;
+                n = n_nxt;
                 have = more;
-                ++n;
             }
         }
         __syncwarp();
@@ -250,9 +290,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int64_t *_
             const int row = tid & 127;                                       // query row = tensor-memory lane
             const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
             AtWalker w(cu_seqlens, n_seq, heads, max_qt);
-            AtItem it;
-            for (uint32_t n = 0; w.pop(it); ++n) {
-                if (NSB == 2 && (int)(n & 1u) != grp) continue;
+            uint32_t n_pop = 0;
+            auto pop_own = [&](AtItem &o, uint32_t &n_o) -> bool {           // next item of THIS group's buffer
+                while (w.pop(o)) {
+                    const uint32_t n_cur = n_pop++;
+                    if (NSB == 2 && (int)(n_cur & 1u) != grp) continue;
+                    n_o = n_cur;
+                    return true;
+                }
+                return false;
+            };
+            AtItem it, nxt;
+            uint32_t n = 0, n_nxt = 0;
+            bool have = pop_own(it, n), more = false;
+            for (; have; it = nxt, n = n_nxt, have = more) {
                 const int sb = (NSB == 2) ? grp : 0;
                 const uint32_t use = (NSB == 2) ? (n >> 1) : n;
                 const int nkb = (it.S + AT_BN - 1) / AT_BN;
@@ -273,7 +324,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int64_t *_
                     const int left = it.S - c * 32;
                     return left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
                 };
+                if (row == 0) AT_STAMP(n, 9);
                 mbar_wait(&bar_s[sb], use & 1);
+                if (row == 0) AT_STAMP(n, 10);
                 tc_fence_after();
                 uint32_t va[32], vb[32];
                 // ---- pass 1: row maximum over the keys that take part (the load of chunk c+1 flies under the work on chunk c)
@@ -332,19 +385,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int64_t *_
                 at_tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bar_p[sb]);
+                if (row == 0) AT_STAMP(n, 11);
+                more = pop_own(nxt, n_nxt);                                  // off the critical path: the P V MMAs are running
 
                 // ---- epilogue: O / l -> fp16 -> one 128-byte row
                 mbar_wait(&bar_o[sb], use & 1);
+                if (row == 0) AT_STAMP(n, 12);
                 tc_fence_after();
                 const float inv = l > 0.f ? 1.f / l : 0.f;
                 const bool store = it.q0 + row < it.S;
                 __half *dst = out + (it.s0 + it.q0 + row) * (int64_t)H + it.h * AT_D;
-                const uint32_t o_col = sbase + (uint32_t)(nkb * AT_BN - AT_D);
-                tmem_ld_32x32(o_col, va);
-                tmem_ld_32x32(o_col + 32u, vb);
+                const bool two = ((it.S + 15) >> 4) >= 2;                    // the second issuer had key steps: O = O_a + O_b
+                uint32_t vc[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld_32x32(sbase + oa_off + (uint32_t)(c * 32), c == 0 ? va : vb);
+                    if (two) {
+                        tmem_ld_32x32(sbase + ob_off + (uint32_t)(c * 32), vc);
+                        tmem_ld_wait();
+                        uint32_t (&dst_v)[32] = c == 0 ? va : vb;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) dst_v[j] = __float_as_uint(__uint_as_float(dst_v[j]) + __uint_as_float(vc[j]));
+                    }
+                }
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&bar_sfree[sb]);                                 // O is in registers: the score buffer may take the next item
+                if (row == 0) AT_STAMP(n, 13);
                 if (store) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -374,9 +441,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int64_t *_
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+#undef AT_STAMP
 }
 
-static size_t at_smem_bytes(int nkb_max) { return (size_t)AT_STAGES * (1 + 2 * nkb_max) * AT_TILE + 384 + 1024; }
+static long long *g_attn_dbg = nullptr;
+
+static size_t at_smem_bytes(int nkb_max)
+{
+    return (size_t)AT_QK_STAGES * (1 + nkb_max) * AT_TILE + (size_t)(nkb_max <= 2 ? 3 : 2) * nkb_max * AT_TILE + 448 + 1024;
+}
 
 // total_tokens: rows of the packed qkv matrix (the tensor map clips / zero-fills beyond it).  Sequences longer than 384
 // tokens are skipped here (the caller runs the mma.sync form for them).
@@ -402,17 +475,35 @@ int attention_varlen_tc(cudaStream_t st, const void *qkv, const int64_t *cu_seql
     const int nkb_max = (cap + AT_BN - 1) / AT_BN;
     const int max_qt = (cap + AT_BM - 1) / AT_BM;
     const int64_t items = (int64_t)n_seq * heads * max_qt;
+    if (items >= (int64_t)1 << 31) return fail(B2S_ERR_INVALID, "attention: too many work items");
     const int grid = (int)(items < n_sm ? items : n_sm);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)AT_D);
+    static long long *dbg = []() -> long long * {
+        const char *e = getenv("B2S_ATTN_TIMING");
+        if (!(e && e[0] == '1')) return nullptr;
+        long long *p = nullptr;
+        if (cudaMalloc(reinterpret_cast<void **>(&p), 256 * sizeof(long long)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, 256 * sizeof(long long));
+        return p;
+    }();
+    g_attn_dbg = dbg;
     if (nkb_max <= 2)
         attention_tc_kernel<2><<<grid, AT_THREADS, at_smem_bytes(nkb_max), st>>>(tm, cu_seqlens, key_mask, static_cast<__half *>(out), n_seq, heads,
-                                                                                  max_qt, nkb_max, scale_log2e);
+                                                                                  max_qt, nkb_max, scale_log2e, dbg);
     else
         attention_tc_kernel<1><<<grid, AT_THREADS, at_smem_bytes(nkb_max), st>>>(tm, cu_seqlens, key_mask, static_cast<__half *>(out), n_seq, heads,
-                                                                                  max_qt, nkb_max, scale_log2e);
+                                                                                  max_qt, nkb_max, scale_log2e, dbg);
     count_launch();
     B2S_CUDA(cudaGetLastError());
     return 0;
 }
 
 }  // namespace b2s
+
+// developer aid: the stamps of the last launch (256 int64), B2S_ATTN_TIMING=1
+extern "C" B2S_API int b2s_debug_attention_stamps(long long *out256)
+{
+    if (!b2s::g_attn_dbg || !out256) return b2s::fail(B2S_ERR_INVALID, "set B2S_ATTN_TIMING=1 and run an attention launch first");
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out256, b2s::g_attn_dbg, 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : b2s::fail(B2S_ERR_CUDA, "copy failed");
+}

@@ -107,6 +107,7 @@ PROTOTYPES = [
     ("b2s_op_embed_layernorm", _i, [_i, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp,
                                     ctypes.c_float, _vp, _vp]),
     ("b2s_op_attention", _i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64]),
+    ("b2s_debug_attention_stamps", _i, [_vp]),
     ("b2s_llm_create", _i, [_i, _P(LlmConfig), _P(_vp)]),
     ("b2s_llm_free", _i, [_vp]),
     ("b2s_llm_init_random", _i, [_vp, _u64, ctypes.c_float]),

@@ -266,3 +266,38 @@ class RemoteB200PreprocessRequest(BasePreprocessRequest):
         tensors = list(data) if isinstance(data, (list, tuple)) and data and isinstance(data[0], np.ndarray) else [np.asarray(data)]
         ep = self.model_endpoint
         return await self._client().request(str(ep.serving_url), tensors, getattr(ep, "version", None) or None)
+
+
+def main():
+    """Engine process of one GPU:  python -m clearml_serving_b200.shm_ipc --endpoints endpoints.json [--name gpu0] [--device 0]
+    The REST workers run `uvicorn clearml_serving_b200.main:app --workers N` with the same endpoints declared as
+    engine_type "b200_remote" + `"b200.engine_socket": "<name>"` in their auxiliary_cfg."""
+    import argparse
+    import signal
+    from .model_request_processor import ModelRequestProcessor
+    from .preprocess_service import B200EngineMixin
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--endpoints", required=True)
+    ap.add_argument("--name", default="gpu0")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--clients", type=int, default=16)
+    ap.add_argument("--slots-per-client", type=int, default=64)
+    ap.add_argument("--slot-bytes", type=int, default=1 << 20)
+    args = ap.parse_args()
+    B200EngineMixin._default_device = args.device
+    proc = ModelRequestProcessor()
+    proc.load_endpoints_file(args.endpoints)
+    for url, ep in list(proc._endpoints.items()):      # build the engines now: the first request should not pay the model load
+        proc._get_engine(url, ep)
+    srv = EngineServer(proc, name=args.name, n_clients=args.clients, slots_per_client=args.slots_per_client, slot_bytes=args.slot_bytes)
+    stop = threading.Event()
+    for sig in (signal.SIGINT, signal.SIGTERM):
+        signal.signal(sig, lambda *_a: stop.set())
+    print("b200 engine process '{}' on cuda:{} serving {}".format(args.name, args.device, sorted(proc._endpoints)), flush=True)
+    stop.wait()
+    srv.close()
+    proc.shutdown()
+
+
+if __name__ == "__main__":
+    main()

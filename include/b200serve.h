@@ -241,6 +241,9 @@ B2S_API int b2s_op_attention(int device, void *cuda_stream, const void *qkv, con
                              const int32_t *key_mask, void *out, int n_seq, int max_seqlen, int heads,
                              int head_dim, int64_t total_tokens);
 
+/* developer aid: SM-clock stamps of the tcgen05 attention kernel's first work items (needs B2S_ATTN_TIMING=1) */
+B2S_API int b2s_debug_attention_stamps(long long *out256);
+
 /* ---- decoder-only LLM endpoint (BASELINE.json configs[4]) -------------------------------------------
  * Replaces the vLLM engine the reference wraps in `VllmPreprocessRequest`
  * (clearml_serving/serving/preprocess_service.py:1097-1348; engine args from `auxiliary_cfg`,
