@@ -89,6 +89,21 @@ def test_bert_base_parity_mixed_lengths(gpu_native):
     assert err <= REL_TOL, "relative error {:.2e}".format(err)
 
 
+def test_bert_base_parity_at_the_baseline_batch(gpu_native):
+    """BASELINE.json configs[3] at its FULL batch: 64 requests, S drawn from {16, 64, 128, 256} (the bench's mix), every
+    row against the torch-CPU-fp32 forward of the same weights -- and the same rows again inside a different batch."""
+    import torch
+    torch.set_num_threads(max(1, min(32, torch.get_num_threads())))
+    model_t = _make(dict())
+    lens = np.random.default_rng(1).choice([16, 64, 128, 256], size=64).tolist()
+    reqs = _requests(lens, 30522, seed=11)
+    ref = _reference(model_t, reqs)
+    got = _run(gpu_native, model_t, reqs)
+    assert got.shape == (64, 2)
+    err = np.abs(got - ref).max(axis=1) / np.abs(ref).max()
+    assert err.max() <= REL_TOL, "worst row {} (S={}): relative error {:.2e}".format(int(err.argmax()), lens[int(err.argmax())], err.max())
+
+
 def test_bert_masked_keys_and_engine_api(gpu_native, tmp_path):
     """attention_mask with padding inside a request + the plugin API (HF example's preprocess output:
     three lists, examples/huggingface/preprocess.py:23)."""

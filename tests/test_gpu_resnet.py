@@ -74,6 +74,23 @@ def test_resnet50_224(gpu_native):
     assert err <= REL_TOL, "relative error {:.2e}".format(err)
 
 
+def test_resnet50_at_the_baseline_batch(gpu_native):
+    """BASELINE.json configs[2] at its FULL batch: 128 single-image requests in one batch, every row against the
+    torch-CPU-fp32 forward of the same weights"""
+    import torch
+    import torchvision
+    from clearml_serving_b200 import formats
+    torch.manual_seed(0)
+    m = _realistic_bn(torchvision.models.resnet50(weights=None))
+    x = np.random.default_rng(5).standard_normal((128, 3, 224, 224)).astype(np.float32)
+    with torch.no_grad():
+        ref = np.concatenate([m(torch.from_numpy(x[i:i + 16])).numpy() for i in range(0, 128, 16)])
+    got = _run(gpu_native, formats.pack_resnet(m), x, 128)
+    assert got.shape == (128, 1000)
+    err = np.abs(got - ref).max(axis=1) / np.abs(ref).max()
+    assert err.max() <= REL_TOL, "worst image {}: relative error {:.2e}".format(int(err.argmax()), err.max())
+
+
 def test_resnet_uint8_input(gpu_native):
     import torch
     import torchvision
