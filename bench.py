@@ -968,6 +968,15 @@ def _llama_workload(native, rank, world, local, dist, waves=3):
         pass
     tf_peak = float(peaks.get("bf16_tflops_sustained", 1431.4) or 1431.4)   # kernels timed inside a long step
     hbm_peak, _ = _peaks()
+    vllm_ref = None
+    vp = os.path.join(ROOT, "profiles", "r02_vllm_tp{}.json".format(tp))
+    if os.path.exists(vp):
+        try:   # the comparator SURVEY.md 2.1 names: vLLM 0.22 on the same workload, measured on a B200 of this pool by
+            with open(vp) as f:   # scripts/vllm_compare.py (a separate process: engine start-up + compilation take minutes)
+                vllm_ref = json.load(f)
+            vllm_ref["note"] = "measured separately with scripts/vllm_compare.py on a B200 of the same pool (not inside this run)"
+        except Exception:  # noqa
+            vllm_ref = None
     return dict(
         workload="Llama-3-8B bf16 random-init (on-device deterministic init), prompt 512 + 128 new tokens, 32 sequences per wave, greedy",
         parallelism="tp{} x {} replica(s)".format(tp, replicas), metric="requests/sec",
@@ -980,7 +989,7 @@ def _llama_workload(native, rank, world, local, dist, waves=3):
                       decode=dict(bound="hbm", achieved=(wbytes + kv_bytes) / (step_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
                                   frac=(wbytes + kv_bytes) / (step_ms * 1e-3) / 1e9 / hbm_peak,
                                   algorithmic_bytes_per_step=int(wbytes + kv_bytes))),
-        serving=serving, tp2_vs_tp1_check=tp_check, wave_vs_generate_agreement=agreement,
+        vllm_reference=vllm_ref, serving=serving, tp2_vs_tp1_check=tp_check, wave_vs_generate_agreement=agreement,
         tokens_checked="first tokens: device-timed wave vs LlmEngine.generate (fp32 atomics make later tokens of a random-init model "
                        "run-dependent)" + ("; the two ranks of every pair: exact" if tp == 2 else ""),
         cpu_baseline=None, cpu_baseline_note="the reference has no CPU path for this endpoint (it wraps vLLM)",

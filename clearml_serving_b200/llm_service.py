@@ -362,7 +362,9 @@ class TensorParallelLeader(object):
 
     def generate(self, prompts, max_new_tokens, on_progress=None, chunk=8):
         # the follower chunks its decode loop the same way, so both ranks synchronise at the same steps
-        self.engine._check(prompts, int(max_new_tokens))   # refuse BEFORE announcing: the follower never sees a doomed call
+        check = getattr(self.engine, "_check", None)
+        if callable(check):
+            check(prompts, int(max_new_tokens))   # refuse BEFORE announcing: the follower never sees a doomed call
         self._announce(("generate", [np.asarray(p, np.int32) for p in prompts], int(max_new_tokens),
                         int(chunk) if on_progress is not None else 0))
         return self.engine.generate(prompts, max_new_tokens, on_progress=on_progress, chunk=chunk)

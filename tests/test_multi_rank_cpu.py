@@ -110,3 +110,50 @@ def test_tensor_parallel_leader_and_follower_replay_the_same_calls(tmp_path):
         res.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT ")][0][7:]))
     assert res[0]["calls"] == res[1]["calls"] == [[[[1, 2, 3], [4]], 5, 0], [[[9] * 7], 2, 4]]
     assert res[0]["closed"] and res[1]["closed"]
+
+
+def test_continuous_batching_iterations_are_replayed_by_the_follower(tmp_path):
+    """tensor_parallel_size 2 under the continuous scheduler: every scheduler iteration (page-table updates, prefill into
+    slots, decode rows) is announced once and replayed by rank 1 with identical arguments -- both ranks end with the same
+    emulated paged cache and the same tokens"""
+    script = tmp_path / "tp_cb_worker.py"
+    script.write_text(textwrap.dedent('''
+        import json, os, sys
+        sys.path.insert(0, %r)
+        import numpy as np
+        import torch.distributed as dist
+        from clearml_serving_b200 import llm_service as S
+        from tests.test_llm_service import FakePagedLlm, _expected
+
+        dist.init_process_group("gloo")
+        rank = dist.get_rank()
+        group = dist.new_group(ranks=[0, 1], backend="gloo")
+        eng = FakePagedLlm(max_batch=4, max_ctx=256, n_pages=9)
+        ok = True
+        if rank == 0:
+            lead = S.TensorParallelLeader(eng, group)
+            b = S.ContinuousBatcher(lead, max_batch=4, max_ctx=256, chunk=3)
+            rng = np.random.default_rng(0)
+            reqs = [(rng.integers(0, 1000, int(rng.integers(1, 120))), int(rng.integers(1, 30))) for _ in range(10)]
+            futs = [b.submit(p, n) for p, n in reqs]
+            ok = all(f.result(timeout=60).tolist() == _expected(p, n) for (p, n), f in zip(reqs, futs))
+            b.close()
+            lead.close()
+        else:
+            S.follower_loop(eng, group)
+        print("RESULT " + json.dumps(dict(rank=rank, ok=ok, calls=eng.calls, pool=int(eng.pool.sum()), closed=eng.closed)), flush=True)
+        dist.destroy_process_group()
+    ''' % ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29734", WORLD_SIZE="2")
+    procs = []
+    for r in range(2):
+        e = dict(env, RANK=str(r), LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    import json
+    res = []
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        res.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT ")][0][7:]))
+    assert res[0]["ok"] and res[0]["calls"] == res[1]["calls"] and len(res[0]["calls"]) > 3
+    assert res[0]["pool"] == res[1]["pool"] and res[0]["closed"] and res[1]["closed"]
