@@ -45,7 +45,9 @@ int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *k
                      int max_seqlen, int hq_r, int kvh_r, float scale);
 int llm_attn_decode(cudaStream_t st, float *ws_qkv, void *kc, void *vc, const int32_t *ctx_len, const int32_t *slots,
                     const int32_t *page_table, int pages_per_seq, const float *rope_cos, const float *rope_sin, void *out,
-                    int ld_out, int n_seq, int hq_r, int kvh_r, int max_ctx, float scale);
+                    int ld_out, int n_seq, int hq_r, int kvh_r, int max_ctx, float scale, const CUtensorMap *tmap_k,
+                    const CUtensorMap *tmap_v, float *part_ws, int *part_cnt, int n_cta, int stream_form);
+int make_tmap_2d_kmajor(CUtensorMap *out, const void *base, int64_t rows, int64_t K, int64_t ld_elems, int box_rows, int is_bf16);
 
 constexpr int LLM_MAXB = 32;          // decode batch (rows of the skinny GEMM)
 constexpr int LLM_HD = 128;           // head dim
@@ -457,6 +459,7 @@ struct LlmLayer {
     __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr;
     float *ln1 = nullptr, *ln2 = nullptr;
     CUtensorMap m_qkv_w, m_o_w, m_gu_w, m_down_w;   // skinny-GEMM weight maps
+    CUtensorMap m_kc, m_vc;                         // this layer's K / V page pool as [pages * kv_heads * 64, 128] (decode attention)
 };
 
 struct Llm {
@@ -476,6 +479,11 @@ struct Llm {
     float *h = nullptr;
     __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *gu = nullptr, *act = nullptr, *xlast = nullptr;
     float *ws_qkv = nullptr, *ws_gu = nullptr, *ws_logits = nullptr, *keep_logits = nullptr;
+    float *attn_part = nullptr;   // decode attention: (m, l, o) partials of split (sequence, kv head) segments, 2 slots per CTA
+    int *attn_cnt = nullptr;      // arrivals per (sequence, kv head)
+    int n_sm = 148;
+    int attn_stream = 1;          // decode attention: 1 = key blocks dealt to the SMs (split sequences, merge order depends on the batch),
+                                  // 0 = one CTA per (sequence, kv head): slower, bit-identical whatever else is in the batch
     // exchange block (one allocation, exported through cudaIpc)
     unsigned char *comm = nullptr, *peer_comm = nullptr;
     size_t comm_bytes = 0, off_amax = 0, off_pdec[2] = {0, 0}, off_ppre[2] = {0, 0};
@@ -594,6 +602,10 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     LA(m->ws_qkv, (int64_t)LLM_MAXB * m->qkv_n);
     LA(m->ws_gu, (int64_t)LLM_MAXB * 2 * m->I_r);
     LA(m->ws_logits, (int64_t)LLM_MAXB * m->V_r);
+    cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (const char *e = getenv("B2S_LLM_ATTN_STREAM")) m->attn_stream = e[0] != '0';   // read per model, at creation
+    LA(m->attn_part, (int64_t)m->n_sm * 2 * 2 * 8 * 132);   // up to 2 CTAs per SM, 2 slots each
+    LA(m->attn_cnt, (int64_t)LLM_MAXB * m->kvh_r);
     // exchange block
     m->off_amax = LLM_FLAGS * 4;
     size_t off = m->off_amax + 2 * LLM_MAXB * sizeof(AmaxSlot);
@@ -642,6 +654,9 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
         if (!rc) rc = skinny_make_maps(&y.m_o_w, &m->m_x_attn, y.wo, H, m->hq_r * LLM_HD, m->attn, LLM_MAXB);
         if (!rc) rc = skinny_make_maps(&y.m_gu_w, &m->m_x_xn, y.wgu, 2 * m->I_r, H, m->xn, LLM_MAXB);
         if (!rc) rc = skinny_make_maps(&y.m_down_w, &m->m_x_act, y.wdown, H, m->I_r, m->act, LLM_MAXB);
+        const int64_t kv_rows = (int64_t)m->n_pages * m->kvh_r * 64;
+        if (!rc) rc = make_tmap_2d_kmajor(&y.m_kc, m->kcache + m->kv_layer_stride * l, kv_rows, LLM_HD, LLM_HD, 64, 1);
+        if (!rc) rc = make_tmap_2d_kmajor(&y.m_vc, m->vcache + m->kv_layer_stride * l, kv_rows, LLM_HD, LLM_HD, 64, 1);
     }
     if (!rc) rc = skinny_make_maps(&m->m_lm_w, &m->m_x_last, m->lm_head, m->V_r, H, m->xlast, LLM_MAXB);
     if (rc) { delete m; return rc; }
@@ -854,8 +869,11 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
     // in-pipeline cost of each one can be read off the step time: 1 attention, 2 reduce_rms, 4 swiglu, 8 qkv,
     // 16 o, 32 gate/up, 64 down, 128 lm_head + argmax
     static const int skip = []() { const char *e = getenv("B2S_LLM_SKIP"); return e ? atoi(e) : 0; }();
-    B2S_CUDA(launch_dependent(llm_embed_rms_kernel, dim3(n_seq), dim3(256), st, m->d_next_tok, m->embed, m->layers[0].ln1, m->h, m->xn, H,
-                              m->cfg.vocab, m->cfg.rms_eps));
+    // The step's first kernel is a PLAIN launch: everything of this step starts after the previous step (or the prefill, or a
+    // host update of slots / pages) has completed, so context lengths, slots and the page table are constant for every kernel
+    // of the step -- the decode attention reads them, and streams cached K / V, before its programmatic dependency resolves.
+    llm_embed_rms_kernel<<<n_seq, 256, 0, st>>>(m->d_next_tok, m->embed, m->layers[0].ln1, m->h, m->xn, H, m->cfg.vocab, m->cfg.rms_eps);
+    B2S_CUDA(cudaGetLastError());
     ++nl;
     LLM_MARK(1);
     int k = 0;
@@ -865,7 +883,8 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
         if (!(skip & 8)) B2S_TRY(skinny_gemm_maps(st, y.m_qkv_w, m->m_x_xn, m->ws_qkv, m->qkv_n, H, n_seq));
         LLM_MARK(2);
         if (!(skip & 1)) B2S_TRY(llm_attn_decode(st, m->ws_qkv, kc, vc, m->d_ctx_len, m->d_slots, m->d_page_table, m->pages_per_seq, m->rope_cos,
-                                m->rope_sin, m->attn, m->hq_r * LLM_HD, n_seq, m->hq_r, m->kvh_r, m->cfg.max_ctx, scale));
+                                m->rope_sin, m->attn, m->hq_r * LLM_HD, n_seq, m->hq_r, m->kvh_r, m->cfg.max_ctx, scale, &y.m_kc, &y.m_vc,
+                                m->attn_part, m->attn_cnt, m->n_sm, m->attn_stream));
         LLM_MARK(4);
         nl += 2;
         for (int half = 0; half < 2; ++half, ++k) {

@@ -62,7 +62,7 @@ __device__ __forceinline__ void red_add(float *addr, float a)
 template <int SK_STAGES>
 __global__ void __launch_bounds__(SK_THREADS, SK_STAGES > 5 ? 1 : 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                   float *__restrict__ y, int n_out, int m_rows, int num_k, int total_units)
+                   float *__restrict__ y, int n_out, int m_rows, int num_k, int total_units, int l2_ahead)
 {
     using S = SkSmem<SK_STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -110,6 +110,13 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 const int u = u0 + i, tile = u / num_k, kb = u - tile * num_k;
                 mbar_arrive_expect_tx(&full_bar[i], S::STAGE_BYTES);
                 tma_load_2d(smem + i * S::STAGE_BYTES, &tmap_w, &full_bar[i], kb * SK_BK, tile * SK_BM);
+            }
+            // ... and the units after the ring are pulled into L2 (126 MB): the predecessor is a small kernel that leaves HBM
+            // idle for several microseconds, and a shared-memory ring alone can only bank 200 KB per SM of that time
+            const int ahead = min(u1 - u0, pre + l2_ahead);
+            for (int i = pre; i < ahead; ++i) {
+                const int u = u0 + i, tile = u / num_k, kb = u - tile * num_k;
+                tma_prefetch_l2_2d(&tmap_w, kb * SK_BK, tile * SK_BM);
             }
             griddep_wait();
             for (int i = 0; i < pre; ++i) {
@@ -237,7 +244,10 @@ static int skinny_launch(cudaStream_t st, const CUtensorMap &tw, const CUtensorM
     static const bool pdl = []() { const char *e = getenv("B2S_SKINNY_PDL"); return !(e && e[0] == '0'); }();
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    B2S_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<STAGES>, tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units));
+    // units per CTA prefetched into L2 behind the ring while the kernel waits for its predecessor (B2S_SKINNY_L2_AHEAD, 0 = off)
+    static const int l2_ahead = []() { const char *e = getenv("B2S_SKINNY_L2_AHEAD"); return e ? atoi(e) : 0; }();
+    B2S_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<STAGES>, tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units,
+                                l2_ahead));
     count_launch();
     return 0;
 }

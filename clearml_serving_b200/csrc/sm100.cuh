@@ -81,6 +81,13 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m)
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
 // 2-D tiled load: coordinates are (c0 = innermost element index, c1 = row)
+// pull one box of a tiled tensor into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *m, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1)
 {
     asm volatile(

@@ -13,6 +13,60 @@ sys.path.insert(0, ROOT)
 from clearml_serving_b200 import llm as L  # noqa: E402
 
 
+def trace_steps(m, prompts, out_path, steps=4):
+    """Kernel timeline of graph-launched decode steps (CUPTI through torch.profiler; nothing under it is a bench number).
+    For every kernel: start, end, and how far it moved the completion frontier (end - max(previous ends)): the frontier
+    increments of a step add up to the step time, so they attribute it to kernels INCLUDING launch gaps and dependency stalls."""
+    import collections
+    import tempfile
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    m.prefill(prompts)
+    m.decode(4, use_graph=True)
+    m.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        m.decode(steps, use_graph=True)
+        m.synchronize()
+        torch.cuda.synchronize()
+    tmp = tempfile.mktemp(suffix=".json")
+    prof.export_chrome_trace(tmp)
+    ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") == "kernel"]
+    ev.sort(key=lambda e: e["ts"])
+    names = [e["name"].split("(")[0].split("<")[0].replace("b2s::", "") for e in ev]
+    ends = [i for i, n in enumerate(names) if "step_end" in n]
+    lines = []
+    if len(ends) >= 3:
+        lo, hi = ends[-3] + 1, ends[-2] + 1          # the second-to-last traced step
+        seq = ev[lo:hi]
+        t0 = ev[lo - 1]["ts"] + ev[lo - 1]["dur"]
+        frontier = t0
+        agg = collections.OrderedDict()
+        per = []
+        idx_in_layer = collections.Counter()
+        for e, n in zip(seq, names[lo:hi]):
+            st, en = e["ts"], e["ts"] + e["dur"]
+            inc = max(0.0, en - frontier)
+            key = n + "#" + str(idx_in_layer[n] % (4 if "skinny" in n else 2 if "reduce_rms" in n else 1)) if ("skinny" in n or "reduce_rms" in n) else n
+            idx_in_layer[n] += 1
+            a_ = agg.setdefault(key, [0, 0.0, 0.0, 0.0])
+            a_[0] += 1; a_[1] += inc; a_[2] += e["dur"]; a_[3] += st - frontier
+            per.append((n, st - t0, en - t0, e["dur"], inc, st - frontier))
+            frontier = max(frontier, en)
+        total = frontier - t0
+        lines.append("step time (frontier) %.1f us over %d kernels" % (total, len(seq)))
+        lines.append("%-44s %5s %12s %12s %14s" % ("kernel#slot", "n", "frontier us", "sum dur us", "mean start-frontier"))
+        for k, v in agg.items():
+            lines.append("%-44s %5d %12.1f %12.1f %14.2f" % (k, v[0], v[1], v[2], v[3] / v[0]))
+        lines.append("")
+        lines.append("first 3 layers, per kernel: name, start, end, dur, frontier increment, start - frontier (negative = overlapped its predecessor)")
+        for r in per[:27]:
+            lines.append("%-40s %9.2f %9.2f %8.2f %8.2f %8.2f" % r)
+    else:
+        lines.append("trace holds %d kernels, %d step ends" % (len(ev), len(ends)))
+    open(out_path, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[:40]), file=sys.stderr)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--layers", type=int, default=32)
@@ -22,6 +76,7 @@ def main():
     ap.add_argument("--waves", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--timing", action="store_true", help="per-kernel device times of eager decode steps (stderr)")
+    ap.add_argument("--trace", default="", help="CUPTI (torch.profiler) kernel timeline of graph-mode decode steps -> this text file")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -53,6 +108,8 @@ def main():
         m.prefill(prompts)
         m.decode(12, use_graph=2)
         m.synchronize()
+    if a.trace:
+        trace_steps(m, prompts, a.trace)
     pre, dec = np.median([r[0] for r in res[1:] or res]), np.median([r[1] for r in res[1:] or res])
     tp = 2 if world == 2 else 1
     step_ms = dec / (a.gen - 1)
