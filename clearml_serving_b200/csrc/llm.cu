@@ -137,10 +137,7 @@ __device__ __forceinline__ void tp_exchange_point(uint32_t *my_flags, uint32_t *
     if (peer_flags == nullptr) return;
     if (threadIdx.x == 0) {
         const uint32_t want = *reinterpret_cast<const volatile uint32_t *>(gen) + 1u;
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            st_release_sys(peer_flags + k, want);
-        }
+        if (blockIdx.x == 0) st_release_sys(peer_flags + k, want);   // release at system scope: the partial (previous kernel, in L2) is ordered before the flag
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(my_flags + k) - want) < 0) {
             if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a lost peer must not hang the GPU
@@ -225,35 +222,50 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
     sm100::griddep_wait();
     tp_exchange_point(my_flags, peer_flags, gen, k);
     const int t = blockIdx.x;
-    float4 v[8];
+    // Every load of the row is issued before the first use: the peer's partial comes over NVLink (~2.5 us per round trip), and
+    // a load -> add -> store loop pays that once per 1024 columns (4 round trips at H = 4096: 10 of the 15 us this kernel took in
+    // the TP 2 step, profiles/r02_llm_decode_trace_tp2.txt); the volatile peer loads also pinned the local loads behind them.
+    float4 v[8], pa[8], pr[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = (it * 256 + threadIdx.x) * 4;
+        pr[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < H && peer) {
+            if (F32) {
+                const uint4 u = ld_peer_v4(static_cast<const float *>(peer) + (int64_t)t * H + i);
+                pr[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+            } else {
+                const uint2 q = ld_peer_v2(static_cast<const __nv_bfloat16 *>(peer) + (int64_t)t * H + i);
+                const __nv_bfloat162 *pq = reinterpret_cast<const __nv_bfloat162 *>(&q);
+                const float2 q0 = __bfloat1622float2(pq[0]), q1 = __bfloat1622float2(pq[1]);
+                pr[it] = make_float4(q0.x, q0.y, q1.x, q1.y);
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = (it * 256 + threadIdx.x) * 4;
+        pa[it] = v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < H) {
+            if (F32) {
+                pa[it] = __ldcg(reinterpret_cast<const float4 *>(static_cast<const float *>(mine) + (int64_t)t * H + i));
+            } else {
+                const uint2 u = *reinterpret_cast<const uint2 *>(static_cast<const __nv_bfloat16 *>(mine) + (int64_t)t * H + i);
+                const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
+                const float2 m0 = __bfloat1622float2(p[0]), m1 = __bfloat1622float2(p[1]);
+                pa[it] = make_float4(m0.x, m0.y, m1.x, m1.y);
+            }
+            v[it] = *reinterpret_cast<const float4 *>(h + (int64_t)t * H + i);
+        }
+    }
     float ss = 0.f;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int i = (it * 256 + threadIdx.x) * 4;
         if (i < H) {
-            float4 a;
-            if (F32) {
-                a = *reinterpret_cast<const float4 *>(static_cast<const float *>(mine) + (int64_t)t * H + i);
-                if (peer) {
-                    const uint4 u = ld_peer_v4(static_cast<const float *>(peer) + (int64_t)t * H + i);
-                    a.x += __uint_as_float(u.x); a.y += __uint_as_float(u.y);
-                    a.z += __uint_as_float(u.z); a.w += __uint_as_float(u.w);
-                }
-                if (zero_buf) *reinterpret_cast<float4 *>(zero_buf + (int64_t)t * H + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                const uint2 u = *reinterpret_cast<const uint2 *>(static_cast<const __nv_bfloat16 *>(mine) + (int64_t)t * H + i);
-                const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&u);
-                const float2 m0 = __bfloat1622float2(p[0]), m1 = __bfloat1622float2(p[1]);
-                a = make_float4(m0.x, m0.y, m1.x, m1.y);
-                if (peer) {
-                    const uint2 q = ld_peer_v2(static_cast<const __nv_bfloat16 *>(peer) + (int64_t)t * H + i);
-                    const __nv_bfloat162 *pq = reinterpret_cast<const __nv_bfloat162 *>(&q);
-                    const float2 q0 = __bfloat1622float2(pq[0]), q1 = __bfloat1622float2(pq[1]);
-                    a.x += q0.x; a.y += q0.y; a.z += q1.x; a.w += q1.y;
-                }
-            }
-            float4 r = *reinterpret_cast<const float4 *>(h + (int64_t)t * H + i);
-            r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+            float4 r = v[it];
+            r.x += pa[it].x + pr[it].x; r.y += pa[it].y + pr[it].y; r.z += pa[it].z + pr[it].z; r.w += pa[it].w + pr[it].w;
+            if (F32 && zero_buf) *reinterpret_cast<float4 *>(zero_buf + (int64_t)t * H + i) = make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4 *>(h + (int64_t)t * H + i) = r;
             v[it] = r;
             ss += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;

@@ -109,7 +109,7 @@ def main():
         m.decode(12, use_graph=2)
         m.synchronize()
     if a.trace:
-        trace_steps(m, prompts, a.trace)
+        trace_steps(m, prompts, a.trace if world == 1 else "{}.rank{}".format(a.trace, rank))
     pre, dec = np.median([r[0] for r in res[1:] or res]), np.median([r[1] for r in res[1:] or res])
     tp = 2 if world == 2 else 1
     step_ms = dec / (a.gen - 1)
