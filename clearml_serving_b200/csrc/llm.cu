@@ -39,7 +39,8 @@ namespace b2s {
 int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t ldb, int M, int N, int K,
             const GemmEpilogue &ep);
 int skinny_make_maps(CUtensorMap *tw, CUtensorMap *tx, const void *W, int64_t n_out, int64_t K, const void *X, int64_t x_rows);
-int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows);
+int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows,
+                     const uint32_t *idle_flag = nullptr, const uint32_t *gen = nullptr, int idle_want = 0);
 int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *kc, const void *vc, const int32_t *cu_seqlens,
                      const int32_t *slots, const int32_t *page_table, int pages_per_seq, void *out, int ld_out, int n_seq,
                      int max_seqlen, int hq_r, int kvh_r, float scale);
@@ -215,11 +216,15 @@ template <bool F32>
 __global__ void __launch_bounds__(256)
 llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *zero_buf, uint32_t *my_flags, uint32_t *peer_flags,
                       const uint32_t *gen, int k, const float *__restrict__ w, float *__restrict__ h,
-                      __nv_bfloat16 *__restrict__ xn, int H, float eps)
+                      __nv_bfloat16 *__restrict__ xn, int H, float eps, uint32_t *idle_flag)
 {
     __shared__ float red[8];
     sm100::griddep_launch_dependents();
     sm100::griddep_wait();
+    // the projection before this kernel has completed: tell the NEXT projection (already resident, ring full, spinning before its
+    // own dependency wait) that HBM is idle for the next few microseconds (skinny.cu)
+    if (idle_flag && blockIdx.x == 0 && threadIdx.x == 0)
+        *reinterpret_cast<volatile uint32_t *>(idle_flag) = *reinterpret_cast<const volatile uint32_t *>(gen) * 1024u + (uint32_t)(k + 1);
     tp_exchange_point(my_flags, peer_flags, gen, k);
     const int t = blockIdx.x;
     // Every load of the row is issued before the first use: the peer's partial comes over NVLink (~2.5 us per round trip), and
@@ -341,10 +346,13 @@ llm_rope_cache_prefill_kernel(__nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__
 __device__ __forceinline__ float silu_mul(float g, float u) { return g / (1.0f + __expf(-g)) * u; }
 
 __global__ void __launch_bounds__(256)
-llm_swiglu_decode_kernel(float *__restrict__ gu, __nv_bfloat16 *__restrict__ act, int64_t rows, int I)
+llm_swiglu_decode_kernel(float *__restrict__ gu, __nv_bfloat16 *__restrict__ act, int64_t rows, int I, uint32_t *idle_flag,
+                         const uint32_t *gen, int idle_id)
 {
     sm100::griddep_launch_dependents();
     sm100::griddep_wait();
+    if (idle_flag && blockIdx.x == 0 && threadIdx.x == 0)     // see llm_reduce_rms_kernel
+        *reinterpret_cast<volatile uint32_t *>(idle_flag) = *reinterpret_cast<const volatile uint32_t *>(gen) * 1024u + (uint32_t)idle_id;
     const int64_t n4 = rows * (I / 4);
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n4; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = idx / (I / 4);
@@ -503,6 +511,7 @@ struct Llm {
     int32_t *d_tokens = nullptr, *d_tok_seq = nullptr, *d_tok_pos = nullptr, *d_cu = nullptr, *d_slots = nullptr,
             *d_ctx_len = nullptr, *d_next_tok = nullptr, *d_out_tokens = nullptr, *d_out_pos = nullptr;
     uint32_t *d_gen = nullptr;
+    uint32_t *d_idle = nullptr;   // [2] idle-HBM signals of the decode step (raised by reduce_rms / SwiGLU, polled by the next projection)
     int32_t *h_stage = nullptr;   // pinned staging for token metadata
     int max_new_cap = 0;
     int n_seq = 0;                // sequences of the current wave
@@ -636,6 +645,7 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     LA(m->d_out_pos, LLM_MAXB);
     LA(m->d_out_tokens, (int64_t)LLM_MAXB * m->max_new_cap);
     LA(m->d_gen, 4);
+    LA(m->d_idle, 4);
 #undef LA
     cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&m->h_stage), (size_t)(3 * Tp + 4 * LLM_MAXB + 8) * 4);
     if (e != cudaSuccess) { delete m; return fail_cuda(e, "cudaMallocHost(llm staging)"); }
@@ -812,7 +822,7 @@ static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens
                 B2S_TRY(llm_gemm_bf16(st, m->act, m->I_r, y.wdown, Ti, H, m->I_r, mine));
             }
             const float *w = half == 0 ? y.ln2 : (l + 1 < L ? m->layers[l + 1].ln1 : m->final_norm);
-            llm_reduce_rms_kernel<false><<<Ti, 256, 0, st>>>(mine, peer, nullptr, myf, peerf, m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps);
+            llm_reduce_rms_kernel<false><<<Ti, 256, 0, st>>>(mine, peer, nullptr, myf, peerf, m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps, nullptr);
             count_launch();
         }
     }
@@ -892,7 +902,8 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
     for (int l = 0; l < L; ++l) {
         LlmLayer &y = m->layers[l];
         __nv_bfloat16 *kc = m->kcache + m->kv_layer_stride * l, *vc = m->vcache + m->kv_layer_stride * l;
-        if (!(skip & 8)) B2S_TRY(skinny_gemm_maps(st, y.m_qkv_w, m->m_x_xn, m->ws_qkv, m->qkv_n, H, n_seq));
+        // (idle-HBM signal of the kernel before each projection: reduce_rms k raises idle[0] to gen * 1024 + k + 1, SwiGLU of layer l idle[1] to + l + 1)
+        if (!(skip & 8)) B2S_TRY(skinny_gemm_maps(st, y.m_qkv_w, m->m_x_xn, m->ws_qkv, m->qkv_n, H, n_seq, l > 0 ? m->d_idle : nullptr, m->d_gen, 2 * l));
         LLM_MARK(2);
         if (!(skip & 1)) B2S_TRY(llm_attn_decode(st, m->ws_qkv, kc, vc, m->d_ctx_len, m->d_slots, m->d_page_table, m->pages_per_seq, m->rope_cos,
                                 m->rope_sin, m->attn, m->hq_r * LLM_HD, n_seq, m->hq_r, m->kvh_r, m->cfg.max_ctx, scale, &y.m_kc, &y.m_vc,
@@ -908,24 +919,24 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
                 LLM_MARK(5);
                 ++nl;
             } else {
-                if (!(skip & 32)) B2S_TRY(skinny_gemm_maps(st, y.m_gu_w, m->m_x_xn, m->ws_gu, 2 * m->I_r, H, n_seq));
+                if (!(skip & 32)) B2S_TRY(skinny_gemm_maps(st, y.m_gu_w, m->m_x_xn, m->ws_gu, 2 * m->I_r, H, n_seq, m->d_idle, m->d_gen, 2 * l + 1));
                 LLM_MARK(7);
                 if (!(skip & 4)) B2S_CUDA(launch_dependent(llm_swiglu_decode_kernel, dim3((n_seq * (m->I_r / 4) + 255) / 256), dim3(256), st, m->ws_gu, m->act,
-                                          (int64_t)n_seq, m->I_r));
+                                          (int64_t)n_seq, m->I_r, m->d_idle + 1, (const uint32_t *)m->d_gen, l + 1));
                 LLM_MARK(8);
-                if (!(skip & 64)) B2S_TRY(skinny_gemm_maps(st, y.m_down_w, m->m_x_act, mine, H, m->I_r, n_seq));
+                if (!(skip & 64)) B2S_TRY(skinny_gemm_maps(st, y.m_down_w, m->m_x_act, mine, H, m->I_r, n_seq, m->d_idle + 1, m->d_gen, l + 1));
                 LLM_MARK(9);
                 nl += 3;
             }
             const float *w = half == 0 ? y.ln2 : (l + 1 < L ? m->layers[l + 1].ln1 : m->final_norm);
             if (!(skip & 2)) B2S_CUDA(launch_dependent(llm_reduce_rms_kernel<true>, dim3(n_seq), dim3(256), st, (const void *)mine, peer, older, myf, peerf,
-                                      (const uint32_t *)m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps));
+                                      (const uint32_t *)m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps, m->d_idle));
             LLM_MARK(half == 0 ? 6 : 10);
             ++nl;
         }
     }
     // xn rows 0..n_seq-1 are the final-normed hidden states: lm_head reads them through the xn map
-    if (!(skip & 128)) B2S_TRY(skinny_gemm_maps(st, m->m_lm_w, m->m_x_xn, m->ws_logits, m->V_r, H, n_seq));
+    if (!(skip & 128)) B2S_TRY(skinny_gemm_maps(st, m->m_lm_w, m->m_x_xn, m->ws_logits, m->V_r, H, n_seq, m->d_idle, m->d_gen, 2 * L));
     LLM_MARK(11);
     if (!(skip & 128)) B2S_CUDA(launch_dependent(llm_argmax_kernel, dim3(n_seq), dim3(256), st, m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r,
                               m->amax(m->comm), m->peer_comm ? m->amax(m->peer_comm) : (AmaxSlot *)nullptr, myf, peerf,

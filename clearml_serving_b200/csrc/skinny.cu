@@ -62,7 +62,8 @@ __device__ __forceinline__ void red_add(float *addr, float a)
 template <int SK_STAGES>
 __global__ void __launch_bounds__(SK_THREADS, SK_STAGES > 5 ? 1 : 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                   float *__restrict__ y, int n_out, int m_rows, int num_k, int total_units, int l2_ahead)
+                   float *__restrict__ y, int n_out, int m_rows, int num_k, int total_units, int l2_ahead,
+                   const uint32_t *idle_flag, const uint32_t *gen, int idle_want)
 {
     using S = SkSmem<SK_STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -111,12 +112,27 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 mbar_arrive_expect_tx(&full_bar[i], S::STAGE_BYTES);
                 tma_load_2d(smem + i * S::STAGE_BYTES, &tmap_w, &full_bar[i], kb * SK_BK, tile * SK_BM);
             }
-            // ... and the units after the ring are pulled into L2 (126 MB): the predecessor is a small kernel that leaves HBM
-            // idle for several microseconds, and a shared-memory ring alone can only bank 200 KB per SM of that time
-            const int ahead = min(u1 - u0, pre + l2_ahead);
-            for (int i = pre; i < ahead; ++i) {
-                const int u = u0 + i, tile = u / num_k, kb = u - tile * num_k;
-                tma_prefetch_l2_2d(&tmap_w, kb * SK_BK, tile * SK_BM);
+            // ... and once HBM goes IDLE the units behind the ring are pulled into L2.  "Idle" is signalled by the small kernel
+            // between the previous projection and this one (RMSNorm / SwiGLU): it raises `idle_flag` as soon as ITS dependency
+            // has resolved, i.e. when the previous projection has stopped streaming; for the few microseconds that kernel then
+            // needs, the ring (200 KB per SM) is full and nothing else would use the memory system.  Prefetching at kernel
+            // start instead competes with the predecessor's tail and is slower at every depth
+            // (profiles/r02_llm_attn_decode_stream.txt).  Bounded poll: a missing signal only costs the prefetch.
+            if (idle_flag && l2_ahead > 0 && u0 + pre < u1) {
+                const uint32_t want = *reinterpret_cast<const volatile uint32_t *>(gen) * 1024u + (uint32_t)idle_want;
+                const long long t0 = clock64();
+                bool idle = false;
+                while (clock64() - t0 < 60000) {
+                    if ((int32_t)(*reinterpret_cast<const volatile uint32_t *>(idle_flag) - want) >= 0) { idle = true; break; }
+                    __nanosleep(100);
+                }
+                if (idle) {
+                    const int ahead = min(u1 - u0, pre + l2_ahead);
+                    for (int i = pre; i < ahead; ++i) {
+                        const int u = u0 + i, tile = u / num_k, kb = u - tile * num_k;
+                        tma_prefetch_l2_2d(&tmap_w, kb * SK_BK, tile * SK_BM);
+                    }
+                }
             }
             griddep_wait();
             for (int i = 0; i < pre; ++i) {
@@ -221,7 +237,7 @@ int skinny_make_maps(CUtensorMap *tw, CUtensorMap *tx, const void *W, int64_t n_
 
 template <int STAGES>
 static int skinny_launch(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int m_rows, int num_k,
-                         int64_t units, int ctas_per_sm)
+                         int64_t units, int ctas_per_sm, const uint32_t *idle_flag, const uint32_t *gen, int idle_want)
 {
     using S = SkSmem<STAGES>;
     static std::once_flag once;
@@ -244,15 +260,16 @@ static int skinny_launch(cudaStream_t st, const CUtensorMap &tw, const CUtensorM
     static const bool pdl = []() { const char *e = getenv("B2S_SKINNY_PDL"); return !(e && e[0] == '0'); }();
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    // units per CTA prefetched into L2 behind the ring while the kernel waits for its predecessor (B2S_SKINNY_L2_AHEAD, 0 = off)
-    static const int l2_ahead = []() { const char *e = getenv("B2S_SKINNY_L2_AHEAD"); return e ? atoi(e) : 0; }();
+    // units per CTA prefetched into L2 behind the ring once the predecessor signals an idle HBM (B2S_SKINNY_L2_AHEAD, 0 = off)
+    static const int l2_ahead = []() { const char *e = getenv("B2S_SKINNY_L2_AHEAD"); return e ? atoi(e) : 4; }();
     B2S_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<STAGES>, tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units,
-                                l2_ahead));
+                                l2_ahead, idle_flag, gen, idle_want));
     count_launch();
     return 0;
 }
 
-int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows)
+int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows,
+                     const uint32_t *idle_flag, const uint32_t *gen, int idle_want)
 {
     if (n_out <= 0 || K <= 0) return 0;
     const int num_k = (K + SK_BK - 1) / SK_BK;
@@ -260,8 +277,8 @@ int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &
     const int64_t units = (int64_t)tiles * num_k;
     if (units > INT32_MAX) return fail(B2S_ERR_INVALID, "skinny gemm: problem too large");
     static const int per_sm = []() { const char *e = getenv("B2S_SKINNY_CTAS"); return (e && e[0] == '1') ? 1 : 2; }();
-    return per_sm == 1 ? skinny_launch<10>(st, tw, tx, y, n_out, m_rows, num_k, units, 1)
-                       : skinny_launch<5>(st, tw, tx, y, n_out, m_rows, num_k, units, 2);
+    return per_sm == 1 ? skinny_launch<10>(st, tw, tx, y, n_out, m_rows, num_k, units, 1, idle_flag, gen, idle_want)
+                       : skinny_launch<5>(st, tw, tx, y, n_out, m_rows, num_k, units, 2, idle_flag, gen, idle_want);
 }
 
 }  // namespace b2s
@@ -275,5 +292,5 @@ extern "C" B2S_API int b2s_op_skinny_gemm(int device, void *cuda_stream, const v
     B2S_CUDA(cudaSetDevice(device));
     CUtensorMap tw, tx;
     B2S_TRY(skinny_make_maps(&tw, &tx, W, n_out, K, X, m));
-    return skinny_gemm_maps(static_cast<cudaStream_t>(cuda_stream), tw, tx, y, n_out, K, m);
+    return skinny_gemm_maps(static_cast<cudaStream_t>(cuda_stream), tw, tx, y, n_out, K, m, nullptr, nullptr, 0);
 }
