@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 
 N_TREES, DEPTH, N_FEATURES, MAX_BATCH = 1000, 6, 32, 64
 WORKLOAD = "xgboost-synth-1000trees-depth6-32feat-f32_maxbatch64"
+WORKLOAD_MIN_STEPS = 200     # BERT / ResNet sections: timed steps whatever --steps says (2.6-3 ms each: >= 0.5 s per leg)
 MIN_TIMED_S, MIN_REPEATS, MAX_LEG_WALL_S = 0.5, 5, 25.0
 
 
@@ -605,6 +606,8 @@ def _bert_workload(native, device, steps, warmup, cpu_seconds, dist=None, local=
     stream.synchronize()
     launches0 = native.launch_count()
     _barrier_sync(dist, local)
+    # >= 200 steps whatever --steps says: ~0.55 s of timed device work, and an e2e loop long enough to amortise pipeline fill / drain
+    steps = max(steps, WORKLOAD_MIN_STEPS)
     total_ms, flops = 0.0, 0.0
     for k in range(steps):
         bufs, doff = dsets[k % n_sets]
@@ -707,6 +710,7 @@ def _resnet_workload(native, device, steps, warmup, cpu_seconds, dist=None, loca
     stream.synchronize()
     launches0 = native.launch_count()
     _barrier_sync(dist, local)
+    steps = max(steps, WORKLOAD_MIN_STEPS)      # ~0.6 s of timed device work whatever --steps says
     total_ms = 0.0
     for k in range(steps):
         stream.flush_l2()
@@ -723,7 +727,7 @@ def _resnet_workload(native, device, steps, warmup, cpu_seconds, dist=None, loca
     rel = float(np.abs(got - ref).max() / np.abs(ref).max())
     # e2e: 128 single-image requests per step through the C ABI (77 MB of fp32 pixels host -> device)
     reqs = [[[X[s][i:i + 1]] for i in range(B)] for s in range(n_sets)]
-    e2e_steps = max(3, min(steps, 8))
+    e2e_steps = steps       # the 8-batch loop of round 1 spent 12 % of its time filling and draining the 2-deep pipeline
     for k in range(3):   # warm-up: first touch of the pinned slots, collate workers started
         item = stream.infer_batch(reqs[k % n_sets])   # (event, outputs, keep-alive): the scatter writes into `outputs`
         stream.wait(item[0])
@@ -781,11 +785,14 @@ def _resnet_workload(native, device, steps, warmup, cpu_seconds, dist=None, loca
             peak = float(json.load(f).get("bf16_tflops_sustained", peak))
     flops_per_img = 8.178e9   # BASELINE.md section 3 (torch FlopCounterMode, 2*MAC)
     achieved = flops_per_img * B * steps / (total_ms * 1e-3) / 1e12
+    e2e_f32 = dict(value=world * B * e2e_steps / e2e_s, unit="images/s", ms_per_step=e2e_s / e2e_steps * 1e3, in_flight=2,
+                   h2d_bytes_per_step=B * 3 * 224 * 224 * 4, d2h_bytes_per_step=B * 4000, pixels="float32")
     res = dict(workload="resnet50-fp16_3x224x224_maxbatch128", metric="images/sec", replicas=world,
                value=world * B * steps / (total_ms * 1e-3), ms_per_step=total_ms / steps, steps=steps,
-               e2e=dict(value=world * B * e2e_steps / e2e_s, unit="images/s", ms_per_step=e2e_s / e2e_steps * 1e3, in_flight=2,
-                        h2d_bytes_per_step=B * 3 * 224 * 224 * 4, d2h_bytes_per_step=B * 4000, pixels="float32"),
-               e2e_uint8_pixels=e2e_u8,
+               # an image endpoint receives uint8 pixels (examples/pytorch/preprocess.py): that is the end-to-end figure; the
+               # float32 form (4x the host -> device bytes, host-memcpy bound when several ranks share a host) is kept beside it
+               e2e=e2e_u8 if isinstance(e2e_u8, dict) and "value" in e2e_u8 else e2e_f32,
+               e2e_float32_pixels=e2e_f32,
                gpu_launches_per_step=launches / steps, parity_rel_err_vs_torch_cpu_fp32=rel,
                roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
                              peak_source="MEASURED_PEAKS.json bf16_tflops_sustained", flops_per_image=flops_per_img,
