@@ -381,29 +381,55 @@ llm_gather_last_kernel(const __nv_bfloat16 *__restrict__ xn, const int32_t *__re
 }
 
 // ------------------------------------------------------------------------------------------------
-// greedy sampling over the vocabulary shard + cross-rank exchange.  One CTA per sequence.
+// greedy sampling over the vocabulary shard + cross-rank exchange.  B2S_LLM_AMAX_SPLIT (32) CTAs per sequence (grid = n_seq x SPLIT): with
+// one CTA per sequence the 16 MB read-and-clear of the logits ran on 32 SMs (33 us per step; 30 -> 7 us of the step with 32 x 32 CTAs); the per-CTA maxima meet in a packed
+// 64-bit atomicMax (ordered value bits high, ~index low: the smallest index wins a tie, as before) and the last CTA of a
+// sequence finishes the row.
 // logits fp32 [32, V_r] (skinny GEMM accumulator, cleared here; optionally copied to `keep` first).
 // ------------------------------------------------------------------------------------------------
 struct AmaxSlot { float val; int32_t idx; };
+static int llm_amax_split()
+{
+    static const int v = []() { const char *e = getenv("B2S_LLM_AMAX_SPLIT"); const int x = e ? atoi(e) : 32; return x < 1 ? 1 : (x > 64 ? 64 : x); }();
+    return v;
+}
 
 __global__ void __launch_bounds__(256)
 llm_argmax_kernel(float *__restrict__ logits, float *__restrict__ keep, int V_r, int v_offset, AmaxSlot *my_slots, AmaxSlot *peer_slots,
                   uint32_t *my_flags, uint32_t *peer_flags, const uint32_t *gen, int k, int32_t *__restrict__ next_tok,
-                  int32_t *__restrict__ out_tokens, const int32_t *__restrict__ out_pos, int max_new)
+                  int32_t *__restrict__ out_tokens, const int32_t *__restrict__ out_pos, int max_new,
+                  unsigned long long *__restrict__ row_key, int *__restrict__ row_cnt)
 {
     __shared__ float s_val[256];
     __shared__ int s_idx[256];
+    __shared__ int s_last;
     sm100::griddep_launch_dependents();
     sm100::griddep_wait();
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, part = blockIdx.y, n_rows = gridDim.x;
     float *row = logits + (int64_t)b * V_r;
+    const int n_split = gridDim.y;
+    const int chunk = (V_r + n_split - 1) / n_split;
+    const int c0 = part * chunk, c1 = min(V_r, c0 + chunk);
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < V_r; i += 256) {
-        const float v = row[i];
-        if (keep) keep[(int64_t)b * V_r + i] = v;
-        row[i] = 0.f;
-        if (v > best) { best = v; bi = i; }   // strided scan: first maximum per thread
+    // eight independent loads per thread before the first use: as a load -> compare -> clear loop the compiler kept one L2 round
+    // trip per element in flight (247 us for the 128 k columns of a row on one CTA)
+    for (int i0 = c0 + threadIdx.x; i0 < c1; i0 += 256 * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            v[u] = i < c1 ? __ldcg(row + i) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            if (i < c1) {
+                if (keep) keep[(int64_t)b * V_r + i] = v[u];
+                row[i] = 0.f;
+                if (v[u] > best) { best = v[u]; bi = i; }   // ascending i: first maximum per thread
+            }
+        }
     }
     s_val[threadIdx.x] = best;
     s_idx[threadIdx.x] = bi;
@@ -419,6 +445,26 @@ llm_argmax_kernel(float *__restrict__ logits, float *__restrict__ keep, int V_r,
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        // (value, index) -> one orderable 64-bit key: larger value first, then smaller index
+        const uint32_t fb = __float_as_uint(s_val[0]);
+        const uint32_t ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+        const unsigned long long key = ((unsigned long long)ord << 32) | (unsigned long long)(0xffffffffu - (uint32_t)s_idx[0]);
+        atomicMax(row_key + b, key);
+        __threadfence();
+        const int old = atomicAdd(row_cnt + b, 1);
+        s_last = (old == n_split - 1);
+        if (s_last) {
+            row_cnt[b] = 0;
+            const unsigned long long w = atomicExch(row_key + b, 0ull);    // read the row's winner and clear it for the next step
+            const uint32_t o2 = (uint32_t)(w >> 32);
+            const uint32_t f2 = (o2 & 0x80000000u) ? (o2 & 0x7fffffffu) : ~o2;
+            s_val[0] = __uint_as_float(f2);
+            s_idx[0] = (int)(0xffffffffu - (uint32_t)(w & 0xffffffffull));
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
     const uint32_t g = *reinterpret_cast<const volatile uint32_t *>(gen);
     const int par = (int)(g & 1u) * LLM_MAXB;
     float val = s_val[0];
@@ -434,7 +480,7 @@ llm_argmax_kernel(float *__restrict__ logits, float *__restrict__ keep, int V_r,
             *reinterpret_cast<volatile int32_t *>(&peer_slots[par + b].idx) = s.idx;
             __threadfence_system();
             const uint32_t done = atomicAdd(&my_flags[LLM_FLAGS - 1], 1u);
-            if (done == gridDim.x - 1) {
+            if (done == (uint32_t)n_rows - 1) {
                 my_flags[LLM_FLAGS - 1] = 0u;
                 __threadfence_system();
                 st_release_sys(peer_flags + k, g + 1u);
@@ -511,6 +557,8 @@ struct Llm {
     int32_t *d_tokens = nullptr, *d_tok_seq = nullptr, *d_tok_pos = nullptr, *d_cu = nullptr, *d_slots = nullptr,
             *d_ctx_len = nullptr, *d_next_tok = nullptr, *d_out_tokens = nullptr, *d_out_pos = nullptr;
     uint32_t *d_gen = nullptr;
+    unsigned long long *d_amax_key = nullptr;   // [LLM_MAXB] packed (value, index) maxima of the split argmax
+    int *d_amax_cnt = nullptr;                  // [LLM_MAXB] arrivals
     uint32_t *d_idle = nullptr;   // [2] idle-HBM signals of the decode step (raised by reduce_rms / SwiGLU, polled by the next projection)
     int32_t *h_stage = nullptr;   // pinned staging for token metadata
     int max_new_cap = 0;
@@ -646,6 +694,8 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     LA(m->d_out_tokens, (int64_t)LLM_MAXB * m->max_new_cap);
     LA(m->d_gen, 4);
     LA(m->d_idle, 4);
+    LA(m->d_amax_key, LLM_MAXB);
+    LA(m->d_amax_cnt, LLM_MAXB);
 #undef LA
     cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&m->h_stage), (size_t)(3 * Tp + 4 * LLM_MAXB + 8) * 4);
     if (e != cudaSuccess) { delete m; return fail_cuda(e, "cudaMallocHost(llm staging)"); }
@@ -829,9 +879,9 @@ static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens
     llm_gather_last_kernel<<<n_seq, 256, 0, st>>>(m->xn, m->d_cu, m->xlast, H);
     count_launch();
     B2S_TRY(skinny_gemm_maps(st, m->m_lm_w, m->m_x_last, m->ws_logits, m->V_r, H, n_seq));
-    llm_argmax_kernel<<<n_seq, 256, 0, st>>>(m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r, m->amax(m->comm),
+    llm_argmax_kernel<<<dim3(n_seq, llm_amax_split()), 256, 0, st>>>(m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r, m->amax(m->comm),
                                              m->peer_comm ? m->amax(m->peer_comm) : nullptr, myf, peerf, m->d_gen, k, m->d_next_tok,
-                                             m->d_out_tokens, m->d_out_pos, m->max_new_cap);
+                                             m->d_out_tokens, m->d_out_pos, m->max_new_cap, m->d_amax_key, m->d_amax_cnt);
     llm_step_end_kernel<<<1, 32, 0, st>>>(m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 0);
     count_launch(2);
     B2S_CUDA(cudaGetLastError());
@@ -938,9 +988,10 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
     // xn rows 0..n_seq-1 are the final-normed hidden states: lm_head reads them through the xn map
     if (!(skip & 128)) B2S_TRY(skinny_gemm_maps(st, m->m_lm_w, m->m_x_xn, m->ws_logits, m->V_r, H, n_seq, m->d_idle, m->d_gen, 2 * L));
     LLM_MARK(11);
-    if (!(skip & 128)) B2S_CUDA(launch_dependent(llm_argmax_kernel, dim3(n_seq), dim3(256), st, m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r,
+    if (!(skip & 128)) B2S_CUDA(launch_dependent(llm_argmax_kernel, dim3(n_seq, llm_amax_split()), dim3(256), st, m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r,
                               m->amax(m->comm), m->peer_comm ? m->amax(m->peer_comm) : (AmaxSlot *)nullptr, myf, peerf,
-                              (const uint32_t *)m->d_gen, k, m->d_next_tok, m->d_out_tokens, (const int32_t *)m->d_out_pos, m->max_new_cap));
+                              (const uint32_t *)m->d_gen, k, m->d_next_tok, m->d_out_tokens, (const int32_t *)m->d_out_pos, m->max_new_cap,
+                              m->d_amax_key, m->d_amax_cnt));
     LLM_MARK(12);
     B2S_CUDA(launch_dependent(llm_step_end_kernel, dim3(1), dim3(32), st, m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 1));
     LLM_MARK(13);

@@ -889,11 +889,29 @@ llm_attn_decode_stream_kernel(const __grid_constant__ CUtensorMap tmap_k, const 
         for (int idx = ct; idx < G * 64; idx += NC) {
             const int r = idx >> 6, d = (idx & 63) * 2;
             float M = -INFINITY, num0 = 0.f, num1 = 0.f, den = 0.f;
-#pragma unroll 4
-            for (int p = 0; p < parts; ++p) {       // in part order: the result does not depend on which CTA merges
-                const float *pp = part_ws + ((int64_t)(c_first + p) * 2 + (p == 0 ? 1 : 0)) * 8 * LDS_PART_LD + r * LDS_PART_LD;
-                const float2 ml = __ldcg(reinterpret_cast<const float2 *>(pp + 128));
-                const float2 ov = __ldcg(reinterpret_cast<const float2 *>(pp + d));
+            // in part order (the result does not depend on which CTA merges).  The first four parts -- all of them unless a
+            // sequence is spread over more than four CTAs -- are loaded before the first use: one L2 round trip, not one per part
+            float2 ml4[4], ov4[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                ml4[p] = make_float2(-INFINITY, 0.f);
+                ov4[p] = make_float2(0.f, 0.f);
+                if (p < parts) {
+                    const float *pp = part_ws + ((int64_t)(c_first + p) * 2 + (p == 0 ? 1 : 0)) * 8 * LDS_PART_LD + r * LDS_PART_LD;
+                    ml4[p] = __ldcg(reinterpret_cast<const float2 *>(pp + 128));
+                    ov4[p] = __ldcg(reinterpret_cast<const float2 *>(pp + d));
+                }
+            }
+            for (int p = 0; p < parts; ++p) {
+                float2 ml, ov;
+                if (p < 4) {
+                    ml = p == 0 ? ml4[0] : p == 1 ? ml4[1] : p == 2 ? ml4[2] : ml4[3];
+                    ov = p == 0 ? ov4[0] : p == 1 ? ov4[1] : p == 2 ? ov4[2] : ov4[3];
+                } else {
+                    const float *pp = part_ws + ((int64_t)(c_first + p) * 2) * 8 * LDS_PART_LD + r * LDS_PART_LD;
+                    ml = __ldcg(reinterpret_cast<const float2 *>(pp + 128));
+                    ov = __ldcg(reinterpret_cast<const float2 *>(pp + d));
+                }
                 const float Mn = fmaxf(M, ml.x);
                 const float ca = (M == -INFINITY) ? 0.f : exp2f(M - Mn), cb = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - Mn);
                 num0 = num0 * ca + ov.x * cb;

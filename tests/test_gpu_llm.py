@@ -70,12 +70,12 @@ def test_device_init_is_the_numpy_twin(native, tp_size, tp_rank):
         m.free()
 
 
-def _check_step(logits, ref_logits, tok, ref_tok, what):
+def _check_step(logits, ref_logits, tok, ref_tok, what, bar=2e-2):
     scale = np.abs(ref_logits).max()
     err = np.abs(logits - ref_logits).max()
-    assert err <= 2e-2 * scale, "{}: logits off by {:.3e} (scale {:.3e})".format(what, err, scale)
+    assert err <= bar * scale, "{}: logits off by {:.3e} (scale {:.3e})".format(what, err, scale)
     top2 = np.sort(ref_logits)[-2:]
-    if top2[1] - top2[0] > 4e-2 * scale:
+    if top2[1] - top2[0] > 2 * bar * scale:
         assert tok == ref_tok, "{}: token {} != {}".format(what, tok, ref_tok)
     return tok == ref_tok
 
@@ -165,6 +165,42 @@ def test_full_batch_of_ragged_contexts_matches_oracle(native):
                 if alive[i]:
                     alive[i] = _check_step(lg[i], refs[i][1][step], int(toks[i]), int(refs[i][0][step]), "seq {} (len {}) step {}".format(i, lens[i], step))
         assert sum(alive) >= len(prompts) - 8     # same 3-in-4 allowance as the 4-sequence test above
+    finally:
+        m.free()
+
+
+def test_group_of_eight_query_heads_matches_oracle(native):
+    # n_heads / n_kv_heads = 8 selects the other shape of the stream-form decode attention (two consumer groups on an even ring,
+    # one CTA per SM: the merge area of 8 x 8 states does not fit twice) and fills all 8 columns of its transposed MMA tiles
+    from oracle import llm_oracle
+    spec = L.LlamaSpec(vocab_size=512, hidden_size=1024, intermediate_size=512, num_hidden_layers=2, num_attention_heads=8,
+                       num_key_value_heads=1, head_dim=128, rope_theta=500000.0, rms_norm_eps=1e-5)
+    sd = L.random_state_dict(spec, seed=44, std=0.05)
+    rng = np.random.default_rng(5)
+    lens = [5, 70, 130, 64, 200, 1]
+    prompts = [rng.integers(0, spec.vocab_size, n) for n in lens]
+    n_new = 4
+    m = native.Llm(device=0, vocab=spec.vocab_size, hidden=spec.hidden_size, inter=spec.intermediate_size,
+                   n_layers=spec.num_hidden_layers, n_heads=spec.num_attention_heads, n_kv_heads=spec.num_key_value_heads,
+                   max_batch=8, max_ctx=256, rope_theta=spec.rope_theta, rms_eps=spec.rms_norm_eps)
+    try:
+        for (name, layer), arr in L.shard_state_dict(sd, spec).items():
+            m.load_tensor(name, layer, arr)
+        m.keep_logits(True)
+        m.prefill(prompts)
+        refs = [llm_oracle.greedy_generate(sd, spec, p, n_new) for p in prompts]
+        alive = [True] * len(prompts)
+        for step in range(n_new):
+            if step:
+                m.decode(1, use_graph=bool(step & 1))
+            lg = m.logits()
+            toks = m.tokens(step + 1)[:, step]
+            for i in range(len(prompts)):
+                if alive[i]:
+                    # hidden 1024 (twice the width the 2e-2 bar was calibrated on): bf16 deviation of the PREFILL logits reaches 2.5e-2
+                    alive[i] = _check_step(lg[i], refs[i][1][step], int(toks[i]), int(refs[i][0][step]),
+                                           "seq {} (len {}) step {}".format(i, lens[i], step), bar=4e-2)
+        assert sum(alive) >= len(prompts) - 2
     finally:
         m.free()
 
