@@ -40,7 +40,8 @@ int gemm_tn(cudaStream_t st, const void *A, int64_t lda, const void *B, int64_t 
             const GemmEpilogue &ep);
 int skinny_make_maps(CUtensorMap *tw, CUtensorMap *tx, const void *W, int64_t n_out, int64_t K, const void *X, int64_t x_rows);
 int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows,
-                     const uint32_t *idle_flag = nullptr, const uint32_t *gen = nullptr, int idle_want = 0);
+                     const uint32_t *idle_flag = nullptr, const uint32_t *gen = nullptr, int idle_want = 0, float *y_peer = nullptr,
+                     uint32_t *peer_done = nullptr, int *grid_out = nullptr);
 int llm_attn_prefill(cudaStream_t st, const void *qkv, int ld_qkv, const void *kc, const void *vc, const int32_t *cu_seqlens,
                      const int32_t *slots, const int32_t *page_table, int pages_per_seq, void *out, int ld_out, int n_seq,
                      int max_seqlen, int hq_r, int kvh_r, float scale);
@@ -216,7 +217,8 @@ template <bool F32>
 __global__ void __launch_bounds__(256)
 llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *zero_buf, uint32_t *my_flags, uint32_t *peer_flags,
                       const uint32_t *gen, int k, const float *__restrict__ w, float *__restrict__ h,
-                      __nv_bfloat16 *__restrict__ xn, int H, float eps, uint32_t *idle_flag)
+                      __nv_bfloat16 *__restrict__ xn, int H, float eps, uint32_t *idle_flag, const uint32_t *pushed_cnt = nullptr,
+                      const uint32_t *dstep = nullptr, int pushes_per_step = 0)
 {
     __shared__ float red[8];
     sm100::griddep_launch_dependents();
@@ -225,7 +227,24 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
     // own dependency wait) that HBM is idle for the next few microseconds (skinny.cu)
     if (idle_flag && blockIdx.x == 0 && threadIdx.x == 0)
         *reinterpret_cast<volatile uint32_t *>(idle_flag) = *reinterpret_cast<const volatile uint32_t *>(gen) * 1024u + (uint32_t)(k + 1);
-    tp_exchange_point(my_flags, peer_flags, gen, k);
+    // PUSH form of the exchange (decode): the peer's projection has ADDED its partial into `mine` over NVLink and counted every
+    // one of its CTAs on pushed_cnt[k]; once (step + 1) x grid counts are in, `mine` is the full sum -- no flag that a later
+    // kernel of the peer would have to send, no peer read.  PULL form (prefill): flag exchange, then the peer's partial is read.
+    const bool pushed = F32 && pushed_cnt != nullptr;
+    if (pushed) {
+        if (threadIdx.x == 0) {
+            const uint32_t want = (*reinterpret_cast<const volatile uint32_t *>(dstep) + 1u) * (uint32_t)pushes_per_step;
+            const long long t0 = clock64();
+            while ((int32_t)(ld_acquire_sys(pushed_cnt + k) - want) < 0) {
+                if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a lost peer must not hang the GPU
+                __nanosleep(32);
+            }
+        }
+        __syncthreads();
+        peer = nullptr;
+    } else {
+        tp_exchange_point(my_flags, peer_flags, gen, k);
+    }
     const int t = blockIdx.x;
     // Every load of the row is issued before the first use: the peer's partial comes over NVLink (~2.5 us per round trip), and
     // a load -> add -> store loop pays that once per 1024 columns (4 round trips at H = 4096: 10 of the 15 us this kernel took in
@@ -270,7 +289,7 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
         if (i < H) {
             float4 r = v[it];
             r.x += pa[it].x + pr[it].x; r.y += pa[it].y + pr[it].y; r.z += pa[it].z + pr[it].z; r.w += pa[it].w + pr[it].w;
-            if (F32 && zero_buf) *reinterpret_cast<float4 *>(zero_buf + (int64_t)t * H + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (F32 && zero_buf) *reinterpret_cast<float4 *>(zero_buf + (int64_t)t * H + i) = make_float4(0.f, 0.f, 0.f, 0.f);   // pull: the OLDER buffer; push: `mine` itself
             *reinterpret_cast<float4 *>(h + (int64_t)t * H + i) = r;
             v[it] = r;
             ss += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
@@ -506,7 +525,7 @@ llm_argmax_kernel(float *__restrict__ logits, float *__restrict__ keep, int V_r,
 }
 
 // end of a step: the step counter advances; decode steps also advance context lengths / output positions
-__global__ void llm_step_end_kernel(uint32_t *gen, int32_t *ctx_len, int32_t *out_pos, int n_seq, int is_decode)
+__global__ void llm_step_end_kernel(uint32_t *gen, int32_t *ctx_len, int32_t *out_pos, int n_seq, int is_decode, uint32_t *dstep)
 {
     sm100::griddep_launch_dependents();
     sm100::griddep_wait();
@@ -515,7 +534,10 @@ __global__ void llm_step_end_kernel(uint32_t *gen, int32_t *ctx_len, int32_t *ou
         if (is_decode) ctx_len[b] += 1;
         out_pos[b] += 1;
     }
-    if (b == 0) *gen += 1u;
+    if (b == 0) {
+        *gen += 1u;
+        if (is_decode && dstep) *dstep += 1u;     // decode steps completed: the pushed-partial counters of a TP pair advance with it
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -559,6 +581,10 @@ struct Llm {
     uint32_t *d_gen = nullptr;
     unsigned long long *d_amax_key = nullptr;   // [LLM_MAXB] packed (value, index) maxima of the split argmax
     int *d_amax_cnt = nullptr;                  // [LLM_MAXB] arrivals
+    uint32_t *d_dstep = nullptr;  // decode steps completed (device side)
+    size_t off_cnt = 0;           // exchange block: per exchange point, CTAs of the peer's projection that have pushed their partial
+    int tp_push = 0;              // decode all-reduce: 0 = pull (flag + peer read); 1 (B2S_LLM_TP_PUSH=1) = push (remote reductions + counts):
+                                  // measured SLOWER, 3.21 vs 2.60 ms per step -- NVLink atomics are no substitute for one bulk read
     uint32_t *d_idle = nullptr;   // [2] idle-HBM signals of the decode step (raised by reduce_rms / SwiGLU, polled by the next projection)
     int32_t *h_stage = nullptr;   // pinned staging for token metadata
     int max_new_cap = 0;
@@ -572,6 +598,7 @@ struct Llm {
 
     uint32_t *flags(unsigned char *base) const { return reinterpret_cast<uint32_t *>(base); }
     AmaxSlot *amax(unsigned char *base) const { return reinterpret_cast<AmaxSlot *>(base + off_amax); }
+    uint32_t *pushed(unsigned char *base) const { return reinterpret_cast<uint32_t *>(base + off_cnt); }
 
     ~Llm()
     {
@@ -681,7 +708,10 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     off = (size_t)round_up((int64_t)off, 256);
     for (int i = 0; i < 2; ++i) { m->off_pdec[i] = off; off += (size_t)LLM_MAXB * H * 4; }
     for (int i = 0; i < 2; ++i) { m->off_ppre[i] = off; off += (size_t)Tp * H * 2; }
+    m->off_cnt = off;
+    off += (size_t)LLM_FLAGS * 4;
     m->comm_bytes = off;
+    if (const char *e = getenv("B2S_LLM_TP_PUSH")) m->tp_push = e[0] != '0';
     LA(m->comm, off);
     LA(m->d_tokens, Tp);
     LA(m->d_tok_seq, Tp);
@@ -694,6 +724,7 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     LA(m->d_out_tokens, (int64_t)LLM_MAXB * m->max_new_cap);
     LA(m->d_gen, 4);
     LA(m->d_idle, 4);
+    LA(m->d_dstep, 4);
     LA(m->d_amax_key, LLM_MAXB);
     LA(m->d_amax_cnt, LLM_MAXB);
 #undef LA
@@ -882,7 +913,7 @@ static int llm_prefill(Llm *m, cudaStream_t st, int n_seq, const int32_t *tokens
     llm_argmax_kernel<<<dim3(n_seq, llm_amax_split()), 256, 0, st>>>(m->ws_logits, m->keep_logits, m->V_r, m->cfg.tp_rank * m->V_r, m->amax(m->comm),
                                              m->peer_comm ? m->amax(m->peer_comm) : nullptr, myf, peerf, m->d_gen, k, m->d_next_tok,
                                              m->d_out_tokens, m->d_out_pos, m->max_new_cap, m->d_amax_key, m->d_amax_cnt);
-    llm_step_end_kernel<<<1, 32, 0, st>>>(m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 0);
+    llm_step_end_kernel<<<1, 32, 0, st>>>(m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 0, m->d_dstep);
     count_launch(2);
     B2S_CUDA(cudaGetLastError());
     return 0;
@@ -964,8 +995,14 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
             float *mine = reinterpret_cast<float *>(m->comm + m->off_pdec[k & 1]);
             float *older = reinterpret_cast<float *>(m->comm + m->off_pdec[(k & 1) ^ 1]);
             const void *peer = m->peer_comm ? m->peer_comm + m->off_pdec[k & 1] : nullptr;
+            // tensor-parallel pair, push form: this rank's projection also adds its partial into the PEER's buffer and counts
+            // its CTAs there; the consumer below then reads (and clears) only local memory
+            const bool push = m->peer_comm != nullptr && m->tp_push;
+            float *push_to = push ? reinterpret_cast<float *>(m->peer_comm + m->off_pdec[k & 1]) : nullptr;
+            uint32_t *push_cnt = push ? m->pushed(m->peer_comm) + k : nullptr;
+            int pushes = 0;
             if (half == 0) {
-                if (!(skip & 16)) B2S_TRY(skinny_gemm_maps(st, y.m_o_w, m->m_x_attn, mine, H, m->hq_r * LLM_HD, n_seq));
+                if (!(skip & 16)) B2S_TRY(skinny_gemm_maps(st, y.m_o_w, m->m_x_attn, mine, H, m->hq_r * LLM_HD, n_seq, nullptr, nullptr, 0, push_to, push_cnt, &pushes));
                 LLM_MARK(5);
                 ++nl;
             } else {
@@ -974,13 +1011,14 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
                 if (!(skip & 4)) B2S_CUDA(launch_dependent(llm_swiglu_decode_kernel, dim3((n_seq * (m->I_r / 4) + 255) / 256), dim3(256), st, m->ws_gu, m->act,
                                           (int64_t)n_seq, m->I_r, m->d_idle + 1, (const uint32_t *)m->d_gen, l + 1));
                 LLM_MARK(8);
-                if (!(skip & 64)) B2S_TRY(skinny_gemm_maps(st, y.m_down_w, m->m_x_act, mine, H, m->I_r, n_seq, m->d_idle + 1, m->d_gen, l + 1));
+                if (!(skip & 64)) B2S_TRY(skinny_gemm_maps(st, y.m_down_w, m->m_x_act, mine, H, m->I_r, n_seq, m->d_idle + 1, m->d_gen, l + 1, push_to, push_cnt, &pushes));
                 LLM_MARK(9);
                 nl += 3;
             }
             const float *w = half == 0 ? y.ln2 : (l + 1 < L ? m->layers[l + 1].ln1 : m->final_norm);
-            if (!(skip & 2)) B2S_CUDA(launch_dependent(llm_reduce_rms_kernel<true>, dim3(n_seq), dim3(256), st, (const void *)mine, peer, older, myf, peerf,
-                                      (const uint32_t *)m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps, m->d_idle));
+            if (!(skip & 2)) B2S_CUDA(launch_dependent(llm_reduce_rms_kernel<true>, dim3(n_seq), dim3(256), st, (const void *)mine, peer, push ? mine : older,
+                                      myf, peerf, (const uint32_t *)m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps, m->d_idle,
+                                      push ? (const uint32_t *)m->pushed(m->comm) : (const uint32_t *)nullptr, (const uint32_t *)m->d_dstep, pushes));
             LLM_MARK(half == 0 ? 6 : 10);
             ++nl;
         }
@@ -993,7 +1031,7 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
                               (const uint32_t *)m->d_gen, k, m->d_next_tok, m->d_out_tokens, (const int32_t *)m->d_out_pos, m->max_new_cap,
                               m->d_amax_key, m->d_amax_cnt));
     LLM_MARK(12);
-    B2S_CUDA(launch_dependent(llm_step_end_kernel, dim3(1), dim3(32), st, m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 1));
+    B2S_CUDA(launch_dependent(llm_step_end_kernel, dim3(1), dim3(32), st, m->d_gen, m->d_ctx_len, m->d_out_pos, n_seq, 1, m->d_dstep));
     LLM_MARK(13);
     nl += 3;
     B2S_CUDA(cudaGetLastError());

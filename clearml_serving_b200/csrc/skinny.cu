@@ -55,6 +55,11 @@ __device__ __forceinline__ void red_add(float *addr, float a)
 {
     asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(a) : "memory");
 }
+// system scope: the accumulator is also the target of the tensor-parallel peer's reductions (over NVLink)
+__device__ __forceinline__ void red_add_sys(float *addr, float a)
+{
+    asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(a) : "memory");
+}
 
 // SK_STAGES = 10: one CTA per SM; SK_STAGES = 5: two CTAs per SM (same bytes in flight per SM) -- the second
 // form lets the CTAs of the NEXT projection move in, and start streaming their weights, as soon as half an SM
@@ -63,7 +68,7 @@ template <int SK_STAGES>
 __global__ void __launch_bounds__(SK_THREADS, SK_STAGES > 5 ? 1 : 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                    float *__restrict__ y, int n_out, int m_rows, int num_k, int total_units, int l2_ahead,
-                   const uint32_t *idle_flag, const uint32_t *gen, int idle_want)
+                   const uint32_t *idle_flag, const uint32_t *gen, int idle_want, float *__restrict__ y_peer, uint32_t *peer_done)
 {
     using S = SkSmem<SK_STAGES>;
     extern __shared__ unsigned char smem_raw[];
@@ -197,12 +202,28 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
             const int n = tile * SK_BM + q * 32 + lane;
-            if (n < n_out) {
+            if (n < n_out && !y_peer) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (j < m_rows) red_add(y + (size_t)j * n_out + n, __uint_as_float(v[j]));
+            } else if (n < n_out) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < m_rows) red_add_sys(y + (size_t)j * n_out + n, __uint_as_float(v[j]));
+                // tensor-parallel pair: the same partial is ALSO added into the peer's accumulator over NVLink (a row-parallel
+                // projection's all-reduce as two pushes: afterwards both ranks hold the full sum locally, llm.cu)
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < m_rows) red_add_sys(y_peer + (size_t)j * n_out + n, __uint_as_float(v[j]));
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+        if (peer_done) {
+            // this CTA's pushes are complete: count it on the PEER (release at system scope after a barrier of the four
+            // epilogue warps, so every warp's reductions are ordered before the count).  The peer's consumer kernel waits
+            // for (step + 1) x grid counts instead of a flag that a LATER kernel of this rank would have to send.
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            if (warp == 4 && lane == 0) asm volatile("red.release.sys.global.add.u32 [%0], 1;\n" ::"l"(peer_done) : "memory");
         }
     }
 
@@ -237,7 +258,8 @@ int skinny_make_maps(CUtensorMap *tw, CUtensorMap *tx, const void *W, int64_t n_
 
 template <int STAGES>
 static int skinny_launch(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int m_rows, int num_k,
-                         int64_t units, int ctas_per_sm, const uint32_t *idle_flag, const uint32_t *gen, int idle_want)
+                         int64_t units, int ctas_per_sm, const uint32_t *idle_flag, const uint32_t *gen, int idle_want, float *y_peer,
+                         uint32_t *peer_done, int *grid_out)
 {
     using S = SkSmem<STAGES>;
     static std::once_flag once;
@@ -263,13 +285,14 @@ static int skinny_launch(cudaStream_t st, const CUtensorMap &tw, const CUtensorM
     // units per CTA prefetched into L2 behind the ring once the predecessor signals an idle HBM (B2S_SKINNY_L2_AHEAD, 0 = off)
     static const int l2_ahead = []() { const char *e = getenv("B2S_SKINNY_L2_AHEAD"); return e ? atoi(e) : 4; }();
     B2S_CUDA(cudaLaunchKernelEx(&cfg, skinny_gemm_kernel<STAGES>, tw, tx, y, n_out, m_rows < SK_BN ? m_rows : SK_BN, num_k, (int)units,
-                                l2_ahead, idle_flag, gen, idle_want));
+                                l2_ahead, idle_flag, gen, idle_want, y_peer, peer_done));
+    if (grid_out) *grid_out = grid;
     count_launch();
     return 0;
 }
 
 int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &tx, float *y, int n_out, int K, int m_rows,
-                     const uint32_t *idle_flag, const uint32_t *gen, int idle_want)
+                     const uint32_t *idle_flag, const uint32_t *gen, int idle_want, float *y_peer, uint32_t *peer_done, int *grid_out)
 {
     if (n_out <= 0 || K <= 0) return 0;
     const int num_k = (K + SK_BK - 1) / SK_BK;
@@ -277,8 +300,8 @@ int skinny_gemm_maps(cudaStream_t st, const CUtensorMap &tw, const CUtensorMap &
     const int64_t units = (int64_t)tiles * num_k;
     if (units > INT32_MAX) return fail(B2S_ERR_INVALID, "skinny gemm: problem too large");
     static const int per_sm = []() { const char *e = getenv("B2S_SKINNY_CTAS"); return (e && e[0] == '1') ? 1 : 2; }();
-    return per_sm == 1 ? skinny_launch<10>(st, tw, tx, y, n_out, m_rows, num_k, units, 1, idle_flag, gen, idle_want)
-                       : skinny_launch<5>(st, tw, tx, y, n_out, m_rows, num_k, units, 2, idle_flag, gen, idle_want);
+    return per_sm == 1 ? skinny_launch<10>(st, tw, tx, y, n_out, m_rows, num_k, units, 1, idle_flag, gen, idle_want, y_peer, peer_done, grid_out)
+                       : skinny_launch<5>(st, tw, tx, y, n_out, m_rows, num_k, units, 2, idle_flag, gen, idle_want, y_peer, peer_done, grid_out);
 }
 
 }  // namespace b2s
@@ -292,5 +315,5 @@ extern "C" B2S_API int b2s_op_skinny_gemm(int device, void *cuda_stream, const v
     B2S_CUDA(cudaSetDevice(device));
     CUtensorMap tw, tx;
     B2S_TRY(skinny_make_maps(&tw, &tx, W, n_out, K, X, m));
-    return skinny_gemm_maps(static_cast<cudaStream_t>(cuda_stream), tw, tx, y, n_out, K, m, nullptr, nullptr, 0);
+    return skinny_gemm_maps(static_cast<cudaStream_t>(cuda_stream), tw, tx, y, n_out, K, m, nullptr, nullptr, 0, nullptr, nullptr, nullptr);
 }
