@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256)
 llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *zero_buf, uint32_t *my_flags, uint32_t *peer_flags,
                       const uint32_t *gen, int k, const float *__restrict__ w, float *__restrict__ h,
                       __nv_bfloat16 *__restrict__ xn, int H, float eps, uint32_t *idle_flag, const uint32_t *pushed_cnt = nullptr,
-                      const uint32_t *dstep = nullptr, int pushes_per_step = 0)
+                      const uint32_t *dstep = nullptr, int pushes_per_step = 0, int data_pushed = 0)
 {
     __shared__ float red[8];
     sm100::griddep_launch_dependents();
@@ -227,9 +227,12 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
     // own dependency wait) that HBM is idle for the next few microseconds (skinny.cu)
     if (idle_flag && blockIdx.x == 0 && threadIdx.x == 0)
         *reinterpret_cast<volatile uint32_t *>(idle_flag) = *reinterpret_cast<const volatile uint32_t *>(gen) * 1024u + (uint32_t)(k + 1);
-    // PUSH form of the exchange (decode): the peer's projection has ADDED its partial into `mine` over NVLink and counted every
-    // one of its CTAs on pushed_cnt[k]; once (step + 1) x grid counts are in, `mine` is the full sum -- no flag that a later
-    // kernel of the peer would have to send, no peer read.  PULL form (prefill): flag exchange, then the peer's partial is read.
+    // Decode exchange, COUNT form (B2S_LLM_TP_PUSH=0): every CTA of the peer's projection counts itself on pushed_cnt[k] when its partial
+    // sums are out (red.release.sys after its epilogue); once (step + 1) x grid counts are in, the peer's partial is complete and
+    // is read over NVLink -- without waiting for the peer's NEXT kernel (this one, on its side) to start and send a flag.
+    // PUSH form (data_pushed, B2S_LLM_TP_PUSH=1, slower): the peer has also ADDED its partial into `mine`: no peer read.
+    // FLAG form (default, and the prefill): tp_exchange_point, then the peer's partial is read.  Measured 2.57 / 2.78 / 3.21 ms per
+    // TP2 decode step for flag / count / push: system-scope traffic inside the projection costs more than it saves.
     const bool pushed = F32 && pushed_cnt != nullptr;
     if (pushed) {
         if (threadIdx.x == 0) {
@@ -241,7 +244,7 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
             }
         }
         __syncthreads();
-        peer = nullptr;
+        if (data_pushed) peer = nullptr;        // else: COUNT form -- the count replaces the flag, the partial is still pulled
     } else {
         tp_exchange_point(my_flags, peer_flags, gen, k);
     }
@@ -583,8 +586,10 @@ struct Llm {
     int *d_amax_cnt = nullptr;                  // [LLM_MAXB] arrivals
     uint32_t *d_dstep = nullptr;  // decode steps completed (device side)
     size_t off_cnt = 0;           // exchange block: per exchange point, CTAs of the peer's projection that have pushed their partial
-    int tp_push = 0;              // decode all-reduce: 0 = pull (flag + peer read); 1 (B2S_LLM_TP_PUSH=1) = push (remote reductions + counts):
-                                  // measured SLOWER, 3.21 vs 2.60 ms per step -- NVLink atomics are no substitute for one bulk read
+    int tp_push = -1;             // decode all-reduce (B2S_LLM_TP_PUSH): -1 = flag from the consumer kernel + peer read (default, 2.57 ms per
+                                  // TP2 step); 0 = per-CTA arrival counts on the peer + peer read (2.78: 296 system-scope releases per projection
+                                  // delay every CTA's exit); 1 = push, remote reductions + counts (3.21: NVLink atomics are no substitute for
+                                  // one bulk read)
     uint32_t *d_idle = nullptr;   // [2] idle-HBM signals of the decode step (raised by reduce_rms / SwiGLU, polled by the next projection)
     int32_t *h_stage = nullptr;   // pinned staging for token metadata
     int max_new_cap = 0;
@@ -711,7 +716,7 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     m->off_cnt = off;
     off += (size_t)LLM_FLAGS * 4;
     m->comm_bytes = off;
-    if (const char *e = getenv("B2S_LLM_TP_PUSH")) m->tp_push = e[0] != '0';
+    if (const char *e = getenv("B2S_LLM_TP_PUSH")) m->tp_push = atoi(e);
     LA(m->comm, off);
     LA(m->d_tokens, Tp);
     LA(m->d_tok_seq, Tp);
@@ -997,9 +1002,9 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
             const void *peer = m->peer_comm ? m->peer_comm + m->off_pdec[k & 1] : nullptr;
             // tensor-parallel pair, push form: this rank's projection also adds its partial into the PEER's buffer and counts
             // its CTAs there; the consumer below then reads (and clears) only local memory
-            const bool push = m->peer_comm != nullptr && m->tp_push;
+            const bool push = m->peer_comm != nullptr && m->tp_push == 1, counted = m->peer_comm != nullptr && m->tp_push >= 0;
             float *push_to = push ? reinterpret_cast<float *>(m->peer_comm + m->off_pdec[k & 1]) : nullptr;
-            uint32_t *push_cnt = push ? m->pushed(m->peer_comm) + k : nullptr;
+            uint32_t *push_cnt = counted ? m->pushed(m->peer_comm) + k : nullptr;
             int pushes = 0;
             if (half == 0) {
                 if (!(skip & 16)) B2S_TRY(skinny_gemm_maps(st, y.m_o_w, m->m_x_attn, mine, H, m->hq_r * LLM_HD, n_seq, nullptr, nullptr, 0, push_to, push_cnt, &pushes));
@@ -1018,7 +1023,8 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
             const float *w = half == 0 ? y.ln2 : (l + 1 < L ? m->layers[l + 1].ln1 : m->final_norm);
             if (!(skip & 2)) B2S_CUDA(launch_dependent(llm_reduce_rms_kernel<true>, dim3(n_seq), dim3(256), st, (const void *)mine, peer, push ? mine : older,
                                       myf, peerf, (const uint32_t *)m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps, m->d_idle,
-                                      push ? (const uint32_t *)m->pushed(m->comm) : (const uint32_t *)nullptr, (const uint32_t *)m->d_dstep, pushes));
+                                      counted ? (const uint32_t *)m->pushed(m->comm) : (const uint32_t *)nullptr, (const uint32_t *)m->d_dstep, pushes,
+                                      push ? 1 : 0));
             LLM_MARK(half == 0 ? 6 : 10);
             ++nl;
         }
