@@ -533,6 +533,7 @@ llm_attn_decode_stream_kernel(const __grid_constant__ CUtensorMap tmap_k, const 
     float *sm_m = reinterpret_cast<float *>(smem + SM::OFF_MERGE), *sm_l = sm_m + 8 * NW, *sm_o = sm_l + 8 * NW;
     int *prefix = reinterpret_cast<int *>(smem + SM::OFF_MISC);
     int *s_flag = prefix + 34;      // [2]
+    int *s_fast = prefix + 33;      // prefix[] uses 0 .. 32
     int *s_pos = prefix + 36, *s_slot = s_pos + 32;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + SM::OFF_MISC + 100 * 4);
     uint64_t *empty_bar = full_bar + LDS_STAGES;
@@ -627,11 +628,70 @@ llm_attn_decode_stream_kernel(const __grid_constant__ CUtensorMap tmap_k, const 
     long long wait_cycles = 0;
     int n_seg = 0;
     int n_pend = 0, pend_b[2] = {0, 0}, pend_h[2] = {0, 0}, pend_parts[2] = {0, 0}, pend_first[2] = {0, 0};   // split segments of this range (head and / or tail)
+    // merge the parts of a split (b, h) from the workspace, in part order, and clear its slice of the QKV accumulator
+    auto merge_from_ws = [&](int b, int h, int parts, int c_first) {
+        for (int idx = ct; idx < G * 64; idx += NC) {
+            const int r = idx >> 6, d = (idx & 63) * 2;
+            float M = -INFINITY, num0 = 0.f, num1 = 0.f, den = 0.f;
+            // in part order (the result does not depend on which CTA merges).  The first four parts -- all of them unless a
+            // sequence is spread over more than four CTAs -- are loaded before the first use: one L2 round trip, not one per part
+            float2 ml4[4], ov4[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                ml4[p] = make_float2(-INFINITY, 0.f);
+                ov4[p] = make_float2(0.f, 0.f);
+                if (p < parts) {
+                    const float *pp = part_ws + ((int64_t)(c_first + p) * 2 + (p == 0 ? 1 : 0)) * 8 * LDS_PART_LD + r * LDS_PART_LD;
+                    ml4[p] = __ldcg(reinterpret_cast<const float2 *>(pp + 128));
+                    ov4[p] = __ldcg(reinterpret_cast<const float2 *>(pp + d));
+                }
+            }
+            for (int p = 0; p < parts; ++p) {
+                float2 ml, ov;
+                if (p < 4) {
+                    ml = p == 0 ? ml4[0] : p == 1 ? ml4[1] : p == 2 ? ml4[2] : ml4[3];
+                    ov = p == 0 ? ov4[0] : p == 1 ? ov4[1] : p == 2 ? ov4[2] : ov4[3];
+                } else {
+                    const float *pp = part_ws + ((int64_t)(c_first + p) * 2) * 8 * LDS_PART_LD + r * LDS_PART_LD;
+                    ml = __ldcg(reinterpret_cast<const float2 *>(pp + 128));
+                    ov = __ldcg(reinterpret_cast<const float2 *>(pp + d));
+                }
+                const float Mn = fmaxf(M, ml.x);
+                const float ca = (M == -INFINITY) ? 0.f : exp2f(M - Mn), cb = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - Mn);
+                num0 = num0 * ca + ov.x * cb;
+                num1 = num1 * ca + ov.y * cb;
+                den = den * ca + ml.y * cb;
+                M = Mn;
+            }
+            const float inv = den > 0.f ? 1.0f / den : 0.f;
+            *reinterpret_cast<__nv_bfloat162 *>(out + (int64_t)b * ld_out + (h * G + r) * LA_D + d) = __floats2bfloat162_rn(num0 * inv, num1 * inv);
+        }
+        float *row = ws_qkv + (int64_t)b * QKV;
+        for (int idx = ct; idx < G * LA_D; idx += NC) row[h * G * LA_D + idx] = 0.f;
+        for (int idx = ct; idx < 2 * LA_D; idx += NC) row[(idx < LA_D ? hq_r + h : hq_r + kvh_r + h) * LA_D + (idx & (LA_D - 1))] = 0.f;
+    };
     while (f < f1) {
         const int b = w.b, h = w.h, j0 = w.j, nb = w.nb;
         const int seg0 = f - j0;                                       // flattened index of block 0 of (b, h)
         const int j1 = (f1 - seg0) < nb ? (f1 - seg0) : nb;            // blocks [j0, j1) are ours
         const bool whole = (j0 == 0 && j1 == nb);
+        int parts = 1, part = 0, c_first = cta;                        // the CTAs that share (b, h): consecutive, in block order
+        if (!whole) {
+            c_first = lds_owner(seg0, T, n_cta);
+            parts = lds_owner(seg0 + nb - 1, T, n_cta) - c_first + 1;
+            part = cta - c_first;
+        }
+        const int pkey = b * kvh_r + h;
+        // Part 0 is the TAIL of its CTA's range (processed last), every other part the HEAD of its CTA's range (processed first):
+        // the heads arrive on the pair's counter as soon as they are done, so when part 0 starts it normally finds all of them
+        // in, fetches their partials WHILE it works on its own blocks and finishes the row without an arrival of its own --
+        // no atomic and no dependent L2 round trip after the kernel's last block.  Anything else takes the arrival path below.
+        const bool try_fast = (parts >= 2 && parts <= 4 && part == 0);
+        if (try_fast && ct == 0) {
+            int seen;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(part_cnt + pkey) : "memory");
+            *s_fast = (seen == parts - 1);
+        }
         const int pos = s_pos[b];
         const int n_ctx = pos + 1;
         const bool has_last = (j1 == nb);
@@ -688,6 +748,25 @@ llm_attn_decode_stream_kernel(const __grid_constant__ CUtensorMap tmap_k, const 
         }
         lds_bar_consumers<NC>();
         if (warp == 1 && n_seg == 0) LDS_STAMP(3);
+        bool fast = try_fast && (*s_fast != 0);
+        float2 pf_ml[2][3], pf_ov[2][3];        // the other parts' (m, l) and o pair for this thread's (row, dim pair) items
+        auto fetch_parts = [&]() {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int idx = ct + it * NC;
+#pragma unroll
+                for (int p = 1; p < 4; ++p) {
+                    pf_ml[it][p - 1] = make_float2(-INFINITY, 0.f);
+                    pf_ov[it][p - 1] = make_float2(0.f, 0.f);
+                    if (p < parts && idx < G * 64) {
+                        const float *pp = part_ws + ((int64_t)(c_first + p) * 2) * 8 * LDS_PART_LD + (idx >> 6) * LDS_PART_LD;
+                        pf_ml[it][p - 1] = __ldcg(reinterpret_cast<const float2 *>(pp + 128));
+                        pf_ov[it][p - 1] = __ldcg(reinterpret_cast<const float2 *>(pp + (idx & 63) * 2));
+                    }
+                }
+            }
+        };
+        if (fast) fetch_parts();
         // TRANSPOSED products (the 8 columns of an m16n8k16 tile are the q heads of the group, no padded rows):
         //   S^T[16 keys, 8 heads] = K[16 keys, 128] . Q^T        8 MMAs per warp and block (the [16 q rows] form needs 16)
         //   O^T[128 dims, 8 heads] += V^T[128, 16 keys] . P^T    8 MMAs (16)
@@ -812,15 +891,23 @@ llm_attn_decode_stream_kernel(const __grid_constant__ CUtensorMap tmap_k, const 
                 }
             }
         }
+        // second chance for a tail part that started before its heads were in (a range that is ONE tail segment starts with the
+        // kernel): if they have arrived by now, fetch their partials here -- one L2 round trip, still no arrival of its own
+        if (try_fast && !fast && ct == 0) {
+            int seen;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(seen) : "l"(part_cnt + pkey) : "memory");
+            *s_fast = (seen == parts - 1);
+        }
         lds_bar_consumers<NC>();
-        int parts = 1, part = 0, c_first = cta;
-        if (!whole) {
-            c_first = lds_owner(seg0, T, n_cta);
-            parts = lds_owner(seg0 + nb - 1, T, n_cta) - c_first + 1;
-            part = cta - c_first;
+        if (try_fast && !fast && *s_fast != 0) {
+            fast = true;
+            fetch_parts();
         }
         float *my_part = part_ws + ((int64_t)cta * 2 + (part == 0 ? 1 : 0)) * 8 * LDS_PART_LD;
-        for (int idx = ct; idx < G * 64; idx += NC) {       // (row, dim pair) items
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {                    // (row, dim pair) items: G * 64 <= 2 NC
+            const int idx = ct + it * NC;
+            if (idx >= G * 64) break;
             const int r = idx >> 6, d = (idx & 63) * 2;
             float M = -INFINITY;
 #pragma unroll
@@ -835,7 +922,25 @@ llm_attn_decode_stream_kernel(const __grid_constant__ CUtensorMap tmap_k, const 
                 num1 = fmaf(wgt, ov.y, num1);
                 den = fmaf(wgt, sm_l[x * 8 + r], den);
             }
-            if (parts == 1) {
+            if (fast) {
+                // this CTA holds part 0 in registers and the other parts prefetched: merge in part order (same arithmetic, same
+                // order as merge_from_ws below: the row's bits do not depend on which path finished it)
+                float Mr = M, n0 = num0, n1 = num1, dn = den;
+#pragma unroll
+                for (int p = 1; p < 4; ++p) {
+                    if (p < parts) {
+                        const float2 ml = pf_ml[it][p - 1], ov = pf_ov[it][p - 1];
+                        const float Mn = fmaxf(Mr, ml.x);
+                        const float ca = (Mr == -INFINITY) ? 0.f : exp2f(Mr - Mn), cb = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - Mn);
+                        n0 = n0 * ca + ov.x * cb;
+                        n1 = n1 * ca + ov.y * cb;
+                        dn = dn * ca + ml.y * cb;
+                        Mr = Mn;
+                    }
+                }
+                M = Mr; num0 = n0; num1 = n1; den = dn;
+            }
+            if (parts == 1 || fast) {
                 const float inv = den > 0.f ? 1.0f / den : 0.f;
                 *reinterpret_cast<__nv_bfloat162 *>(out + (int64_t)b * ld_out + (h * G + r) * LA_D + d) = __floats2bfloat162_rn(num0 * inv, num1 * inv);
             } else {
@@ -843,12 +948,25 @@ llm_attn_decode_stream_kernel(const __grid_constant__ CUtensorMap tmap_k, const 
                 if (d == 0) __stcg(reinterpret_cast<float2 *>(my_part + r * LDS_PART_LD + 128), make_float2(M, den));
             }
         }
-        if (parts == 1) {
-            // sole reader of this (b, h): clear its slice of the accumulator for the next layer's projection
+        if (parts == 1 || fast) {
+            // this CTA finished (b, h): clear its slice of the accumulator for the next layer's projection
             for (int idx = ct; idx < G * LA_D; idx += NC) row[h * G * LA_D + idx] = 0.f;
             for (int idx = ct; idx < 2 * LA_D; idx += NC) row[(idx < LA_D ? hq_r + h : hq_r + kvh_r + h) * LA_D + (idx & (LA_D - 1))] = 0.f;
+            if (fast && ct == 0) part_cnt[pkey] = 0;        // every part has arrived: nobody touches the counter again in this launch
+        } else if (part > 0) {
+            // a HEAD part: arrive now (release / acquire at GPU scope by one thread between CTA barriers), the tail finds it in
+            lds_bar_consumers<NC>();
+            if (ct == 0) {
+                int old;
+                asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;\n" : "=r"(old) : "l"(part_cnt + pkey) : "memory");
+                const int last = (old == parts - 1);
+                if (last) part_cnt[pkey] = 0;
+                s_flag[0] = last;
+            }
+            lds_bar_consumers<NC>();
+            if (s_flag[0]) merge_from_ws(b, h, parts, c_first);   // the tail had already arrived (it took the arrival path)
         } else {
-            // split (b, h): the arrival (one fence + one atomic round trip) is paid once per CTA, after its range
+            // the TAIL part without the fast path: arrival after the range (one fence + one atomic round trip per CTA)
             if (n_pend == 0) { pend_b[0] = b; pend_h[0] = h; pend_parts[0] = parts; pend_first[0] = c_first; }
             else { pend_b[1] = b; pend_h[1] = h; pend_parts[1] = parts; pend_first[1] = c_first; }
             ++n_pend;
@@ -885,46 +1003,7 @@ llm_attn_decode_stream_kernel(const __grid_constant__ CUtensorMap tmap_k, const 
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         if (i >= n_pend || !s_flag[i]) continue;
-        const int b = pend_b[i], h = pend_h[i], parts = pend_parts[i], c_first = pend_first[i];
-        for (int idx = ct; idx < G * 64; idx += NC) {
-            const int r = idx >> 6, d = (idx & 63) * 2;
-            float M = -INFINITY, num0 = 0.f, num1 = 0.f, den = 0.f;
-            // in part order (the result does not depend on which CTA merges).  The first four parts -- all of them unless a
-            // sequence is spread over more than four CTAs -- are loaded before the first use: one L2 round trip, not one per part
-            float2 ml4[4], ov4[4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                ml4[p] = make_float2(-INFINITY, 0.f);
-                ov4[p] = make_float2(0.f, 0.f);
-                if (p < parts) {
-                    const float *pp = part_ws + ((int64_t)(c_first + p) * 2 + (p == 0 ? 1 : 0)) * 8 * LDS_PART_LD + r * LDS_PART_LD;
-                    ml4[p] = __ldcg(reinterpret_cast<const float2 *>(pp + 128));
-                    ov4[p] = __ldcg(reinterpret_cast<const float2 *>(pp + d));
-                }
-            }
-            for (int p = 0; p < parts; ++p) {
-                float2 ml, ov;
-                if (p < 4) {
-                    ml = p == 0 ? ml4[0] : p == 1 ? ml4[1] : p == 2 ? ml4[2] : ml4[3];
-                    ov = p == 0 ? ov4[0] : p == 1 ? ov4[1] : p == 2 ? ov4[2] : ov4[3];
-                } else {
-                    const float *pp = part_ws + ((int64_t)(c_first + p) * 2) * 8 * LDS_PART_LD + r * LDS_PART_LD;
-                    ml = __ldcg(reinterpret_cast<const float2 *>(pp + 128));
-                    ov = __ldcg(reinterpret_cast<const float2 *>(pp + d));
-                }
-                const float Mn = fmaxf(M, ml.x);
-                const float ca = (M == -INFINITY) ? 0.f : exp2f(M - Mn), cb = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - Mn);
-                num0 = num0 * ca + ov.x * cb;
-                num1 = num1 * ca + ov.y * cb;
-                den = den * ca + ml.y * cb;
-                M = Mn;
-            }
-            const float inv = den > 0.f ? 1.0f / den : 0.f;
-            *reinterpret_cast<__nv_bfloat162 *>(out + (int64_t)b * ld_out + (h * G + r) * LA_D + d) = __floats2bfloat162_rn(num0 * inv, num1 * inv);
-        }
-        float *row = ws_qkv + (int64_t)b * QKV;
-        for (int idx = ct; idx < G * LA_D; idx += NC) row[h * G * LA_D + idx] = 0.f;
-        for (int idx = ct; idx < 2 * LA_D; idx += NC) row[(idx < LA_D ? hq_r + h : hq_r + kvh_r + h) * LA_D + (idx & (LA_D - 1))] = 0.f;
+        merge_from_ws(pend_b[i], pend_h[i], pend_parts[i], pend_first[i]);
     }
     if (warp == 1) LDS_STAMP(8);
 #undef LDS_STAMP
