@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(256)
 llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *zero_buf, uint32_t *my_flags, uint32_t *peer_flags,
                       const uint32_t *gen, int k, const float *__restrict__ w, float *__restrict__ h,
                       __nv_bfloat16 *__restrict__ xn, int H, float eps, uint32_t *idle_flag, const uint32_t *pushed_cnt = nullptr,
-                      const uint32_t *dstep = nullptr, int pushes_per_step = 0, int data_pushed = 0)
+                      const uint32_t *dstep = nullptr, int pushes_per_step = 0, int data_pushed = 0, float *mail_out = nullptr,
+                      float *mail_in = nullptr)
 {
     __shared__ float red[8];
     sm100::griddep_launch_dependents();
@@ -233,8 +234,15 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
     // PUSH form (data_pushed, B2S_LLM_TP_PUSH=1, slower): the peer has also ADDED its partial into `mine`: no peer read.
     // FLAG form (default, and the prefill): tp_exchange_point, then the peer's partial is read.  Measured 2.57 / 2.78 / 3.21 ms per
     // TP2 decode step for flag / count / push: system-scope traffic inside the projection costs more than it saves.
-    const bool pushed = F32 && pushed_cnt != nullptr;
-    if (pushed) {
+    // MAIL form (default for the decode, B2S_LLM_TP_PUSH=2): no flag at all.  Each rank stores its partial row into the PEER's
+    // mailbox (plain 16-byte stores over NVLink) and polls its OWN mailbox, whose slots hold a sentinel until the peer's values
+    // land: the value is its own arrival flag (the forest kernel's row exchange, across two GPUs).  One NVLink flight instead of
+    // flag flight + poll + read round trip.
+    const bool mailed = F32 && mail_in != nullptr;
+    const bool pushed = F32 && !mailed && pushed_cnt != nullptr;
+    if (mailed) {
+        peer = nullptr;
+    } else if (pushed) {
         if (threadIdx.x == 0) {
             const uint32_t want = (*reinterpret_cast<const volatile uint32_t *>(dstep) + 1u) * (uint32_t)pushes_per_step;
             const long long t0 = clock64();
@@ -283,6 +291,36 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
                 pa[it] = make_float4(m0.x, m0.y, m1.x, m1.y);
             }
             v[it] = *reinterpret_cast<const float4 *>(h + (int64_t)t * H + i);
+        }
+    }
+    if (mailed) {
+        constexpr uint32_t EMPTY = 0xffffffffu;     // a NaN no computation produces; an (impossible) equal value is sent as 0x7fffffff
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int i = (it * 256 + threadIdx.x) * 4;
+            if (i < H) {
+                uint32_t a0 = __float_as_uint(pa[it].x), a1 = __float_as_uint(pa[it].y), a2 = __float_as_uint(pa[it].z), a3 = __float_as_uint(pa[it].w);
+                a0 = a0 == EMPTY ? 0x7fffffffu : a0; a1 = a1 == EMPTY ? 0x7fffffffu : a1;
+                a2 = a2 == EMPTY ? 0x7fffffffu : a2; a3 = a3 == EMPTY ? 0x7fffffffu : a3;
+                asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"l"(mail_out + (int64_t)t * H + i), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+            }
+        }
+        const long long t0 = clock64();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int i = (it * 256 + threadIdx.x) * 4;
+            if (i < H) {
+                float *slot = mail_in + (int64_t)t * H + i;
+                uint4 u;
+                for (;;) {
+                    u = ld_peer_v4(slot);       // relaxed, system scope: never served from L1
+                    if (u.x != EMPTY && u.y != EMPTY && u.z != EMPTY && u.w != EMPTY) break;
+                    if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a lost peer must not hang the GPU
+                }
+                pr[it] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+                // empty the slot for exchange k + 2 (the peer writes it again only after it has seen this rank's push for k + 1)
+                asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%1,%1,%1};\n" ::"l"(slot), "r"(EMPTY) : "memory");
+            }
         }
     }
     float ss = 0.f;
@@ -585,9 +623,10 @@ struct Llm {
     unsigned long long *d_amax_key = nullptr;   // [LLM_MAXB] packed (value, index) maxima of the split argmax
     int *d_amax_cnt = nullptr;                  // [LLM_MAXB] arrivals
     uint32_t *d_dstep = nullptr;  // decode steps completed (device side)
+    size_t off_mail[2] = {0, 0};  // exchange block: decode mailboxes, [32][H] fp32 each, slots hold 0xffffffff until the peer's partial lands
     size_t off_cnt = 0;           // exchange block: per exchange point, CTAs of the peer's projection that have pushed their partial
-    int tp_push = -1;             // decode all-reduce (B2S_LLM_TP_PUSH): -1 = flag from the consumer kernel + peer read (default, 2.57 ms per
-                                  // TP2 step); 0 = per-CTA arrival counts on the peer + peer read (2.78: 296 system-scope releases per projection
+    int tp_push = 2;              // decode all-reduce (B2S_LLM_TP_PUSH): 2 = mailboxes, the value is its own arrival flag (default, 2.46 ms);
+                                  // -1 = flag from the consumer kernel + peer read (2.57 ms per TP2 step); 0 = per-CTA arrival counts on the peer + peer read (2.78: 296 system-scope releases per projection
                                   // delay every CTA's exit); 1 = push, remote reductions + counts (3.21: NVLink atomics are no substitute for
                                   // one bulk read)
     uint32_t *d_idle = nullptr;   // [2] idle-HBM signals of the decode step (raised by reduce_rms / SwiGLU, polled by the next projection)
@@ -715,9 +754,12 @@ static int llm_create(int device, const b2s_llm_config *c, Llm **out)
     for (int i = 0; i < 2; ++i) { m->off_ppre[i] = off; off += (size_t)Tp * H * 2; }
     m->off_cnt = off;
     off += (size_t)LLM_FLAGS * 4;
+    off = (size_t)round_up((int64_t)off, 256);
+    for (int i = 0; i < 2; ++i) { m->off_mail[i] = off; off += (size_t)LLM_MAXB * H * 4; }
     m->comm_bytes = off;
     if (const char *e = getenv("B2S_LLM_TP_PUSH")) m->tp_push = atoi(e);
     LA(m->comm, off);
+    for (int i = 0; i < 2; ++i) cudaMemset(m->comm + m->off_mail[i], 0xff, (size_t)LLM_MAXB * H * 4);
     LA(m->d_tokens, Tp);
     LA(m->d_tok_seq, Tp);
     LA(m->d_tok_pos, Tp);
@@ -1002,7 +1044,8 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
             const void *peer = m->peer_comm ? m->peer_comm + m->off_pdec[k & 1] : nullptr;
             // tensor-parallel pair, push form: this rank's projection also adds its partial into the PEER's buffer and counts
             // its CTAs there; the consumer below then reads (and clears) only local memory
-            const bool push = m->peer_comm != nullptr && m->tp_push == 1, counted = m->peer_comm != nullptr && m->tp_push >= 0;
+            const bool push = m->peer_comm != nullptr && m->tp_push == 1, counted = m->peer_comm != nullptr && (m->tp_push == 0 || m->tp_push == 1);
+            const bool mail = m->peer_comm != nullptr && m->tp_push == 2;
             float *push_to = push ? reinterpret_cast<float *>(m->peer_comm + m->off_pdec[k & 1]) : nullptr;
             uint32_t *push_cnt = counted ? m->pushed(m->peer_comm) + k : nullptr;
             int pushes = 0;
@@ -1024,7 +1067,8 @@ static int llm_decode_enqueue(Llm *m, cudaStream_t st, int *n_launch, LlmTiming 
             if (!(skip & 2)) B2S_CUDA(launch_dependent(llm_reduce_rms_kernel<true>, dim3(n_seq), dim3(256), st, (const void *)mine, peer, push ? mine : older,
                                       myf, peerf, (const uint32_t *)m->d_gen, k, w, m->h, m->xn, H, m->cfg.rms_eps, m->d_idle,
                                       counted ? (const uint32_t *)m->pushed(m->comm) : (const uint32_t *)nullptr, (const uint32_t *)m->d_dstep, pushes,
-                                      push ? 1 : 0));
+                                      push ? 1 : 0, mail ? reinterpret_cast<float *>(m->peer_comm + m->off_mail[k & 1]) : (float *)nullptr,
+                                      mail ? reinterpret_cast<float *>(m->comm + m->off_mail[k & 1]) : (float *)nullptr));
             LLM_MARK(half == 0 ? 6 : 10);
             ++nl;
         }
