@@ -1047,7 +1047,9 @@ int llm_attn_decode(cudaStream_t st, float *ws_qkv, void *kc, void *vc, const in
             dbg_arg = dbg;
         }
         const bool two_per_sm = G <= 4;         // n_cta = SM count; the workspace holds 2 slots for each of 2 * n_cta CTAs
-        const int grid = two_per_sm ? 2 * n_cta : n_cta;
+        // B2S_LLM_ATTN_CTAS_PER_SM=1: launch the 2-per-SM shape with one CTA per SM (fewer, longer ranges: fewer split sequences)
+        static const int per_sm = []() { const char *e = getenv("B2S_LLM_ATTN_CTAS_PER_SM"); return (e && e[0] == '1') ? 1 : 2; }();
+        const int grid = two_per_sm ? per_sm * n_cta : n_cta;
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(two_per_sm ? 160 : 288);
         cfg.dynamicSmemBytes = two_per_sm ? LdsSmem<3, 1>::total(G) : LdsSmem<4, 2>::total(G);
