@@ -991,6 +991,10 @@ def _llama_workload(native, rank, world, local, dist, waves=3):
     return dict(
         workload="Llama-3-8B bf16 random-init (on-device deterministic init), prompt 512 + 128 new tokens, 32 sequences per wave, greedy",
         parallelism="tp{} x {} replica(s)".format(tp, replicas), metric="requests/sec",
+        kernels=dict(decode_attention="stream form (key blocks dealt to all SMs)" if os.environ.get("B2S_LLM_ATTN_STREAM", "1") != "0"
+                     else "one CTA per (sequence, kv head)",
+                     tp_decode_allreduce=(None if tp == 1 else {"2": "mailboxes (value = arrival flag)", "-1": "flag + peer read", "0": "arrival counts + peer read",
+                                                                "1": "remote reductions"}.get(os.environ.get("B2S_LLM_TP_PUSH", "2"), "mailboxes (value = arrival flag)"))),
         value=replicas * batch / ((pre + dec) * 1e-3), gen_tokens_per_s=replicas * batch * gen / ((pre + dec) * 1e-3),
         prefill_ms=pre, decode_ms=dec, decode_step_ms=step_ms, gpu_launches_per_wave=int(launches),
         e2e=dict(value=replicas * batch / e2e_s, unit="requests/s", path="LlmEngine.generate(host token ids) -> host token ids, wall clock",
