@@ -50,7 +50,8 @@ def _config():
     return dict(workload=WORKLOAD, step="one scheduler batch of 64 single-row requests", max_batch=MAX_BATCH,
                 n_trees=N_TREES, depth=DEPTH, n_features=N_FEATURES,
                 timing="K-step region repeated until >= {} s of timed work and >= {} repeats; median region".format(
-                    MIN_TIMED_S, MIN_REPEATS))
+                    MIN_TIMED_S, MIN_REPEATS),
+                l2="GPU arm: flushed (256 MiB memset on the launching stream) before every timed step of `value`")
 
 
 def _repeat_region(region, min_timed_s=MIN_TIMED_S, min_repeats=MIN_REPEATS, max_wall_s=MAX_LEG_WALL_S):
