@@ -223,6 +223,14 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
 {
     __shared__ float red[8];
     sm100::griddep_launch_dependents();
+    // the norm weights are constants: fetched before the dependency resolves instead of after the row reduction (one L2 round trip
+    // less on the step's critical path, twice per layer)
+    float4 gam[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = (it * 256 + threadIdx.x) * 4;
+        gam[it] = i < H ? __ldg(reinterpret_cast<const float4 *>(w + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     sm100::griddep_wait();
     // the projection before this kernel has completed: tell the NEXT projection (already resident, ring full, spinning before its
     // own dependency wait) that HBM is idle for the next few microseconds (skinny.cu)
@@ -341,7 +349,7 @@ llm_reduce_rms_kernel(const void *__restrict__ mine, const void *peer, float *ze
     for (int it = 0; it < 8; ++it) {
         const int i = (it * 256 + threadIdx.x) * 4;
         if (i < H) {
-            const float4 g = __ldg(reinterpret_cast<const float4 *>(w + i));
+            const float4 g = gam[it];
             __nv_bfloat162 o0 = __floats2bfloat162_rn(v[it].x * inv * g.x, v[it].y * inv * g.y);
             __nv_bfloat162 o1 = __floats2bfloat162_rn(v[it].z * inv * g.z, v[it].w * inv * g.w);
             uint2 u;
