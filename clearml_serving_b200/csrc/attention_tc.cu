@@ -306,7 +306,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const int64_t *_
             for (; have; it = nxt, n = n_nxt, have = more) {
                 const int sb = (NSB == 2) ? grp : 0;
                 const uint32_t use = (NSB == 2) ? (n >> 1) : n;
-                const int nkb = (it.S + AT_BN - 1) / AT_BN;
                 const int n_chunks = (it.S + 31) >> 5;                       // 32-key chunks that hold at least one key of the sequence
                 const uint32_t sbase = tmem_base + (uint32_t)(sb * sbuf_cols) + lane_base;
                 uint32_t *kb_words = kbits + (grp * 2 + (int)(use & 1u)) * 12;
