@@ -12,7 +12,7 @@ hypothesis = pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
 
 from clearml_serving_b200 import llm_service as S  # noqa: E402
-from test_llm_service import FakePagedLlm, _expected  # noqa: E402
+from tests.test_llm_service import FakePagedLlm, _expected  # noqa: E402
 
 request = st.tuples(st.integers(1, 120), st.integers(1, 40), st.integers(0, 3), st.booleans())
 
